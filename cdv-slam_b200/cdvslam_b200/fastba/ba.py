@@ -1,0 +1,11 @@
+"""Mirror of the reference's cdvslam/fastba/ba.py (same names, same argument order)."""
+import cuda_ba
+
+neighbors = cuda_ba.neighbors
+reproject = cuda_ba.reproject
+
+
+def BA(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, t0, t1, M, iterations, eff_impl=False):
+    """In-place patch-graph bundle adjustment; signature of cdvslam/fastba/ba.py:7-8."""
+    return cuda_ba.forward(poses.data, patches, intrinsics, target, weight, lmbda, ii, jj, kk, M, t0, t1, iterations,
+                           eff_impl)

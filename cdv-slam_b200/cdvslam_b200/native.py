@@ -1,0 +1,104 @@
+"""ctypes binding of libpgba.so (the C ABI declared in include/pgba.h and include/pcorr.h).
+
+PyTorch is only the owner of device memory and streams here: tensors are passed as raw device pointers
+(`tensor.data_ptr()`) together with `torch.cuda.current_stream().cuda_stream`.  There is no CPU or eager fallback:
+importing this module without the built library, or calling an op with CPU tensors, raises.
+"""
+import ctypes
+import os
+import subprocess
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PKG_ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(PKG_ROOT, "lib", "libpgba.so")
+BUILD_SCRIPT = os.path.join(PKG_ROOT, "csrc", "build.sh")
+
+c_i64, c_int, c_vp, c_sz = ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t
+
+
+class Strides(ctypes.Structure):
+    _fields_ = [(n, c_i64) for n in ("poses", "patches", "intrinsics", "target", "weight", "lmbda", "ii", "jj", "kk")]
+
+
+# name -> (restype, argtypes); mirrors include/pgba.h and include/pcorr.h one to one
+SIGNATURES = {
+    "pgba_error_string": (ctypes.c_char_p, [c_int]),
+    "pgba_version": (c_int, []),
+    "pgba_ba_workspace_bytes": (c_int, [c_i64, c_i64, c_i64, c_int, c_int, c_i64, ctypes.POINTER(c_sz)]),
+    "pgba_ba_solve": (c_int, [c_vp] * 9 + [c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_sz,
+                                           c_vp]),
+    "pgba_ba_solve_batched": (c_int, [c_vp] * 10 + [ctypes.POINTER(Strides), c_i64, c_i64, c_i64, c_i64, c_int, c_int,
+                                                     c_int, c_int, c_int, c_int, c_vp, c_sz, c_vp]),
+    "pgba_ba_linearize_debug": (c_int, [c_vp] * 9 + [c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int] + [c_vp] * 10 +
+                                [c_vp, c_sz, c_vp]),
+    "pgba_ba_status_ptr": (c_vp, [c_vp, c_sz, c_i64]),
+    "pgba_reproject": (c_int, [c_vp] * 6 + [c_i64, c_i64, c_i64, c_int, c_int, c_vp, c_vp]),
+    "pcorr_forward": (c_int, [c_vp] * 5 + [c_int, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_vp,
+                                           c_vp]),
+    "pcorr_forward_pyramid2": (c_int, [c_vp] * 6 + [c_int, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int,
+                                                    c_int, c_int, c_int, c_vp, c_vp]),
+    "pcorr_backward": (c_int, [c_vp] * 6 + [c_int, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_vp,
+                                            c_vp, c_vp]),
+    "pcorr_patchify_forward": (c_int, [c_vp, c_vp, c_int, c_i64, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "pcorr_patchify_backward": (c_int, [c_vp, c_vp, c_int, c_i64, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+}
+
+_lib = None
+
+
+def build(verbose=False):
+    """Compile libpgba.so for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    res = subprocess.run(["bash", BUILD_SCRIPT], capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout[-4000:])
+        print(res.stderr[-4000:])
+    if res.returncode != 0:
+        raise RuntimeError("building libpgba.so failed")
+    return LIB_PATH
+
+
+def lib():
+    """The loaded library; raises if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libpgba.so is missing at %s -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(or bash cdv-slam_b200/csrc/build.sh); there is no CPU fallback" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError("%s failed: %s (code %d)" % (what, lib().pgba_error_string(rc).decode(), rc))
+
+
+def stream_ptr(device=None):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if not t.is_cuda:
+            raise RuntimeError("cdvslam_b200 ops run on CUDA tensors only (got a %s tensor); there is no CPU path"
+                               % t.device)
+
+
+_workspaces = {}
+
+
+def workspace(nbytes, device):
+    """Grow-only per-device scratch buffer (the C ABI never allocates)."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf

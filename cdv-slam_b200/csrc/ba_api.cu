@@ -1,0 +1,204 @@
+// extern "C" entry points of the BA part of libpgba.so (see include/pgba.h) + the reproject kernel.
+#include <stdio.h>
+
+#include "ba_common.cuh"
+
+namespace pgba {
+void launch_plan(const Problem& pb, int64_t batch, cudaStream_t stream);
+size_t plan_bucket_smem_bytes(const Layout& L);
+cudaError_t launch_iteration(const Problem& pb, int64_t batch, bool apply, cudaStream_t stream);
+bool solve_small_supported(int N);
+
+// all PxP pixels of every edge's patch, frame ii -> jj  (reference: cdvslam/fastba/ba_cuda.cu:408-458)
+// one thread per (edge, pixel); coords [E, 2, P, P]
+__global__ void reproject_kernel(const float* __restrict__ poses, const float* __restrict__ patches,
+                                 const float* __restrict__ intr, const int64_t* __restrict__ ii,
+                                 const int64_t* __restrict__ jj, const int64_t* __restrict__ kk, int64_t E, int P,
+                                 int clamp_depth, float* __restrict__ coords) {
+  const int PP = P * P;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= E * PP) return;
+  const int64_t n = idx / PP;
+  const int px = (int)(idx - n * PP);
+  const float fx = intr[0], fy = intr[1], cx = intr[2], cy = intr[3];
+  float R[9], t[3];
+  rel_pose(poses + 7 * ii[n], poses + 7 * jj[n], R, t);
+  const float* pr = patches + kk[n] * 3 * PP;
+  const float xi0 = (pr[px] - cx) / fx, xi1 = (pr[PP + px] - cy) / fy, pd = pr[2 * PP + px];
+  const float X = R[0] * xi0 + R[1] * xi1 + R[2] + pd * t[0];
+  const float Y = R[3] * xi0 + R[4] * xi1 + R[5] + pd * t[1];
+  const float Z = R[6] * xi0 + R[7] * xi1 + R[8] + pd * t[2];
+  float u, v;
+  if (clamp_depth) {                       // projective_ops.proj: d = 1 / Z.clamp(min=0.1)  (projective_ops.py:43)
+    const float d = 1.0f / fmaxf(Z, 0.1f);
+    u = fx * (d * X) + cx;
+    v = fy * (d * Y) + cy;
+  } else {                                 // ba_cuda.cu:451-452
+    u = fx * (X / Z) + cx;
+    v = fy * (Y / Z) + cy;
+  }
+  coords[n * 2 * PP + px] = u;
+  coords[n * 2 * PP + PP + px] = v;
+}
+
+__global__ void export_debug_kernel(Problem pb, float* S, float* y, float* dX, int64_t* patch_ids, float* C, float* u,
+                                    float* Q, float* dZ, int32_t* n_unique, int32_t* status) {
+  const WinPtrs wp = win_ptrs(pb.ws, pb.L, 0);
+  const size_t n6 = (size_t)6 * (pb.t1 - pb.t0);
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, T = (size_t)gridDim.x * blockDim.x;
+  const float lm = pb.lmbda[0];
+  if (S) for (size_t x = tid; x < n6 * n6; x += T) S[x] = wp.S[x];
+  if (y) for (size_t x = tid; x < n6; x += T) y[x] = wp.y[x];
+  if (dX) for (size_t x = tid; x < n6; x += T) dX[x] = wp.dX[x];
+  const int M = wp.hdr->n_patches;
+  for (size_t x = tid; x < (size_t)M; x += T) {
+    if (patch_ids) patch_ids[x] = wp.kx[x];
+    if (Q) Q[x] = wp.Q[x];
+    if (C) C[x] = 1.0f / wp.Q[x] - lm;
+    if (u) u[x] = wp.u[x];
+    if (dZ) dZ[x] = wp.dZ[x];
+  }
+  if (tid == 0) {
+    if (n_unique) *n_unique = M;
+    if (status) *status = wp.hdr->status;
+  }
+}
+
+static int check_common(const void* poses, const void* patches, const void* intrinsics, const void* target,
+                        const void* weight, const void* lmbda, const void* ii, const void* jj, const void* kk,
+                        int64_t E, int64_t F, int64_t K, int P, int t0, int t1) {
+  if (!poses || !patches || !intrinsics || !lmbda) return PGBA_ERR_NULL;
+  if (E > 0 && (!target || !weight || !ii || !jj || !kk)) return PGBA_ERR_NULL;
+  if (E < 0 || F <= 0 || K <= 0 || P < 2 || t0 < 0 || t1 < t0 || t1 > F) return PGBA_ERR_SHAPE;
+  if (E >= (int64_t)1 << 31 || K >= (int64_t)1 << 31) return PGBA_ERR_UNSUPPORTED;
+  if (F > PGBA_MAX_POSE_ROWS) return PGBA_ERR_UNSUPPORTED;
+  return PGBA_OK;
+}
+
+static Problem make_problem(float* poses, float* patches, const float* intrinsics, const float* target,
+                            const float* weight, const float* lmbda, const int64_t* ii, const int64_t* jj,
+                            const int64_t* kk, const int32_t* n_edges_dev, const pgba_strides* st, int64_t E,
+                            int64_t F, int64_t K, int P, int t0, int t1, void* ws) {
+  Problem pb{};
+  pb.poses = poses; pb.patches = patches; pb.intrinsics = intrinsics; pb.target = target; pb.weight = weight;
+  pb.lmbda = lmbda; pb.ii = ii; pb.jj = jj; pb.kk = kk; pb.n_edges_dev = n_edges_dev;
+  if (st) pb.st = *st;
+  pb.E = E; pb.F = (int)F; pb.K = (int)K; pb.P = P; pb.t0 = t0; pb.t1 = t1; pb.with_schur = 1;
+  pb.ws = ws;
+  pb.L = make_layout(E, F, K, t1 - t0);
+  return pb;
+}
+}  // namespace pgba
+
+using namespace pgba;
+
+extern "C" {
+
+const char* pgba_error_string(int code) {
+  switch (code) {
+    case PGBA_OK: return "ok";
+    case PGBA_ERR_NULL: return "pgba: required pointer is NULL";
+    case PGBA_ERR_SHAPE: return "pgba: invalid size / shape argument";
+    case PGBA_ERR_WORKSPACE: return "pgba: workspace too small or misaligned";
+    case PGBA_ERR_UNSUPPORTED: return "pgba: configuration outside the implemented range";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "pgba: unknown error";
+  }
+}
+
+int pgba_version(void) { return 100; }
+
+int pgba_ba_workspace_bytes(int64_t n_edges, int64_t n_pose_rows, int64_t n_patch_rows, int t0, int t1,
+                            int64_t batch, size_t* bytes) {
+  if (!bytes) return PGBA_ERR_NULL;
+  if (n_edges < 0 || n_pose_rows <= 0 || n_patch_rows <= 0 || t1 < t0 || batch <= 0) return PGBA_ERR_SHAPE;
+  const Layout L = make_layout(n_edges, n_pose_rows, n_patch_rows, t1 - t0);
+  *bytes = L.win_bytes * (size_t)batch;
+  return PGBA_OK;
+}
+
+int pgba_ba_solve_batched(float* poses, float* patches, const float* intrinsics, const float* target,
+                          const float* weight, const float* lmbda, const int64_t* ii, const int64_t* jj,
+                          const int64_t* kk, const int32_t* n_edges_dev, const pgba_strides* strides, int64_t batch,
+                          int64_t n_edges, int64_t n_pose_rows, int64_t n_patch_rows, int P, int ppf, int t0, int t1,
+                          int iterations, int eff_impl, void* workspace, size_t workspace_bytes,
+                          pgba_stream_t stream) {
+  (void)ppf; (void)eff_impl;
+  int rc = check_common(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, n_edges, n_pose_rows,
+                        n_patch_rows, P, t0, t1);
+  if (rc) return rc;
+  if (batch <= 0 || iterations < 0) return PGBA_ERR_SHAPE;
+  if (batch > 1 && !strides) return PGBA_ERR_NULL;
+  if (batch > 65535) return PGBA_ERR_UNSUPPORTED;
+  if (!workspace || ((uintptr_t)workspace & 255)) return PGBA_ERR_WORKSPACE;
+  Problem pb = make_problem(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, n_edges_dev, strides,
+                            n_edges, n_pose_rows, n_patch_rows, P, t0, t1, workspace);
+  if (pb.L.win_bytes * (size_t)batch > workspace_bytes) return PGBA_ERR_WORKSPACE;
+  if (plan_bucket_smem_bytes(pb.L) > 227 * 1024) return PGBA_ERR_UNSUPPORTED;
+  if (t1 > t0 && !solve_small_supported(t1 - t0)) return PGBA_ERR_UNSUPPORTED;
+  if (iterations == 0 || n_edges == 0) return PGBA_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  launch_plan(pb, batch, s);
+  for (int it = 0; it < iterations; ++it) {
+    cudaError_t e = launch_iteration(pb, batch, true, s);
+    if (e != cudaSuccess) return (int)e;
+  }
+  return (int)cudaGetLastError();
+}
+
+int pgba_ba_solve(float* poses, float* patches, const float* intrinsics, const float* target, const float* weight,
+                  const float* lmbda, const int64_t* ii, const int64_t* jj, const int64_t* kk, int64_t n_edges,
+                  int64_t n_pose_rows, int64_t n_patch_rows, int P, int ppf, int t0, int t1, int iterations,
+                  int eff_impl, void* workspace, size_t workspace_bytes, pgba_stream_t stream) {
+  pgba_strides st{};
+  return pgba_ba_solve_batched(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, nullptr, &st, 1,
+                               n_edges, n_pose_rows, n_patch_rows, P, ppf, t0, t1, iterations, eff_impl, workspace,
+                               workspace_bytes, stream);
+}
+
+int pgba_ba_linearize_debug(const float* poses, const float* patches, const float* intrinsics, const float* target,
+                            const float* weight, const float* lmbda, const int64_t* ii, const int64_t* jj,
+                            const int64_t* kk, int64_t n_edges, int64_t n_pose_rows, int64_t n_patch_rows, int P,
+                            int t0, int t1, int with_schur, float* S, float* y, float* dX, int64_t* patch_ids,
+                            float* C, float* u, float* Q, float* dZ, int32_t* n_unique, int32_t* status,
+                            void* workspace, size_t workspace_bytes, pgba_stream_t stream) {
+  int rc = check_common(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, n_edges, n_pose_rows,
+                        n_patch_rows, P, t0, t1);
+  if (rc) return rc;
+  if (!workspace || ((uintptr_t)workspace & 255)) return PGBA_ERR_WORKSPACE;
+  pgba_strides st{};
+  Problem pb = make_problem((float*)poses, (float*)patches, intrinsics, target, weight, lmbda, ii, jj, kk, nullptr,
+                            &st, n_edges, n_pose_rows, n_patch_rows, P, t0, t1, workspace);
+  pb.with_schur = with_schur ? 1 : 0;
+  if (pb.L.win_bytes > workspace_bytes) return PGBA_ERR_WORKSPACE;
+  if (plan_bucket_smem_bytes(pb.L) > 227 * 1024) return PGBA_ERR_UNSUPPORTED;
+  if (t1 > t0 && !solve_small_supported(t1 - t0)) return PGBA_ERR_UNSUPPORTED;
+  cudaStream_t s = (cudaStream_t)stream;
+  launch_plan(pb, 1, s);
+  cudaError_t e = launch_iteration(pb, 1, false, s);
+  if (e != cudaSuccess) return (int)e;
+  export_debug_kernel<<<64, 256, 0, s>>>(pb, S, y, dX, patch_ids, C, u, Q, dZ, n_unique, status);
+  return (int)cudaGetLastError();
+}
+
+const int32_t* pgba_ba_status_ptr(const void* workspace, size_t window_bytes, int64_t b) {
+  if (!workspace || b < 0) return nullptr;
+  const WinHeader* h = (const WinHeader*)((const char*)workspace + (size_t)b * window_bytes);   // header is first
+  return &h->status;
+}
+
+int pgba_reproject(const float* poses, const float* patches, const float* intrinsics, const int64_t* ii,
+                   const int64_t* jj, const int64_t* kk, int64_t n_edges, int64_t n_pose_rows, int64_t n_patch_rows,
+                   int P, int clamp_depth, float* coords, pgba_stream_t stream) {
+  (void)n_pose_rows; (void)n_patch_rows;
+  if (n_edges == 0) return PGBA_OK;
+  if (!poses || !patches || !intrinsics || !ii || !jj || !kk || !coords) return PGBA_ERR_NULL;
+  if (n_edges < 0 || P < 1) return PGBA_ERR_SHAPE;
+  const int64_t total = n_edges * P * P;
+  const int64_t blocks = (total + 255) / 256;
+  if (blocks >= (int64_t)1 << 31) return PGBA_ERR_UNSUPPORTED;
+  reproject_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(poses, patches, intrinsics, ii, jj, kk,
+                                                                      n_edges, P, clamp_depth, coords);
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

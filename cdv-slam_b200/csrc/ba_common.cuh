@@ -1,0 +1,170 @@
+// Shared device helpers and workspace layout of the patch-graph BA kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pgba.h"
+
+namespace pgba {
+
+constexpr int PMAX = 128;                 // patches per chunk (one source frame, <= PMAX consecutive patch ids)
+constexpr int SMAX = PGBA_MAX_SLOTS;      // distinct target frames per chunk
+constexpr int EBUDGET = 12288;            // floats of shared memory for the per-batch E tile (48 KB)
+
+// ---------------------------------------------------------------------------------------------------------------
+// Workspace (per window).  All offsets are byte offsets from the window's base; every array is 256-byte aligned.
+// ---------------------------------------------------------------------------------------------------------------
+struct WinHeader {      // device side, zeroed at the start of every call
+  int n_chunks;
+  int n_patches;        // bump cursor: unique (source frame, patch) rows allocated so far
+  int n_slots;          // bump cursor into slot_frames
+  int n_cells;          // bump cursor into cells
+  int n_ecells;         // bump cursor into ecells (units of 6 floats)
+  int n_dups;           // duplicate (patch, target frame) edges
+  int status;           // PGBA_ST_* bits
+  int n_valid_edges;
+};
+
+struct Chunk {          // 64 bytes
+  int frame;            // source frame i
+  int kbase;            // patch ids covered: [kbase, kbase + PMAX)
+  int edge_begin, edge_end;
+  int n_patches, n_slots;
+  int patch_base, slot_base, cell_base, ecell_base;
+  int first_free;       // slots [first_free, first_free + n_free) are free poses (slots are sorted by frame)
+  int n_free;
+  int icol;             // E column of the source frame (-1 when the source pose is fixed)
+  int ncols;            // n_free (+1 when the source frame is free and not itself a target)
+  int pad0, pad1;
+};
+
+struct DupEdge { int chunk, p, s, n; };
+
+struct Layout {         // host-computed
+  int64_t E, F, K;      // edges (max per window), pose rows, patch rows
+  int N;                // free poses
+  int64_t ch_max, patch_max, slot_max, cell_cap, ecell_cap;
+  size_t o_hdr, o_chunks, o_perm, o_kx, o_slots, o_cells, o_dups, o_ecells, o_Q, o_u, o_dZ, o_S, o_y, o_dX;
+  size_t win_bytes;
+};
+
+inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+inline Layout make_layout(int64_t E, int64_t F, int64_t K, int N) {
+  Layout L{};
+  L.E = E; L.F = F; L.K = K; L.N = N;
+  int64_t e1 = E > 0 ? E : 1;
+  L.ch_max = F + K / PMAX + 1;
+  if (L.ch_max > e1) L.ch_max = e1;
+  L.patch_max = K < e1 ? K : e1;
+  if (L.patch_max < 1) L.patch_max = 1;
+  L.slot_max = e1;
+  L.cell_cap = 8 * e1 + 1024;
+  L.ecell_cap = N > 0 ? (L.cell_cap + L.patch_max) : 1;
+  size_t o = 0;
+  L.o_hdr = o;    o = align256(o + sizeof(WinHeader));
+  L.o_chunks = o; o = align256(o + sizeof(Chunk) * (size_t)L.ch_max);
+  L.o_perm = o;   o = align256(o + 4 * (size_t)e1);
+  L.o_kx = o;     o = align256(o + 4 * (size_t)L.patch_max);
+  L.o_slots = o;  o = align256(o + 4 * (size_t)L.slot_max);
+  L.o_cells = o;  o = align256(o + 4 * (size_t)L.cell_cap);
+  L.o_dups = o;   o = align256(o + sizeof(DupEdge) * (size_t)e1);
+  L.o_ecells = o; o = align256(o + 24 * (size_t)L.ecell_cap);
+  L.o_Q = o;      o = align256(o + 4 * (size_t)L.patch_max);
+  L.o_u = o;      o = align256(o + 4 * (size_t)L.patch_max);
+  L.o_dZ = o;     o = align256(o + 4 * (size_t)L.patch_max);
+  size_t n6 = (size_t)6 * (size_t)(N > 0 ? N : 1);
+  L.o_S = o;      o = align256(o + 4 * n6 * n6);
+  L.o_y = o;      o = align256(o + 4 * n6);
+  L.o_dX = o;     o = align256(o + 4 * n6);
+  L.win_bytes = o;
+  return L;
+}
+
+// Pointers of one window, resolved on the device from (workspace base, window index, layout).
+struct WinPtrs {
+  WinHeader* hdr; Chunk* chunks; int* perm; int* kx; int* slots; int* cells; DupEdge* dups; float* ecells;
+  float* Q; float* u; float* dZ; float* S; float* y; float* dX;
+};
+
+__host__ __device__ inline WinPtrs win_ptrs(void* ws, const Layout& L, int64_t b) {
+  char* base = (char*)ws + (size_t)b * L.win_bytes;
+  WinPtrs p;
+  p.hdr = (WinHeader*)(base + L.o_hdr);
+  p.chunks = (Chunk*)(base + L.o_chunks);
+  p.perm = (int*)(base + L.o_perm);
+  p.kx = (int*)(base + L.o_kx);
+  p.slots = (int*)(base + L.o_slots);
+  p.cells = (int*)(base + L.o_cells);
+  p.dups = (DupEdge*)(base + L.o_dups);
+  p.ecells = (float*)(base + L.o_ecells);
+  p.Q = (float*)(base + L.o_Q);
+  p.u = (float*)(base + L.o_u);
+  p.dZ = (float*)(base + L.o_dZ);
+  p.S = (float*)(base + L.o_S);
+  p.y = (float*)(base + L.o_y);
+  p.dX = (float*)(base + L.o_dX);
+  return p;
+}
+
+// Problem description shared by all kernels (passed by value).
+struct Problem {
+  float* poses; float* patches; const float* intrinsics; const float* target; const float* weight; const float* lmbda;
+  const int64_t* ii; const int64_t* jj; const int64_t* kk; const int32_t* n_edges_dev;
+  pgba_strides st;
+  int64_t E; int F; int K; int P; int t0; int t1; int with_schur;
+  void* ws; Layout L;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// SE3 helpers.  Same arithmetic as the reference's device helpers (cdvslam/fastba/ba_cuda.cu:36-174) but organised
+// around the 3x3 matrix of the (possibly non-unit) relative quaternion so that it is computed once per frame pair.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void rot_q(const float q[4], const float X[3], float Y[3]) {   // ba_cuda.cu:36-46
+  float uv0 = 2.0f * (q[1] * X[2] - q[2] * X[1]);
+  float uv1 = 2.0f * (q[2] * X[0] - q[0] * X[2]);
+  float uv2 = 2.0f * (q[0] * X[1] - q[1] * X[0]);
+  Y[0] = X[0] + q[3] * uv0 + (q[1] * uv2 - q[2] * uv1);
+  Y[1] = X[1] + q[3] * uv1 + (q[2] * uv0 - q[0] * uv2);
+  Y[2] = X[2] + q[3] * uv2 + (q[0] * uv1 - q[1] * uv0);
+}
+
+// Relative transform Gij = Gj * Gi^-1 as (R row-major [9], t [3])   (ba_cuda.cu:74-85)
+__device__ __forceinline__ void rel_pose(const float* __restrict__ Pi, const float* __restrict__ Pj, float R[9],
+                                         float t[3]) {
+  const float qi[4] = {Pi[3], Pi[4], Pi[5], Pi[6]}, qj[4] = {Pj[3], Pj[4], Pj[5], Pj[6]};
+  float q[4];
+  q[0] = -qj[3] * qi[0] + qj[0] * qi[3] - qj[1] * qi[2] + qj[2] * qi[1];
+  q[1] = -qj[3] * qi[1] + qj[1] * qi[3] - qj[2] * qi[0] + qj[0] * qi[2];
+  q[2] = -qj[3] * qi[2] + qj[2] * qi[3] - qj[0] * qi[1] + qj[1] * qi[0];
+  q[3] = qj[3] * qi[3] + qj[0] * qi[0] + qj[1] * qi[1] + qj[2] * qi[2];
+  const float ti[3] = {Pi[0], Pi[1], Pi[2]};
+  float r[3];
+  rot_q(q, ti, r);
+  t[0] = Pj[0] - r[0]; t[1] = Pj[1] - r[1]; t[2] = Pj[2] - r[2];
+  const float ex[3] = {1.f, 0.f, 0.f}, ey[3] = {0.f, 1.f, 0.f}, ez[3] = {0.f, 0.f, 1.f};
+  float c0[3], c1[3], c2[3];
+  rot_q(q, ex, c0); rot_q(q, ey, c1); rot_q(q, ez, c2);
+  R[0] = c0[0]; R[1] = c1[0]; R[2] = c2[0];
+  R[3] = c0[1]; R[4] = c1[1]; R[5] = c2[1];
+  R[6] = c0[2]; R[7] = c1[2]; R[8] = c2[2];
+}
+
+// The map the reference calls adjSE3 (ba_cuda.cu:57-72): Y[:3] = R^T a, Y[3:] = R^T (b + a x t), X = (a, b).
+__device__ __forceinline__ void adj_map(const float R[9], const float t[3], const float X[6], float Y[6]) {
+  const float a0 = X[0], a1 = X[1], a2 = X[2];
+  const float b0 = X[3] + (a1 * t[2] - a2 * t[1]);
+  const float b1 = X[4] + (a2 * t[0] - a0 * t[2]);
+  const float b2 = X[5] + (a0 * t[1] - a1 * t[0]);
+  Y[0] = R[0] * a0 + R[3] * a1 + R[6] * a2;
+  Y[1] = R[1] * a0 + R[4] * a1 + R[7] * a2;
+  Y[2] = R[2] * a0 + R[5] * a1 + R[8] * a2;
+  Y[3] = R[0] * b0 + R[3] * b1 + R[6] * b2;
+  Y[4] = R[1] * b0 + R[4] * b1 + R[7] * b2;
+  Y[5] = R[2] * b0 + R[5] * b1 + R[8] * b2;
+}
+
+// Upper-triangular packing of a symmetric 6x6: index of (r, c) with r <= c.
+__host__ __device__ constexpr int sym6(int r, int c) { return r * 6 - (r * (r - 1)) / 2 + (c - r); }
+
+}  // namespace pgba

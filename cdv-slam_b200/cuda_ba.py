@@ -1,0 +1,101 @@
+"""Drop-in replacement for the reference's compiled extension module `cuda_ba`
+(pybind table: cdvslam/fastba/ba.cpp:183-188; imported by cdvslam/fastba/ba.py:2 and loop_closure/optim_utils.py:1).
+
+Same function names, argument order and in-place semantics; the work is done by libpgba.so through the C ABI of
+include/pgba.h.  Put the directory containing this file on sys.path ahead of the reference's build products and
+`import cuda_ba` resolves here.
+"""
+import ctypes
+
+import torch
+
+from cdvslam_b200 import native
+
+
+def _prep(t, dtype, name):
+    if t.dtype != dtype:
+        raise RuntimeError("cuda_ba: %s must be %s (got %s)" % (name, dtype, t.dtype))
+    native.require_cuda(t)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def forward(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, PPF, t0, t1, iterations, eff_impl=False):
+    """cuda_ba.forward (ba.cpp:32-45 -> cuda_ba(), ba_cuda.cu:462-611).  Mutates `poses` rows t0..t1-1 and the
+    inverse-depth channel of `patches` in place; returns [] like the reference."""
+    for name, t in (("poses", poses), ("patches", patches)):
+        if not t.is_contiguous():
+            raise RuntimeError("cuda_ba.forward: %s must be contiguous (it is updated in place)" % name)
+    poses_ = _prep(poses, torch.float32, "poses")
+    patches_ = _prep(patches, torch.float32, "patches")
+    intrinsics = _prep(intrinsics, torch.float32, "intrinsics")
+    target = _prep(target, torch.float32, "target")
+    weight = _prep(weight, torch.float32, "weight")
+    lmbda = _prep(lmbda, torch.float32, "lmbda")
+    ii = _prep(ii, torch.int64, "ii")
+    jj = _prep(jj, torch.int64, "jj")
+    kk = _prep(kk, torch.int64, "kk")
+    P = patches_.shape[-1]
+    F = poses_.numel() // 7
+    K = patches_.numel() // (3 * P * P)
+    E = ii.numel()
+    if target.numel() != 2 * E or weight.numel() != 2 * E or jj.numel() != E or kk.numel() != E:
+        raise RuntimeError("cuda_ba.forward: target/weight/ii/jj/kk sizes disagree")
+    L = native.lib()
+    nbytes = ctypes.c_size_t(0)
+    native.check(L.pgba_ba_workspace_bytes(E, F, K, int(t0), int(t1), 1, ctypes.byref(nbytes)),
+                 "pgba_ba_workspace_bytes")
+    with torch.cuda.device(poses_.device):
+        ws = native.workspace(nbytes.value, poses_.device)
+        rc = L.pgba_ba_solve(poses_.data_ptr(), patches_.data_ptr(), intrinsics.data_ptr(), target.data_ptr(),
+                             weight.data_ptr(), lmbda.data_ptr(), ii.data_ptr(), jj.data_ptr(), kk.data_ptr(),
+                             E, F, K, P, int(PPF), int(t0), int(t1), int(iterations), int(bool(eff_impl)),
+                             ws.data_ptr(), ws.numel(), native.stream_ptr(poses_.device))
+    native.check(rc, "pgba_ba_solve")
+    return []
+
+
+def reproject(poses, patches, intrinsics, ii, jj, kk, clamp_depth=False):
+    """cuda_ba.reproject (ba.cpp:48-56 -> cuda_reproject(), ba_cuda.cu:614-645): coords f32 [1, E, 2, P, P]."""
+    poses = _prep(poses, torch.float32, "poses")
+    patches = _prep(patches, torch.float32, "patches")
+    intrinsics = _prep(intrinsics, torch.float32, "intrinsics")
+    ii = _prep(ii, torch.int64, "ii")
+    jj = _prep(jj, torch.int64, "jj")
+    kk = _prep(kk, torch.int64, "kk")
+    P = patches.shape[-1]
+    E = ii.numel()
+    coords = torch.empty((1, E, 2, P, P), dtype=torch.float32, device=poses.device)
+    with torch.cuda.device(poses.device):
+        rc = native.lib().pgba_reproject(poses.data_ptr(), patches.data_ptr(), intrinsics.data_ptr(), ii.data_ptr(),
+                                         jj.data_ptr(), kk.data_ptr(), E, poses.numel() // 7,
+                                         patches.numel() // (3 * P * P), P, int(bool(clamp_depth)), coords.data_ptr(),
+                                         native.stream_ptr(poses.device))
+    native.check(rc, "pgba_reproject")
+    return coords
+
+
+def neighbors(ii, jj):
+    """cuda_ba.neighbors (ba.cpp:59-97): for edges grouped by `ii` and stably ordered by `jj`, the index of the
+    previous / next edge of the same group (-1 at the ends).  Runs on the device the tensors live on, without the
+    reference's D2H -> CPU stable_sort -> H2D round trip (not part of the BA arithmetic)."""
+    n = ii.numel()
+    dev = ii.device
+    if n == 0:
+        e = torch.empty(0, dtype=torch.int64, device=dev)
+        return [e, e.clone()]
+    o1 = torch.sort(jj, stable=True).indices
+    order = o1[torch.sort(ii[o1], stable=True).indices]
+    g = ii[order]
+    same = g[1:] == g[:-1]
+    ix = torch.full((n,), -1, dtype=torch.int64, device=dev)
+    jx = torch.full((n,), -1, dtype=torch.int64, device=dev)
+    minus1 = torch.full((n - 1,), -1, dtype=torch.int64, device=dev)
+    ix[order[1:]] = torch.where(same, order[:-1], minus1)
+    jx[order[:-1]] = torch.where(same, order[1:], minus1)
+    return [ix, jx]
+
+
+def solve_system(J_Ginv_i, J_Ginv_j, ii, jj, res, ep, lm, freen):
+    """cuda_ba.solve_system (ba.cpp:120-180): Sim3 pose-graph normal equations + sparse Cholesky on the CPU (Eigen).
+    Only used by the optional classical loop closure; out of scope for this round."""
+    raise NotImplementedError("cuda_ba.solve_system (classical loop-closure PGO) is not part of the B200 hot path yet")

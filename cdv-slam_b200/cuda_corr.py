@@ -1,0 +1,116 @@
+"""Drop-in replacement for the reference's compiled extension module `cuda_corr`
+(pybind table: cdvslam/altcorr/correlation.cpp:57-63; imported by cdvslam/altcorr/correlation.py:2).
+Same function names, argument order and return conventions (lists of tensors); the work is done by libpgba.so
+through the C ABI of include/pcorr.h."""
+import torch
+
+from cdvslam_b200 import native
+
+_DT = {torch.float32: 0, torch.float16: 1}
+
+
+def _dt(t, what):
+    if t.dtype not in _DT:
+        raise RuntimeError("cuda_corr.%s: feature maps must be float32 or float16 (got %s)" % (what, t.dtype))
+    return _DT[t.dtype]
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def forward(fmap1, fmap2, coords, ii, jj, radius):
+    """cuda_corr.forward (correlation.cpp:28-35 -> corr_cuda_forward, correlation_kernel.cu:193-233).
+    Returns [corr] with corr [B, E, 2R+1 (x-off), 2R+1 (y-off), P, P] in fmap1's dtype."""
+    native.require_cuda(fmap1, fmap2, coords, ii, jj)
+    dt = _dt(fmap1, "forward")
+    if fmap2.dtype != fmap1.dtype:
+        raise RuntimeError("cuda_corr.forward: fmap1 and fmap2 dtypes differ")
+    fmap1, fmap2, ii, jj = _c(fmap1), _c(fmap2), _c(ii.long()), _c(jj.long())
+    coords = _c(coords.float())
+    B, E, _, P, _ = coords.shape
+    K, C = fmap1.shape[1], fmap1.shape[2]
+    F, H2, W2 = fmap2.shape[1], fmap2.shape[3], fmap2.shape[4]
+    D = 2 * radius + 1
+    out = torch.empty((B, E, D, D, P, P), dtype=fmap1.dtype, device=fmap1.device)
+    with torch.cuda.device(fmap1.device):
+        rc = native.lib().pcorr_forward(fmap1.data_ptr(), fmap2.data_ptr(), coords.data_ptr(), ii.data_ptr(),
+                                        jj.data_ptr(), B, E, K, F, C, H2, W2, P, int(radius), dt, out.data_ptr(),
+                                        native.stream_ptr(fmap1.device))
+    native.check(rc, "pcorr_forward")
+    return [out]
+
+
+def forward_pyramid2(fmap1, fmap2_l0, fmap2_l1, coords, ii, jj, radius):
+    """Fused two-level lookup (extension): equals torch.stack([corr(l0, coords), corr(l1, coords / 4)], -1) of
+    cdvslam/slam.py:321-323.  Returns [B, E, 2R+1, 2R+1, P, P, 2]."""
+    native.require_cuda(fmap1, fmap2_l0, fmap2_l1, coords, ii, jj)
+    dt = _dt(fmap1, "forward_pyramid2")
+    fmap1, fmap2_l0, fmap2_l1, ii, jj = _c(fmap1), _c(fmap2_l0), _c(fmap2_l1), _c(ii.long()), _c(jj.long())
+    coords = _c(coords.float())
+    B, E, _, P, _ = coords.shape
+    K, C = fmap1.shape[1], fmap1.shape[2]
+    F = fmap2_l0.shape[1]
+    D = 2 * radius + 1
+    out = torch.empty((B, E, D, D, P, P, 2), dtype=fmap1.dtype, device=fmap1.device)
+    with torch.cuda.device(fmap1.device):
+        rc = native.lib().pcorr_forward_pyramid2(fmap1.data_ptr(), fmap2_l0.data_ptr(), fmap2_l1.data_ptr(),
+                                                 coords.data_ptr(), ii.data_ptr(), jj.data_ptr(), B, E, K, F, C,
+                                                 fmap2_l0.shape[3], fmap2_l0.shape[4], fmap2_l1.shape[3],
+                                                 fmap2_l1.shape[4], P, int(radius), dt, out.data_ptr(),
+                                                 native.stream_ptr(fmap1.device))
+    native.check(rc, "pcorr_forward_pyramid2")
+    return out
+
+
+def backward(fmap1, fmap2, coords, ii, jj, corr_grad, radius):
+    """cuda_corr.backward (correlation.cpp:37-45 -> corr_cuda_backward, correlation_kernel.cu:236-286)."""
+    native.require_cuda(fmap1, fmap2, coords, ii, jj, corr_grad)
+    dt = _dt(fmap1, "backward")
+    fmap1, fmap2, ii, jj = _c(fmap1), _c(fmap2), _c(ii.long()), _c(jj.long())
+    coords = _c(coords.float())
+    grad = _c(corr_grad.float())
+    B, E, _, P, _ = coords.shape
+    K, C = fmap1.shape[1], fmap1.shape[2]
+    F, H2, W2 = fmap2.shape[1], fmap2.shape[3], fmap2.shape[4]
+    g1 = torch.zeros_like(fmap1)
+    g2 = torch.zeros_like(fmap2)
+    with torch.cuda.device(fmap1.device):
+        rc = native.lib().pcorr_backward(fmap1.data_ptr(), fmap2.data_ptr(), coords.data_ptr(), ii.data_ptr(),
+                                         jj.data_ptr(), grad.data_ptr(), B, E, K, F, C, H2, W2, P, int(radius), dt,
+                                         g1.data_ptr(), g2.data_ptr(), native.stream_ptr(fmap1.device))
+    native.check(rc, "pcorr_backward")
+    return [g1, g2]
+
+
+def patchify_forward(net, coords, radius):
+    """cuda_corr.patchify_forward (correlation.cpp:47-50 -> patchify_cuda_forward, correlation_kernel.cu:288-307)."""
+    native.require_cuda(net, coords)
+    dt = _dt(net, "patchify_forward")
+    net = _c(net)
+    coords = _c(coords.float())
+    B, C, H, W = net.shape
+    M = coords.shape[1]
+    D = 2 * radius + 2
+    patches = torch.empty((B, M, C, D, D), dtype=net.dtype, device=net.device)
+    with torch.cuda.device(net.device):
+        rc = native.lib().pcorr_patchify_forward(net.data_ptr(), coords.data_ptr(), B, M, C, H, W, int(radius), dt,
+                                                 patches.data_ptr(), native.stream_ptr(net.device))
+    native.check(rc, "pcorr_patchify_forward")
+    return [patches]
+
+
+def patchify_backward(net, coords, gradient, radius):
+    """cuda_corr.patchify_backward (correlation.cpp:52-55 -> patchify_cuda_backward, correlation_kernel.cu:310-333)."""
+    native.require_cuda(net, coords, gradient)
+    dt = _dt(net, "patchify_backward")
+    coords = _c(coords.float())
+    gradient = _c(gradient.to(net.dtype))
+    B, C, H, W = net.shape
+    M = coords.shape[1]
+    net_grad = torch.zeros_like(net, memory_format=torch.contiguous_format)
+    with torch.cuda.device(net.device):
+        rc = native.lib().pcorr_patchify_backward(gradient.data_ptr(), coords.data_ptr(), B, M, C, H, W, int(radius),
+                                                  dt, net_grad.data_ptr(), native.stream_ptr(net.device))
+    native.check(rc, "pcorr_patchify_backward")
+    return [net_grad]

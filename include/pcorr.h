@@ -1,0 +1,66 @@
+/*
+ * pcorr.h -- C ABI of the B200-native patch correlation lookup / patch gather (libpgba.so).
+ *
+ * Drop-in boundary for the `cuda_corr` extension module of FrankYard/CDV-SLAM
+ * (reference pybind table: cdvslam/altcorr/correlation.cpp:57-63; python: cdvslam/altcorr/correlation.py).
+ * Plain device pointers and sizes; return value 0 = ok, negative = PCORR_ERR_*, positive = cudaError_t.
+ * No host synchronisation, no allocation.
+ */
+#ifndef PCORR_H_
+#define PCORR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* pcorr_stream_t; /* == cudaStream_t */
+
+enum { PCORR_OK = 0, PCORR_ERR_NULL = -1, PCORR_ERR_SHAPE = -2, PCORR_ERR_DTYPE = -3, PCORR_ERR_UNSUPPORTED = -4 };
+enum { PCORR_F32 = 0, PCORR_F16 = 1 };
+
+/* Correlation lookup.  Replaces cuda_corr.forward == corr_cuda_forward() (reference:
+ * cdvslam/altcorr/correlation_kernel.cu:83-136 kernel, :193-233 host incl. the bilinear blend and the final
+ * permute(0,1,3,2,4,5)).
+ *   fmap1  [B, K, C, P, P]      patch features (dtype f32 or f16)
+ *   fmap2  [B, F, C, H2, W2]    frame feature maps, same dtype
+ *   coords f32 [B, E, 2, P, P]  (ch0 = x, ch1 = y) reprojected pixel positions in fmap2's resolution
+ *   ii i64 [E] (index into K), jj i64 [E] (index into F)
+ *   out    [B, E, 2R+1 (x offset), 2R+1 (y offset), P, P], dtype of fmap1, CONTIGUOUS (the reference returns the
+ *          same logical tensor as a permuted view).
+ * Window taps outside the map contribute 0.  Accumulation is fp32 for both dtypes. */
+int pcorr_forward(const void* fmap1, const void* fmap2, const float* coords, const int64_t* ii, const int64_t* jj,
+                  int B, int64_t E, int64_t K, int64_t F, int C, int H2, int W2, int P, int radius, int dtype,
+                  void* out, pcorr_stream_t stream);
+
+/* Fused two-level lookup: what cdvslam/slam.py:316-323 does with two corr() calls + torch.stack(..., -1):
+ * level 0 uses coords, level 1 uses coords / 4 on fmap2_l1; out [B, E, 2R+1, 2R+1, P, P, 2] contiguous. */
+int pcorr_forward_pyramid2(const void* fmap1, const void* fmap2_l0, const void* fmap2_l1, const float* coords,
+                           const int64_t* ii, const int64_t* jj, int B, int64_t E, int64_t K, int64_t F, int C,
+                           int H0, int W0, int H1, int W1, int P, int radius, int dtype, void* out,
+                           pcorr_stream_t stream);
+
+/* Gradient of pcorr_forward w.r.t. fmap1 and fmap2.  Replaces cuda_corr.backward == corr_cuda_backward()
+ * (reference: correlation_kernel.cu:140-190, 236-286).  grad is the gradient of `out` in out's layout, f32;
+ * fmap1_grad / fmap2_grad have the shapes and dtype of fmap1 / fmap2 and must be zero-filled by the caller. */
+int pcorr_backward(const void* fmap1, const void* fmap2, const float* coords, const int64_t* ii, const int64_t* jj,
+                   const float* grad, int B, int64_t E, int64_t K, int64_t F, int C, int H2, int W2, int P,
+                   int radius, int dtype, void* fmap1_grad, void* fmap2_grad, pcorr_stream_t stream);
+
+/* Patch gather.  Replaces cuda_corr.patchify_forward == patchify_cuda_forward() (reference:
+ * correlation_kernel.cu:17-47, 288-307).  net [B, C, H, W]; coords f32 [B, M, 2] (x, y);
+ * patches [B, M, C, D, D] with D = 2R+2, patches[b,m,c,i,j] = net[b,c,floor(y)+i-R,floor(x)+j-R] or 0 outside. */
+int pcorr_patchify_forward(const void* net, const float* coords, int B, int64_t M, int C, int H, int W, int radius,
+                           int dtype, void* patches, pcorr_stream_t stream);
+
+/* Replaces cuda_corr.patchify_backward (reference: correlation_kernel.cu:50-80, 310-333): scatter-add of the
+ * patch gradient [B, M, C, D, D] into net_grad [B, C, H, W] (zero-filled by the caller). */
+int pcorr_patchify_backward(const void* patch_grad, const float* coords, int B, int64_t M, int C, int H, int W,
+                            int radius, int dtype, void* net_grad, pcorr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCORR_H_ */

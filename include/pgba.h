@@ -1,0 +1,114 @@
+/*
+ * pgba.h -- C ABI of the B200-native patch-graph bundle adjustment (libpgba.so).
+ *
+ * Drop-in boundary for the `cuda_ba` extension module of FrankYard/CDV-SLAM
+ * (reference pybind table: cdvslam/fastba/ba.cpp:183-188; python shim: cdvslam/fastba/ba.py:4-8).
+ * Plain pointers and sizes only -- no torch types.  All data pointers are DEVICE pointers unless marked host.
+ * Every entry point returns 0 on success, a negative PGBA_ERR_* for an invalid argument and a positive value
+ * (a cudaError_t) for a CUDA failure; nothing throws, exits or synchronises the host, and nothing allocates:
+ * temporaries live in a caller-owned workspace, so a whole call can be captured in a CUDA graph.
+ *
+ * Tensor layouts are the reference's:
+ *   poses      f32 [n_pose_rows, 7]     (tx ty tz qx qy qz qw), world->camera, updated IN PLACE for rows t0..t1-1
+ *   patches    f32 [n_patch_rows, 3, P, P]  ch0 = x, ch1 = y, ch2 = inverse depth, ch2 updated IN PLACE
+ *   intrinsics f32 [>=1, 4]             (fx fy cx cy); only row 0 is used (reference: ba_cuda.cu:253-259)
+ *   target     f32 [n_edges, 2]   weight f32 [n_edges, 2]   lmbda f32 [1]
+ *   ii, jj, kk i64 [n_edges]            source frame, target frame, global patch id
+ */
+#ifndef PGBA_H_
+#define PGBA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* pgba_stream_t; /* == cudaStream_t */
+
+enum {
+  PGBA_OK = 0,
+  PGBA_ERR_NULL = -1,        /* a required pointer is NULL */
+  PGBA_ERR_SHAPE = -2,       /* negative / inconsistent size, P < 2, t1 < t0, ... */
+  PGBA_ERR_WORKSPACE = -3,   /* workspace too small or misaligned (needs 256-byte alignment) */
+  PGBA_ERR_UNSUPPORTED = -4  /* configuration outside the implemented range (see pgba_ba_limits) */
+};
+
+/* Bits of the device-side status word (pgba_ba_status): set by kernels when the edge list cannot be processed. */
+enum {
+  PGBA_ST_INDEX_RANGE = 1,   /* an ii/jj/kk value is outside [0, n_pose_rows) / [0, n_patch_rows) */
+  PGBA_ST_TOO_MANY_SLOTS = 2,/* a source frame sees more distinct target frames than PGBA_MAX_SLOTS */
+  PGBA_ST_CAPACITY = 4,      /* internal table capacity exceeded (extremely sparse patch x frame incidence) */
+  PGBA_ST_MIXED_SOURCE = 8   /* (informational) a patch id appears with two different source frames */
+};
+
+#define PGBA_MAX_SLOTS 128   /* distinct target frames per (source frame, 128-patch chunk) */
+#define PGBA_MAX_POSE_ROWS 8192
+
+const char* pgba_error_string(int code);
+int pgba_version(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Bundle adjustment.  Replaces cuda_ba.forward == cuda_ba() (reference: cdvslam/fastba/ba_cuda.cu:462-611; the
+ * block-sparse variant cdvslam/fastba/block_e.cu:43-300 selected there by eff_impl).  `iterations` Gauss-Newton
+ * steps; per step: per-edge SE3 reprojection residual + Jacobians (ba_cuda.cu:265-343), assembly of the normal
+ * equations (:346-403), Q = 1/(C+lmbda), Schur complement S = B - E Q E^T, damping S += I*(1e-4*S + 1), Cholesky
+ * solve, dZ = Q (u - E^T dX) (:548-592), SE3 / inverse-depth retraction (:178-229).  t1 == t0 is the reference's
+ * structure-only branch (:550-560).  `ppf` (the reference's PPF/M) and `eff_impl` are accepted for signature
+ * parity; the implementation always uses its own block-sparse layout, which is valid for both settings.
+ *
+ * Batched form: `batch` independent windows with identical shapes, tensor b at base + b*stride (strides in
+ * ELEMENTS of the tensor's dtype; a stride of 0 shares the tensor, e.g. intrinsics or lmbda).  n_edges_dev, when
+ * not NULL, is an i32 [batch] device array of per-window edge counts (<= n_edges) for ragged batches.
+ * ------------------------------------------------------------------------------------------------------------- */
+int pgba_ba_workspace_bytes(int64_t n_edges, int64_t n_pose_rows, int64_t n_patch_rows, int t0, int t1,
+                            int64_t batch, size_t* bytes /* host, out */);
+
+int pgba_ba_solve(float* poses, float* patches, const float* intrinsics, const float* target, const float* weight,
+                  const float* lmbda, const int64_t* ii, const int64_t* jj, const int64_t* kk, int64_t n_edges,
+                  int64_t n_pose_rows, int64_t n_patch_rows, int P, int ppf, int t0, int t1, int iterations,
+                  int eff_impl, void* workspace, size_t workspace_bytes, pgba_stream_t stream);
+
+typedef struct {
+  int64_t poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk; /* per-window strides, in elements */
+} pgba_strides;
+
+int pgba_ba_solve_batched(float* poses, float* patches, const float* intrinsics, const float* target,
+                          const float* weight, const float* lmbda, const int64_t* ii, const int64_t* jj,
+                          const int64_t* kk, const int32_t* n_edges_dev, const pgba_strides* strides /* host */,
+                          int64_t batch, int64_t n_edges, int64_t n_pose_rows, int64_t n_patch_rows, int P, int ppf,
+                          int t0, int t1, int iterations, int eff_impl, void* workspace, size_t workspace_bytes,
+                          pgba_stream_t stream);
+
+/* Debug / parity export (the reference API never exposes the Hessian or gradient the tolerance is stated on).
+ * Runs ONE linearisation (no retraction, nothing is modified) of a single window and copies out, when the pointer
+ * is not NULL:  S f32 [6N,6N] (full symmetric; before damping), y f32 [6N], dX f32 [6N] (solution of the damped
+ * system), patch_ids i64 [n_unique] (internal order), C, u, Q, dZ f32 [n_unique] in the same order, n_unique
+ * i32 [1], status i32 [1].  with_schur = 0 skips the E Q E^T terms, so S == B and y == v of ba_cuda.cu:364-398. */
+int pgba_ba_linearize_debug(const float* poses, const float* patches, const float* intrinsics, const float* target,
+                            const float* weight, const float* lmbda, const int64_t* ii, const int64_t* jj,
+                            const int64_t* kk, int64_t n_edges, int64_t n_pose_rows, int64_t n_patch_rows, int P,
+                            int t0, int t1, int with_schur, float* S, float* y, float* dX, int64_t* patch_ids,
+                            float* C, float* u, float* Q, float* dZ, int32_t* n_unique, int32_t* status,
+                            void* workspace, size_t workspace_bytes, pgba_stream_t stream);
+
+/* Status word of window `b` of the last call that used `workspace` (device pointer to an i32; read it after the
+ * stream has been synchronised).  0 means every edge was processed.  window_bytes is what
+ * pgba_ba_workspace_bytes(..., batch = 1, &window_bytes) returns for the same sizes. */
+const int32_t* pgba_ba_status_ptr(const void* workspace, size_t window_bytes, int64_t b);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Reprojection of all PxP pixels of each edge's patch from frame ii to frame jj.  Replaces cuda_ba.reproject ==
+ * cuda_reproject() (reference: cdvslam/fastba/ba_cuda.cu:408-458, 614-645).  coords f32 [n_edges, 2, P, P].
+ * clamp_depth = 0 reproduces the kernel (unguarded X/Z); clamp_depth = 1 applies Z.clamp(min=0.1) as
+ * projective_ops.proj does (cdvslam/projective_ops.py:43), which is what slam.py's reproject() uses (slam.py:328).
+ * ------------------------------------------------------------------------------------------------------------- */
+int pgba_reproject(const float* poses, const float* patches, const float* intrinsics, const int64_t* ii,
+                   const int64_t* jj, const int64_t* kk, int64_t n_edges, int64_t n_pose_rows, int64_t n_patch_rows,
+                   int P, int clamp_depth, float* coords, pgba_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGBA_H_ */

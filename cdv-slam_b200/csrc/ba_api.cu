@@ -1,13 +1,19 @@
 // extern "C" entry points of the BA part of libpgba.so (see include/pgba.h) + the reproject kernel.
 #include <stdio.h>
 
+#include <atomic>
+
 #include "ba_common.cuh"
 
 namespace pgba {
 void launch_plan(const Problem& pb, int64_t batch, cudaStream_t stream);
 size_t plan_bucket_smem_bytes(const Layout& L);
-cudaError_t launch_iteration(const Problem& pb, int64_t batch, bool apply, cudaStream_t stream);
+cudaError_t launch_iteration(const Problem& pb, int64_t batch, bool apply, cudaStream_t stream, cudaEvent_t* ev);
 bool solve_small_supported(int N);
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 // all PxP pixels of every edge's patch, frame ii -> jj  (reference: cdvslam/fastba/ba_cuda.cu:408-458)
 // one thread per (edge, pixel); coords [E, 2, P, P]
@@ -139,11 +145,48 @@ int pgba_ba_solve_batched(float* poses, float* patches, const float* intrinsics,
   cudaStream_t s = (cudaStream_t)stream;
   launch_plan(pb, batch, s);
   for (int it = 0; it < iterations; ++it) {
-    cudaError_t e = launch_iteration(pb, batch, true, s);
+    cudaError_t e = launch_iteration(pb, batch, true, s, nullptr);
     if (e != cudaSuccess) return (int)e;
   }
   return (int)cudaGetLastError();
 }
+
+int pgba_ba_solve_profiled(float* poses, float* patches, const float* intrinsics, const float* target,
+                           const float* weight, const float* lmbda, const int64_t* ii, const int64_t* jj,
+                           const int64_t* kk, const pgba_strides* strides, int64_t batch, int64_t n_edges,
+                           int64_t n_pose_rows, int64_t n_patch_rows, int P, int t0, int t1, int iterations,
+                           void* workspace, size_t workspace_bytes, pgba_stream_t stream, float* stage_ms) {
+  int rc = check_common(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, n_edges, n_pose_rows,
+                        n_patch_rows, P, t0, t1);
+  if (rc) return rc;
+  if (!stage_ms || (batch > 1 && !strides)) return PGBA_ERR_NULL;
+  if (batch <= 0 || batch > 65535 || iterations <= 0 || iterations > 16 || n_edges == 0) return PGBA_ERR_SHAPE;
+  if (!workspace || ((uintptr_t)workspace & 255)) return PGBA_ERR_WORKSPACE;
+  Problem pb = make_problem(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, nullptr, strides, n_edges,
+                            n_pose_rows, n_patch_rows, P, t0, t1, workspace);
+  if (pb.L.win_bytes * (size_t)batch > workspace_bytes) return PGBA_ERR_WORKSPACE;
+  if (plan_bucket_smem_bytes(pb.L) > 227 * 1024) return PGBA_ERR_UNSUPPORTED;
+  if (t1 > t0 && !solve_small_supported(t1 - t0)) return PGBA_ERR_UNSUPPORTED;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nev = 2 + 6 * iterations;
+  cudaEvent_t ev[2 + 6 * 16];
+  for (int i = 0; i < nev; ++i) cudaEventCreate(&ev[i]);
+  cudaEventRecord(ev[0], s);
+  launch_plan(pb, batch, s);
+  cudaEventRecord(ev[1], s);
+  cudaError_t e = cudaSuccess;
+  for (int it = 0; it < iterations && e == cudaSuccess; ++it) e = launch_iteration(pb, batch, true, s, ev + 2 + 6 * it);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess) {
+    cudaEventElapsedTime(&stage_ms[0], ev[0], ev[1]);
+    for (int it = 0; it < iterations; ++it)
+      for (int k = 0; k < 5; ++k) cudaEventElapsedTime(&stage_ms[1 + 5 * it + k], ev[2 + 6 * it + k], ev[2 + 6 * it + k + 1]);
+  }
+  for (int i = 0; i < nev; ++i) cudaEventDestroy(ev[i]);
+  return (int)e;
+}
+
+long long pgba_launch_count(void) { return launch_count(); }
 
 int pgba_ba_solve(float* poses, float* patches, const float* intrinsics, const float* target, const float* weight,
                   const float* lmbda, const int64_t* ii, const int64_t* jj, const int64_t* kk, int64_t n_edges,
@@ -174,9 +217,10 @@ int pgba_ba_linearize_debug(const float* poses, const float* patches, const floa
   if (t1 > t0 && !solve_small_supported(t1 - t0)) return PGBA_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
   launch_plan(pb, 1, s);
-  cudaError_t e = launch_iteration(pb, 1, false, s);
+  cudaError_t e = launch_iteration(pb, 1, false, s, nullptr);
   if (e != cudaSuccess) return (int)e;
   export_debug_kernel<<<64, 256, 0, s>>>(pb, S, y, dX, patch_ids, C, u, Q, dZ, n_unique, status);
+  count_launch();
   return (int)cudaGetLastError();
 }
 
@@ -198,6 +242,7 @@ int pgba_reproject(const float* poses, const float* patches, const float* intrin
   if (blocks >= (int64_t)1 << 31) return PGBA_ERR_UNSUPPORTED;
   reproject_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(poses, patches, intrinsics, ii, jj, kk,
                                                                       n_edges, P, clamp_depth, coords);
+  count_launch();
   return (int)cudaGetLastError();
 }
 

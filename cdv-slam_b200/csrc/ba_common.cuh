@@ -164,6 +164,10 @@ __device__ __forceinline__ void adj_map(const float R[9], const float t[3], cons
   Y[5] = R[2] * b0 + R[5] * b1 + R[8] * b2;
 }
 
+// Host-side count of kernel launches issued by this library (reported by bench.py as `gpu_launches`).
+void count_launch();
+long long launch_count();
+
 // Upper-triangular packing of a symmetric 6x6: index of (r, c) with r <= c.
 __host__ __device__ constexpr int sym6(int r, int c) { return r * 6 - (r * (r - 1)) / 2 + (c - r); }
 

@@ -571,26 +571,42 @@ static int chunk_grid(const Problem& pb, int64_t batch) {
   return (int)(g < cap ? g : cap);
 }
 
-cudaError_t launch_iteration(const Problem& pb, int64_t batch, bool apply, cudaStream_t stream) {
+// ev (optional): 6 events recorded before zero / linearize / solve / pose_retr / update and after update
+cudaError_t launch_iteration(const Problem& pb, int64_t batch, bool apply, cudaStream_t stream, cudaEvent_t* ev) {
   const int N = pb.t1 - pb.t0;
   const int gx = chunk_grid(pb, batch);
+  if (ev) cudaEventRecord(ev[0], stream);
   if (N > 0) {
     const size_t n6 = (size_t)6 * N;
     int zb = (int)((n6 * n6 + 255) / 256);
     if (zb > 148 * 8) zb = 148 * 8;
     if (zb < 1) zb = 1;
     zero_kernel<<<dim3((unsigned)zb, (unsigned)batch), 256, 0, stream>>>(pb);
+    count_launch();
   }
+  if (ev) cudaEventRecord(ev[1], stream);
   cudaFuncSetAttribute(linearize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LIN_SMEM_BYTES);
   linearize_kernel<<<dim3((unsigned)gx, (unsigned)batch), 256, LIN_SMEM_BYTES, stream>>>(pb);
+  count_launch();
+  if (ev) cudaEventRecord(ev[2], stream);
   if (N > 0) {
     const int n = 6 * N;
     const size_t smem = sizeof(double) * ((size_t)n * (n + 1) + n);
     cudaFuncSetAttribute(solve_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     solve_small_kernel<<<(unsigned)batch, 256, smem, stream>>>(pb);
-    if (apply) pose_retr_kernel<<<dim3((unsigned)((N + 63) / 64), (unsigned)batch), 64, 0, stream>>>(pb);
+    count_launch();
+    if (ev) cudaEventRecord(ev[3], stream);
+    if (apply) {
+      pose_retr_kernel<<<dim3((unsigned)((N + 63) / 64), (unsigned)batch), 64, 0, stream>>>(pb);
+      count_launch();
+    }
+  } else if (ev) {
+    cudaEventRecord(ev[3], stream);
   }
+  if (ev) cudaEventRecord(ev[4], stream);
   update_kernel<<<dim3((unsigned)gx, (unsigned)batch), 128, 0, stream>>>(pb, apply ? 1 : 0);
+  count_launch();
+  if (ev) cudaEventRecord(ev[5], stream);
   return cudaGetLastError();
 }
 

@@ -236,15 +236,13 @@ __global__ void __launch_bounds__(256) plan_cells_kernel(Problem pb) {
 
 void launch_plan(const Problem& pb, int64_t batch, cudaStream_t stream) {
   const size_t smem = sizeof(int) * (3 * (size_t)pb.F + 2 * (size_t)pb.L.ch_max + 64);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(plan_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    attr_set = true;
-  }
+  cudaFuncSetAttribute(plan_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   plan_bucket_kernel<<<dim3(1, (unsigned)batch), 1024, smem, stream>>>(pb);
+  count_launch();
   int gx = (int)(pb.L.ch_max < 148 * 4 ? pb.L.ch_max : 148 * 4);
   if (batch > 1) gx = (int)(pb.L.ch_max < 32 ? pb.L.ch_max : 32);
   plan_cells_kernel<<<dim3((unsigned)gx, (unsigned)batch), 256, 0, stream>>>(pb);
+  count_launch();
 }
 
 size_t plan_bucket_smem_bytes(const Layout& L) {

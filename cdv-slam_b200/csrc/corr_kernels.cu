@@ -15,6 +15,8 @@
 
 #include "../../include/pcorr.h"
 
+namespace pgba { void count_launch(); }
+
 namespace pcorr {
 
 template <typename T> __device__ __forceinline__ float to_f(T v);
@@ -201,6 +203,7 @@ static int launch_corr(const void* fmap1, CorrLevel l0, CorrLevel l1, const floa
   if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   kern<<<dim3((unsigned)E, (unsigned)B), 256, smem, s>>>((const T*)fmap1, l0, l1, coords, ii, jj, E, K, F, C, P, R,
                                                          (T*)out);
+  pgba::count_launch();
   return (int)cudaGetLastError();
 }
 
@@ -262,6 +265,7 @@ int pcorr_backward(const void* fmap1, const void* fmap2, const float* coords, co
                                                          (__half*)fmap2_grad);
   else
     return PCORR_ERR_DTYPE;
+  pgba::count_launch();
   return (int)cudaGetLastError();
 }
 
@@ -281,6 +285,7 @@ int pcorr_patchify_forward(const void* net, const float* coords, int B, int64_t 
     patchify_forward_kernel<__half><<<grid, threads, 0, s>>>((const __half*)net, coords, M, C, H, W, radius, (__half*)patches);
   else
     return PCORR_ERR_DTYPE;
+  pgba::count_launch();
   return (int)cudaGetLastError();
 }
 
@@ -298,6 +303,7 @@ int pcorr_patchify_backward(const void* patch_grad, const float* coords, int B, 
     patchify_backward_kernel<__half><<<grid, 256, 0, s>>>((const __half*)patch_grad, coords, M, C, H, W, radius, (__half*)net_grad);
   else
     return PCORR_ERR_DTYPE;
+  pgba::count_launch();
   return (int)cudaGetLastError();
 }
 

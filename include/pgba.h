@@ -81,6 +81,17 @@ int pgba_ba_solve_batched(float* poses, float* patches, const float* intrinsics,
                           int t0, int t1, int iterations, int eff_impl, void* workspace, size_t workspace_bytes,
                           pgba_stream_t stream);
 
+/* Measurement hooks (used by bench.py only).  pgba_ba_solve_profiled runs exactly the launch sequence of
+ * pgba_ba_solve_batched with cudaEvents between the stages, SYNCHRONISES the stream and fills the host array
+ * stage_ms [1 + 5*iterations]: plan, then per iteration {zero, linearize+Schur, solve, pose retraction, back-
+ * substitution+depth retraction}.  pgba_launch_count returns the number of kernels this library has launched. */
+int pgba_ba_solve_profiled(float* poses, float* patches, const float* intrinsics, const float* target,
+                           const float* weight, const float* lmbda, const int64_t* ii, const int64_t* jj,
+                           const int64_t* kk, const pgba_strides* strides /* host */, int64_t batch, int64_t n_edges,
+                           int64_t n_pose_rows, int64_t n_patch_rows, int P, int t0, int t1, int iterations,
+                           void* workspace, size_t workspace_bytes, pgba_stream_t stream, float* stage_ms /* host */);
+long long pgba_launch_count(void);
+
 /* Debug / parity export (the reference API never exposes the Hessian or gradient the tolerance is stated on).
  * Runs ONE linearisation (no retraction, nothing is modified) of a single window and copies out, when the pointer
  * is not NULL:  S f32 [6N,6N] (full symmetric; before damping), y f32 [6N], dX f32 [6N] (solution of the damped

@@ -234,7 +234,7 @@ class GpuArm:
         nbytes = ctypes.c_size_t(0)
         native.check(L.pgba_ba_workspace_bytes(E, F, K, p.t0, p.t1, self.B, ctypes.byref(nbytes)), "workspace_bytes")
         ws = native.workspace(nbytes.value, d["poses"].device)
-        n = 1 + 5 * ITERATIONS
+        n = 1 + 3 * ITERATIONS
         buf = (ctypes.c_float * n)()
         acc = np.zeros(n)
         for _ in range(steps):
@@ -249,10 +249,10 @@ class GpuArm:
             native.check(rc, "pgba_ba_solve_profiled")
             acc += np.array(list(buf))
         acc /= steps
-        names = ["zero", "linearize_schur", "solve", "pose_retr", "backsub_retr"]
+        names = ["linearize_schur", "solve_retr", "backsub_retr"]
         stages = {"plan": float(acc[0])}
         for k, nme in enumerate(names):
-            stages[nme] = float(np.mean([acc[1 + 5 * it + k] for it in range(ITERATIONS)]))
+            stages[nme] = float(np.mean([acc[1 + 3 * it + k] for it in range(ITERATIONS)]))
         return stages
 
 

@@ -36,7 +36,7 @@ SIGNATURES = {
     "pgba_ba_solve_profiled": (c_int, [c_vp] * 9 + [ctypes.POINTER(Strides), c_i64, c_i64, c_i64, c_i64, c_int, c_int,
                                                      c_int, c_int, c_vp, c_sz, c_vp, ctypes.POINTER(ctypes.c_float)]),
     "pgba_launch_count": (ctypes.c_longlong, []),
-    "pgba_ba_status_ptr": (c_vp, [c_vp, c_sz, c_i64]),
+    "pgba_ba_status_ptr": (c_vp, [c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_i64, c_i64]),
     "pgba_reproject": (c_int, [c_vp] * 6 + [c_i64, c_i64, c_i64, c_int, c_int, c_vp, c_vp]),
     "pcorr_forward": (c_int, [c_vp] * 5 + [c_int, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_vp,
                                            c_vp]),

@@ -1,5 +1,6 @@
 // extern "C" entry points of the BA part of libpgba.so (see include/pgba.h) + the reproject kernel.
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -7,8 +8,7 @@
 
 namespace pgba {
 void launch_plan(const Problem& pb, int64_t batch, cudaStream_t stream);
-size_t plan_bucket_smem_bytes(const Layout& L);
-cudaError_t launch_iteration(const Problem& pb, int64_t batch, bool apply, cudaStream_t stream, cudaEvent_t* ev);
+cudaError_t launch_iteration(const Problem& pb, int64_t batch, cudaStream_t stream, cudaEvent_t* ev);
 bool solve_small_supported(int N);
 
 static std::atomic<long long> g_launches{0};
@@ -53,7 +53,10 @@ __global__ void export_debug_kernel(Problem pb, float* S, float* y, float* dX, i
   const size_t n6 = (size_t)6 * (pb.t1 - pb.t0);
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, T = (size_t)gridDim.x * blockDim.x;
   const float lm = pb.lmbda[0];
-  if (S) for (size_t x = tid; x < n6 * n6; x += T) S[x] = wp.S[x];
+  if (S) for (size_t x = tid; x < n6 * n6; x += T) {       // only the lower block triangle is accumulated
+    const size_t r = x / n6, c = x - r * n6;
+    S[x] = (c / 6 <= r / 6) ? wp.S[x] : wp.S[c * n6 + r];
+  }
   if (y) for (size_t x = tid; x < n6; x += T) y[x] = wp.y[x];
   if (dX) for (size_t x = tid; x < n6; x += T) dX[x] = wp.dX[x];
   const int M = wp.hdr->n_patches;
@@ -81,18 +84,34 @@ static int check_common(const void* poses, const void* patches, const void* intr
   return PGBA_OK;
 }
 
+// patches per chunk: heuristic, or the PGBA_PC environment variable (8..128, power of two) for tuning
+static int pick_pc(int64_t E, int64_t batch) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("PGBA_PC");
+    int v = e ? atoi(e) : 0;
+    forced = (v == 8 || v == 16 || v == 32 || v == 64 || v == 128) ? v : 0;
+  }
+  return forced ? forced : choose_pc(E, batch);
+}
+
 static Problem make_problem(float* poses, float* patches, const float* intrinsics, const float* target,
                             const float* weight, const float* lmbda, const int64_t* ii, const int64_t* jj,
                             const int64_t* kk, const int32_t* n_edges_dev, const pgba_strides* st, int64_t E,
-                            int64_t F, int64_t K, int P, int t0, int t1, void* ws) {
+                            int64_t F, int64_t K, int P, int t0, int t1, void* ws, int64_t batch) {
   Problem pb{};
   pb.poses = poses; pb.patches = patches; pb.intrinsics = intrinsics; pb.target = target; pb.weight = weight;
   pb.lmbda = lmbda; pb.ii = ii; pb.jj = jj; pb.kk = kk; pb.n_edges_dev = n_edges_dev;
   if (st) pb.st = *st;
-  pb.E = E; pb.F = (int)F; pb.K = (int)K; pb.P = P; pb.t0 = t0; pb.t1 = t1; pb.with_schur = 1;
+  pb.E = E; pb.F = (int)F; pb.K = (int)K; pb.P = P; pb.t0 = t0; pb.t1 = t1; pb.with_schur = 1; pb.apply = 1;
   pb.ws = ws;
-  pb.L = make_layout(E, F, K, t1 - t0);
+  pb.L = make_layout(E, F, K, t1 - t0, batch, pick_pc(E, batch));
   return pb;
+}
+
+// one memset for the zero regions of all windows (headers, frame statistics, chunk counters, S, y)
+static cudaError_t clear_workspace(const Problem& pb, int64_t batch, cudaStream_t s) {
+  return cudaMemsetAsync(pb.ws, 0, pb.L.zero_bytes * (size_t)batch, s);
 }
 }  // namespace pgba
 
@@ -117,8 +136,27 @@ int pgba_ba_workspace_bytes(int64_t n_edges, int64_t n_pose_rows, int64_t n_patc
                             int64_t batch, size_t* bytes) {
   if (!bytes) return PGBA_ERR_NULL;
   if (n_edges < 0 || n_pose_rows <= 0 || n_patch_rows <= 0 || t1 < t0 || batch <= 0) return PGBA_ERR_SHAPE;
-  const Layout L = make_layout(n_edges, n_pose_rows, n_patch_rows, t1 - t0);
-  *bytes = L.win_bytes * (size_t)batch;
+  const Layout L = make_layout(n_edges, n_pose_rows, n_patch_rows, t1 - t0, batch, pick_pc(n_edges, batch));
+  *bytes = total_bytes(L, batch);
+  return PGBA_OK;
+}
+
+static int prepare(Problem& pb, float* poses, float* patches, const float* intrinsics, const float* target,
+                   const float* weight, const float* lmbda, const int64_t* ii, const int64_t* jj, const int64_t* kk,
+                   const int32_t* n_edges_dev, const pgba_strides* strides, int64_t batch, int64_t n_edges,
+                   int64_t n_pose_rows, int64_t n_patch_rows, int P, int t0, int t1, void* workspace,
+                   size_t workspace_bytes) {
+  int rc = check_common(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, n_edges, n_pose_rows,
+                        n_patch_rows, P, t0, t1);
+  if (rc) return rc;
+  if (batch <= 0) return PGBA_ERR_SHAPE;
+  if (batch > 1 && !strides) return PGBA_ERR_NULL;
+  if (batch > 65535) return PGBA_ERR_UNSUPPORTED;
+  if (!workspace || ((uintptr_t)workspace & 255)) return PGBA_ERR_WORKSPACE;
+  pb = make_problem(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, n_edges_dev, strides, n_edges,
+                    n_pose_rows, n_patch_rows, P, t0, t1, workspace, batch);
+  if (total_bytes(pb.L, batch) > workspace_bytes) return PGBA_ERR_WORKSPACE;
+  if (t1 > t0 && !solve_small_supported(t1 - t0)) return PGBA_ERR_UNSUPPORTED;
   return PGBA_OK;
 }
 
@@ -129,23 +167,18 @@ int pgba_ba_solve_batched(float* poses, float* patches, const float* intrinsics,
                           int iterations, int eff_impl, void* workspace, size_t workspace_bytes,
                           pgba_stream_t stream) {
   (void)ppf; (void)eff_impl;
-  int rc = check_common(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, n_edges, n_pose_rows,
-                        n_patch_rows, P, t0, t1);
+  if (iterations < 0) return PGBA_ERR_SHAPE;
+  Problem pb;
+  int rc = prepare(pb, poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, n_edges_dev, strides, batch,
+                   n_edges, n_pose_rows, n_patch_rows, P, t0, t1, workspace, workspace_bytes);
   if (rc) return rc;
-  if (batch <= 0 || iterations < 0) return PGBA_ERR_SHAPE;
-  if (batch > 1 && !strides) return PGBA_ERR_NULL;
-  if (batch > 65535) return PGBA_ERR_UNSUPPORTED;
-  if (!workspace || ((uintptr_t)workspace & 255)) return PGBA_ERR_WORKSPACE;
-  Problem pb = make_problem(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, n_edges_dev, strides,
-                            n_edges, n_pose_rows, n_patch_rows, P, t0, t1, workspace);
-  if (pb.L.win_bytes * (size_t)batch > workspace_bytes) return PGBA_ERR_WORKSPACE;
-  if (plan_bucket_smem_bytes(pb.L) > 227 * 1024) return PGBA_ERR_UNSUPPORTED;
-  if (t1 > t0 && !solve_small_supported(t1 - t0)) return PGBA_ERR_UNSUPPORTED;
   if (iterations == 0 || n_edges == 0) return PGBA_OK;
   cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = clear_workspace(pb, batch, s);
+  if (e != cudaSuccess) return (int)e;
   launch_plan(pb, batch, s);
   for (int it = 0; it < iterations; ++it) {
-    cudaError_t e = launch_iteration(pb, batch, true, s, nullptr);
+    e = launch_iteration(pb, batch, s, nullptr);
     if (e != cudaSuccess) return (int)e;
   }
   return (int)cudaGetLastError();
@@ -156,31 +189,26 @@ int pgba_ba_solve_profiled(float* poses, float* patches, const float* intrinsics
                            const int64_t* kk, const pgba_strides* strides, int64_t batch, int64_t n_edges,
                            int64_t n_pose_rows, int64_t n_patch_rows, int P, int t0, int t1, int iterations,
                            void* workspace, size_t workspace_bytes, pgba_stream_t stream, float* stage_ms) {
-  int rc = check_common(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, n_edges, n_pose_rows,
-                        n_patch_rows, P, t0, t1);
+  if (!stage_ms) return PGBA_ERR_NULL;
+  if (iterations <= 0 || iterations > 16 || n_edges == 0) return PGBA_ERR_SHAPE;
+  Problem pb;
+  int rc = prepare(pb, poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, nullptr, strides, batch,
+                   n_edges, n_pose_rows, n_patch_rows, P, t0, t1, workspace, workspace_bytes);
   if (rc) return rc;
-  if (!stage_ms || (batch > 1 && !strides)) return PGBA_ERR_NULL;
-  if (batch <= 0 || batch > 65535 || iterations <= 0 || iterations > 16 || n_edges == 0) return PGBA_ERR_SHAPE;
-  if (!workspace || ((uintptr_t)workspace & 255)) return PGBA_ERR_WORKSPACE;
-  Problem pb = make_problem(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, nullptr, strides, n_edges,
-                            n_pose_rows, n_patch_rows, P, t0, t1, workspace);
-  if (pb.L.win_bytes * (size_t)batch > workspace_bytes) return PGBA_ERR_WORKSPACE;
-  if (plan_bucket_smem_bytes(pb.L) > 227 * 1024) return PGBA_ERR_UNSUPPORTED;
-  if (t1 > t0 && !solve_small_supported(t1 - t0)) return PGBA_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
-  const int nev = 2 + 6 * iterations;
-  cudaEvent_t ev[2 + 6 * 16];
+  const int nev = 2 + 4 * iterations;
+  cudaEvent_t ev[2 + 4 * 16];
   for (int i = 0; i < nev; ++i) cudaEventCreate(&ev[i]);
   cudaEventRecord(ev[0], s);
+  cudaError_t e = clear_workspace(pb, batch, s);
   launch_plan(pb, batch, s);
   cudaEventRecord(ev[1], s);
-  cudaError_t e = cudaSuccess;
-  for (int it = 0; it < iterations && e == cudaSuccess; ++it) e = launch_iteration(pb, batch, true, s, ev + 2 + 6 * it);
+  for (int it = 0; it < iterations && e == cudaSuccess; ++it) e = launch_iteration(pb, batch, s, ev + 2 + 4 * it);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);
   if (e == cudaSuccess) {
     cudaEventElapsedTime(&stage_ms[0], ev[0], ev[1]);
     for (int it = 0; it < iterations; ++it)
-      for (int k = 0; k < 5; ++k) cudaEventElapsedTime(&stage_ms[1 + 5 * it + k], ev[2 + 6 * it + k], ev[2 + 6 * it + k + 1]);
+      for (int k = 0; k < 3; ++k) cudaEventElapsedTime(&stage_ms[1 + 3 * it + k], ev[2 + 4 * it + k], ev[2 + 4 * it + k + 1]);
   }
   for (int i = 0; i < nev; ++i) cudaEventDestroy(ev[i]);
   return (int)e;
@@ -204,29 +232,29 @@ int pgba_ba_linearize_debug(const float* poses, const float* patches, const floa
                             int t0, int t1, int with_schur, float* S, float* y, float* dX, int64_t* patch_ids,
                             float* C, float* u, float* Q, float* dZ, int32_t* n_unique, int32_t* status,
                             void* workspace, size_t workspace_bytes, pgba_stream_t stream) {
-  int rc = check_common(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, n_edges, n_pose_rows,
-                        n_patch_rows, P, t0, t1);
-  if (rc) return rc;
-  if (!workspace || ((uintptr_t)workspace & 255)) return PGBA_ERR_WORKSPACE;
   pgba_strides st{};
-  Problem pb = make_problem((float*)poses, (float*)patches, intrinsics, target, weight, lmbda, ii, jj, kk, nullptr,
-                            &st, n_edges, n_pose_rows, n_patch_rows, P, t0, t1, workspace);
+  Problem pb;
+  int rc = prepare(pb, (float*)poses, (float*)patches, intrinsics, target, weight, lmbda, ii, jj, kk, nullptr, &st, 1,
+                   n_edges, n_pose_rows, n_patch_rows, P, t0, t1, workspace, workspace_bytes);
+  if (rc) return rc;
   pb.with_schur = with_schur ? 1 : 0;
-  if (pb.L.win_bytes > workspace_bytes) return PGBA_ERR_WORKSPACE;
-  if (plan_bucket_smem_bytes(pb.L) > 227 * 1024) return PGBA_ERR_UNSUPPORTED;
-  if (t1 > t0 && !solve_small_supported(t1 - t0)) return PGBA_ERR_UNSUPPORTED;
+  pb.apply = 0;                                  // nothing is modified; S, y stay in the workspace for the export
   cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = clear_workspace(pb, 1, s);
+  if (e != cudaSuccess) return (int)e;
   launch_plan(pb, 1, s);
-  cudaError_t e = launch_iteration(pb, 1, false, s, nullptr);
+  e = launch_iteration(pb, 1, s, nullptr);
   if (e != cudaSuccess) return (int)e;
   export_debug_kernel<<<64, 256, 0, s>>>(pb, S, y, dX, patch_ids, C, u, Q, dZ, n_unique, status);
   count_launch();
   return (int)cudaGetLastError();
 }
 
-const int32_t* pgba_ba_status_ptr(const void* workspace, size_t window_bytes, int64_t b) {
-  if (!workspace || b < 0) return nullptr;
-  const WinHeader* h = (const WinHeader*)((const char*)workspace + (size_t)b * window_bytes);   // header is first
+const int32_t* pgba_ba_status_ptr(const void* workspace, int64_t n_edges, int64_t n_pose_rows, int64_t n_patch_rows,
+                                  int t0, int t1, int64_t batch, int64_t b) {
+  if (!workspace || b < 0 || b >= batch || n_pose_rows <= 0 || n_patch_rows <= 0 || t1 < t0) return nullptr;
+  const Layout L = make_layout(n_edges, n_pose_rows, n_patch_rows, t1 - t0, batch, pick_pc(n_edges, batch));
+  const WinHeader* h = (const WinHeader*)((const char*)workspace + (size_t)b * L.zero_bytes + L.z_hdr);
   return &h->status;
 }
 

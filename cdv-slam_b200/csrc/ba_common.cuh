@@ -7,14 +7,16 @@
 
 namespace pgba {
 
-constexpr int PMAX = 128;                 // patches per chunk (one source frame, <= PMAX consecutive patch ids)
+constexpr int PMAX = 128;                 // upper bound of patches per chunk (one source frame, consecutive patch ids)
 constexpr int SMAX = PGBA_MAX_SLOTS;      // distinct target frames per chunk
 constexpr int EBUDGET = 12288;            // floats of shared memory for the per-batch E tile (48 KB)
+constexpr int SOLVE_NMAX = 156;           // 6N handled by the single-CTA shared-memory solve (N <= 26)
 
 // ---------------------------------------------------------------------------------------------------------------
-// Workspace (per window).  All offsets are byte offsets from the window's base; every array is 256-byte aligned.
+// Workspace.  [ zero region of window 0 | ... | zero region of window B-1 | body of window 0 | ... ]
+// The zero regions are cleared by one memset at the start of every call; all offsets are 256-byte aligned.
 // ---------------------------------------------------------------------------------------------------------------
-struct WinHeader {      // device side, zeroed at the start of every call
+struct WinHeader {      // first thing in the zero region
   int n_chunks;
   int n_patches;        // bump cursor: unique (source frame, patch) rows allocated so far
   int n_slots;          // bump cursor into slot_frames
@@ -23,11 +25,14 @@ struct WinHeader {      // device side, zeroed at the start of every call
   int n_dups;           // duplicate (patch, target frame) edges
   int status;           // PGBA_ST_* bits
   int n_valid_edges;
+  int ticket[4];        // "last block done" counters of the plan kernels
+  int chol_info;        // 0, or 1 + index of the first non-positive pivot (big solve)
+  int pad[3];
 };
 
 struct Chunk {          // 64 bytes
   int frame;            // source frame i
-  int kbase;            // patch ids covered: [kbase, kbase + PMAX)
+  int kbase;            // patch ids covered: [kbase, kbase + pc)
   int edge_begin, edge_end;
   int n_patches, n_slots;
   int patch_base, slot_base, cell_base, ecell_base;
@@ -43,26 +48,50 @@ struct DupEdge { int chunk, p, s, n; };
 struct Layout {         // host-computed
   int64_t E, F, K;      // edges (max per window), pose rows, patch rows
   int N;                // free poses
+  int pc;               // patches per chunk (power of two, 8..128)
+  int big;              // 1: dense S too large for the shared-memory solve -> blocked global-memory Cholesky
   int64_t ch_max, patch_max, slot_max, cell_cap, ecell_cap;
-  size_t o_hdr, o_chunks, o_perm, o_kx, o_slots, o_cells, o_dups, o_ecells, o_Q, o_u, o_dZ, o_S, o_y, o_dX;
-  size_t win_bytes;
+  // zero region (relative to the window's zero base)
+  size_t z_hdr, z_fmaxinv, z_fkmax1, z_ccnt, z_y, z_S, zero_bytes;
+  // body (relative to the window's body base)
+  size_t o_fbase, o_ccur, o_chunks, o_perm, o_kx, o_slots, o_cells, o_dups, o_ecells, o_Q, o_u, o_dZ, o_dX, body_bytes;
+  size_t body0;         // offset of the first body = batch * zero_bytes (aligned)
 };
 
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
-inline Layout make_layout(int64_t E, int64_t F, int64_t K, int N) {
+inline int choose_pc(int64_t E, int64_t batch) {
+  // aim at >= ~1.5 CTAs per SM for the chunk-parallel kernels, assuming ~24 edges per patch
+  int64_t want = (E * batch) / (148 * 3 / 2 * 24);
+  int pc = 8;
+  while (pc * 2 <= want && pc < PMAX) pc *= 2;
+  return pc;
+}
+
+inline Layout make_layout(int64_t E, int64_t F, int64_t K, int N, int64_t batch, int pc) {
   Layout L{};
-  L.E = E; L.F = F; L.K = K; L.N = N;
+  L.E = E; L.F = F; L.K = K; L.N = N; L.pc = pc;
+  L.big = (6 * N > SOLVE_NMAX) ? 1 : 0;
   int64_t e1 = E > 0 ? E : 1;
-  L.ch_max = F + K / PMAX + 1;
+  L.ch_max = F + K / pc + 1;
   if (L.ch_max > e1) L.ch_max = e1;
   L.patch_max = K < e1 ? K : e1;
   if (L.patch_max < 1) L.patch_max = 1;
   L.slot_max = e1;
   L.cell_cap = 8 * e1 + 1024;
   L.ecell_cap = N > 0 ? (L.cell_cap + L.patch_max) : 1;
+  const size_t n6 = (size_t)6 * (size_t)(N > 0 ? N : 1);
   size_t o = 0;
-  L.o_hdr = o;    o = align256(o + sizeof(WinHeader));
+  L.z_hdr = o;     o = align256(o + sizeof(WinHeader));
+  L.z_fmaxinv = o; o = align256(o + 4 * (size_t)F);
+  L.z_fkmax1 = o;  o = align256(o + 4 * (size_t)F);
+  L.z_ccnt = o;    o = align256(o + 4 * (size_t)L.ch_max);
+  L.z_y = o;       o = align256(o + 4 * n6);
+  L.z_S = o;       o = align256(o + 4 * n6 * n6);
+  L.zero_bytes = o;
+  o = 0;
+  L.o_fbase = o;  o = align256(o + 4 * (size_t)F);
+  L.o_ccur = o;   o = align256(o + 4 * (size_t)L.ch_max);
   L.o_chunks = o; o = align256(o + sizeof(Chunk) * (size_t)L.ch_max);
   L.o_perm = o;   o = align256(o + 4 * (size_t)e1);
   L.o_kx = o;     o = align256(o + 4 * (size_t)L.patch_max);
@@ -73,24 +102,33 @@ inline Layout make_layout(int64_t E, int64_t F, int64_t K, int N) {
   L.o_Q = o;      o = align256(o + 4 * (size_t)L.patch_max);
   L.o_u = o;      o = align256(o + 4 * (size_t)L.patch_max);
   L.o_dZ = o;     o = align256(o + 4 * (size_t)L.patch_max);
-  size_t n6 = (size_t)6 * (size_t)(N > 0 ? N : 1);
-  L.o_S = o;      o = align256(o + 4 * n6 * n6);
-  L.o_y = o;      o = align256(o + 4 * n6);
   L.o_dX = o;     o = align256(o + 4 * n6);
-  L.win_bytes = o;
+  L.body_bytes = o;
+  L.body0 = L.zero_bytes * (size_t)batch;
   return L;
 }
 
+inline size_t total_bytes(const Layout& L, int64_t batch) { return (L.zero_bytes + L.body_bytes) * (size_t)batch; }
+
 // Pointers of one window, resolved on the device from (workspace base, window index, layout).
 struct WinPtrs {
-  WinHeader* hdr; Chunk* chunks; int* perm; int* kx; int* slots; int* cells; DupEdge* dups; float* ecells;
-  float* Q; float* u; float* dZ; float* S; float* y; float* dX;
+  WinHeader* hdr; int* fmaxinv; int* fkmax1; int* ccnt; float* y; float* S;
+  int* fbase; int* ccur; Chunk* chunks; int* perm; int* kx; int* slots; int* cells; DupEdge* dups; float* ecells;
+  float* Q; float* u; float* dZ; float* dX;
 };
 
 __host__ __device__ inline WinPtrs win_ptrs(void* ws, const Layout& L, int64_t b) {
-  char* base = (char*)ws + (size_t)b * L.win_bytes;
+  char* z = (char*)ws + (size_t)b * L.zero_bytes;
+  char* base = (char*)ws + L.body0 + (size_t)b * L.body_bytes;
   WinPtrs p;
-  p.hdr = (WinHeader*)(base + L.o_hdr);
+  p.hdr = (WinHeader*)(z + L.z_hdr);
+  p.fmaxinv = (int*)(z + L.z_fmaxinv);
+  p.fkmax1 = (int*)(z + L.z_fkmax1);
+  p.ccnt = (int*)(z + L.z_ccnt);
+  p.y = (float*)(z + L.z_y);
+  p.S = (float*)(z + L.z_S);
+  p.fbase = (int*)(base + L.o_fbase);
+  p.ccur = (int*)(base + L.o_ccur);
   p.chunks = (Chunk*)(base + L.o_chunks);
   p.perm = (int*)(base + L.o_perm);
   p.kx = (int*)(base + L.o_kx);
@@ -101,8 +139,6 @@ __host__ __device__ inline WinPtrs win_ptrs(void* ws, const Layout& L, int64_t b
   p.Q = (float*)(base + L.o_Q);
   p.u = (float*)(base + L.o_u);
   p.dZ = (float*)(base + L.o_dZ);
-  p.S = (float*)(base + L.o_S);
-  p.y = (float*)(base + L.o_y);
   p.dX = (float*)(base + L.o_dX);
   return p;
 }
@@ -112,7 +148,7 @@ struct Problem {
   float* poses; float* patches; const float* intrinsics; const float* target; const float* weight; const float* lmbda;
   const int64_t* ii; const int64_t* jj; const int64_t* kk; const int32_t* n_edges_dev;
   pgba_strides st;
-  int64_t E; int F; int K; int P; int t0; int t1; int with_schur;
+  int64_t E; int F; int K; int P; int t0; int t1; int with_schur; int apply;
   void* ws; Layout L;
 };
 
@@ -162,6 +198,46 @@ __device__ __forceinline__ void adj_map(const float R[9], const float t[3], cons
   Y[3] = R[0] * b0 + R[3] * b1 + R[6] * b2;
   Y[4] = R[1] * b0 + R[4] * b1 + R[7] * b2;
   Y[5] = R[2] * b0 + R[5] * b1 + R[8] * b2;
+}
+
+// SE3 retraction of one pose row: P <- Exp(xi) * P, xi = (tau, phi)   (ba_cuda.cu:88-174, used by :178-206)
+__device__ __forceinline__ void retract_pose(float* P, const float* xi) {
+  const float tau[3] = {xi[0], xi[1], xi[2]}, phi[3] = {xi[3], xi[4], xi[5]};
+  // expSO3 (ba_cuda.cu:88-110)
+  const float theta_sq = phi[0] * phi[0] + phi[1] * phi[1] + phi[2] * phi[2];
+  const float theta_p4 = theta_sq * theta_sq;
+  const float theta = sqrtf(theta_sq);
+  float imag, real;
+  if (theta_sq < 1e-8f) {
+    imag = 0.5f - (1.0f / 48.0f) * theta_sq + (1.0f / 3840.0f) * theta_p4;
+    real = 1.0f - (1.0f / 8.0f) * theta_sq + (1.0f / 384.0f) * theta_p4;
+  } else {
+    imag = sinf(0.5f * theta) / theta;
+    real = cosf(0.5f * theta);
+  }
+  const float dq[4] = {imag * phi[0], imag * phi[1], imag * phi[2], real};
+  // expSE3 translation part (ba_cuda.cu:125-153)
+  float dt[3] = {tau[0], tau[1], tau[2]};
+  if (theta > 1e-4f) {
+    const float a = (1.0f - cosf(theta)) / theta_sq;
+    const float c1[3] = {phi[1] * tau[2] - phi[2] * tau[1], phi[2] * tau[0] - phi[0] * tau[2],
+                         phi[0] * tau[1] - phi[1] * tau[0]};
+    const float b = (theta - sinf(theta)) / (theta * theta_sq);
+    const float c2[3] = {phi[1] * c1[2] - phi[2] * c1[1], phi[2] * c1[0] - phi[0] * c1[2],
+                         phi[0] * c1[1] - phi[1] * c1[0]};
+#pragma unroll
+    for (int x = 0; x < 3; ++x) dt[x] += a * c1[x] + b * c2[x];
+  }
+  // retrSE3 (ba_cuda.cu:156-174): no re-normalisation of the quaternion
+  const float t[3] = {P[0], P[1], P[2]}, q[4] = {P[3], P[4], P[5], P[6]};
+  float q1[4], t1[3];
+  q1[0] = dq[3] * q[0] + dq[0] * q[3] + dq[1] * q[2] - dq[2] * q[1];
+  q1[1] = dq[3] * q[1] + dq[1] * q[3] + dq[2] * q[0] - dq[0] * q[2];
+  q1[2] = dq[3] * q[2] + dq[2] * q[3] + dq[0] * q[1] - dq[1] * q[0];
+  q1[3] = dq[3] * q[3] - dq[0] * q[0] - dq[1] * q[1] - dq[2] * q[2];
+  rot_q(dq, t, t1);
+  P[0] = t1[0] + dt[0]; P[1] = t1[1] + dt[1]; P[2] = t1[2] + dt[2];
+  P[3] = q1[0]; P[4] = q1[1]; P[5] = q1[2]; P[6] = q1[3];
 }
 
 // Host-side count of kernel launches issued by this library (reported by bench.py as `gpu_launches`).

@@ -1,7 +1,7 @@
-// Numeric phase of the patch-graph BA (sm_100a): linearisation + Schur complement, small dense solve,
-// back-substitution + retraction.
+// Numeric phase of the patch-graph BA (sm_100a): linearisation + Schur complement, small dense solve + pose
+// retraction, back-substitution + inverse-depth retraction.
 //
-//   linearize_kernel   per chunk (one source frame i, <= 128 patches, <= 128 target-frame slots):
+//   linearize_kernel   per chunk (one source frame i, <= pc patches, <= 128 target-frame slots):
 //                      lanes <-> target-frame slots, loop over patches.  Per edge (reference arithmetic:
 //                      cdvslam/fastba/ba_cuda.cu:265-343): reprojection residual, Jj rows, Jz.  Because
 //                      Ji = Ad^T(Gij) Jj is the same linear map for every edge of a frame pair (ba_cuda.cu:353,
@@ -10,22 +10,18 @@
 //                      per frame pair (ba_cuda.cu:364-398).  Per patch: C, u, E columns (ba_cuda.cu:380-402) by
 //                      warp shuffles; Q = 1/(C+lambda); the chunk's Schur update S -= E Q E^T, y -= E Q u
 //                      (ba_cuda.cu:583-587, block_e.cu:147-234) is applied from shared memory; E is kept for the
-//                      back-substitution in a compact [patch][column][6] layout.
-//   solve_small_kernel S += I*(1e-4*S+1) (ba_cuda.cu:575/589), Cholesky + solves (ba_cuda.cu:576-577/590-591) in
-//                      fp64 shared memory, one CTA per window, 6N <= 156.
+//                      back-substitution in a compact [patch][column][6] layout.  Only the lower block triangle
+//                      of S (full diagonal blocks) is accumulated, with 8-byte vector reductions.
+//   solve_small_kernel S += I*(1e-4*S+1) (ba_cuda.cu:575/589), blocked Cholesky + solves (ba_cuda.cu:576-577/
+//                      590-591) in fp64 shared memory, one CTA per window, 6N <= 156; then the SE3 retraction of
+//                      the free poses (ba_cuda.cu:88-206) and re-zeroing of S, y for the next iteration.
 //   update_kernel      dZ = Q (u - E^T dX) (ba_cuda.cu:592, block_e.cu:253-283) + inverse-depth retraction
 //                      (ba_cuda.cu:209-229)
-//   pose_retr_kernel   SE3 retraction (ba_cuda.cu:88-206)
 #include "ba_common.cuh"
 
 namespace pgba {
 
-struct EdgeOut {
-  float H[21];   // sum_rows w * Jj Jj^T (upper triangle)
-  float g[6];    // sum_rows w * r * Jj
-  float e[6];    // sum_rows w * Jz * Jj
-  float c, u;    // sum_rows w * Jz^2, sum_rows w * r * Jz
-};
+int chunk_grid(const Problem& pb, int64_t batch);
 
 // Per-edge terms.  px, py, pd: patch centre and inverse depth; R, t: relative pose Gij.
 __device__ __forceinline__ void edge_terms(float px, float py, float pd, float fx, float fy, float cx, float cy,
@@ -69,20 +65,26 @@ __device__ __forceinline__ void edge_terms(float px, float py, float pd, float f
 }
 
 // Shared-memory carve-up of linearize_kernel (floats unless noted)
+constexpr int HW_STRIDE = 29;                       // odd stride: conflict-free per-lane rows
+constexpr int LIN_FIXED_FLOATS = SMAX * 12 + SMAX * 28 + 8 * 32 * HW_STRIDE + 48 + SMAX;
+
 struct LinSmem {
   float* sRt;      // [SMAX][12]  relative pose per slot (R row-major, t)
-  float* sH;       // [SMAX][28]  H (21) + g (6) per slot, reduced over warps
-  float* sPatch;   // [PMAX][4]   px, py, pd, -
-  float* sC;       // [PMAX]
-  float* sU;       // [PMAX]
-  float* sQ;       // [PMAX]
-  float* sEi;      // [PMAX][6]   source-frame column accumulators
+  float* sH;       // [SMAX][28]  H (21) + g (6) per slot, reduced over warps and patch batches
+  float* sHw;      // [8][32][29] per-warp partials of the current slot block; reused as sAH [SMAX][36]
   float* sBii;     // [36 + 6]    B_ii and v_i of the chunk
-  float* sE;       // [EBUDGET]   E tile [patch][col][6]
   int* sFrame;     // [SMAX]
+  float* sPatch;   // [pc][4]     px, py, pd, -
+  float* sC;       // [pc]
+  float* sU;       // [pc]
+  float* sQ;       // [pc]
+  float* sEi;      // [pc][6]     source-frame column accumulators
+  float* sE;       // [ebudget]   E tile [patch][col][6]
 };
-constexpr int LIN_SMEM_FLOATS = SMAX * 12 + SMAX * 28 + PMAX * 4 + PMAX * 3 + PMAX * 6 + 48 + EBUDGET + SMAX;
-constexpr size_t LIN_SMEM_BYTES = sizeof(float) * LIN_SMEM_FLOATS;
+
+size_t lin_smem_bytes(int pc, int ebudget) {
+  return sizeof(float) * ((size_t)LIN_FIXED_FLOATS + (size_t)pc * (4 + 3 + 6) + (size_t)ebudget);
+}
 
 __device__ __forceinline__ int pow2_ceil(int x) {
   int p = 1;
@@ -90,20 +92,27 @@ __device__ __forceinline__ int pow2_ceil(int x) {
   return p;
 }
 
-// grid = (gx, batch), block = 256, dynamic smem = LIN_SMEM_BYTES
-__global__ void __launch_bounds__(256, 2) linearize_kernel(Problem pb) {
+__device__ __forceinline__ void red_add2(float* p, float a, float b) {       // p 8-byte aligned
+  atomicAdd(reinterpret_cast<float2*>(p), make_float2(a, b));
+}
+
+// grid = (gx, batch), block = 256, dynamic smem = lin_smem_bytes(pc, ebudget)
+__global__ void __launch_bounds__(256, 2) linearize_kernel(Problem pb, int ebudget) {
   extern __shared__ float smem[];
+  const int pc = pb.L.pc;
   LinSmem s;
   s.sRt = smem;
   s.sH = s.sRt + SMAX * 12;
-  s.sPatch = s.sH + SMAX * 28;
-  s.sC = s.sPatch + PMAX * 4;
-  s.sU = s.sC + PMAX;
-  s.sQ = s.sU + PMAX;
-  s.sEi = s.sQ + PMAX;
-  s.sBii = s.sEi + PMAX * 6;
-  s.sE = s.sBii + 48;
-  s.sFrame = (int*)(s.sE + EBUDGET);
+  s.sHw = s.sH + SMAX * 28;
+  s.sBii = s.sHw + 8 * 32 * HW_STRIDE;
+  s.sFrame = (int*)(s.sBii + 48);
+  s.sPatch = (float*)(s.sFrame + SMAX);
+  s.sC = s.sPatch + pc * 4;
+  s.sU = s.sC + pc;
+  s.sQ = s.sU + pc;
+  s.sEi = s.sQ + pc;
+  s.sE = s.sEi + pc * 6;
+  float* sAH = s.sHw;
 
   const int w = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
@@ -124,7 +133,7 @@ __global__ void __launch_bounds__(256, 2) linearize_kernel(Problem pb) {
     const Chunk ch = wp.chunks[c];
     if (ch.n_patches == 0) continue;
     __syncthreads();
-    const int ns = ch.n_slots, ncols = ch.ncols, fi = ch.frame;
+    const int ns = ch.n_slots, ncols = ch.ncols, fi = ch.frame, np = ch.n_patches;
     const bool i_free = ch.icol >= 0;
     const int* cells = wp.cells + ch.cell_base;
     const int* kx = wp.kx + ch.patch_base;
@@ -140,24 +149,19 @@ __global__ void __launch_bounds__(256, 2) linearize_kernel(Problem pb) {
       for (int x = 0; x < 3; ++x) s.sRt[sl * 12 + 9 + x] = t[x];
     }
     for (int x = tid; x < ns * 28; x += 256) s.sH[x] = 0.f;
-    if (tid < 48) s.sBii[tid] = 0.f;
 
     const int estride = ncols * 6;
-    const int PB = (estride > 0) ? min(ch.n_patches, max(EBUDGET / estride, 1)) : ch.n_patches;
-    for (int b0 = 0; b0 < ch.n_patches; b0 += PB) {
-      const int b1 = min(b0 + PB, ch.n_patches);
+    const int PB = (estride > 0) ? min(np, max(ebudget / estride, 1)) : np;
+    for (int b0 = 0; b0 < np; b0 += PB) {
+      const int b1 = min(b0 + PB, np);
       __syncthreads();
-      // ---- stage patch centres, zero per-patch accumulators and the E tile
+      // ---- stage patch centres, zero the E tile
       for (int p = b0 + tid; p < b1; p += 256) {
         const float* pr = patches + (int64_t)kx[p] * pstride;
         const int q = p - b0;
         s.sPatch[q * 4 + 0] = pr[cidx];
         s.sPatch[q * 4 + 1] = pr[PP + cidx];
         s.sPatch[q * 4 + 2] = pr[2 * PP + cidx];
-        s.sC[q] = 0.f;
-        s.sU[q] = 0.f;
-#pragma unroll
-        for (int a = 0; a < 6; ++a) s.sEi[q * 6 + a] = 0.f;
       }
       for (int x = tid; x < (b1 - b0) * estride; x += 256) s.sE[x] = 0.f;
       __syncthreads();
@@ -214,58 +218,77 @@ __global__ void __launch_bounds__(256, 2) linearize_kernel(Problem pb) {
               for (int a = 0; a < 6; ++a) ei[a] += __shfl_xor_sync(0xffffffffu, ei[a], o);
             }
           }
-          if ((lane & (DW - 1)) == 0 && p < b1) {
+          if ((lane & (DW - 1)) == 0 && p < b1) {       // exactly one lane group owns patch p in this slot block
             const int q = p - b0;
-            atomicAdd(&s.sC[q], ck);
-            atomicAdd(&s.sU[q], uk);
-            if (i_free) {
+            if (sb == 0) {
+              s.sC[q] = ck;
+              s.sU[q] = uk;
 #pragma unroll
-              for (int a = 0; a < 6; ++a) atomicAdd(&s.sEi[q * 6 + a], -ei[a]);     // E_i -= w Jz Ji
+              for (int a = 0; a < 6; ++a) s.sEi[q * 6 + a] = -ei[a];     // E_i -= w Jz Ji
+            } else {
+              s.sC[q] += ck;
+              s.sU[q] += uk;
+#pragma unroll
+              for (int a = 0; a < 6; ++a) s.sEi[q * 6 + a] -= ei[a];
             }
           }
         }
-        if (slot_ok) {
+        // fold the lane groups that hold the same slot, then reduce over warps through shared memory
+        for (int o = DW; o < 32; o <<= 1) {
 #pragma unroll
-          for (int x = 0; x < 21; ++x) atomicAdd(&s.sH[sl * 28 + x], H[x]);
+          for (int x = 0; x < 21; ++x) H[x] += __shfl_xor_sync(0xffffffffu, H[x], o);
 #pragma unroll
-          for (int x = 0; x < 6; ++x) atomicAdd(&s.sH[sl * 28 + 21 + x], g[x]);
+          for (int x = 0; x < 6; ++x) g[x] += __shfl_xor_sync(0xffffffffu, g[x], o);
         }
-      }
-      __syncthreads();
-
-      // ---- duplicated (patch, slot) edges: rare slow path, shared-memory atomics
-      if (n_dups > 0) {
-        for (int dix = tid; dix < n_dups; dix += 256) {
-          const DupEdge de = wp.dups[dix];
-          if (de.chunk != c || de.p < b0 || de.p >= b1) continue;
-          const int q = de.p - b0, sl = de.s;
-          float R[9], t[3], H[21], g[6], e[6], ei[6], ck, uk;
+        {
+          float* dst = s.sHw + (warp * 32 + lane) * HW_STRIDE;
 #pragma unroll
-          for (int x = 0; x < 9; ++x) R[x] = s.sRt[sl * 12 + x];
+          for (int x = 0; x < 21; ++x) dst[x] = H[x];
 #pragma unroll
-          for (int x = 0; x < 3; ++x) t[x] = s.sRt[sl * 12 + 9 + x];
+          for (int x = 0; x < 6; ++x) dst[21 + x] = g[x];
+        }
+        __syncthreads();
+        for (int x = tid; x < ns_here * 27; x += 256) {
+          const int sx = x / 27, v = x - sx * 27;
+          float acc = 0.f;
 #pragma unroll
-          for (int x = 0; x < 21; ++x) H[x] = 0.f;
-#pragma unroll
-          for (int x = 0; x < 6; ++x) g[x] = 0.f;
-          edge_terms(s.sPatch[q * 4], s.sPatch[q * 4 + 1], s.sPatch[q * 4 + 2], fx, fy, cx, cy, R, t,
-                     __ldg(target + de.n), __ldg(weight + de.n), H, g, e, ck, uk);
-          const int col = sl - ch.first_free;
-          if (col >= 0 && col < ch.n_free && schur)
-            for (int a = 0; a < 6; ++a) atomicAdd(&s.sE[q * estride + col * 6 + a], e[a]);
-          if (i_free) {
-            adj_map(R, t, e, ei);
-            for (int a = 0; a < 6; ++a) atomicAdd(&s.sEi[q * 6 + a], -ei[a]);
-          }
-          atomicAdd(&s.sC[q], ck);
-          atomicAdd(&s.sU[q], uk);
-          for (int x = 0; x < 21; ++x) atomicAdd(&s.sH[sl * 28 + x], H[x]);
-          for (int x = 0; x < 6; ++x) atomicAdd(&s.sH[sl * 28 + 21 + x], g[x]);
+          for (int ww = 0; ww < 8; ++ww) acc += s.sHw[(ww * 32 + sx) * HW_STRIDE + v];
+          s.sH[(sb + sx) * 28 + v] += acc;
         }
         __syncthreads();
       }
 
-      // ---- per patch: fold the source-frame column, Q = 1/(C + lambda), export Q, u, E
+      // ---- duplicated (patch, slot) edges: rare slow path, one thread (deterministic, no shared atomics)
+      if (n_dups > 0) {
+        if (tid == 0) {
+          for (int dix = 0; dix < n_dups; ++dix) {
+            const DupEdge de = wp.dups[dix];
+            if (de.chunk != c || de.p < b0 || de.p >= b1) continue;
+            const int q = de.p - b0, sl = de.s;
+            float R[9], t[3], H[21], g[6], e[6], ei[6], ck, uk;
+            for (int x = 0; x < 9; ++x) R[x] = s.sRt[sl * 12 + x];
+            for (int x = 0; x < 3; ++x) t[x] = s.sRt[sl * 12 + 9 + x];
+            for (int x = 0; x < 21; ++x) H[x] = 0.f;
+            for (int x = 0; x < 6; ++x) g[x] = 0.f;
+            edge_terms(s.sPatch[q * 4], s.sPatch[q * 4 + 1], s.sPatch[q * 4 + 2], fx, fy, cx, cy, R, t,
+                       __ldg(target + de.n), __ldg(weight + de.n), H, g, e, ck, uk);
+            const int col = sl - ch.first_free;
+            if (col >= 0 && col < ch.n_free && schur)
+              for (int a = 0; a < 6; ++a) s.sE[q * estride + col * 6 + a] += e[a];
+            if (i_free) {
+              adj_map(R, t, e, ei);
+              for (int a = 0; a < 6; ++a) s.sEi[q * 6 + a] -= ei[a];
+            }
+            s.sC[q] += ck;
+            s.sU[q] += uk;
+            for (int x = 0; x < 21; ++x) s.sH[sl * 28 + x] += H[x];
+            for (int x = 0; x < 6; ++x) s.sH[sl * 28 + 21 + x] += g[x];
+          }
+        }
+        __syncthreads();
+      }
+
+      // ---- per patch: fold the source-frame column, Q = 1/(C + lambda), export Q, u
       for (int p = b0 + tid; p < b1; p += 256) {
         const int q = p - b0;
         const float Q = 1.0f / (s.sC[q] + lmbda);
@@ -282,43 +305,42 @@ __global__ void __launch_bounds__(256, 2) linearize_kernel(Problem pb) {
         float* eg = wp.ecells + 6 * ((int64_t)ch.ecell_base + (int64_t)b0 * ncols);
         for (int x = tid; x < (b1 - b0) * estride; x += 256) eg[x] = s.sE[x];
 
-        // ---- Schur update of this batch: S[ca, cb] -= sum_p Q_p E_p[ca] E_p[cb]^T  (lower block triangle + mirror)
+        // ---- Schur update of this batch.  Item = (column pair ca >= cb, row a): six sums over the patches.
+        //      M = sum_p Q_p E_p[ca] E_p[cb]^T is block (ca, cb); it lands at (frame(ca), frame(cb)) or transposed.
         const int npairs = ncols * (ncols + 1) / 2;
-        for (int pr = tid; pr < npairs; pr += 256) {
+        const int nq = b1 - b0;
+        for (int it = tid; it < npairs * 6; it += 256) {
+          const int pr = it / 6, a = it - pr * 6;
           int ca = (int)((sqrtf(8.f * pr + 1.f) - 1.f) * 0.5f);
           while (ca * (ca + 1) / 2 > pr) --ca;
           while ((ca + 1) * (ca + 2) / 2 <= pr) ++ca;
           const int cb = pr - ca * (ca + 1) / 2;
-          float acc[36];
-#pragma unroll
-          for (int x = 0; x < 36; ++x) acc[x] = 0.f;
-          for (int q = 0; q < b1 - b0; ++q) {
-            const float Q = s.sQ[q];
-            const float* ea = s.sE + q * estride + ca * 6;
-            const float* eb = s.sE + q * estride + cb * 6;
-            float va[6], vb[6];
-#pragma unroll
-            for (int a = 0; a < 6; ++a) { va[a] = Q * ea[a]; vb[a] = eb[a]; }
-#pragma unroll
-            for (int a = 0; a < 6; ++a)
-#pragma unroll
-              for (int b = 0; b < 6; ++b) acc[a * 6 + b] += va[a] * vb[b];
+          float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          const float* ea = s.sE + ca * 6 + a;
+          const float* eb = s.sE + cb * 6;
+          for (int q = 0; q < nq; ++q) {
+            const float va = s.sQ[q] * ea[q * estride];
+            const float2 b01 = *reinterpret_cast<const float2*>(eb + q * estride);
+            const float2 b23 = *reinterpret_cast<const float2*>(eb + q * estride + 2);
+            const float2 b45 = *reinterpret_cast<const float2*>(eb + q * estride + 4);
+            acc[0] += va * b01.x; acc[1] += va * b01.y; acc[2] += va * b23.x;
+            acc[3] += va * b23.y; acc[4] += va * b45.x; acc[5] += va * b45.y;
           }
           const int fa = ((ca < ch.n_free) ? s.sFrame[ch.first_free + ca] : fi) - t0;
           const int fb = ((cb < ch.n_free) ? s.sFrame[ch.first_free + cb] : fi) - t0;
+          if (fa >= fb) {                       // block (fa, fb), row a
+            float* dst = wp.S + (size_t)(6 * fa + a) * n6 + 6 * fb;
+            red_add2(dst, -acc[0], -acc[1]); red_add2(dst + 2, -acc[2], -acc[3]); red_add2(dst + 4, -acc[4], -acc[5]);
+          } else {                              // transposed into block (fb, fa): column a
 #pragma unroll
-          for (int a = 0; a < 6; ++a)
-#pragma unroll
-            for (int b = 0; b < 6; ++b) {
-              atomicAdd(&wp.S[(size_t)(6 * fa + a) * n6 + 6 * fb + b], -acc[a * 6 + b]);
-              if (ca != cb) atomicAdd(&wp.S[(size_t)(6 * fb + b) * n6 + 6 * fa + a], -acc[a * 6 + b]);
-            }
+            for (int b = 0; b < 6; ++b) atomicAdd(&wp.S[(size_t)(6 * fb + b) * n6 + 6 * fa + a], -acc[b]);
+          }
         }
         // y[ca] -= sum_p Q_p u_p E_p[ca]
         for (int x = tid; x < ncols * 6; x += 256) {
           const int ca = x / 6, a = x - ca * 6;
           float acc = 0.f;
-          for (int q = 0; q < b1 - b0; ++q) acc += s.sQ[q] * s.sU[q] * s.sE[q * estride + x];
+          for (int q = 0; q < nq; ++q) acc += s.sQ[q] * s.sU[q] * s.sE[q * estride + x];
           const int fa = ((ca < ch.n_free) ? s.sFrame[ch.first_free + ca] : fi) - t0;
           atomicAdd(&wp.y[6 * fa + a], -acc);
         }
@@ -326,196 +348,297 @@ __global__ void __launch_bounds__(256, 2) linearize_kernel(Problem pb) {
     }
     __syncthreads();
 
-    // ---- pose blocks of this chunk: one thread per target-frame slot
+    // ---- pose blocks of this chunk (ba_cuda.cu:364-398)
     if (N > 0) {
-      for (int sl = tid; sl < ns; sl += 256) {
-        const int fj = s.sFrame[sl];
-        const bool j_free = (fj >= t0 && fj < pb.t1);
-        if (!j_free && !i_free) continue;
-        float Hm[36], g[6], R[9], t[3];
+      const int io = 6 * (fi - t0);
+      if (i_free) {
+        // B1: AH_s = A_s H_s, column b per warp (warps 0..5), slots on lanes; warp 6: v_i -= sum_s A_s g_s
+        float vi[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int sb = 0; sb < ns; sb += 32) {
+          const int sl = sb + lane;
+          if (warp < 7 && sl < ns) {
+            float R[9], t[3], colv[6], outv[6];
 #pragma unroll
-        for (int a = 0; a < 6; ++a)
+            for (int x = 0; x < 9; ++x) R[x] = s.sRt[sl * 12 + x];
 #pragma unroll
-          for (int b = a; b < 6; ++b) {
-            const float v = s.sH[sl * 28 + sym6(a, b)];
-            Hm[a * 6 + b] = v;
-            Hm[b * 6 + a] = v;
-          }
+            for (int x = 0; x < 3; ++x) t[x] = s.sRt[sl * 12 + 9 + x];
+            if (warp < 6) {
 #pragma unroll
-        for (int a = 0; a < 6; ++a) g[a] = s.sH[sl * 28 + 21 + a];
+              for (int a = 0; a < 6; ++a) colv[a] = s.sH[sl * 28 + (a <= warp ? sym6(a, warp) : sym6(warp, a))];
+              adj_map(R, t, colv, outv);
 #pragma unroll
-        for (int x = 0; x < 9; ++x) R[x] = s.sRt[sl * 12 + x];
+              for (int a = 0; a < 6; ++a) sAH[sl * 36 + a * 6 + warp] = outv[a];
+            } else {
 #pragma unroll
-        for (int x = 0; x < 3; ++x) t[x] = s.sRt[sl * 12 + 9 + x];
-        const int jo = 6 * (fj - t0), io = 6 * (fi - t0);
-        if (j_free) {
+              for (int a = 0; a < 6; ++a) colv[a] = s.sH[sl * 28 + 21 + a];
+              adj_map(R, t, colv, outv);
 #pragma unroll
-          for (int a = 0; a < 6; ++a) {
-#pragma unroll
-            for (int b = 0; b < 6; ++b) atomicAdd(&wp.S[(size_t)(jo + a) * n6 + jo + b], Hm[a * 6 + b]);
-            atomicAdd(&wp.y[jo + a], g[a]);                               // v_j += w r Jj
+              for (int a = 0; a < 6; ++a) vi[a] += outv[a];
+            }
           }
         }
-        if (i_free) {
-          // AH = A * H (A applied to every column of H); B_ij -= AH ; B_ii += AH A^T ; v_i -= A g
-          float AH[36];
+        if (warp == 6) {
+#pragma unroll
+          for (int a = 0; a < 6; ++a) {
+            float v = vi[a];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) s.sBii[36 + a] = -v;
+          }
+        }
+        __syncthreads();
+        // B2: B_ii = sum_s AH_s A_s^T ; row a per warp: (AH A^T)[a][:] = A * (AH[a][:])^T
+        if (warp < 6) {
+          float bi[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          for (int sb = 0; sb < ns; sb += 32) {
+            const int sl = sb + lane;
+            if (sl < ns) {
+              float R[9], t[3], rowv[6], outv[6];
+#pragma unroll
+              for (int x = 0; x < 9; ++x) R[x] = s.sRt[sl * 12 + x];
+#pragma unroll
+              for (int x = 0; x < 3; ++x) t[x] = s.sRt[sl * 12 + 9 + x];
+#pragma unroll
+              for (int b = 0; b < 6; ++b) rowv[b] = sAH[sl * 36 + warp * 6 + b];
+              adj_map(R, t, rowv, outv);
+#pragma unroll
+              for (int b = 0; b < 6; ++b) bi[b] += outv[b];
+            }
+          }
 #pragma unroll
           for (int b = 0; b < 6; ++b) {
-            float colv[6], outv[6];
+            float v = bi[b];
 #pragma unroll
-            for (int a = 0; a < 6; ++a) colv[a] = Hm[a * 6 + b];
-            adj_map(R, t, colv, outv);
-#pragma unroll
-            for (int a = 0; a < 6; ++a) AH[a * 6 + b] = outv[a];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) s.sBii[warp * 6 + b] = v;
           }
-          if (j_free) {
+        }
+        __syncthreads();
+      }
+      // B3: scatter.  Item = (slot, row a).
+      for (int it = tid; it < ns * 6; it += 256) {
+        const int sl = it / 6, a = it - sl * 6;
+        const int fj = s.sFrame[sl];
+        if (fj < t0 || fj >= pb.t1) continue;
+        const int jo = 6 * (fj - t0);
+        {                                                               // B_jj += H ; v_j += g
+          float h[6];
 #pragma unroll
-            for (int a = 0; a < 6; ++a)
-#pragma unroll
-              for (int b = 0; b < 6; ++b) {
-                atomicAdd(&wp.S[(size_t)(io + a) * n6 + jo + b], -AH[a * 6 + b]);
-                atomicAdd(&wp.S[(size_t)(jo + b) * n6 + io + a], -AH[a * 6 + b]);
-              }
+          for (int b = 0; b < 6; ++b) h[b] = s.sH[sl * 28 + (a <= b ? sym6(a, b) : sym6(b, a))];
+          float* dst = wp.S + (size_t)(jo + a) * n6 + jo;
+          red_add2(dst, h[0], h[1]); red_add2(dst + 2, h[2], h[3]); red_add2(dst + 4, h[4], h[5]);
+          atomicAdd(&wp.y[jo + a], s.sH[sl * 28 + 21 + a]);
+        }
+        if (i_free) {                                                   // B_ij -= AH, B_ji -= AH^T
+          if (fi > fj) {
+            float* dst = wp.S + (size_t)(io + a) * n6 + jo;
+            const float* r = sAH + sl * 36 + a * 6;
+            red_add2(dst, -r[0], -r[1]); red_add2(dst + 2, -r[2], -r[3]); red_add2(dst + 4, -r[4], -r[5]);
+          } else if (fi < fj) {
+            float* dst = wp.S + (size_t)(jo + a) * n6 + io;              // row a of AH^T = column a of AH
+            const float* r = sAH + sl * 36 + a;
+            red_add2(dst, -r[0], -r[6]); red_add2(dst + 2, -r[12], -r[18]); red_add2(dst + 4, -r[24], -r[30]);
+          } else {
+            float* dst = wp.S + (size_t)(io + a) * n6 + io;
+            const float* r = sAH + sl * 36;
+            red_add2(dst, -(r[a * 6 + 0] + r[0 * 6 + a]), -(r[a * 6 + 1] + r[1 * 6 + a]));
+            red_add2(dst + 2, -(r[a * 6 + 2] + r[2 * 6 + a]), -(r[a * 6 + 3] + r[3 * 6 + a]));
+            red_add2(dst + 4, -(r[a * 6 + 4] + r[4 * 6 + a]), -(r[a * 6 + 5] + r[5 * 6 + a]));
           }
-#pragma unroll
-          for (int a = 0; a < 6; ++a) {
-            float rowv[6], outv[6];
-#pragma unroll
-            for (int b = 0; b < 6; ++b) rowv[b] = AH[a * 6 + b];
-            adj_map(R, t, rowv, outv);                                    // (AH A^T)[a][:] = A * (AH[a][:])^T
-#pragma unroll
-            for (int b = 0; b < 6; ++b) atomicAdd(&s.sBii[a * 6 + b], outv[b]);
-          }
-          float Ag[6];
-          adj_map(R, t, g, Ag);
-#pragma unroll
-          for (int a = 0; a < 6; ++a) atomicAdd(&s.sBii[36 + a], -Ag[a]);
         }
       }
-      __syncthreads();
-      if (i_free && tid < 42) {
-        const int io = 6 * (fi - t0);
-        if (tid < 36) atomicAdd(&wp.S[(size_t)(io + tid / 6) * n6 + io + tid % 6], s.sBii[tid]);
-        else atomicAdd(&wp.y[io + tid - 36], s.sBii[tid]);
+      if (i_free && tid < 6) {                                          // B_ii, v_i
+        float* dst = wp.S + (size_t)(io + tid) * n6 + io;
+        const float* r = s.sBii + tid * 6;
+        red_add2(dst, r[0], r[1]); red_add2(dst + 2, r[2], r[3]); red_add2(dst + 4, r[4], r[5]);
+        atomicAdd(&wp.y[io + tid], s.sBii[36 + tid]);
       }
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Small dense solve: one CTA per window, fp64 in shared memory.
+// Small dense solve: one CTA per window, fp64 in shared memory, blocked (6 wide) right-looking Cholesky on the
+// matrix augmented with the right-hand side as an extra row (so the forward substitution comes for free), warp-level
+// backward substitution, then the SE3 retraction of the free poses.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int SOLVE_NMAX = 156;   // 6N <= 156 (N <= 26): 156*157*8 B = 196 KB of shared memory
+size_t solve_small_smem_bytes(int n) {
+  const int ld = n | 1;
+  return sizeof(double) * ((size_t)(n + 1) * ld + n + 8);
+}
+
+// Cholesky of the 6x6 diagonal block at kb (lower triangle, in place) by ONE thread; rd = 1 / diag(L).
+// rsqrt of a non-positive pivot gives NaN/inf, which propagates like the reference's unchecked potrf (info ignored).
+__device__ __forceinline__ void factor_diag6(double* A, double* rd, int ld, int kb) {
+  double Lk[6][6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int c = 0; c <= r; ++c) Lk[r][c] = A[(kb + r) * ld + kb + c];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    double d = Lk[c][c];
+#pragma unroll
+    for (int e = 0; e < c; ++e) d -= Lk[c][e] * Lk[c][e];
+    const double ri = rsqrt(d);
+    Lk[c][c] = d * ri;
+    rd[kb + c] = ri;
+#pragma unroll
+    for (int r = c + 1; r < 6; ++r) {
+      double v = Lk[r][c];
+#pragma unroll
+      for (int e = 0; e < c; ++e) v -= Lk[r][e] * Lk[c][e];
+      Lk[r][c] = v * ri;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int c = 0; c <= r; ++c) A[(kb + r) * ld + kb + c] = Lk[r][c];
+}
 
 __global__ void __launch_bounds__(256, 1) solve_small_kernel(Problem pb) {
   extern __shared__ double sd[];
-  const int w = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  const int w = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
-  const int n = 6 * (pb.t1 - pb.t0), ld = n + 1;
-  double* A = sd;            // [n][ld]
-  double* b = sd + n * ld;   // [n]
-  for (int x = tid; x < n * n; x += 256) {
-    const int r = x / n, c = x - r * n;
-    double v = (double)wp.S[x];
-    if (r == c) v += 1e-4 * v + 1.0;                 // S += I * (1e-4 * S + 1)   (ba_cuda.cu:575/589)
-    A[r * ld + c] = v;
-  }
-  for (int x = tid; x < n; x += 256) b[x] = (double)wp.y[x];
-  __syncthreads();
-  // right-looking Cholesky, lower triangle
-  for (int k = 0; k < n; ++k) {
-    const double dkk = sqrt(A[k * ld + k]);          // NaN for an indefinite matrix, like the reference (info ignored)
-    __syncthreads();
-    if (tid == 0) A[k * ld + k] = dkk;
-    const double inv = 1.0 / dkk;
-    for (int i = k + 1 + tid; i < n; i += 256) A[i * ld + k] *= inv;
-    __syncthreads();
-    const int m = n - k - 1;
-    for (int x = tid; x < m * m; x += 256) {
-      const int i = k + 1 + x / m, j = k + 1 + x % m;
-      if (j <= i) A[i * ld + j] -= A[i * ld + k] * A[j * ld + k];
-    }
-    __syncthreads();
-  }
-  // forward / backward substitution by warp 0
-  if (tid < 32) {
-    for (int i = 0; i < n; ++i) {
-      double sacc = 0.0;
-      for (int j = lane; j < i; j += 32) sacc += A[i * ld + j] * b[j];
+  const int N = pb.t1 - pb.t0, n = 6 * N, ld = n | 1;
+  double* A = sd;                  // [n + 1][ld]; row n = right-hand side
+  double* rd = sd + (n + 1) * ld;  // [n] reciprocal diagonal of L
+  const bool rezero = pb.apply != 0;
+  // prefetch the pose rows that are retracted at the end
+  float* prow = pb.poses + (int64_t)w * pb.st.poses + 7 * (int64_t)(pb.t0 + tid);
+  float pose[7];
+  if (tid < N) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
-      if (lane == 0) b[i] = (b[i] - sacc) / A[i * ld + i];
-      __syncwarp();
-    }
-    for (int i = n - 1; i >= 0; --i) {
-      double sacc = 0.0;
-      for (int j = i + 1 + lane; j < n; j += 32) sacc += A[j * ld + i] * b[j];
+    for (int x = 0; x < 7; ++x) pose[x] = prow[x];
+  }
+  // ---- load S (only the lower block triangle is meaningful) with the damping S += I * (1e-4 * S + 1)
+  //      (ba_cuda.cu:575/589); all loads are independent.  n*n is a multiple of 4.
+  {
+    const float4* S4 = reinterpret_cast<const float4*>(wp.S);
+    const int n4 = (n * n) >> 2;
+    for (int x4 = tid; x4 < n4; x4 += 256) {
+      const float4 v4 = S4[x4];
+      const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+      int r = (4 * x4) / n, c = 4 * x4 - r * n;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
-      if (lane == 0) b[i] = (b[i] - sacc) / A[i * ld + i];
-      __syncwarp();
+      for (int k = 0; k < 4; ++k) {
+        double v = (double)vv[k];
+        if (r == c) v += 1e-4 * v + 1.0;
+        A[r * ld + c] = v;
+        if (++c == n) { c = 0; ++r; }
+      }
     }
+    for (int x = tid; x < n; x += 256) A[n * ld + x] = (double)wp.y[x];
   }
   __syncthreads();
-  for (int x = tid; x < n; x += 256) wp.dX[x] = (float)b[x];
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// SE3 retraction of the free poses: poses[t] <- Exp(dX[t - t0]) * poses[t]   (ba_cuda.cu:88-206)
-// ---------------------------------------------------------------------------------------------------------------
-__global__ void pose_retr_kernel(Problem pb) {
-  const int w = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int N = pb.t1 - pb.t0;
-  if (i >= N) return;
-  const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
-  float* P = pb.poses + (int64_t)w * pb.st.poses + 7 * (int64_t)(pb.t0 + i);
-  const float* xi = wp.dX + 6 * i;
-  const float tau[3] = {xi[0], xi[1], xi[2]}, phi[3] = {xi[3], xi[4], xi[5]};
-  // expSO3 (ba_cuda.cu:88-110)
-  const float theta_sq = phi[0] * phi[0] + phi[1] * phi[1] + phi[2] * phi[2];
-  const float theta_p4 = theta_sq * theta_sq;
-  const float theta = sqrtf(theta_sq);
-  float imag, real;
-  if (theta_sq < 1e-8f) {
-    imag = 0.5f - (1.0f / 48.0f) * theta_sq + (1.0f / 3840.0f) * theta_p4;
-    real = 1.0f - (1.0f / 8.0f) * theta_sq + (1.0f / 384.0f) * theta_p4;
-  } else {
-    imag = sinf(0.5f * theta) / theta;
-    real = cosf(0.5f * theta);
+  if (rezero) {                    // S, y are consumed: clear them for the next iteration's accumulation
+    float4* S4 = reinterpret_cast<float4*>(wp.S);
+    const int n4 = (n * n) >> 2;
+    for (int x4 = tid; x4 < n4; x4 += 256) S4[x4] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int x = tid; x < n; x += 256) wp.y[x] = 0.f;
   }
-  const float dq[4] = {imag * phi[0], imag * phi[1], imag * phi[2], real};
-  // expSE3 translation part (ba_cuda.cu:125-153)
-  float dt[3] = {tau[0], tau[1], tau[2]};
-  if (theta > 1e-4f) {
-    const float a = (1.0f - cosf(theta)) / theta_sq;
-    const float c1[3] = {phi[1] * tau[2] - phi[2] * tau[1], phi[2] * tau[0] - phi[0] * tau[2],
-                         phi[0] * tau[1] - phi[1] * tau[0]};
-    const float b = (theta - sinf(theta)) / (theta * theta_sq);
-    const float c2[3] = {phi[1] * c1[2] - phi[2] * c1[1], phi[2] * c1[0] - phi[0] * c1[2],
-                         phi[0] * c1[1] - phi[1] * c1[0]};
+  if (tid == 0) factor_diag6(A, rd, ld, 0);
+  __syncthreads();
+  for (int kb = 0; kb < n; kb += 6) {
+    // (b) panel: rows below (incl. the rhs row n): x L11^T = a
+    for (int r = kb + 6 + tid; r <= n; r += 256) {
+      double x[6];
 #pragma unroll
-    for (int x = 0; x < 3; ++x) dt[x] += a * c1[x] + b * c2[x];
+      for (int c = 0; c < 6; ++c) {
+        double v = A[r * ld + kb + c];
+#pragma unroll
+        for (int e = 0; e < c; ++e) v -= x[e] * A[(kb + c) * ld + kb + e];
+        x[c] = v * rd[kb + c];
+      }
+#pragma unroll
+      for (int c = 0; c < 6; ++c) A[r * ld + kb + c] = x[c];
+    }
+    __syncthreads();
+    const int nb = kb + 6;
+    if (nb >= n) break;
+    if (warp == 0) {
+      // look-ahead: update and factor the next diagonal block while the other warps update the rest
+      if (lane < 21) {
+        int r = 0, c = lane;
+        while (c > r) { c -= r + 1; ++r; }          // lane -> (r, c), c <= r < 6
+        double acc = 0.0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) acc += A[(nb + r) * ld + kb + a] * A[(nb + c) * ld + kb + a];
+        A[(nb + r) * ld + nb + c] -= acc;
+      }
+      __syncwarp();
+      if (lane == 0) factor_diag6(A, rd, ld, nb);
+    } else {
+      // (c) trailing update of rows >= nb + 6 (incl. rhs row): item = (row r, column block cb <= r)
+      const int rb0 = nb + 6;
+      const int nrows = n + 1 - rb0;
+      const int nblk = (n - nb) / 6;                // column blocks nb, nb+6, ..., n-6
+      for (int it = tid - 32; it < nrows * nblk; it += 224) {
+        const int r = rb0 + it / nblk, cb = nb + 6 * (it % nblk);
+        if (cb > r) continue;
+        double lr[6];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) lr[a] = A[r * ld + kb + a];
+#pragma unroll
+        for (int b = 0; b < 6; ++b) {
+          const double* lc = A + (cb + b) * ld + kb;
+          double acc = 0.0;
+#pragma unroll
+          for (int a = 0; a < 6; ++a) acc += lr[a] * lc[a];
+          A[r * ld + cb + b] -= acc;
+        }
+      }
+    }
+    __syncthreads();
   }
-  // retrSE3 (ba_cuda.cu:156-174): no re-normalisation of the quaternion
-  const float t[3] = {P[0], P[1], P[2]}, q[4] = {P[3], P[4], P[5], P[6]};
-  float q1[4], t1[3];
-  q1[0] = dq[3] * q[0] + dq[0] * q[3] + dq[1] * q[2] - dq[2] * q[1];
-  q1[1] = dq[3] * q[1] + dq[1] * q[3] + dq[2] * q[0] - dq[0] * q[2];
-  q1[2] = dq[3] * q[2] + dq[2] * q[3] + dq[0] * q[1] - dq[1] * q[0];
-  q1[3] = dq[3] * q[3] - dq[0] * q[0] - dq[1] * q[1] - dq[2] * q[2];
-  rot_q(dq, t, t1);
-  P[0] = t1[0] + dt[0]; P[1] = t1[1] + dt[1]; P[2] = t1[2] + dt[2];
-  P[3] = q1[0]; P[4] = q1[1]; P[5] = q1[2]; P[6] = q1[3];
+  // ---- backward substitution L^T x = y by warp 0 (row n of A holds y and is overwritten with x)
+  if (warp == 0) {
+    double* xv = A + n * ld;
+    for (int kb = n - 6; kb >= 0; kb -= 6) {
+      if (lane == 0) {
+        double x[6];
+#pragma unroll
+        for (int c = 5; c >= 0; --c) {
+          double v = xv[kb + c];
+#pragma unroll
+          for (int e = c + 1; e < 6; ++e) v -= A[(kb + e) * ld + kb + c] * x[e];
+          x[c] = v * rd[kb + c];
+        }
+#pragma unroll
+        for (int c = 0; c < 6; ++c) xv[kb + c] = x[c];
+      }
+      __syncwarp();
+      for (int c = lane; c < kb; c += 32) {
+        double v = xv[c];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) v -= A[(kb + a) * ld + c] * xv[kb + a];
+        xv[c] = v;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  const double* xv = A + n * ld;
+  for (int x = tid; x < n; x += 256) wp.dX[x] = (float)xv[x];
+  // ---- SE3 retraction of the free poses (ba_cuda.cu:178-206)
+  if (pb.apply && tid < N) {
+    float xi[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) xi[a] = (float)xv[6 * tid + a];
+    retract_pose(pose, xi);
+#pragma unroll
+    for (int x = 0; x < 7; ++x) prow[x] = pose[x];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // Back-substitution dZ = Q (u - E^T dX) and inverse-depth retraction (ba_cuda.cu:592, 209-229; block_e.cu:253-283)
-// grid = (gx, batch), block = 128.  apply = 0 only computes dZ (debug export).
+// grid = (gx, batch), block = 256: one warp per patch, lanes over the E row.  apply = 0 only computes dZ.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) update_kernel(Problem pb, int apply) {
+__global__ void __launch_bounds__(256) update_kernel(Problem pb) {
   __shared__ float sdx[(SMAX + 1) * 6];
-  const int w = blockIdx.y, tid = threadIdx.x;
+  const int w = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
   float* patches = pb.patches + (int64_t)w * pb.st.patches;
   const int N = pb.t1 - pb.t0, t0 = pb.t0;
@@ -527,86 +650,66 @@ __global__ void __launch_bounds__(128) update_kernel(Problem pb, int apply) {
     if (ch.n_patches == 0) continue;
     __syncthreads();
     const int ncols = (N > 0 && schur) ? ch.ncols : 0;
-    for (int x = tid; x < ncols * 6; x += 128) {
+    for (int x = tid; x < ncols * 6; x += 256) {
       const int col = x / 6, a = x - col * 6;
       const int f = (col < ch.n_free) ? wp.slots[ch.slot_base + ch.first_free + col] : ch.frame;
       sdx[x] = wp.dX[6 * (f - t0) + a];
     }
     __syncthreads();
-    for (int p = tid; p < ch.n_patches; p += 128) {
-      const float Q = wp.Q[ch.patch_base + p];
-      float acc = wp.u[ch.patch_base + p];
+    const int len = ncols * 6;
+    for (int p = warp; p < ch.n_patches; p += 8) {
       const float* eg = wp.ecells + 6 * ((int64_t)ch.ecell_base + (int64_t)p * ch.ncols);
-      for (int x = 0; x < ncols * 6; ++x) acc -= eg[x] * sdx[x];
-      const float dz = Q * acc;
-      wp.dZ[ch.patch_base + p] = dz;
-      if (apply) {
+      float acc = 0.f;
+      for (int x = lane; x < len; x += 32) acc += eg[x] * sdx[x];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      const float dz = wp.Q[ch.patch_base + p] * (wp.u[ch.patch_base + p] - acc);
+      if (lane == 0) wp.dZ[ch.patch_base + p] = dz;
+      if (pb.apply) {
         float* pr = patches + (int64_t)wp.kx[ch.patch_base + p] * pstride + 2 * PP;
         float d = pr[0] + dz;                   // reads [2][0][0] (ba_cuda.cu:218)
         d = (d > 20.f) ? 1.0f : d;
         d = fmaxf(d, 1e-4f);
-        for (int x = 0; x < PP; ++x) pr[x] = d;
+        __syncwarp();
+        for (int x = lane; x < PP; x += 32) pr[x] = d;
       }
     }
   }
 }
 
-__global__ void zero_kernel(Problem pb) {
-  const int w = blockIdx.y;
-  const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
-  const size_t n6 = (size_t)6 * (pb.t1 - pb.t0);
-  const size_t total = n6 * n6;
-  for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (size_t)gridDim.x * blockDim.x)
-    wp.S[x] = 0.f;
-  for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < n6; x += (size_t)gridDim.x * blockDim.x)
-    wp.y[x] = 0.f;
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // Host-side launch sequence of one Gauss-Newton iteration
 // ---------------------------------------------------------------------------------------------------------------
-static int chunk_grid(const Problem& pb, int64_t batch) {
-  int64_t g = pb.L.ch_max;
-  const int64_t cap = batch > 1 ? 48 : 148 * 2;
-  return (int)(g < cap ? g : cap);
+int lin_ebudget(const Problem& pb) {
+  const int N = pb.t1 - pb.t0;
+  const int64_t cols = (N < SMAX ? N : SMAX) + 1;
+  int64_t need = (int64_t)pb.L.pc * 6 * cols;
+  if (need > EBUDGET) need = EBUDGET;
+  if (need < 64) need = 64;
+  return (int)need;
 }
 
-// ev (optional): 6 events recorded before zero / linearize / solve / pose_retr / update and after update
-cudaError_t launch_iteration(const Problem& pb, int64_t batch, bool apply, cudaStream_t stream, cudaEvent_t* ev) {
+// ev (optional): 4 events recorded before linearize / solve / update and after update
+cudaError_t launch_iteration(const Problem& pb, int64_t batch, cudaStream_t stream, cudaEvent_t* ev) {
   const int N = pb.t1 - pb.t0;
   const int gx = chunk_grid(pb, batch);
   if (ev) cudaEventRecord(ev[0], stream);
-  if (N > 0) {
-    const size_t n6 = (size_t)6 * N;
-    int zb = (int)((n6 * n6 + 255) / 256);
-    if (zb > 148 * 8) zb = 148 * 8;
-    if (zb < 1) zb = 1;
-    zero_kernel<<<dim3((unsigned)zb, (unsigned)batch), 256, 0, stream>>>(pb);
-    count_launch();
-  }
-  if (ev) cudaEventRecord(ev[1], stream);
-  cudaFuncSetAttribute(linearize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LIN_SMEM_BYTES);
-  linearize_kernel<<<dim3((unsigned)gx, (unsigned)batch), 256, LIN_SMEM_BYTES, stream>>>(pb);
+  const int ebudget = lin_ebudget(pb);
+  const size_t lsm = lin_smem_bytes(pb.L.pc, ebudget);
+  cudaFuncSetAttribute(linearize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm);
+  linearize_kernel<<<dim3((unsigned)gx, (unsigned)batch), 256, lsm, stream>>>(pb, ebudget);
   count_launch();
-  if (ev) cudaEventRecord(ev[2], stream);
+  if (ev) cudaEventRecord(ev[1], stream);
   if (N > 0) {
-    const int n = 6 * N;
-    const size_t smem = sizeof(double) * ((size_t)n * (n + 1) + n);
+    const size_t smem = solve_small_smem_bytes(6 * N);
     cudaFuncSetAttribute(solve_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     solve_small_kernel<<<(unsigned)batch, 256, smem, stream>>>(pb);
     count_launch();
-    if (ev) cudaEventRecord(ev[3], stream);
-    if (apply) {
-      pose_retr_kernel<<<dim3((unsigned)((N + 63) / 64), (unsigned)batch), 64, 0, stream>>>(pb);
-      count_launch();
-    }
-  } else if (ev) {
-    cudaEventRecord(ev[3], stream);
   }
-  if (ev) cudaEventRecord(ev[4], stream);
-  update_kernel<<<dim3((unsigned)gx, (unsigned)batch), 128, 0, stream>>>(pb, apply ? 1 : 0);
+  if (ev) cudaEventRecord(ev[2], stream);
+  update_kernel<<<dim3((unsigned)gx, (unsigned)batch), 256, 0, stream>>>(pb);
   count_launch();
-  if (ev) cudaEventRecord(ev[5], stream);
+  if (ev) cudaEventRecord(ev[3], stream);
   return cudaGetLastError();
 }
 

@@ -5,7 +5,10 @@
 // eff_impl=True, with the EfficentE constructor on the CPU (cdvslam/fastba/block_e.cu:43-145: unique over frame
 // pairs, patch_to_ku, index_tensor), without host synchronisation, sort or host tables.
 //
-//   plan_bucket_kernel   one CTA per window: counting sort of the edges by (source frame, 128-patch sub-range)
+// Four grid-wide kernels (blockIdx.y = window); the first two end with a "last block done" epilogue:
+//   plan_frames_kernel   per source frame: min / max patch id   -> epilogue: chunk table (frame, kbase)
+//   plan_count_kernel    edges per chunk                        -> epilogue: chunk edge ranges
+//   plan_scatter_kernel  counting-sort scatter of the edge ids by chunk (perm)
 //   plan_cells_kernel    per chunk: compact patch list, sorted target-frame slots, cell table cells[p][s] = edge
 #include "ba_common.cuh"
 
@@ -47,87 +50,149 @@ __device__ int block_exclusive_scan(int* a, int n, int* scratch) {
   return total;
 }
 
-// grid = (1, batch), block = 1024, dynamic smem = (3*F + 2*ch_max + 64) ints
-__global__ void __launch_bounds__(1024, 1) plan_bucket_kernel(Problem pb) {
-  extern __shared__ int sm[];
-  const int w = blockIdx.y;
+struct EdgeIdx { int i, j, k; bool ok; };
+
+__device__ __forceinline__ EdgeIdx load_edge(const Problem& pb, const int64_t* ii, const int64_t* jj,
+                                             const int64_t* kk, int e, int E) {
+  EdgeIdx r;
+  r.ok = false; r.i = -1; r.j = 0; r.k = 0;
+  if (e < E) {
+    const int64_t i = ii[e], j = jj[e], k = kk[e];
+    r.ok = !(i < 0 || i >= pb.F || j < 0 || j >= pb.F || k < 0 || k >= pb.K);
+    if (r.ok) { r.i = (int)i; r.j = (int)j; r.k = (int)k; }
+  }
+  return r;
+}
+
+__device__ __forceinline__ int window_edges(const Problem& pb, int w) {
+  return pb.n_edges_dev ? min((int)pb.E, max(pb.n_edges_dev[w], 0)) : (int)pb.E;
+}
+
+// True in exactly one block per window: the one that finishes last.  All global writes of the other blocks made
+// before their call are visible to it (read them with __ldcg).
+__device__ __forceinline__ bool last_block_done(int* ticket) {
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  const bool last = s_last != 0;
+  if (last) __threadfence();
+  return last;
+}
+
+// grid = (gx, batch), block = 256
+__global__ void __launch_bounds__(256) plan_frames_kernel(Problem pb) {
+  __shared__ int scratch[40];
+  const int w = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
   const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
-  const int F = pb.F, K = pb.K;
-  const int ch_max = (int)pb.L.ch_max;
-  int* cnt = sm;                // [F]  count -> sub-chunk count -> chunk base
-  int* kmin = cnt + F;          // [F]
-  int* kmax = kmin + F;         // [F]
-  int* ccnt = kmax + F;         // [ch_max] edges per chunk -> chunk edge offset
-  int* ccur = ccnt + ch_max;    // [ch_max] fill cursor
-  int* scratch = ccur + ch_max; // [64]
-  const int tid = threadIdx.x, T = blockDim.x;
   const int64_t* ii = pb.ii + (int64_t)w * pb.st.ii;
   const int64_t* jj = pb.jj + (int64_t)w * pb.st.jj;
   const int64_t* kk = pb.kk + (int64_t)w * pb.st.kk;
-  const int E = pb.n_edges_dev ? min((int)pb.E, max(pb.n_edges_dev[w], 0)) : (int)pb.E;
-
-  if (tid == 0) {
-    WinHeader h{};
-    *wp.hdr = h;
-  }
-  for (int f = tid; f < F; f += T) { cnt[f] = 0; kmin[f] = 0x7fffffff; kmax[f] = -1; }
-  __syncthreads();
-
+  const int E = window_edges(pb, w);
+  const int stride = gridDim.x * blockDim.x;
   int bad = 0;
-  for (int e = tid; e < E; e += T) {
-    const int64_t i = ii[e], j = jj[e], k = kk[e];
-    if (i < 0 || i >= F || j < 0 || j >= F || k < 0 || k >= K) { bad = 1; continue; }
-    atomicAdd(&cnt[(int)i], 1);
-    atomicMin(&kmin[(int)i], (int)k);
-    atomicMax(&kmax[(int)i], (int)k);
+  for (int e0 = blockIdx.x * blockDim.x; e0 < E; e0 += stride) {     // warp-uniform trip count
+    const int e = e0 + tid;
+    const EdgeIdx x = load_edge(pb, ii, jj, kk, e, E);
+    if (e < E && !x.ok) bad = 1;
+    const unsigned grp = __match_any_sync(0xffffffffu, x.i);
+    const int kmn = __reduce_min_sync(grp, x.k), kmx = __reduce_max_sync(grp, x.k);
+    if (x.ok && lane == __ffs(grp) - 1) {
+      atomicMax(&wp.fmaxinv[x.i], 0x7fffffff - kmn);      // zero-initialised "min": stores max of (INT_MAX - k)
+      atomicMax(&wp.fkmax1[x.i], kmx + 1);
+    }
   }
   if (bad) atomicOr(&wp.hdr->status, PGBA_ST_INDEX_RANGE);
+  if (!last_block_done(&wp.hdr->ticket[0])) return;
+
+  // ---- epilogue (one block per window): chunk table
+  const int F = pb.F, pc = pb.L.pc, T = blockDim.x;
+  const int ch_max = (int)pb.L.ch_max;
+  int* fbase = wp.fbase;
+  for (int f = tid; f < F; f += T) {
+    const int mx1 = __ldcg(&wp.fkmax1[f]);
+    fbase[f] = mx1 > 0 ? ((mx1 - 1) - (0x7fffffff - __ldcg(&wp.fmaxinv[f]))) / pc + 1 : 0;
+  }
   __syncthreads();
-  for (int f = tid; f < F; f += T) cnt[f] = cnt[f] > 0 ? (kmax[f] - kmin[f]) / PMAX + 1 : 0;
-  __syncthreads();
-  int n_chunks = block_exclusive_scan(cnt, F, scratch);
-  if (n_chunks > ch_max) {     // cannot happen for consistent sizes; keep the kernel memory-safe anyway
+  int n_chunks = block_exclusive_scan(fbase, F, scratch);
+  if (n_chunks > ch_max) {     // cannot happen when every patch has one source frame; stay memory-safe anyway
     if (tid == 0) atomicOr(&wp.hdr->status, PGBA_ST_CAPACITY);
     n_chunks = 0;
   }
-  for (int c = tid; c < n_chunks; c += T) ccnt[c] = 0;
-  __syncthreads();
-  if (n_chunks > 0) {
-    for (int e = tid; e < E; e += T) {
-      const int64_t i = ii[e], j = jj[e], k = kk[e];
-      if (i < 0 || i >= F || j < 0 || j >= F || k < 0 || k >= K) continue;
-      atomicAdd(&ccnt[cnt[(int)i] + ((int)k - kmin[(int)i]) / PMAX], 1);
-    }
-  }
-  __syncthreads();
-  const int n_valid = block_exclusive_scan(ccnt, n_chunks, scratch);
-  for (int c = tid; c < n_chunks; c += T) {
-    ccur[c] = ccnt[c];
-    Chunk ch{};
-    ch.edge_begin = ccnt[c];
-    ch.edge_end = (c + 1 < n_chunks) ? ccnt[c + 1] : n_valid;
-    wp.chunks[c] = ch;
-  }
-  __syncthreads();
   for (int f = tid; f < F; f += T) {
-    if (kmax[f] < 0) continue;
-    const int nsub = (kmax[f] - kmin[f]) / PMAX + 1;
-    for (int s = 0; s < nsub && cnt[f] + s < n_chunks; ++s) {
-      wp.chunks[cnt[f] + s].frame = f;
-      wp.chunks[cnt[f] + s].kbase = kmin[f] + s * PMAX;
+    const int mx1 = __ldcg(&wp.fkmax1[f]);
+    if (mx1 <= 0 || n_chunks == 0) continue;
+    const int kmin = 0x7fffffff - __ldcg(&wp.fmaxinv[f]);
+    const int nsub = ((mx1 - 1) - kmin) / pc + 1;
+    for (int s = 0; s < nsub; ++s) {
+      Chunk ch{};
+      ch.frame = f;
+      ch.kbase = kmin + s * pc;
+      wp.chunks[fbase[f] + s] = ch;
     }
   }
+  if (tid == 0) wp.hdr->n_chunks = n_chunks;
+}
+
+__device__ __forceinline__ int chunk_of(const WinPtrs& wp, const EdgeIdx& x, int pc) {
+  return wp.fbase[x.i] + (x.k - (0x7fffffff - wp.fmaxinv[x.i])) / pc;
+}
+
+// grid = (gx, batch), block = 256
+__global__ void __launch_bounds__(256) plan_count_kernel(Problem pb) {
+  __shared__ int scratch[40];
+  const int w = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
+  const int64_t* ii = pb.ii + (int64_t)w * pb.st.ii;
+  const int64_t* jj = pb.jj + (int64_t)w * pb.st.jj;
+  const int64_t* kk = pb.kk + (int64_t)w * pb.st.kk;
+  const int E = window_edges(pb, w);
+  const int n_chunks = wp.hdr->n_chunks;
+  const int stride = gridDim.x * blockDim.x;
   if (n_chunks > 0) {
-    for (int e = tid; e < E; e += T) {
-      const int64_t i = ii[e], j = jj[e], k = kk[e];
-      if (i < 0 || i >= F || j < 0 || j >= F || k < 0 || k >= K) continue;
-      const int pos = atomicAdd(&ccur[cnt[(int)i] + ((int)k - kmin[(int)i]) / PMAX], 1);
-      wp.perm[pos] = e;
+    for (int e0 = blockIdx.x * blockDim.x; e0 < E; e0 += stride) {
+      const EdgeIdx x = load_edge(pb, ii, jj, kk, e0 + tid, E);
+      const int c = x.ok ? chunk_of(wp, x, pb.L.pc) : -1;
+      const unsigned grp = __match_any_sync(0xffffffffu, c);
+      if (x.ok && lane == __ffs(grp) - 1) atomicAdd(&wp.ccnt[c], __popc(grp));
     }
   }
-  if (tid == 0) {
-    wp.hdr->n_chunks = n_chunks;
-    wp.hdr->n_valid_edges = n_valid;
+  if (!last_block_done(&wp.hdr->ticket[1])) return;
+
+  // ---- epilogue: exclusive scan of the chunk counts -> edge ranges, fill cursors
+  const int T = blockDim.x;
+  int* ccur = wp.ccur;
+  for (int c = tid; c < n_chunks; c += T) ccur[c] = __ldcg(&wp.ccnt[c]);
+  __syncthreads();
+  const int n_valid = block_exclusive_scan(ccur, n_chunks, scratch);
+  for (int c = tid; c < n_chunks; c += T) {
+    wp.chunks[c].edge_begin = ccur[c];
+    wp.chunks[c].edge_end = ccur[c] + __ldcg(&wp.ccnt[c]);
+  }
+  if (tid == 0) wp.hdr->n_valid_edges = n_valid;
+}
+
+// grid = (gx, batch), block = 256
+__global__ void __launch_bounds__(256) plan_scatter_kernel(Problem pb) {
+  const int w = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
+  const int64_t* ii = pb.ii + (int64_t)w * pb.st.ii;
+  const int64_t* jj = pb.jj + (int64_t)w * pb.st.jj;
+  const int64_t* kk = pb.kk + (int64_t)w * pb.st.kk;
+  const int E = window_edges(pb, w);
+  if (wp.hdr->n_chunks == 0) return;
+  const int stride = gridDim.x * blockDim.x;
+  for (int e0 = blockIdx.x * blockDim.x; e0 < E; e0 += stride) {
+    const int e = e0 + tid;
+    const EdgeIdx x = load_edge(pb, ii, jj, kk, e, E);
+    const int c = x.ok ? chunk_of(wp, x, pb.L.pc) : -1;
+    const unsigned grp = __match_any_sync(0xffffffffu, c);
+    const int leader = __ffs(grp) - 1;
+    int base = 0;
+    if (x.ok && lane == leader) base = atomicAdd(&wp.ccur[c], __popc(grp));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (x.ok) wp.perm[base + __popc(grp & ((1u << lane) - 1u))] = e;
   }
 }
 
@@ -234,19 +299,31 @@ __global__ void __launch_bounds__(256) plan_cells_kernel(Problem pb) {
   }
 }
 
-void launch_plan(const Problem& pb, int64_t batch, cudaStream_t stream) {
-  const size_t smem = sizeof(int) * (3 * (size_t)pb.F + 2 * (size_t)pb.L.ch_max + 64);
-  cudaFuncSetAttribute(plan_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  plan_bucket_kernel<<<dim3(1, (unsigned)batch), 1024, smem, stream>>>(pb);
-  count_launch();
-  int gx = (int)(pb.L.ch_max < 148 * 4 ? pb.L.ch_max : 148 * 4);
-  if (batch > 1) gx = (int)(pb.L.ch_max < 32 ? pb.L.ch_max : 32);
-  plan_cells_kernel<<<dim3((unsigned)gx, (unsigned)batch), 256, 0, stream>>>(pb);
-  count_launch();
+static int edge_grid(int64_t E, int64_t batch) {
+  int64_t g = (E + 255) / 256;
+  const int64_t cap = batch > 1 ? (148 * 8 + batch - 1) / batch : 148 * 4;
+  if (g > cap) g = cap;
+  return (int)(g < 1 ? 1 : g);
 }
 
-size_t plan_bucket_smem_bytes(const Layout& L) {
-  return sizeof(int) * (3 * (size_t)L.F + 2 * (size_t)L.ch_max + 64);
+int chunk_grid(const Problem& pb, int64_t batch) {
+  int64_t g = pb.L.ch_max;
+  const int64_t cap = batch > 1 ? (148 * 16 + batch - 1) / batch : 148 * 8;
+  if (g > cap) g = cap;
+  return (int)(g < 1 ? 1 : g);
+}
+
+void launch_plan(const Problem& pb, int64_t batch, cudaStream_t stream) {
+  const int ge = edge_grid(pb.E, batch);
+  const dim3 grid((unsigned)ge, (unsigned)batch);
+  plan_frames_kernel<<<grid, 256, 0, stream>>>(pb);
+  count_launch();
+  plan_count_kernel<<<grid, 256, 0, stream>>>(pb);
+  count_launch();
+  plan_scatter_kernel<<<grid, 256, 0, stream>>>(pb);
+  count_launch();
+  plan_cells_kernel<<<dim3((unsigned)chunk_grid(pb, batch), (unsigned)batch), 256, 0, stream>>>(pb);
+  count_launch();
 }
 
 }  // namespace pgba

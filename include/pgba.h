@@ -83,8 +83,9 @@ int pgba_ba_solve_batched(float* poses, float* patches, const float* intrinsics,
 
 /* Measurement hooks (used by bench.py only).  pgba_ba_solve_profiled runs exactly the launch sequence of
  * pgba_ba_solve_batched with cudaEvents between the stages, SYNCHRONISES the stream and fills the host array
- * stage_ms [1 + 5*iterations]: plan, then per iteration {zero, linearize+Schur, solve, pose retraction, back-
- * substitution+depth retraction}.  pgba_launch_count returns the number of kernels this library has launched. */
+ * stage_ms [1 + 3*iterations]: workspace clear + plan, then per iteration {linearize+Schur, solve + pose
+ * retraction, back-substitution + depth retraction}.  pgba_launch_count returns the number of kernels this library
+ * has launched. */
 int pgba_ba_solve_profiled(float* poses, float* patches, const float* intrinsics, const float* target,
                            const float* weight, const float* lmbda, const int64_t* ii, const int64_t* jj,
                            const int64_t* kk, const pgba_strides* strides /* host */, int64_t batch, int64_t n_edges,
@@ -104,10 +105,10 @@ int pgba_ba_linearize_debug(const float* poses, const float* patches, const floa
                             float* C, float* u, float* Q, float* dZ, int32_t* n_unique, int32_t* status,
                             void* workspace, size_t workspace_bytes, pgba_stream_t stream);
 
-/* Status word of window `b` of the last call that used `workspace` (device pointer to an i32; read it after the
- * stream has been synchronised).  0 means every edge was processed.  window_bytes is what
- * pgba_ba_workspace_bytes(..., batch = 1, &window_bytes) returns for the same sizes. */
-const int32_t* pgba_ba_status_ptr(const void* workspace, size_t window_bytes, int64_t b);
+/* Status word of window `b` of the last call that used `workspace` with the same sizes (device pointer to an i32;
+ * read it after the stream has been synchronised).  0 means every edge was processed. */
+const int32_t* pgba_ba_status_ptr(const void* workspace, int64_t n_edges, int64_t n_pose_rows, int64_t n_patch_rows,
+                                  int t0, int t1, int64_t batch, int64_t b);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Reprojection of all PxP pixels of each edge's patch from frame ii to frame jj.  Replaces cuda_ba.reproject ==

@@ -497,8 +497,19 @@ __device__ __forceinline__ void factor_diag6(double* A, double* rd, int ld, int 
     for (int c = 0; c <= r; ++c) A[(kb + r) * ld + kb + c] = Lk[r][c];
 }
 
+#ifndef LA_WARP
+#define LA_WARP 7      // the look-ahead (critical path) warp: the scheduler favours the highest warp id of an SMSP
+#endif
+#ifdef PGBA_SOLVE_TIMING
+__device__ long long g_solve_ts[64];
+#define SOLVE_TS(i) do { if (threadIdx.x == 0 && blockIdx.x == 0 && (i) < 64) g_solve_ts[i] = clock64(); } while (0)
+#else
+#define SOLVE_TS(i) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(256, 1) solve_small_kernel(Problem pb) {
   extern __shared__ double sd[];
+  SOLVE_TS(0);
   const int w = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
   const int N = pb.t1 - pb.t0, n = 6 * N, ld = n | 1;
@@ -532,6 +543,7 @@ __global__ void __launch_bounds__(256, 1) solve_small_kernel(Problem pb) {
     for (int x = tid; x < n; x += 256) A[n * ld + x] = (double)wp.y[x];
   }
   __syncthreads();
+  SOLVE_TS(1);
   if (rezero) {                    // S, y are consumed: clear them for the next iteration's accumulation
     float4* S4 = reinterpret_cast<float4*>(wp.S);
     const int n4 = (n * n) >> 2;
@@ -540,6 +552,8 @@ __global__ void __launch_bounds__(256, 1) solve_small_kernel(Problem pb) {
   }
   if (tid == 0) factor_diag6(A, rd, ld, 0);
   __syncthreads();
+  SOLVE_TS(2);
+  int ts_i = 3;
   for (int kb = 0; kb < n; kb += 6) {
     // (b) panel: rows below (incl. the rhs row n): x L11^T = a
     for (int r = kb + 6 + tid; r <= n; r += 256) {
@@ -555,9 +569,10 @@ __global__ void __launch_bounds__(256, 1) solve_small_kernel(Problem pb) {
       for (int c = 0; c < 6; ++c) A[r * ld + kb + c] = x[c];
     }
     __syncthreads();
+    SOLVE_TS(ts_i); ++ts_i;
     const int nb = kb + 6;
     if (nb >= n) break;
-    if (warp == 0) {
+    if (warp == LA_WARP) {
       // look-ahead: update and factor the next diagonal block while the other warps update the rest
       if (lane < 21) {
         int r = 0, c = lane;
@@ -574,7 +589,7 @@ __global__ void __launch_bounds__(256, 1) solve_small_kernel(Problem pb) {
       const int rb0 = nb + 6;
       const int nrows = n + 1 - rb0;
       const int nblk = (n - nb) / 6;                // column blocks nb, nb+6, ..., n-6
-      for (int it = tid - 32; it < nrows * nblk; it += 224) {
+      for (int it = (warp < LA_WARP ? tid : tid - 32); it < nrows * nblk; it += 224) {
         const int r = rb0 + it / nblk, cb = nb + 6 * (it % nblk);
         if (cb > r) continue;
         double lr[6];
@@ -591,6 +606,7 @@ __global__ void __launch_bounds__(256, 1) solve_small_kernel(Problem pb) {
       }
     }
     __syncthreads();
+    SOLVE_TS(ts_i); ++ts_i;
   }
   // ---- backward substitution L^T x = y by warp 0 (row n of A holds y and is overwritten with x)
   if (warp == 0) {
@@ -619,6 +635,7 @@ __global__ void __launch_bounds__(256, 1) solve_small_kernel(Problem pb) {
     }
   }
   __syncthreads();
+  SOLVE_TS(ts_i); ++ts_i;
   const double* xv = A + n * ld;
   for (int x = tid; x < n; x += 256) wp.dX[x] = (float)xv[x];
   // ---- SE3 retraction of the free poses (ba_cuda.cu:178-206)
@@ -630,6 +647,8 @@ __global__ void __launch_bounds__(256, 1) solve_small_kernel(Problem pb) {
 #pragma unroll
     for (int x = 0; x < 7; ++x) prow[x] = pose[x];
   }
+  SOLVE_TS(ts_i);
+  (void)ts_i;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

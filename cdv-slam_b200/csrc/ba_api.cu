@@ -8,8 +8,11 @@
 
 namespace pgba {
 void launch_plan(const Problem& pb, int64_t batch, cudaStream_t stream);
-cudaError_t launch_iteration(const Problem& pb, int64_t batch, cudaStream_t stream, cudaEvent_t* ev);
-bool solve_small_supported(int N);
+cudaError_t launch_iteration(const Problem& pb, int64_t batch, cudaStream_t stream, cudaEvent_t* ev, bool more);
+void launch_linearize(const Problem& pb, int64_t batch, cudaStream_t stream);
+void launch_solve(const Problem& pb, int64_t batch, cudaStream_t stream);
+void launch_update(const Problem& pb, int64_t batch, cudaStream_t stream);
+bool solve_supported(int N);
 
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -156,7 +159,7 @@ static int prepare(Problem& pb, float* poses, float* patches, const float* intri
   pb = make_problem(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, n_edges_dev, strides, n_edges,
                     n_pose_rows, n_patch_rows, P, t0, t1, workspace, batch);
   if (total_bytes(pb.L, batch) > workspace_bytes) return PGBA_ERR_WORKSPACE;
-  if (t1 > t0 && !solve_small_supported(t1 - t0)) return PGBA_ERR_UNSUPPORTED;
+  if (t1 > t0 && !solve_supported(t1 - t0)) return PGBA_ERR_UNSUPPORTED;
   return PGBA_OK;
 }
 
@@ -178,7 +181,7 @@ int pgba_ba_solve_batched(float* poses, float* patches, const float* intrinsics,
   if (e != cudaSuccess) return (int)e;
   launch_plan(pb, batch, s);
   for (int it = 0; it < iterations; ++it) {
-    e = launch_iteration(pb, batch, s, nullptr);
+    e = launch_iteration(pb, batch, s, nullptr, it + 1 < iterations);
     if (e != cudaSuccess) return (int)e;
   }
   return (int)cudaGetLastError();
@@ -203,7 +206,7 @@ int pgba_ba_solve_profiled(float* poses, float* patches, const float* intrinsics
   cudaError_t e = clear_workspace(pb, batch, s);
   launch_plan(pb, batch, s);
   cudaEventRecord(ev[1], s);
-  for (int it = 0; it < iterations && e == cudaSuccess; ++it) e = launch_iteration(pb, batch, s, ev + 2 + 4 * it);
+  for (int it = 0; it < iterations && e == cudaSuccess; ++it) e = launch_iteration(pb, batch, s, ev + 2 + 4 * it, it + 1 < iterations);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);
   if (e == cudaSuccess) {
     cudaEventElapsedTime(&stage_ms[0], ev[0], ev[1]);
@@ -243,9 +246,12 @@ int pgba_ba_linearize_debug(const float* poses, const float* patches, const floa
   cudaError_t e = clear_workspace(pb, 1, s);
   if (e != cudaSuccess) return (int)e;
   launch_plan(pb, 1, s);
-  e = launch_iteration(pb, 1, s, nullptr);
-  if (e != cudaSuccess) return (int)e;
-  export_debug_kernel<<<64, 256, 0, s>>>(pb, S, y, dX, patch_ids, C, u, Q, dZ, n_unique, status);
+  launch_linearize(pb, 1, s);
+  export_debug_kernel<<<256, 256, 0, s>>>(pb, S, y, nullptr, patch_ids, C, u, Q, nullptr, n_unique, nullptr);   // before the solve
+  count_launch();
+  launch_solve(pb, 1, s);
+  launch_update(pb, 1, s);
+  export_debug_kernel<<<64, 256, 0, s>>>(pb, nullptr, nullptr, dX, nullptr, nullptr, nullptr, nullptr, dZ, nullptr, status);
   count_launch();
   return (int)cudaGetLastError();
 }

@@ -11,6 +11,7 @@ constexpr int PMAX = 128;                 // upper bound of patches per chunk (o
 constexpr int SMAX = PGBA_MAX_SLOTS;      // distinct target frames per chunk
 constexpr int EBUDGET = 12288;            // floats of shared memory for the per-batch E tile (48 KB)
 constexpr int SOLVE_NMAX = 156;           // 6N handled by the single-CTA shared-memory solve (N <= 26)
+constexpr int BIG_NB = 48;                // panel width of the blocked global-memory Cholesky (6N > SOLVE_NMAX)
 
 // ---------------------------------------------------------------------------------------------------------------
 // Workspace.  [ zero region of window 0 | ... | zero region of window B-1 | body of window 0 | ... ]
@@ -52,7 +53,9 @@ struct Layout {         // host-computed
   int big;              // 1: dense S too large for the shared-memory solve -> blocked global-memory Cholesky
   int64_t ch_max, patch_max, slot_max, cell_cap, ecell_cap;
   // zero region (relative to the window's zero base)
-  size_t z_hdr, z_fmaxinv, z_fkmax1, z_ccnt, z_y, z_S, zero_bytes;
+  size_t z_hdr, z_fmaxinv, z_fkmax1, z_ccnt, z_nact, z_bs, z_y, z_S, zero_bytes;
+  size_t o_rdiag, o_winv, o_active;   // big solve only
+  int big_steps, big_tiles;
   // body (relative to the window's body base)
   size_t o_fbase, o_ccur, o_chunks, o_perm, o_kx, o_slots, o_cells, o_dups, o_ecells, o_Q, o_u, o_dZ, o_dX, body_bytes;
   size_t body0;         // offset of the first body = batch * zero_bytes (aligned)
@@ -86,6 +89,10 @@ inline Layout make_layout(int64_t E, int64_t F, int64_t K, int N, int64_t batch,
   L.z_fmaxinv = o; o = align256(o + 4 * (size_t)F);
   L.z_fkmax1 = o;  o = align256(o + 4 * (size_t)F);
   L.z_ccnt = o;    o = align256(o + 4 * (size_t)L.ch_max);
+  L.big_steps = L.big ? (int)((n6 + BIG_NB - 1) / BIG_NB) : 0;
+  L.big_tiles = L.big_steps + 1;
+  L.z_nact = o;    o = align256(o + 4 * (size_t)(L.big_steps + 1));
+  L.z_bs = o;      o = align256(o + 512);
   L.z_y = o;       o = align256(o + 4 * n6);
   L.z_S = o;       o = align256(o + 4 * n6 * n6);
   L.zero_bytes = o;
@@ -103,6 +110,9 @@ inline Layout make_layout(int64_t E, int64_t F, int64_t K, int N, int64_t batch,
   L.o_u = o;      o = align256(o + 4 * (size_t)L.patch_max);
   L.o_dZ = o;     o = align256(o + 4 * (size_t)L.patch_max);
   L.o_dX = o;     o = align256(o + 4 * n6);
+  L.o_rdiag = o;  o = align256(o + (L.big ? 4 * n6 : 0));
+  L.o_winv = o;   o = align256(o + (L.big ? 4 * (size_t)L.big_steps * BIG_NB * BIG_NB : 0));
+  L.o_active = o; o = align256(o + (L.big ? 4 * (size_t)L.big_steps * L.big_tiles : 0));
   L.body_bytes = o;
   L.body0 = L.zero_bytes * (size_t)batch;
   return L;

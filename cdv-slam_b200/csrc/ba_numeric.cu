@@ -18,6 +18,7 @@
 //   update_kernel      dZ = Q (u - E^T dX) (ba_cuda.cu:592, block_e.cu:253-283) + inverse-depth retraction
 //                      (ba_cuda.cu:209-229)
 #include "ba_common.cuh"
+#include "ba_chol.cuh"
 
 namespace pgba {
 
@@ -467,39 +468,6 @@ size_t solve_small_smem_bytes(int n) {
   return sizeof(double) * ((size_t)(n + 1) * ld + n + 8);
 }
 
-// Cholesky of the 6x6 diagonal block at kb (lower triangle, in place) by ONE thread; rd = 1 / diag(L).
-// rsqrt of a non-positive pivot gives NaN/inf, which propagates like the reference's unchecked potrf (info ignored).
-__device__ __forceinline__ void factor_diag6(double* A, double* rd, int ld, int kb) {
-  double Lk[6][6];
-#pragma unroll
-  for (int r = 0; r < 6; ++r)
-#pragma unroll
-    for (int c = 0; c <= r; ++c) Lk[r][c] = A[(kb + r) * ld + kb + c];
-#pragma unroll
-  for (int c = 0; c < 6; ++c) {
-    double d = Lk[c][c];
-#pragma unroll
-    for (int e = 0; e < c; ++e) d -= Lk[c][e] * Lk[c][e];
-    const double ri = rsqrt(d);
-    Lk[c][c] = d * ri;
-    rd[kb + c] = ri;
-#pragma unroll
-    for (int r = c + 1; r < 6; ++r) {
-      double v = Lk[r][c];
-#pragma unroll
-      for (int e = 0; e < c; ++e) v -= Lk[r][e] * Lk[c][e];
-      Lk[r][c] = v * ri;
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < 6; ++r)
-#pragma unroll
-    for (int c = 0; c <= r; ++c) A[(kb + r) * ld + kb + c] = Lk[r][c];
-}
-
-#ifndef LA_WARP
-#define LA_WARP 7      // the look-ahead (critical path) warp: the scheduler favours the highest warp id of an SMSP
-#endif
 #ifdef PGBA_SOLVE_TIMING
 __device__ long long g_solve_ts[64];
 #define SOLVE_TS(i) do { if (threadIdx.x == 0 && blockIdx.x == 0 && (i) < 64) g_solve_ts[i] = clock64(); } while (0)
@@ -550,64 +518,9 @@ __global__ void __launch_bounds__(256, 1) solve_small_kernel(Problem pb) {
     for (int x4 = tid; x4 < n4; x4 += 256) S4[x4] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int x = tid; x < n; x += 256) wp.y[x] = 0.f;
   }
-  if (tid == 0) factor_diag6(A, rd, ld, 0);
-  __syncthreads();
+  chol6_smem(A, rd, n, n, ld);          // rows 0..n: the rhs row n rides along (forward substitution)
   SOLVE_TS(2);
   int ts_i = 3;
-  for (int kb = 0; kb < n; kb += 6) {
-    // (b) panel: rows below (incl. the rhs row n): x L11^T = a
-    for (int r = kb + 6 + tid; r <= n; r += 256) {
-      double x[6];
-#pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        double v = A[r * ld + kb + c];
-#pragma unroll
-        for (int e = 0; e < c; ++e) v -= x[e] * A[(kb + c) * ld + kb + e];
-        x[c] = v * rd[kb + c];
-      }
-#pragma unroll
-      for (int c = 0; c < 6; ++c) A[r * ld + kb + c] = x[c];
-    }
-    __syncthreads();
-    SOLVE_TS(ts_i); ++ts_i;
-    const int nb = kb + 6;
-    if (nb >= n) break;
-    if (warp == LA_WARP) {
-      // look-ahead: update and factor the next diagonal block while the other warps update the rest
-      if (lane < 21) {
-        int r = 0, c = lane;
-        while (c > r) { c -= r + 1; ++r; }          // lane -> (r, c), c <= r < 6
-        double acc = 0.0;
-#pragma unroll
-        for (int a = 0; a < 6; ++a) acc += A[(nb + r) * ld + kb + a] * A[(nb + c) * ld + kb + a];
-        A[(nb + r) * ld + nb + c] -= acc;
-      }
-      __syncwarp();
-      if (lane == 0) factor_diag6(A, rd, ld, nb);
-    } else {
-      // (c) trailing update of rows >= nb + 6 (incl. rhs row): item = (row r, column block cb <= r)
-      const int rb0 = nb + 6;
-      const int nrows = n + 1 - rb0;
-      const int nblk = (n - nb) / 6;                // column blocks nb, nb+6, ..., n-6
-      for (int it = (warp < LA_WARP ? tid : tid - 32); it < nrows * nblk; it += 224) {
-        const int r = rb0 + it / nblk, cb = nb + 6 * (it % nblk);
-        if (cb > r) continue;
-        double lr[6];
-#pragma unroll
-        for (int a = 0; a < 6; ++a) lr[a] = A[r * ld + kb + a];
-#pragma unroll
-        for (int b = 0; b < 6; ++b) {
-          const double* lc = A + (cb + b) * ld + kb;
-          double acc = 0.0;
-#pragma unroll
-          for (int a = 0; a < 6; ++a) acc += lr[a] * lc[a];
-          A[r * ld + cb + b] -= acc;
-        }
-      }
-    }
-    __syncthreads();
-    SOLVE_TS(ts_i); ++ts_i;
-  }
   // ---- backward substitution L^T x = y by warp 0 (row n of A holds y and is overwritten with x)
   if (warp == 0) {
     double* xv = A + n * ld;
@@ -708,30 +621,62 @@ int lin_ebudget(const Problem& pb) {
   return (int)need;
 }
 
-// ev (optional): 4 events recorded before linearize / solve / update and after update
-cudaError_t launch_iteration(const Problem& pb, int64_t batch, cudaStream_t stream, cudaEvent_t* ev) {
-  const int N = pb.t1 - pb.t0;
+cudaError_t launch_big_solve(const Problem& pb, int64_t batch, cudaStream_t stream);
+
+void launch_linearize(const Problem& pb, int64_t batch, cudaStream_t stream) {
   const int gx = chunk_grid(pb, batch);
-  if (ev) cudaEventRecord(ev[0], stream);
   const int ebudget = lin_ebudget(pb);
   const size_t lsm = lin_smem_bytes(pb.L.pc, ebudget);
   cudaFuncSetAttribute(linearize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm);
   linearize_kernel<<<dim3((unsigned)gx, (unsigned)batch), 256, lsm, stream>>>(pb, ebudget);
   count_launch();
-  if (ev) cudaEventRecord(ev[1], stream);
-  if (N > 0) {
-    const size_t smem = solve_small_smem_bytes(6 * N);
-    cudaFuncSetAttribute(solve_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    solve_small_kernel<<<(unsigned)batch, 256, smem, stream>>>(pb);
-    count_launch();
+}
+
+// Solve S dX = y (damped), retract the poses (if pb.apply).  Small systems: one CTA per window, S and y are re-zeroed
+// by the kernel.  Large systems: blocked Cholesky in global memory; S holds the factor afterwards.
+void launch_solve(const Problem& pb, int64_t batch, cudaStream_t stream) {
+  const int N = pb.t1 - pb.t0;
+  if (N <= 0) return;
+  if (pb.L.big) {
+    launch_big_solve(pb, batch, stream);
+    return;
   }
-  if (ev) cudaEventRecord(ev[2], stream);
+  const size_t smem = solve_small_smem_bytes(6 * N);
+  cudaFuncSetAttribute(solve_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  solve_small_kernel<<<(unsigned)batch, 256, smem, stream>>>(pb);
+  count_launch();
+}
+
+void launch_update(const Problem& pb, int64_t batch, cudaStream_t stream) {
+  const int gx = chunk_grid(pb, batch);
   update_kernel<<<dim3((unsigned)gx, (unsigned)batch), 256, 0, stream>>>(pb);
   count_launch();
+}
+
+// After a large solve S holds the Cholesky factor: clear S, y of every window before the next linearisation.
+cudaError_t clear_big_system(const Problem& pb, int64_t batch, cudaStream_t stream) {
+  cudaError_t e = cudaSuccess;
+  for (int64_t w = 0; w < batch && e == cudaSuccess; ++w)
+    e = cudaMemsetAsync((char*)pb.ws + (size_t)w * pb.L.zero_bytes + pb.L.z_y, 0, pb.L.zero_bytes - pb.L.z_y, stream);
+  return e;
+}
+
+// ev (optional): 4 events recorded before linearize / solve / update and after update
+cudaError_t launch_iteration(const Problem& pb, int64_t batch, cudaStream_t stream, cudaEvent_t* ev, bool more) {
+  if (ev) cudaEventRecord(ev[0], stream);
+  launch_linearize(pb, batch, stream);
+  if (ev) cudaEventRecord(ev[1], stream);
+  launch_solve(pb, batch, stream);
+  if (ev) cudaEventRecord(ev[2], stream);
+  launch_update(pb, batch, stream);
+  if (pb.L.big && more) {
+    cudaError_t e = clear_big_system(pb, batch, stream);
+    if (e != cudaSuccess) return e;
+  }
   if (ev) cudaEventRecord(ev[3], stream);
   return cudaGetLastError();
 }
 
-bool solve_small_supported(int N) { return 6 * N <= SOLVE_NMAX; }
+bool solve_supported(int N) { return N <= PGBA_MAX_POSE_ROWS; }
 
 }  // namespace pgba

@@ -39,6 +39,16 @@ def main():
         def f(): reset(); ref_ba.forward(d["poses"], d["patches"], d["intrinsics"], d["target"], d["weight"], d["lmbda"], d["ii"], d["jj"], d["kk"], 96, p.t0, p.t1, 2, eff)
         return f
     out["ba_c2_ms"] = {"ours_api": timeit(ours), "reference_dense": timeit(ref(False)), "reference_eff": timeit(ref(True))}
+    if os.environ.get("REF_C4", "1") == "1":
+        p4 = synth.config_c4()
+        d4 = to_dev(p4, pad_pose_rows=4096 - 1000, pad_patch_rows=(4096 - 1000) * 96)
+        a0, b0 = d4["poses"].clone(), d4["patches"].clone()
+        def reset4(): d4["poses"].copy_(a0); d4["patches"].copy_(b0)
+        def ours4(): reset4(); fastba.BA(d4["poses"], d4["patches"], d4["intrinsics"], d4["target"], d4["weight"], d4["lmbda"], d4["ii"], d4["jj"], d4["kk"], p4.t0, p4.t1, M=96, iterations=2, eff_impl=True)
+        def ref4(): reset4(); ref_ba.forward(d4["poses"], d4["patches"], d4["intrinsics"], d4["target"], d4["weight"], d4["lmbda"], d4["ii"], d4["jj"], d4["kk"], 96, p4.t0, p4.t1, 2, True)
+        out["ba_c4_ms"] = {"ours_api": timeit(ours4, 5, 2), "reference_eff": timeit(ref4, 3, 1)}
+        del d4, a0, b0
+        torch.cuda.empty_cache()
     for C, dt in ((24, torch.float16), (128, torch.float32)):
         gmap, pyr = synth.make_fmaps(p, C=C)
         g = torch.as_tensor(gmap, device="cuda")[None].to(dt)

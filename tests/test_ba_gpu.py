@@ -70,9 +70,14 @@ def test_normal_equations(maker):
     g1 = fastba.linearize_debug(*args, with_schur=True)
     assert rel_err(g1["S"].cpu().numpy(), o["S"]) < TOL            # Schur complement    (ba_cuda.cu:586)
     assert rel_err(g1["y"].cpu().numpy(), o["y"]) < TOL
-    assert rel_err(g1["dX"].cpu().numpy(), o["dX"]) < 10 * TOL     # cond(S) amplifies fp32 assembly rounding
-    assert rel_err(g1["dZ"].cpu().numpy(), o["dZ"]) < 10 * TOL
-    S = g1["S"].cpu().numpy()
+    # dX, dZ: forward error of a linear solve <= cond(S) * (relative error of S, y).  S and y are assembled in fp32
+    # (like the reference) and are good to ~3e-7, in an order that varies with the atomics; c1 is gauge-deficient
+    # (cond ~ 8e4), so its bound is ~5e-3, the well-posed windows stay at 1e-3.
+    S = g1["S"].cpu().numpy().astype(np.float64)
+    cond = np.linalg.cond(S + np.diag(1e-4 * np.diag(S) + 1.0))
+    tol_x = max(10 * TOL, 0.5 * cond * 2.0 ** -23)
+    assert rel_err(g1["dX"].cpu().numpy(), o["dX"]) < tol_x
+    assert rel_err(g1["dZ"].cpu().numpy(), o["dZ"]) < tol_x
     assert np.abs(S - S.T).max() <= 1e-6 * np.abs(S).max()
 
 
@@ -206,3 +211,54 @@ def test_cpu_tensors_fail_loudly():
     with pytest.raises(RuntimeError):
         fastba.BA(d["poses"], d["patches"], d["intrinsics"], d["target"], d["weight"], d["lmbda"], d["ii"], d["jj"],
                   d["kk"], p.t0, p.t1, M=p.M, iterations=2)
+
+
+def _global_problem(F, M, n_loops, seed):
+    rng = np.random.default_rng(seed)
+    return synth.make_problem("global", F, synth.global_edges(F, M, n_loops, rng), 1, F, seed, M, eff_impl=True)
+
+
+@pytest.mark.parametrize("F,M,n_loops", [(40, 8, 3), (75, 12, 10)])
+def test_global_ba_large_solver_normal_equations(F, M, n_loops):
+    """6N > 156 selects the blocked global-memory Cholesky (reference: dense torch Cholesky on S, ba_cuda.cu:575-591).
+    S, y and the solution dX / dZ against the oracle; F=75 gives a ragged last panel (444 = 9*48 + 12)."""
+    p = _global_problem(F, M, n_loops, 31 + F)
+    d = to_dev(p)
+    o = _normal_equations_oracle(p)
+    g = fastba.linearize_debug(d["poses"], d["patches"], d["intrinsics"], d["target"], d["weight"], d["lmbda"], d["ii"],
+                               d["jj"], d["kk"], p.t0, p.t1, with_schur=True)
+    assert g["status"] == 0
+    assert rel_err(g["S"].cpu().numpy(), o["S"]) < TOL
+    assert rel_err(g["y"].cpu().numpy(), o["y"]) < TOL
+    S = g["S"].cpu().numpy().astype(np.float64)
+    cond = np.linalg.cond(S + np.diag(1e-4 * np.diag(S) + 1.0))
+    tol_x = max(10 * TOL, 0.5 * cond * 2.0 ** -23)             # see test_normal_equations
+    assert rel_err(g["dX"].cpu().numpy(), o["dX"]) < tol_x
+    assert rel_err(g["dZ"].cpu().numpy(), o["dZ"]) < tol_x
+
+
+@pytest.mark.parametrize("eff_impl", [False, True])
+def test_global_ba_matches_oracle(eff_impl):
+    p = _global_problem(75, 12, 10, 5)
+    o_poses, o_patches = _oracle(p, 2)
+    poses, patches = _run_gpu(p, 2, eff_impl=eff_impl)
+    _check_state(p, poses, patches, o_poses, o_patches, tol=2e-4)
+
+
+def test_global_ba_c4_full_size():
+    """BASELINE config c4: 1000 frames, 402 624 edges, 999 free poses (S is 5994^2), eff_impl=True, 2 iterations.
+    Poses to 1e-4 (norm-wise); inverse depths as stated below."""
+    p = synth.config_c4()
+    o_poses, o_patches = _oracle(p, 2)
+    poses, patches = _run_gpu(p, 2, eff_impl=True)
+    assert np.isfinite(poses).all() and np.isfinite(patches).all()
+    assert rel_err(poses, o_poses) < TOL
+    np.testing.assert_array_equal(poses[:p.t0], np.asarray(p.poses, np.float32)[:p.t0].astype(np.float64))
+    d_g, d_o = patches[:, 2, 0, 0], o_patches[:, 2, 0, 0]
+    rel = np.abs(d_g - d_o) / np.abs(d_o)
+    # 96 000 inverse depths: 99.9 % within 1e-4 relative; the handful that collapse towards the 1e-4 clamp
+    # (|d| ~ 1e-3, ill-conditioned, order-of-atomics dependent) are held to 1e-4 absolute instead
+    assert np.percentile(rel, 99.9) < 2 * TOL
+    assert np.abs(d_g - d_o).max() < TOL
+    np.testing.assert_array_equal(patches[:, 2], np.broadcast_to(patches[:, 2, :1, :1], patches[:, 2].shape))
+    np.testing.assert_array_equal(patches[:, :2], np.asarray(p.patches, np.float32)[:, :2].astype(np.float64))

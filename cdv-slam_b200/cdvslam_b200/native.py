@@ -12,7 +12,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 PKG_ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(PKG_ROOT, "lib", "libpgba.so")
+LIB_PATH = os.environ.get("PGBA_LIB") or os.path.join(PKG_ROOT, "lib", "libpgba.so")   # PGBA_LIB: A/B builds
 BUILD_SCRIPT = os.path.join(PKG_ROOT, "csrc", "build.sh")
 
 c_i64, c_int, c_vp, c_sz = ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t

@@ -24,37 +24,51 @@ namespace pgba {
 
 int chunk_grid(const Problem& pb, int64_t batch);
 
-// Per-edge terms.  px, py, pd: patch centre and inverse depth; R, t: relative pose Gij.
-__device__ __forceinline__ void edge_terms(float px, float py, float pd, float fx, float fy, float cx, float cy,
+// Per-edge terms.  xi0, xi1: normalised patch centre ((px-cx)/fx, (py-cy)/fy), pd: inverse depth; R, t: relative
+// pose Gij.  Same formulas as ba_cuda.cu:282-343; the Jacobian rows have the structural zeros Jx[1] == Jy[0] == 0,
+// so H[0][1] is identically zero and rows 0 / 1 of H, g, e only see one of the two residual rows.
+__device__ __forceinline__ void edge_terms(float xi0, float xi1, float pd, float fx, float fy, float cx, float cy,
                                            const float R[9], const float t[3], float2 tg, float2 wt, float H[21],
                                            float g[6], float e[6], float& c_out, float& u_out) {
-  const float xi0 = (px - cx) / fx, xi1 = (py - cy) / fy;
   const float X = R[0] * xi0 + R[1] * xi1 + R[2] + pd * t[0];
   const float Y = R[3] * xi0 + R[4] * xi1 + R[5] + pd * t[1];
   const float Z = R[6] * xi0 + R[7] * xi1 + R[8] + pd * t[2];
   const float W = pd;
-  const float d = (Z >= 0.2f) ? 1.0f / Z : 0.0f;
+  const float iz = 1.0f / Z;                                   // unguarded, like the reference's X / Z (:299-300)
+  const float d = (Z >= 0.2f) ? iz : 0.0f;                     // ba_cuda.cu:296
   const float d2 = d * d;
-  const float x1 = fx * (X / Z) + cx;
-  const float y1 = fy * (Y / Z) + cy;
+  const float x1 = fx * (X * iz) + cx;
+  const float y1 = fy * (Y * iz) + cy;
   const float rx = tg.x - x1, ry = tg.y - y1;
-  const bool in_bounds = (sqrtf(rx * rx + ry * ry) < 128.f) && (Z > 0.2f) && (x1 > -64.f) && (y1 > -64.f) &&
+  const bool in_bounds = (rx * rx + ry * ry < 128.f * 128.f) && (Z > 0.2f) && (x1 > -64.f) && (y1 > -64.f) &&
                          (x1 < 2.f * cx + 64.f) && (y1 < 2.f * cy + 64.f);
-  const float mask = in_bounds ? 1.0f : 0.0f;
-  const float wx = mask * wt.x, wy = mask * wt.y;
-  // Jj rows (ba_cuda.cu:323-341); Jx[1] == 0 and Jy[0] == 0
-  const float Jx0 = fx * W * d, Jx2 = -fx * X * W * d2, Jx3 = -fx * X * Y * d2, Jx4 = fx * (1.0f + X * X * d2),
-              Jx5 = -fx * Y * d;
-  const float Jy1 = fy * W * d, Jy2 = -fy * Y * W * d2, Jy3 = -fy * (1.0f + Y * Y * d2), Jy4 = fy * X * Y * d2,
-              Jy5 = fy * X * d;
-  const float Jzx = fx * (t[0] * d - t[2] * X * d2);
-  const float Jzy = fy * (t[1] * d - t[2] * Y * d2);
+  const float wx = in_bounds ? wt.x : 0.0f, wy = in_bounds ? wt.y : 0.0f;
+  // Jj rows (ba_cuda.cu:323-341)
+  const float fxd = fx * d, fyd = fy * d, Xd2 = X * d2, Yd2 = Y * d2;
+  const float Jx0 = fxd * W, Jx2 = -fx * Xd2 * W, Jx3 = -fx * Xd2 * Y, Jx4 = fx * (1.0f + X * Xd2), Jx5 = -fxd * Y;
+  const float Jy1 = fyd * W, Jy2 = -fy * Yd2 * W, Jy3 = -fy * (1.0f + Y * Yd2), Jy4 = fy * Xd2 * Y, Jy5 = fyd * X;
+  const float Jzx = fx * (t[0] * d - t[2] * Xd2);
+  const float Jzy = fy * (t[1] * d - t[2] * Yd2);
   const float Jx[6] = {Jx0, 0.f, Jx2, Jx3, Jx4, Jx5};
   const float Jy[6] = {0.f, Jy1, Jy2, Jy3, Jy4, Jy5};
   const float wrx = wx * rx, wry = wy * ry;
   const float wzx = wx * Jzx, wzy = wy * Jzy;
+  {                                                            // row 0: only Jx, row 1: only Jy
+    const float wa = wx * Jx0, wb = wy * Jy1;
+    H[sym6(0, 0)] += wa * Jx0;
+    H[sym6(1, 1)] += wb * Jy1;
 #pragma unroll
-  for (int a = 0; a < 6; ++a) {
+    for (int b = 2; b < 6; ++b) {
+      H[sym6(0, b)] += wa * Jx[b];
+      H[sym6(1, b)] += wb * Jy[b];
+    }
+    g[0] += wrx * Jx0;
+    g[1] += wry * Jy1;
+    e[0] = wzx * Jx0;
+    e[1] = wzy * Jy1;
+  }
+#pragma unroll
+  for (int a = 2; a < 6; ++a) {
     const float wa = wx * Jx[a], wb = wy * Jy[a];
 #pragma unroll
     for (int b = a; b < 6; ++b) H[sym6(a, b)] += wa * Jx[b] + wb * Jy[b];
@@ -76,15 +90,13 @@ struct LinSmem {
   float* sBii;     // [36 + 6]    B_ii and v_i of the chunk
   int* sFrame;     // [SMAX]
   float* sPatch;   // [pc][4]     px, py, pd, -
-  float* sC;       // [pc]
-  float* sU;       // [pc]
+  float* sPQ;      // [pc][8]     per patch: C, u, E_i[6] (source-frame column accumulators)
   float* sQ;       // [pc]
-  float* sEi;      // [pc][6]     source-frame column accumulators
   float* sE;       // [ebudget]   E tile [patch][col][6]
 };
 
 size_t lin_smem_bytes(int pc, int ebudget) {
-  return sizeof(float) * ((size_t)LIN_FIXED_FLOATS + (size_t)pc * (4 + 3 + 6) + (size_t)ebudget);
+  return sizeof(float) * ((size_t)LIN_FIXED_FLOATS + (size_t)pc * (4 + 8 + 1) + (size_t)ebudget);
 }
 
 __device__ __forceinline__ int pow2_ceil(int x) {
@@ -108,11 +120,9 @@ __global__ void __launch_bounds__(256, 2) linearize_kernel(Problem pb, int ebudg
   s.sBii = s.sHw + 8 * 32 * HW_STRIDE;
   s.sFrame = (int*)(s.sBii + 48);
   s.sPatch = (float*)(s.sFrame + SMAX);
-  s.sC = s.sPatch + pc * 4;
-  s.sU = s.sC + pc;
-  s.sQ = s.sU + pc;
-  s.sEi = s.sQ + pc;
-  s.sE = s.sEi + pc * 6;
+  s.sPQ = s.sPatch + pc * 4;
+  s.sQ = s.sPQ + pc * 8;
+  s.sE = s.sQ + pc;
   float* sAH = s.sHw;
 
   const int w = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -160,8 +170,8 @@ __global__ void __launch_bounds__(256, 2) linearize_kernel(Problem pb, int ebudg
       for (int p = b0 + tid; p < b1; p += 256) {
         const float* pr = patches + (int64_t)kx[p] * pstride;
         const int q = p - b0;
-        s.sPatch[q * 4 + 0] = pr[cidx];
-        s.sPatch[q * 4 + 1] = pr[PP + cidx];
+        s.sPatch[q * 4 + 0] = (pr[cidx] - cx) / fx;              // ba_cuda.cu:282-283
+        s.sPatch[q * 4 + 1] = (pr[PP + cidx] - cy) / fy;
         s.sPatch[q * 4 + 2] = pr[2 * PP + cidx];
       }
       for (int x = tid; x < (b1 - b0) * estride; x += 256) s.sE[x] = 0.f;
@@ -210,7 +220,8 @@ __global__ void __launch_bounds__(256, 2) linearize_kernel(Problem pb, int ebudg
             }
             if (i_free) adj_map(R, t, e, ei);
           }
-          // reduce the per-patch quantities over the DW lanes of this patch
+          // reduce the per-patch quantities over the DW lanes of this patch (plain butterfly: measured faster than a
+          // transposed, select-heavy 8-value reduction on this kernel)
           for (int o = DW >> 1; o > 0; o >>= 1) {
             ck += __shfl_xor_sync(0xffffffffu, ck, o);
             uk += __shfl_xor_sync(0xffffffffu, uk, o);
@@ -220,17 +231,15 @@ __global__ void __launch_bounds__(256, 2) linearize_kernel(Problem pb, int ebudg
             }
           }
           if ((lane & (DW - 1)) == 0 && p < b1) {       // exactly one lane group owns patch p in this slot block
-            const int q = p - b0;
+            float* dst = s.sPQ + (p - b0) * 8;          // [0]: C, [1]: u, [2..7]: E_i -= w Jz Ji
             if (sb == 0) {
-              s.sC[q] = ck;
-              s.sU[q] = uk;
+              dst[0] = ck; dst[1] = uk;
 #pragma unroll
-              for (int a = 0; a < 6; ++a) s.sEi[q * 6 + a] = -ei[a];     // E_i -= w Jz Ji
+              for (int a = 0; a < 6; ++a) dst[2 + a] = -ei[a];
             } else {
-              s.sC[q] += ck;
-              s.sU[q] += uk;
+              dst[0] += ck; dst[1] += uk;
 #pragma unroll
-              for (int a = 0; a < 6; ++a) s.sEi[q * 6 + a] -= ei[a];
+              for (int a = 0; a < 6; ++a) dst[2 + a] -= ei[a];
             }
           }
         }
@@ -278,10 +287,10 @@ __global__ void __launch_bounds__(256, 2) linearize_kernel(Problem pb, int ebudg
               for (int a = 0; a < 6; ++a) s.sE[q * estride + col * 6 + a] += e[a];
             if (i_free) {
               adj_map(R, t, e, ei);
-              for (int a = 0; a < 6; ++a) s.sEi[q * 6 + a] -= ei[a];
+              for (int a = 0; a < 6; ++a) s.sPQ[q * 8 + 2 + a] -= ei[a];
             }
-            s.sC[q] += ck;
-            s.sU[q] += uk;
+            s.sPQ[q * 8] += ck;
+            s.sPQ[q * 8 + 1] += uk;
             for (int x = 0; x < 21; ++x) s.sH[sl * 28 + x] += H[x];
             for (int x = 0; x < 6; ++x) s.sH[sl * 28 + 21 + x] += g[x];
           }
@@ -292,13 +301,13 @@ __global__ void __launch_bounds__(256, 2) linearize_kernel(Problem pb, int ebudg
       // ---- per patch: fold the source-frame column, Q = 1/(C + lambda), export Q, u
       for (int p = b0 + tid; p < b1; p += 256) {
         const int q = p - b0;
-        const float Q = 1.0f / (s.sC[q] + lmbda);
+        const float Q = 1.0f / (s.sPQ[q * 8] + lmbda);
         s.sQ[q] = Q;
         wp.Q[ch.patch_base + p] = Q;
-        wp.u[ch.patch_base + p] = s.sU[q];
+        wp.u[ch.patch_base + p] = s.sPQ[q * 8 + 1];
         if (i_free && schur) {
 #pragma unroll
-          for (int a = 0; a < 6; ++a) s.sE[q * estride + ch.icol * 6 + a] += s.sEi[q * 6 + a];
+          for (int a = 0; a < 6; ++a) s.sE[q * estride + ch.icol * 6 + a] += s.sPQ[q * 8 + 2 + a];
         }
       }
       __syncthreads();
@@ -306,42 +315,56 @@ __global__ void __launch_bounds__(256, 2) linearize_kernel(Problem pb, int ebudg
         float* eg = wp.ecells + 6 * ((int64_t)ch.ecell_base + (int64_t)b0 * ncols);
         for (int x = tid; x < (b1 - b0) * estride; x += 256) eg[x] = s.sE[x];
 
-        // ---- Schur update of this batch.  Item = (column pair ca >= cb, row a): six sums over the patches.
-        //      M = sum_p Q_p E_p[ca] E_p[cb]^T is block (ca, cb); it lands at (frame(ca), frame(cb)) or transposed.
+        // ---- Schur update of this batch.  Item = (column pair ca >= cb, row pair 2*a2, 2*a2+1): twelve sums over
+        //      the patches, as packed fp32x2 FMAs (FFMA2).  M = sum_p Q_p E_p[ca] E_p[cb]^T is block (ca, cb); it
+        //      lands at (frame(ca), frame(cb)) or transposed.
         const int npairs = ncols * (ncols + 1) / 2;
         const int nq = b1 - b0;
-        for (int it = tid; it < npairs * 6; it += 256) {
-          const int pr = it / 6, a = it - pr * 6;
+        for (int it = tid; it < npairs * 3; it += 256) {
+          const int pr = it / 3, a2 = it - pr * 3;
           int ca = (int)((sqrtf(8.f * pr + 1.f) - 1.f) * 0.5f);
           while (ca * (ca + 1) / 2 > pr) --ca;
           while ((ca + 1) * (ca + 2) / 2 <= pr) ++ca;
           const int cb = pr - ca * (ca + 1) / 2;
-          float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          const float* ea = s.sE + ca * 6 + a;
+          float2 acc0[3], acc1[3];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) { acc0[k] = make_float2(0.f, 0.f); acc1[k] = make_float2(0.f, 0.f); }
+          const float* ea = s.sE + ca * 6 + 2 * a2;
           const float* eb = s.sE + cb * 6;
           for (int q = 0; q < nq; ++q) {
-            const float va = s.sQ[q] * ea[q * estride];
-            const float2 b01 = *reinterpret_cast<const float2*>(eb + q * estride);
-            const float2 b23 = *reinterpret_cast<const float2*>(eb + q * estride + 2);
-            const float2 b45 = *reinterpret_cast<const float2*>(eb + q * estride + 4);
-            acc[0] += va * b01.x; acc[1] += va * b01.y; acc[2] += va * b23.x;
-            acc[3] += va * b23.y; acc[4] += va * b45.x; acc[5] += va * b45.y;
+            const float Q = s.sQ[q];
+            const float2 va = *reinterpret_cast<const float2*>(ea + q * estride);
+            const float2 v0 = make_float2(Q * va.x, Q * va.x), v1 = make_float2(Q * va.y, Q * va.y);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              const float2 bk = *reinterpret_cast<const float2*>(eb + q * estride + 2 * k);
+              acc0[k] = __ffma2_rn(v0, bk, acc0[k]);
+              acc1[k] = __ffma2_rn(v1, bk, acc1[k]);
+            }
           }
           const int fa = ((ca < ch.n_free) ? s.sFrame[ch.first_free + ca] : fi) - t0;
           const int fb = ((cb < ch.n_free) ? s.sFrame[ch.first_free + cb] : fi) - t0;
-          if (fa >= fb) {                       // block (fa, fb), row a
-            float* dst = wp.S + (size_t)(6 * fa + a) * n6 + 6 * fb;
-            red_add2(dst, -acc[0], -acc[1]); red_add2(dst + 2, -acc[2], -acc[3]); red_add2(dst + 4, -acc[4], -acc[5]);
-          } else {                              // transposed into block (fb, fa): column a
+          if (fa >= fb) {                       // block (fa, fb), rows 2*a2, 2*a2 + 1
+            float* dst = wp.S + (size_t)(6 * fa + 2 * a2) * n6 + 6 * fb;
 #pragma unroll
-            for (int b = 0; b < 6; ++b) atomicAdd(&wp.S[(size_t)(6 * fb + b) * n6 + 6 * fa + a], -acc[b]);
+            for (int k = 0; k < 3; ++k) {
+              red_add2(dst + 2 * k, -acc0[k].x, -acc0[k].y);
+              red_add2(dst + n6 + 2 * k, -acc1[k].x, -acc1[k].y);
+            }
+          } else {                              // transposed into block (fb, fa): columns 2*a2, 2*a2 + 1
+            float* dst = wp.S + (size_t)(6 * fb) * n6 + 6 * fa + 2 * a2;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              red_add2(dst + (size_t)(2 * k) * n6, -acc0[k].x, -acc1[k].x);
+              red_add2(dst + (size_t)(2 * k + 1) * n6, -acc0[k].y, -acc1[k].y);
+            }
           }
         }
         // y[ca] -= sum_p Q_p u_p E_p[ca]
         for (int x = tid; x < ncols * 6; x += 256) {
           const int ca = x / 6, a = x - ca * 6;
           float acc = 0.f;
-          for (int q = 0; q < nq; ++q) acc += s.sQ[q] * s.sU[q] * s.sE[q * estride + x];
+          for (int q = 0; q < nq; ++q) acc += s.sQ[q] * s.sPQ[q * 8 + 1] * s.sE[q * estride + x];
           const int fa = ((ca < ch.n_free) ? s.sFrame[ch.first_free + ca] : fi) - t0;
           atomicAdd(&wp.y[6 * fa + a], -acc);
         }

@@ -14,6 +14,15 @@ void launch_solve(const Problem& pb, int64_t batch, cudaStream_t stream);
 void launch_update(const Problem& pb, int64_t batch, cudaStream_t stream);
 bool solve_supported(int N);
 
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PGBA_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
@@ -24,6 +33,8 @@ __global__ void reproject_kernel(const float* __restrict__ poses, const float* _
                                  const float* __restrict__ intr, const int64_t* __restrict__ ii,
                                  const int64_t* __restrict__ jj, const int64_t* __restrict__ kk, int64_t E, int P,
                                  int clamp_depth, float* __restrict__ coords) {
+  pdl_wait();
+  pdl_trigger();
   const int PP = P * P;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= E * PP) return;
@@ -52,6 +63,8 @@ __global__ void reproject_kernel(const float* __restrict__ poses, const float* _
 
 __global__ void export_debug_kernel(Problem pb, float* S, float* y, float* dX, int64_t* patch_ids, float* C, float* u,
                                     float* Q, float* dZ, int32_t* n_unique, int32_t* status) {
+  pdl_wait();
+  pdl_trigger();
   const WinPtrs wp = win_ptrs(pb.ws, pb.L, 0);
   const size_t n6 = (size_t)6 * (pb.t1 - pb.t0);
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, T = (size_t)gridDim.x * blockDim.x;
@@ -247,11 +260,11 @@ int pgba_ba_linearize_debug(const float* poses, const float* patches, const floa
   if (e != cudaSuccess) return (int)e;
   launch_plan(pb, 1, s);
   launch_linearize(pb, 1, s);
-  export_debug_kernel<<<256, 256, 0, s>>>(pb, S, y, nullptr, patch_ids, C, u, Q, nullptr, n_unique, nullptr);   // before the solve
+  launch_k(export_debug_kernel, dim3(256), dim3(256), 0, s, pb, S, y, nullptr, patch_ids, C, u, Q, nullptr, n_unique, nullptr);   // before the solve
   count_launch();
   launch_solve(pb, 1, s);
   launch_update(pb, 1, s);
-  export_debug_kernel<<<64, 256, 0, s>>>(pb, nullptr, nullptr, dX, nullptr, nullptr, nullptr, nullptr, dZ, nullptr, status);
+  launch_k(export_debug_kernel, dim3(64), dim3(256), 0, s, pb, nullptr, nullptr, dX, nullptr, nullptr, nullptr, nullptr, dZ, nullptr, status);
   count_launch();
   return (int)cudaGetLastError();
 }
@@ -274,7 +287,7 @@ int pgba_reproject(const float* poses, const float* patches, const float* intrin
   const int64_t total = n_edges * P * P;
   const int64_t blocks = (total + 255) / 256;
   if (blocks >= (int64_t)1 << 31) return PGBA_ERR_UNSUPPORTED;
-  reproject_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(poses, patches, intrinsics, ii, jj, kk,
+  launch_k(reproject_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, poses, patches, intrinsics, ii, jj, kk,
                                                                       n_edges, P, clamp_depth, coords);
   count_launch();
   return (int)cudaGetLastError();

@@ -38,6 +38,8 @@ __device__ __forceinline__ BigPtrs big_ptrs(const Problem& pb, const WinPtrs& wp
 
 // S += I * (1e-4 * S + 1)   (ba_cuda.cu:575/589)
 __global__ void big_damp_kernel(Problem pb) {
+  pdl_wait();
+  pdl_trigger();
   const int w = blockIdx.y;
   const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
   const int n6 = 6 * (pb.t1 - pb.t0);
@@ -50,6 +52,8 @@ __global__ void big_damp_kernel(Problem pb) {
 
 // grid = (1, batch), block = 256, dynamic smem: (2*NB) x (NB|1) doubles + NB
 __global__ void __launch_bounds__(256, 1) big_potf2_kernel(Problem pb, int step) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ double sd[];
   const int w = blockIdx.y, tid = threadIdx.x;
   const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
@@ -80,6 +84,8 @@ __global__ void __launch_bounds__(256, 1) big_potf2_kernel(Problem pb, int step)
 // Row "tile" t of the rows below panel `step`: t < ntb -> rows [kb+nh + 48 t, +48) of S; t == ntb -> the rhs row y.
 // grid = (ntb + 1, batch), block = 256
 __global__ void __launch_bounds__(256) big_trsm_kernel(Problem pb, int step) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float sA[NB][NB + 1];
   __shared__ float sW[NB][NB + 1];
   const int w = blockIdx.y, tid = threadIdx.x;
@@ -122,6 +128,8 @@ __global__ void __launch_bounds__(256) big_trsm_kernel(Problem pb, int step) {
 // Trailing update over pairs (a >= b) of active row tiles of this panel: S[tile a][tile b] -= X_a X_b^T.
 // Persistent grid: grid = (gx, batch), block = 256 (16 x 16 threads, 3 x 3 outputs each).
 __global__ void __launch_bounds__(256) big_syrk_kernel(Problem pb, int step) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float sXa[NB][NB + 1];     // [k][row]
   __shared__ float sXb[NB][NB + 1];
   const int w = blockIdx.y, tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -182,6 +190,8 @@ __global__ void __launch_bounds__(256) big_syrk_kernel(Problem pb, int step) {
 // Backward substitution, panel `step` (launched for step = last .. 0): x_k = L11^-T (y_k - sum_below L[r][k]^T x[r]).
 // grid = (gx, batch), block = 256.  The active row tiles of this panel are the only rows with non-zero L[r][k].
 __global__ void __launch_bounds__(256) big_back_kernel(Problem pb, int step) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float spart[5][NB];
   __shared__ float sz[NB];
   __shared__ int s_last;
@@ -226,6 +236,8 @@ __global__ void __launch_bounds__(256) big_back_kernel(Problem pb, int step) {
 }
 
 __global__ void big_finish_kernel(Problem pb) {
+  pdl_wait();
+  pdl_trigger();
   const int w = blockIdx.y;
   const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
   const int N = pb.t1 - pb.t0;
@@ -242,28 +254,28 @@ cudaError_t launch_big_solve(const Problem& pb, int64_t batch, cudaStream_t stre
   const int N = pb.t1 - pb.t0, n6 = 6 * N;
   const int nsteps = (n6 + NB - 1) / NB;
   const unsigned B = (unsigned)batch;
-  big_damp_kernel<<<dim3((n6 + 255) / 256, B), 256, 0, stream>>>(pb);
+  launch_k(big_damp_kernel, dim3((n6 + 255) / 256, B), dim3(256), 0, stream, pb);
   count_launch();
   const size_t psm = sizeof(double) * ((size_t)2 * NB * (NB | 1) + NB);
   cudaFuncSetAttribute(big_potf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm);
   const int gx = batch > 1 ? 64 : 148 * 2;
   for (int s = 0; s < nsteps; ++s) {
-    big_potf2_kernel<<<dim3(1, B), 256, psm, stream>>>(pb, s);
+    launch_k(big_potf2_kernel, dim3(1, B), dim3(256), psm, stream, pb, s);
     count_launch();
     const int r0 = s * NB + (n6 - s * NB < NB ? n6 - s * NB : NB);
     const int ntb = (n6 - r0 + NB - 1) / NB;
-    big_trsm_kernel<<<dim3(ntb + 1, B), 256, 0, stream>>>(pb, s);
+    launch_k(big_trsm_kernel, dim3(ntb + 1, B), dim3(256), 0, stream, pb, s);
     count_launch();
     if (ntb > 0) {
-      big_syrk_kernel<<<dim3(gx, B), 256, 0, stream>>>(pb, s);
+      launch_k(big_syrk_kernel, dim3(gx, B), dim3(256), 0, stream, pb, s);
       count_launch();
     }
   }
   for (int s = nsteps - 1; s >= 0; --s) {
-    big_back_kernel<<<dim3(16, B), 256, 0, stream>>>(pb, s);
+    launch_k(big_back_kernel, dim3(16, B), dim3(256), 0, stream, pb, s);
     count_launch();
   }
-  big_finish_kernel<<<dim3((N + 127) / 128, B), 128, 0, stream>>>(pb);
+  launch_k(big_finish_kernel, dim3((N + 127) / 128, B), dim3(128), 0, stream, pb);
   count_launch();
   return cudaGetLastError();
 }

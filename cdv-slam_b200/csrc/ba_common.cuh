@@ -250,6 +250,29 @@ __device__ __forceinline__ void retract_pose(float* P, const float* xi) {
   P[3] = q1[0]; P[4] = q1[1]; P[5] = q1[2]; P[6] = q1[3];
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  Every BA kernel starts with pdl_wait() -- it blocks until the previous
+// kernel of the stream has completed and its writes are visible -- and is launched with the programmatic-stream-
+// serialisation attribute, so its CTAs are scheduled (and run their prologue up to pdl_wait) while the previous
+// kernel drains.  pdl_trigger() lets the next kernel start being scheduled.  PGBA_PDL=0 disables the attribute.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // Host-side count of kernel launches issued by this library (reported by bench.py as `gpu_launches`).
 void count_launch();
 long long launch_count();

@@ -111,6 +111,8 @@ __device__ __forceinline__ void red_add2(float* p, float a, float b) {       // 
 
 // grid = (gx, batch), block = 256, dynamic smem = lin_smem_bytes(pc, ebudget)
 __global__ void __launch_bounds__(256, 2) linearize_kernel(Problem pb, int ebudget) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float smem[];
   const int pc = pb.L.pc;
   LinSmem s;
@@ -499,6 +501,8 @@ __device__ long long g_solve_ts[64];
 #endif
 
 __global__ void __launch_bounds__(256, 1) solve_small_kernel(Problem pb) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ double sd[];
   SOLVE_TS(0);
   const int w = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -592,6 +596,8 @@ __global__ void __launch_bounds__(256, 1) solve_small_kernel(Problem pb) {
 // grid = (gx, batch), block = 256: one warp per patch, lanes over the E row.  apply = 0 only computes dZ.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) update_kernel(Problem pb) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float sdx[(SMAX + 1) * 6];
   const int w = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
@@ -651,7 +657,7 @@ void launch_linearize(const Problem& pb, int64_t batch, cudaStream_t stream) {
   const int ebudget = lin_ebudget(pb);
   const size_t lsm = lin_smem_bytes(pb.L.pc, ebudget);
   cudaFuncSetAttribute(linearize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm);
-  linearize_kernel<<<dim3((unsigned)gx, (unsigned)batch), 256, lsm, stream>>>(pb, ebudget);
+  launch_k(linearize_kernel, dim3((unsigned)gx, (unsigned)batch), dim3(256), lsm, stream, pb, ebudget);
   count_launch();
 }
 
@@ -666,13 +672,13 @@ void launch_solve(const Problem& pb, int64_t batch, cudaStream_t stream) {
   }
   const size_t smem = solve_small_smem_bytes(6 * N);
   cudaFuncSetAttribute(solve_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  solve_small_kernel<<<(unsigned)batch, 256, smem, stream>>>(pb);
+  launch_k(solve_small_kernel, dim3((unsigned)batch), dim3(256), smem, stream, pb);
   count_launch();
 }
 
 void launch_update(const Problem& pb, int64_t batch, cudaStream_t stream) {
   const int gx = chunk_grid(pb, batch);
-  update_kernel<<<dim3((unsigned)gx, (unsigned)batch), 256, 0, stream>>>(pb);
+  launch_k(update_kernel, dim3((unsigned)gx, (unsigned)batch), dim3(256), 0, stream, pb);
   count_launch();
 }
 

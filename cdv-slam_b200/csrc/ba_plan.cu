@@ -83,6 +83,8 @@ __device__ __forceinline__ bool last_block_done(int* ticket) {
 
 // grid = (gx, batch), block = 256
 __global__ void __launch_bounds__(256) plan_frames_kernel(Problem pb) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ int scratch[40];
   const int w = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
   const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
@@ -141,6 +143,8 @@ __device__ __forceinline__ int chunk_of(const WinPtrs& wp, const EdgeIdx& x, int
 
 // grid = (gx, batch), block = 256
 __global__ void __launch_bounds__(256) plan_count_kernel(Problem pb) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ int scratch[40];
   const int w = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
   const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
@@ -175,6 +179,8 @@ __global__ void __launch_bounds__(256) plan_count_kernel(Problem pb) {
 
 // grid = (gx, batch), block = 256
 __global__ void __launch_bounds__(256) plan_scatter_kernel(Problem pb) {
+  pdl_wait();
+  pdl_trigger();
   const int w = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
   const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
   const int64_t* ii = pb.ii + (int64_t)w * pb.st.ii;
@@ -198,6 +204,8 @@ __global__ void __launch_bounds__(256) plan_scatter_kernel(Problem pb) {
 
 // grid = (gx, batch), block = 256, static smem.  Chunks are taken round-robin by blockIdx.x.
 __global__ void __launch_bounds__(256) plan_cells_kernel(Problem pb) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ unsigned pflag[PMAX / 32];
   __shared__ int ppref[PMAX / 32 + 1];
   __shared__ unsigned jflag[PGBA_MAX_POSE_ROWS / 32];
@@ -316,13 +324,13 @@ int chunk_grid(const Problem& pb, int64_t batch) {
 void launch_plan(const Problem& pb, int64_t batch, cudaStream_t stream) {
   const int ge = edge_grid(pb.E, batch);
   const dim3 grid((unsigned)ge, (unsigned)batch);
-  plan_frames_kernel<<<grid, 256, 0, stream>>>(pb);
+  launch_k(plan_frames_kernel, dim3(grid), dim3(256), 0, stream, pb);
   count_launch();
-  plan_count_kernel<<<grid, 256, 0, stream>>>(pb);
+  launch_k(plan_count_kernel, dim3(grid), dim3(256), 0, stream, pb);
   count_launch();
-  plan_scatter_kernel<<<grid, 256, 0, stream>>>(pb);
+  launch_k(plan_scatter_kernel, dim3(grid), dim3(256), 0, stream, pb);
   count_launch();
-  plan_cells_kernel<<<dim3((unsigned)chunk_grid(pb, batch), (unsigned)batch), 256, 0, stream>>>(pb);
+  launch_k(plan_cells_kernel, dim3((unsigned)chunk_grid(pb, batch), (unsigned)batch), dim3(256), 0, stream, pb);
   count_launch();
 }
 

@@ -98,6 +98,203 @@ __global__ void __launch_bounds__(256) corr_forward_kernel(const T* __restrict__
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Staged lookup for the shape slam.py uses (P = 3, R = 3, C % 8 == 0): one WARP per (edge, level) task, persistent
+// CTAs of 4 warps.  The 9 patch pixels land within a few pixels of each other, so their nine 8x8 windows live in one
+// small region of fmap2[jj] (<= 12 x 12 pixels): the region is staged through shared memory 8 channels at a time
+// (coalesced row segments, zero-filled outside the map), every lane owns <= 5 region pixels and accumulates the full
+// [9 patch pixels x its region pixels] block of products with packed fp32x2 FMAs (FFMA2), i.e. each fmap2 value is
+// fetched once per edge instead of once per (patch pixel, tap).  The per-pixel window selection, the bilinear blend
+// (correlation_kernel.cu:221-230) and the final permute (:232) are done from the region volume in shared memory.
+// Edges whose windows do not fit the 12 x 12 region (strong zoom) take the per-tap path inside the same kernel.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int RG = 12;                 // region is RG x RG pixels
+constexpr int RPX = RG * RG;           // 144
+constexpr int CK = 8;                  // channels per staging chunk
+constexpr int SW_WARPS = 4;
+struct __align__(16) WarpSmem {
+  float reg[CK][RPX];                  // staged region chunk (fp32)
+  float f1[CK][12];                    // patch features of the chunk: [c][p] (9 used, padded to 12 for 16-byte rows)
+  float vol[9][RPX + 4];               // region volume: vol[p][region pixel]; slow path: vol[p][64 taps]
+  float sx[9], sy[9];                  // coords of the 9 patch pixels at this level
+  int wox[9], woy[9];                  // window origin of pixel p inside the region
+};
+
+template <typename T, int NLEV>
+__global__ void __launch_bounds__(32 * SW_WARPS) corr_staged_kernel(const T* __restrict__ fmap1, CorrLevel lv0, CorrLevel lv1,
+                                                                   const float* __restrict__ coords,
+                                                                   const int64_t* __restrict__ us,
+                                                                   const int64_t* __restrict__ vs, int B, int64_t E,
+                                                                   int64_t K, int64_t F, int C, T* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  constexpr int R = 3, D = 8, Do = 7, PP = 9;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  WarpSmem& S = reinterpret_cast<WarpSmem*>(smraw)[warp];
+  const int64_t ntask = (int64_t)B * E * NLEV;
+  // output o = lane + 32 t  ->  (p, yo, xo), the same for every task: packed p | (yo*RG + xo) << 8 | (yo*D + xo) << 16
+  constexpr int NOUT = (7 * 7 * 9 + 31) / 32;                      // 14
+  int odec[NOUT];
+#pragma unroll
+  for (int t = 0; t < NOUT; ++t) {
+    const int o = lane + 32 * t;
+    const int p = o % 9, yo = (o / 9) % 7, xo = o / 63;
+    odec[t] = p | ((yo * RG + xo) << 8) | ((yo * 8 + xo) << 16);
+  }
+  for (int64_t task = (int64_t)blockIdx.x * SW_WARPS + warp; task < ntask; task += (int64_t)gridDim.x * SW_WARPS) {
+    const int lev = (int)(task % NLEV);
+    const int64_t be = task / NLEV;
+    const int b = (int)(be / E);
+    const int64_t m = be - (int64_t)b * E;
+    const CorrLevel lv = (NLEV == 1 || lev == 0) ? lv0 : lv1;
+    const int H2 = lv.H2, W2 = lv.W2;
+    const int64_t plane = (int64_t)H2 * W2;
+    const int64_t ix = us[m], jx = vs[m];
+    const T* f1g = fmap1 + ((int64_t)b * K + ix) * C * PP;
+    const T* f2g = (const T*)lv.fmap2 + ((int64_t)b * F + jx) * C * plane;
+    const float* cg = coords + ((int64_t)b * E + m) * 2 * PP;
+    __syncwarp();
+    // ---- per-pixel coordinates, window origins, region bounding box
+    int fxp = 0, fyp = 0;
+    if (lane < PP) {
+      // level > 0 uses coords / 4 computed in fp32 exactly like the caller's `coords / 4` (slam.py:322)
+      const float x = (lev == 0) ? cg[lane] : cg[lane] * lv.inv_scale;
+      const float y = (lev == 0) ? cg[PP + lane] : cg[PP + lane] * lv.inv_scale;
+      S.sx[lane] = x; S.sy[lane] = y;
+      // clamp far-out / non-finite coordinates to "entirely outside the map" (the window is then all zeros)
+      const float xf = floorf(x), yf = floorf(y);
+      fxp = (xf > -1e6f && xf < 1e6f) ? (int)xf : -1000000;
+      fyp = (yf > -1e6f && yf < 1e6f) ? (int)yf : -1000000;
+    }
+    int xmin = (lane < PP) ? fxp : 0x7fffffff, xmax = (lane < PP) ? fxp : -0x7fffffff;
+    int ymin = (lane < PP) ? fyp : 0x7fffffff, ymax = (lane < PP) ? fyp : -0x7fffffff;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o)); xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+      ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o)); ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+    }
+    xmin = __shfl_sync(0xffffffffu, xmin, 0); xmax = __shfl_sync(0xffffffffu, xmax, 0);
+    ymin = __shfl_sync(0xffffffffu, ymin, 0); ymax = __shfl_sync(0xffffffffu, ymax, 0);
+    const int x0 = xmin - R, y0 = ymin - R;                      // region origin in the map
+    const bool fits = (xmax - xmin + D <= RG) && (ymax - ymin + D <= RG);
+    if (lane < PP) { S.wox[lane] = fxp - R - x0; S.woy[lane] = fyp - R - y0; }
+    T* og = out + ((int64_t)b * E + m) * (int64_t)(Do * Do * PP) * NLEV;
+    __syncwarp();
+
+    if (fits) {
+      // ---- which region pixels does this lane own: px = lane + 32 m
+      int goff[5];
+      bool gok[5];
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        const int px = lane + 32 * q;
+        const int ry = px / RG, rx = px - ry * RG;
+        const int gy = y0 + ry, gx = x0 + rx;
+        gok[q] = (px < RPX) && gy >= 0 && gy < H2 && gx >= 0 && gx < W2;
+        goff[q] = gok[q] ? gy * W2 + gx : 0;
+      }
+      float2 acc[5][5];                                          // [owned pixel][patch-pixel pair]; pair 4 = (p8, -)
+#pragma unroll
+      for (int q = 0; q < 5; ++q)
+#pragma unroll
+        for (int pp = 0; pp < 5; ++pp) acc[q][pp] = make_float2(0.f, 0.f);
+      for (int c0 = 0; c0 < C; c0 += CK) {
+        // stage: region chunk (each lane loads its own pixels: coalesced row segments) and the patch features
+        {
+          T tmp[CK][5];
+#pragma unroll
+          for (int c = 0; c < CK; ++c) {
+            const T* src = f2g + (int64_t)(c0 + c) * plane;
+#pragma unroll
+            for (int q = 0; q < 5; ++q) tmp[c][q] = src[goff[q]];       // goff = 0 (always mapped) when masked
+          }
+#pragma unroll
+          for (int c = 0; c < CK; ++c)
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+              const int px = lane + 32 * q;
+              if (q < 4 || px < RPX) S.reg[c][px] = gok[q] ? to_f<T>(tmp[c][q]) : 0.f;
+            }
+        }
+        for (int x = lane; x < CK * PP; x += 32) {
+          const int c = x / PP, p = x - c * PP;
+          S.f1[c][p] = to_f<T>(f1g[(c0 + c) * PP + p]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < CK; ++c) {
+          const float4 fa = *reinterpret_cast<const float4*>(&S.f1[c][0]);
+          const float4 fb = *reinterpret_cast<const float4*>(&S.f1[c][4]);
+          const float f8 = S.f1[c][8];
+          const float2 fp[5] = {make_float2(fa.x, fa.y), make_float2(fa.z, fa.w), make_float2(fb.x, fb.y),
+                                make_float2(fb.z, fb.w), make_float2(f8, 0.f)};
+#pragma unroll
+          for (int q = 0; q < 5; ++q) {
+            const int px = lane + 32 * q;
+            const float r = (px < RPX) ? S.reg[c][px] : 0.f;
+            const float2 rr = make_float2(r, r);
+#pragma unroll
+            for (int pp = 0; pp < 5; ++pp) acc[q][pp] = __ffma2_rn(rr, fp[pp], acc[q][pp]);
+          }
+        }
+        __syncwarp();
+      }
+      // ---- region volume to shared memory
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        const int px = lane + 32 * q;
+        if (px < RPX) {
+#pragma unroll
+          for (int pp = 0; pp < 4; ++pp) { S.vol[2 * pp][px] = acc[q][pp].x; S.vol[2 * pp + 1][px] = acc[q][pp].y; }
+          S.vol[8][px] = acc[q][4].x;
+        }
+      }
+      __syncwarp();
+      // ---- window selection + bilinear blend + permute: out[xo][yo][p] (correlation_kernel.cu:221-232)
+#pragma unroll
+      for (int t = 0; t < NOUT; ++t) {
+        const int o = lane + 32 * t;
+        if (o >= Do * Do * PP) break;
+        const int p = odec[t] & 0xff;
+        const float xs = S.sx[p], ys = S.sy[p];
+        const float dx = xs - floorf(xs), dy = ys - floorf(ys);
+        const float* v = &S.vol[p][S.woy[p] * RG + S.wox[p] + ((odec[t] >> 8) & 0xff)];
+        const float r = (1.f - dx) * (1.f - dy) * v[0] + dx * (1.f - dy) * v[1] + (1.f - dx) * dy * v[RG] +
+                        dx * dy * v[RG + 1];
+        og[(int64_t)o * NLEV + lev] = from_f<T>(r);
+      }
+    } else {
+      // ---- per-tap path (windows too far apart for one region): same arithmetic as corr_forward_kernel
+      for (int o = lane; o < PP * D * D; o += 32) {
+        const int p = o / (D * D), pos = o - p * (D * D);
+        const int io = pos / D, jo = pos - io * D;
+        const float xf = floorf(S.sx[p]), yf = floorf(S.sy[p]);
+        float acc = 0.f;
+        if (xf > -1e6f && xf < 1e6f && yf > -1e6f && yf < 1e6f) {
+          const int i1 = (int)yf + (io - R), j1 = (int)xf + (jo - R);
+          if (i1 >= 0 && i1 < H2 && j1 >= 0 && j1 < W2) {
+            const T* src = f2g + (int64_t)i1 * W2 + j1;
+            for (int c = 0; c < C; ++c) acc += to_f<T>(f1g[c * PP + p]) * to_f<T>(src[c * plane]);
+          }
+        }
+        S.vol[p][pos] = acc;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int t = 0; t < NOUT; ++t) {
+        const int o = lane + 32 * t;
+        if (o >= Do * Do * PP) break;
+        const int p = odec[t] & 0xff;
+        const float xs = S.sx[p], ys = S.sy[p];
+        const float dx = xs - floorf(xs), dy = ys - floorf(ys);
+        const float* v = &S.vol[p][(odec[t] >> 16) & 0xff];
+        const float r = (1.f - dx) * (1.f - dy) * v[0] + dx * (1.f - dy) * v[1] + (1.f - dx) * dy * v[D] +
+                        dx * dy * v[D + 1];
+        og[(int64_t)o * NLEV + lev] = from_f<T>(r);
+      }
+    }
+  }
+}
+
 // Gradient scatter: one CTA per (edge, batch).  grad [B,E,Do(x),Do(y),P,P] f32.
 template <typename T>
 __global__ void __launch_bounds__(256) corr_backward_kernel(const T* __restrict__ fmap1, const T* __restrict__ fmap2,
@@ -196,6 +393,17 @@ template <typename T, int NLEV>
 static int launch_corr(const void* fmap1, CorrLevel l0, CorrLevel l1, const float* coords, const int64_t* ii,
                        const int64_t* jj, int B, int64_t E, int64_t K, int64_t F, int C, int P, int R, void* out,
                        cudaStream_t s) {
+  if (P == 3 && R == 3 && C % CK == 0) {
+    const size_t smem = sizeof(WarpSmem) * SW_WARPS;
+    auto kern = corr_staged_kernel<T, NLEV>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int64_t tasks = (int64_t)B * E * NLEV;
+    int64_t grid = (tasks + SW_WARPS - 1) / SW_WARPS;
+    if (grid > 148 * 5) grid = 148 * 5;
+    kern<<<(unsigned)grid, 32 * SW_WARPS, smem, s>>>((const T*)fmap1, l0, l1, coords, ii, jj, B, E, K, F, C, (T*)out);
+    pgba::count_launch();
+    return (int)cudaGetLastError();
+  }
   const int PP = P * P, D = 2 * R + 2;
   const size_t smem = sizeof(float) * ((size_t)C * PP + (size_t)PP * D * D + 2 * PP);
   if (smem > 200 * 1024) return PCORR_ERR_UNSUPPORTED;

@@ -256,6 +256,75 @@ class GpuArm:
         return stages
 
 
+
+def timed_events(fn, steps, before=None):
+    """Median of CUDA-event timings (ms) of fn() on the current stream."""
+    ts = []
+    for _ in range(steps):
+        if before is not None:
+            before()
+        a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        c.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(c))
+    return float(statistics.median(ts))
+
+
+def extra_corr_c3(dev, peak, flush):
+    """BASELINE config c3: altcorr.corr on the c2 graph, 1/4-res 480x640 pyramid (120x160 + 30x40), radius 3.
+    Algorithmic bytes per level: E*88 + K*9*C*s + Fj*C*H2*W2*s + E*441*s."""
+    from cdvslam_b200 import synth, fastba, altcorr
+    p = synth.config_c2()
+    d = synth.to_torch(p, dev)
+    out = {}
+    for C, dt, s in ((24, torch.float16, 2), (128, torch.float16, 2), (128, torch.float32, 4)):
+        gmap, pyr = synth.make_fmaps(p, C=C)
+        g = torch.as_tensor(gmap, device=dev)[None].to(dt)
+        f0 = torch.as_tensor(pyr[0], device=dev)[None].to(dt)
+        f1 = torch.as_tensor(pyr[1], device=dev)[None].to(dt)
+        coords = fastba.reproject(d["poses"], d["patches"], d["intrinsics"], d["ii"], d["jj"], d["kk"])
+        kk, jj = d["kk"], d["jj"]
+        fn = lambda: altcorr.corr_pyramid2(g, [f0, f1], coords, kk, jj, 3)
+        for _ in range(3):
+            fn()
+        ms = timed_events(fn, 20, before=flush)
+        E, K, Fj = p.E, gmap.shape[0], len(np.unique(p.jj))
+        alg = sum(E * 88 + K * 9 * C * s + Fj * C * h * w * s + E * 441 * s for (h, w) in ((120, 160), (30, 40))) - E * 88 - K * 9 * C * s
+        out["C%d_%s" % (C, str(dt).split(".")[-1])] = {
+            "ms": ms, "edges_per_s": E / (ms * 1e-3), "algorithmic_bytes": int(alg),
+            "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (ms * 1e-3) / 1e9 / peak}}
+        del g, f0, f1
+    return {"workload": "c3: fused 2-level altcorr.corr on the c2 graph (37824 edges), radius 3, L2 flushed", **out}
+
+
+def extra_c4(dev, flush):
+    """BASELINE config c4: global BA, 1000 frames, 402 624 edges, 999 free poses, eff_impl=True, 2 iterations."""
+    from cdvslam_b200 import synth, fastba
+    p = synth.config_c4()
+    d = synth.to_torch(p, dev)
+    p0, q0 = d["poses"].clone(), d["patches"].clone()
+
+    def call():
+        fastba.BA(d["poses"], d["patches"], d["intrinsics"], d["target"], d["weight"], d["lmbda"], d["ii"], d["jj"],
+                  d["kk"], p.t0, p.t1, M=p.M, iterations=ITERATIONS, eff_impl=True)
+
+    def reset():
+        d["poses"].copy_(p0); d["patches"].copy_(q0); flush()
+    for _ in range(2):
+        reset(); call()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        call()
+    ms = timed_events(g.replay, 5, before=reset)
+    return {"workload": "c4: global BA, 1000 frames x 96 patches, 402624 edges, 999 free poses, eff_impl, 2 iterations",
+            "ms_per_call": ms, "value": ITERATIONS / (ms * 1e-3), "unit": "BA iterations/s",
+            "edges_per_s": p.E * ITERATIONS / (ms * 1e-3)}
+
+
 def hbm_peak():
     path = os.path.join(REPO, "MEASURED_PEAKS.json")
     try:
@@ -398,6 +467,13 @@ def main():
                                                "algorithmic_bytes_per_launch": alg5,
                                                "ms_per_launch": st5["linearize_schur"],
                                                "traffic": ncu_traffic("c5")}}
+    if rank == 0 and world == 1 and args.workload == "c2" and not args.no_extra:
+        flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        try:
+            line["corr_c3"] = extra_corr_c3(dev, peak, flush_buf.zero_)
+            line["global_c4"] = extra_c4(dev, flush_buf.zero_)
+        except Exception as e:            # extras must never cost the headline line
+            line["extras_error"] = repr(e)[:200]
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:

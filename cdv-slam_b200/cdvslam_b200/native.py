@@ -42,6 +42,11 @@ SIGNATURES = {
                                            c_vp]),
     "pcorr_forward_pyramid2": (c_int, [c_vp] * 6 + [c_int, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int,
                                                     c_int, c_int, c_int, c_vp, c_vp]),
+    "pcorr_tiled_supported": (c_int, [c_int, c_int, c_int, c_int]),
+    "pcorr_tiled_workspace_bytes": (c_int, [c_int, c_int, c_i64, c_i64, c_int, c_int, c_int, c_int,
+                                            ctypes.POINTER(c_sz)]),
+    "pcorr_forward_tiled": (c_int, [c_vp] * 6 + [c_int, c_int, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int,
+                                                 c_int, c_int, c_int, c_vp, c_vp, c_sz, c_vp]),
     "pcorr_backward": (c_int, [c_vp] * 6 + [c_int, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_vp,
                                             c_vp, c_vp]),
     "pcorr_patchify_forward": (c_int, [c_vp, c_vp, c_int, c_i64, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
@@ -97,9 +102,9 @@ def require_cuda(*tensors):
 _workspaces = {}
 
 
-def workspace(nbytes, device):
+def workspace(nbytes, device, pool="ba"):
     """Grow-only per-device scratch buffer (the C ABI never allocates)."""
-    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    key = (pool, device.type, device.index if device.index is not None else torch.cuda.current_device())
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)

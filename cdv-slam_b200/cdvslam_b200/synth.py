@@ -230,3 +230,13 @@ def make_fmaps(problem, C=24, seed=1234, n_mem=36, levels=(1, 4), dtype=np.float
             h, w = problem.ht // lv, problem.wd // lv
             pyr.append(f0[:, :, :h * lv, :w * lv].reshape(n_mem, C, h, lv, w, lv).mean((3, 5)).astype(dtype))
     return gmap, pyr
+
+
+def to_torch(p, device):
+    """Problem -> dict of torch tensors in the reference's layouts (leading batch dim of 1) on `device`."""
+    import torch
+    f = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32, device=device)
+    l = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.int64, device=device)
+    return dict(poses=f(p.poses)[None], patches=f(p.patches)[None], intrinsics=f(p.intrinsics)[None],
+                target=f(p.target)[None], weight=f(p.weight)[None], lmbda=f([p.lmbda]), ii=l(p.ii), jj=l(p.jj),
+                kk=l(p.kk))

@@ -116,8 +116,10 @@ struct __align__(16) WarpSmem {
   float reg[CK][RPX];                  // staged region chunk (fp32)
   float f1[CK][12];                    // patch features of the chunk: [c][p] (9 used, padded to 12 for 16-byte rows)
   float vol[9][RPX + 4];               // region volume: vol[p][region pixel]; slow path: vol[p][64 taps]
+  float4 wgt[9];                       // bilinear weights of pixel p: (1-dx)(1-dy), dx(1-dy), (1-dx)dy, dx dy
   float sx[9], sy[9];                  // coords of the 9 patch pixels at this level
   int wox[9], woy[9];                  // window origin of pixel p inside the region
+  int vbase[9];                        // p * (RPX + 4) + woy * RG + wox
 };
 
 template <typename T, int NLEV>
@@ -176,7 +178,13 @@ __global__ void __launch_bounds__(32 * SW_WARPS) corr_staged_kernel(const T* __r
     ymin = __shfl_sync(0xffffffffu, ymin, 0); ymax = __shfl_sync(0xffffffffu, ymax, 0);
     const int x0 = xmin - R, y0 = ymin - R;                      // region origin in the map
     const bool fits = (xmax - xmin + D <= RG) && (ymax - ymin + D <= RG);
-    if (lane < PP) { S.wox[lane] = fxp - R - x0; S.woy[lane] = fyp - R - y0; }
+    if (lane < PP) {
+      S.wox[lane] = fxp - R - x0; S.woy[lane] = fyp - R - y0;
+      S.vbase[lane] = lane * (RPX + 4) + (fyp - R - y0) * RG + (fxp - R - x0);
+      const float xs = S.sx[lane], ys = S.sy[lane];
+      const float dx = xs - floorf(xs), dy = ys - floorf(ys);
+      S.wgt[lane] = make_float4((1.f - dx) * (1.f - dy), dx * (1.f - dy), (1.f - dx) * dy, dx * dy);
+    }
     T* og = out + ((int64_t)b * E + m) * (int64_t)(Do * Do * PP) * NLEV;
     __syncwarp();
 
@@ -250,17 +258,18 @@ __global__ void __launch_bounds__(32 * SW_WARPS) corr_staged_kernel(const T* __r
       }
       __syncwarp();
       // ---- window selection + bilinear blend + permute: out[xo][yo][p] (correlation_kernel.cu:221-232)
+      {
+        const float* vol0 = &S.vol[0][0];
 #pragma unroll
-      for (int t = 0; t < NOUT; ++t) {
-        const int o = lane + 32 * t;
-        if (o >= Do * Do * PP) break;
-        const int p = odec[t] & 0xff;
-        const float xs = S.sx[p], ys = S.sy[p];
-        const float dx = xs - floorf(xs), dy = ys - floorf(ys);
-        const float* v = &S.vol[p][S.woy[p] * RG + S.wox[p] + ((odec[t] >> 8) & 0xff)];
-        const float r = (1.f - dx) * (1.f - dy) * v[0] + dx * (1.f - dy) * v[1] + (1.f - dx) * dy * v[RG] +
-                        dx * dy * v[RG + 1];
-        og[(int64_t)o * NLEV + lev] = from_f<T>(r);
+        for (int t = 0; t < NOUT; ++t) {
+          const int o = lane + 32 * t;
+          if (o >= Do * Do * PP) break;
+          const int p = odec[t] & 0xff;
+          const float4 wg = S.wgt[p];
+          const float* v = vol0 + S.vbase[p] + ((odec[t] >> 8) & 0xff);
+          const float r = wg.x * v[0] + wg.y * v[1] + wg.z * v[RG] + wg.w * v[RG + 1];
+          og[(int64_t)o * NLEV + lev] = from_f<T>(r);
+        }
       }
     } else {
       // ---- per-tap path (windows too far apart for one region): same arithmetic as corr_forward_kernel

@@ -2,6 +2,9 @@
 (pybind table: cdvslam/altcorr/correlation.cpp:57-63; imported by cdvslam/altcorr/correlation.py:2).
 Same function names, argument order and return conventions (lists of tensors); the work is done by libpgba.so
 through the C ABI of include/pcorr.h."""
+import ctypes
+import os
+
 import torch
 
 from cdvslam_b200 import native
@@ -19,6 +22,33 @@ def _c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _tiled(fmap1, maps, coords, ii, jj, radius, out):
+    """Tensor-core tiled path (fp16, C <= 24, P = 3, R = 3); returns False when the shape does not qualify.
+    Opt-in (PCORR_TILED=1): on B200 the warp-per-edge staged kernel measured faster on the c3 shape (profiles/r01)."""
+    if os.environ.get("PCORR_TILED", "0") != "1":
+        return False
+    L = native.lib()
+    B, E, _, P, _ = coords.shape
+    K, C = fmap1.shape[1], fmap1.shape[2]
+    F = maps[0].shape[1]
+    if not L.pcorr_tiled_supported(C, P, int(radius), _DT[fmap1.dtype]) or E == 0:
+        return False
+    nlev = len(maps)
+    H0, W0 = maps[0].shape[3], maps[0].shape[4]
+    H1, W1 = (maps[1].shape[3], maps[1].shape[4]) if nlev == 2 else (0, 0)
+    nbytes = ctypes.c_size_t(0)
+    native.check(L.pcorr_tiled_workspace_bytes(nlev, B, E, F, H0, W0, H1, W1, ctypes.byref(nbytes)),
+                 "pcorr_tiled_workspace_bytes")
+    with torch.cuda.device(fmap1.device):
+        ws = native.workspace(nbytes.value, fmap1.device, pool="corr")
+        rc = L.pcorr_forward_tiled(fmap1.data_ptr(), maps[0].data_ptr(), maps[1].data_ptr() if nlev == 2 else None,
+                                   coords.data_ptr(), ii.data_ptr(), jj.data_ptr(), nlev, B, E, K, F, C, H0, W0, H1, W1,
+                                   P, int(radius), _DT[fmap1.dtype], out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                   native.stream_ptr(fmap1.device))
+    native.check(rc, "pcorr_forward_tiled")
+    return True
+
+
 def forward(fmap1, fmap2, coords, ii, jj, radius):
     """cuda_corr.forward (correlation.cpp:28-35 -> corr_cuda_forward, correlation_kernel.cu:193-233).
     Returns [corr] with corr [B, E, 2R+1 (x-off), 2R+1 (y-off), P, P] in fmap1's dtype."""
@@ -33,6 +63,8 @@ def forward(fmap1, fmap2, coords, ii, jj, radius):
     F, H2, W2 = fmap2.shape[1], fmap2.shape[3], fmap2.shape[4]
     D = 2 * radius + 1
     out = torch.empty((B, E, D, D, P, P), dtype=fmap1.dtype, device=fmap1.device)
+    if _tiled(fmap1, [fmap2], coords, ii, jj, radius, out):
+        return [out]
     with torch.cuda.device(fmap1.device):
         rc = native.lib().pcorr_forward(fmap1.data_ptr(), fmap2.data_ptr(), coords.data_ptr(), ii.data_ptr(),
                                         jj.data_ptr(), B, E, K, F, C, H2, W2, P, int(radius), dt, out.data_ptr(),
@@ -53,6 +85,8 @@ def forward_pyramid2(fmap1, fmap2_l0, fmap2_l1, coords, ii, jj, radius):
     F = fmap2_l0.shape[1]
     D = 2 * radius + 1
     out = torch.empty((B, E, D, D, P, P, 2), dtype=fmap1.dtype, device=fmap1.device)
+    if fmap2_l1.dtype == fmap1.dtype == fmap2_l0.dtype and _tiled(fmap1, [fmap2_l0, fmap2_l1], coords, ii, jj, radius, out):
+        return out
     with torch.cuda.device(fmap1.device):
         rc = native.lib().pcorr_forward_pyramid2(fmap1.data_ptr(), fmap2_l0.data_ptr(), fmap2_l1.data_ptr(),
                                                  coords.data_ptr(), ii.data_ptr(), jj.data_ptr(), B, E, K, F, C,

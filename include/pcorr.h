@@ -42,6 +42,19 @@ int pcorr_forward_pyramid2(const void* fmap1, const void* fmap2_l0, const void* 
                            int H0, int W0, int H1, int W1, int P, int radius, int dtype, void* out,
                            pcorr_stream_t stream);
 
+/* Tiled lookup for the production shape (fp16 features, C in {8,16,24}, P = 3, radius = 3): the (edge, level) tasks are
+ * binned by fmap2 tile, each tile is staged in shared memory once and the contraction runs on the tensor cores.
+ * Same results layout as pcorr_forward (nlev = 1; fmap2_l1 may be NULL) / pcorr_forward_pyramid2 (nlev = 2).
+ * Needs a caller-owned, 256-byte aligned workspace of pcorr_tiled_workspace_bytes(); pcorr_tiled_supported() tells
+ * whether a shape qualifies (otherwise use pcorr_forward / pcorr_forward_pyramid2). */
+int pcorr_tiled_supported(int C, int P, int radius, int dtype);
+int pcorr_tiled_workspace_bytes(int nlev, int B, int64_t E, int64_t F, int H0, int W0, int H1, int W1,
+                                size_t* bytes /* host, out */);
+int pcorr_forward_tiled(const void* fmap1, const void* fmap2_l0, const void* fmap2_l1, const float* coords,
+                        const int64_t* ii, const int64_t* jj, int nlev, int B, int64_t E, int64_t K, int64_t F, int C,
+                        int H0, int W0, int H1, int W1, int P, int radius, int dtype, void* out, void* workspace,
+                        size_t workspace_bytes, pcorr_stream_t stream);
+
 /* Gradient of pcorr_forward w.r.t. fmap1 and fmap2.  Replaces cuda_corr.backward == corr_cuda_backward()
  * (reference: correlation_kernel.cu:140-190, 236-286).  grad is the gradient of `out` in out's layout, f32;
  * fmap1_grad / fmap2_grad have the shapes and dtype of fmap1 / fmap2 and must be zero-filled by the caller. */

@@ -16,8 +16,14 @@ for r in rows:
         hdr = r; continue
     if hdr and len(r) > 10 and r[0].strip().isdigit():
         col = {h: i for i, h in enumerate(hdr)}
-        f = lambda k: float(r[col[k]].replace(",", "") or 0) if r[col[k]] not in ("-", "") else 0.0
-        key = (r[0], r[1].strip()[:100])
+        off = len(r) - len(hdr)                      # source text with embedded commas/quotes shifts the columns
+        def f(k):
+            try:
+                v = r[col[k] + off]
+                return float(v.replace(",", "") or 0) if v not in ("-", "") else 0.0
+            except (ValueError, IndexError):
+                return 0.0
+        key = (r[0], ",".join(r[1:2 + off]).strip()[:100])
         agg[key] += f("Instructions Executed"); samples[key] += f("# Samples")
 tot = sum(agg.values()) or 1; ts = sum(samples.values()) or 1
 print("total warp insts %d, samples %d" % (tot, ts))

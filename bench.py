@@ -389,10 +389,8 @@ def main():
         torch.cuda.synchronize()
 
     def max_over_ranks(x):
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        from cdvslam_b200 import shard
+        return shard.max_over_ranks(x, dev, dist)
 
     probs = make_workload(args.workload, rank, args.windows)
     arm = GpuArm(probs, dev)

@@ -80,6 +80,9 @@ __device__ __forceinline__ void edge_terms(float xi0, float xi1, float pd, float
 }
 
 // Shared-memory carve-up of linearize_kernel (floats unless noted)
+#ifndef LIN_MIN_CTAS
+#define LIN_MIN_CTAS 2
+#endif
 constexpr int HW_STRIDE = 29;                       // odd stride: conflict-free per-lane rows
 constexpr int LIN_FIXED_FLOATS = SMAX * 12 + SMAX * 28 + 8 * 32 * HW_STRIDE + 48 + SMAX;
 
@@ -110,7 +113,7 @@ __device__ __forceinline__ void red_add2(float* p, float a, float b) {       // 
 }
 
 // grid = (gx, batch), block = 256, dynamic smem = lin_smem_bytes(pc, ebudget)
-__global__ void __launch_bounds__(256, 2) linearize_kernel(Problem pb, int ebudget) {
+__global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb, int ebudget) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ float smem[];

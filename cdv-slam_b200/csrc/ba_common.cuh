@@ -100,7 +100,7 @@ inline Layout make_layout(int64_t E, int64_t F, int64_t K, int N, int64_t batch,
   L.o_fbase = o;  o = align256(o + 4 * (size_t)F);
   L.o_ccur = o;   o = align256(o + 4 * (size_t)L.ch_max);
   L.o_chunks = o; o = align256(o + sizeof(Chunk) * (size_t)L.ch_max);
-  L.o_perm = o;   o = align256(o + 4 * (size_t)e1);
+  L.o_perm = o;   o = align256(o + 16 * (size_t)e1);       // int4 records: edge, target frame, patch id, -
   L.o_kx = o;     o = align256(o + 4 * (size_t)L.patch_max);
   L.o_slots = o;  o = align256(o + 4 * (size_t)L.slot_max);
   L.o_cells = o;  o = align256(o + 4 * (size_t)L.cell_cap);
@@ -123,7 +123,7 @@ inline size_t total_bytes(const Layout& L, int64_t batch) { return (L.zero_bytes
 // Pointers of one window, resolved on the device from (workspace base, window index, layout).
 struct WinPtrs {
   WinHeader* hdr; int* fmaxinv; int* fkmax1; int* ccnt; float* y; float* S;
-  int* fbase; int* ccur; Chunk* chunks; int* perm; int* kx; int* slots; int* cells; DupEdge* dups; float* ecells;
+  int* fbase; int* ccur; Chunk* chunks; int4* perm; int* kx; int* slots; int* cells; DupEdge* dups; float* ecells;
   float* Q; float* u; float* dZ; float* dX;
 };
 
@@ -140,7 +140,7 @@ __host__ __device__ inline WinPtrs win_ptrs(void* ws, const Layout& L, int64_t b
   p.fbase = (int*)(base + L.o_fbase);
   p.ccur = (int*)(base + L.o_ccur);
   p.chunks = (Chunk*)(base + L.o_chunks);
-  p.perm = (int*)(base + L.o_perm);
+  p.perm = (int4*)(base + L.o_perm);
   p.kx = (int*)(base + L.o_kx);
   p.slots = (int*)(base + L.o_slots);
   p.cells = (int*)(base + L.o_cells);

@@ -208,15 +208,29 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
 #pragma unroll
         for (int x = 0; x < 6; ++x) g[x] = 0.f;
 
-        for (int p0 = b0 + warp * PW; p0 < b1; p0 += 8 * PW) {
+        // software pipeline over the patch steps: the cell index is fetched two steps ahead, target / weight one
+        // step ahead, so the two dependent global loads of an edge are off the critical path
+        const int pstep = 8 * PW;
+        const int p_first = b0 + warp * PW + pl;
+        int n_cur = (slot_ok && p_first < b1) ? cells[p_first * ns + sl] : -1;
+        int n_nxt = (slot_ok && p_first + pstep < b1) ? cells[(p_first + pstep) * ns + sl] : -1;
+        float2 tg_cur = make_float2(0.f, 0.f), wt_cur = make_float2(0.f, 0.f);
+        if (n_cur >= 0) { tg_cur = __ldg(target + n_cur); wt_cur = __ldg(weight + n_cur); }
+        for (int p0 = b0 + warp * PW; p0 < b1; p0 += pstep) {
           const int p = p0 + pl;
-          const bool ok = slot_ok && p < b1;
-          const int n = ok ? cells[p * ns + sl] : -1;
+          const int n = n_cur;
+          const float2 tg = tg_cur, wt = wt_cur;
+          {
+            const int p2 = p + 2 * pstep;
+            const int n_nn = (slot_ok && p2 < b1) ? cells[p2 * ns + sl] : -1;
+            n_cur = n_nxt;
+            if (n_cur >= 0) { tg_cur = __ldg(target + n_cur); wt_cur = __ldg(weight + n_cur); }
+            n_nxt = n_nn;
+          }
           float e[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, ck = 0.f, uk = 0.f;
           float ei[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
           if (n >= 0) {
             const int q = p - b0;
-            const float2 tg = __ldg(target + n), wt = __ldg(weight + n);
             edge_terms(s.sPatch[q * 4], s.sPatch[q * 4 + 1], s.sPatch[q * 4 + 2], fx, fy, cx, cy, R, t, tg, wt, H, g,
                        e, ck, uk);
             if (col_ok && schur) {
@@ -601,8 +615,8 @@ __global__ void __launch_bounds__(256, 1) solve_small_kernel(Problem pb) {
 __global__ void __launch_bounds__(256) update_kernel(Problem pb) {
   pdl_wait();
   pdl_trigger();
-  __shared__ float sdx[(SMAX + 1) * 6];
-  const int w = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ __align__(8) float sdx[(SMAX + 1) * 6];
+  const int w = blockIdx.y, tid = threadIdx.x;
   const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
   float* patches = pb.patches + (int64_t)w * pb.st.patches;
   const int N = pb.t1 - pb.t0, t0 = pb.t0;
@@ -620,22 +634,52 @@ __global__ void __launch_bounds__(256) update_kernel(Problem pb) {
       sdx[x] = wp.dX[6 * (f - t0) + a];
     }
     __syncthreads();
-    const int len = ncols * 6;
-    for (int p = warp; p < ch.n_patches; p += 8) {
-      const float* eg = wp.ecells + 6 * ((int64_t)ch.ecell_base + (int64_t)p * ch.ncols);
-      float acc = 0.f;
-      for (int x = lane; x < len; x += 32) acc += eg[x] * sdx[x];
+    const int len2 = ncols * 3;
+    const float2* dx2 = reinterpret_cast<const float2*>(sdx);
+    if (pb.L.pc > 32) {
+      // large chunks: one thread per patch, its E row (ncols * 6 floats, 8-byte aligned) is read with independent
+      // 8-byte loads (no shuffles; consecutive threads read consecutive rows)
+      for (int p = tid; p < ch.n_patches; p += 256) {
+        const float2* eg = reinterpret_cast<const float2*>(wp.ecells + 6 * ((int64_t)ch.ecell_base + (int64_t)p * ch.ncols));
+        float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 4
+        for (int x = 0; x < len2; ++x) {
+          const float2 e = eg[x], d = dx2[x];
+          acc0 += e.x * d.x;
+          acc1 += e.y * d.y;
+        }
+        const float dz = wp.Q[ch.patch_base + p] * (wp.u[ch.patch_base + p] - (acc0 + acc1));
+        wp.dZ[ch.patch_base + p] = dz;
+        if (pb.apply) {
+          float* pr = patches + (int64_t)wp.kx[ch.patch_base + p] * pstride + 2 * PP;
+          float d = pr[0] + dz;                   // reads [2][0][0] (ba_cuda.cu:218)
+          d = (d > 20.f) ? 1.0f : d;
+          d = fmaxf(d, 1e-4f);
+          for (int x = 0; x < PP; ++x) pr[x] = d;
+        }
+      }
+    } else {
+      // small chunks (single window): one warp per patch, lanes over the E row
+      const int lane = tid & 31, warp = tid >> 5;
+      for (int p = warp; p < ch.n_patches; p += 8) {
+        const float2* eg = reinterpret_cast<const float2*>(wp.ecells + 6 * ((int64_t)ch.ecell_base + (int64_t)p * ch.ncols));
+        float acc = 0.f;
+        for (int x = lane; x < len2; x += 32) {
+          const float2 e = eg[x], d = dx2[x];
+          acc += e.x * d.x + e.y * d.y;
+        }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      const float dz = wp.Q[ch.patch_base + p] * (wp.u[ch.patch_base + p] - acc);
-      if (lane == 0) wp.dZ[ch.patch_base + p] = dz;
-      if (pb.apply) {
-        float* pr = patches + (int64_t)wp.kx[ch.patch_base + p] * pstride + 2 * PP;
-        float d = pr[0] + dz;                   // reads [2][0][0] (ba_cuda.cu:218)
-        d = (d > 20.f) ? 1.0f : d;
-        d = fmaxf(d, 1e-4f);
-        __syncwarp();
-        for (int x = lane; x < PP; x += 32) pr[x] = d;
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        const float dz = wp.Q[ch.patch_base + p] * (wp.u[ch.patch_base + p] - acc);
+        if (lane == 0) wp.dZ[ch.patch_base + p] = dz;
+        if (pb.apply) {
+          float* pr = patches + (int64_t)wp.kx[ch.patch_base + p] * pstride + 2 * PP;
+          float d = pr[0] + dz;
+          d = (d > 20.f) ? 1.0f : d;
+          d = fmaxf(d, 1e-4f);
+          __syncwarp();
+          for (int x = lane; x < PP; x += 32) pr[x] = d;
+        }
       }
     }
   }

@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(256) plan_scatter_kernel(Problem pb) {
     int base = 0;
     if (x.ok && lane == leader) base = atomicAdd(&wp.ccur[c], __popc(grp));
     base = __shfl_sync(0xffffffffu, base, leader);
-    if (x.ok) wp.perm[base + __popc(grp & ((1u << lane) - 1u))] = e;
+    if (x.ok) wp.perm[base + __popc(grp & ((1u << lane) - 1u))] = make_int4(e, x.j, x.k, 0);
   }
 }
 
@@ -214,8 +214,6 @@ __global__ void __launch_bounds__(256) plan_cells_kernel(Problem pb) {
   __shared__ Chunk sch;
   const int w = blockIdx.y, tid = threadIdx.x, T = blockDim.x;
   const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
-  const int64_t* jj = pb.jj + (int64_t)w * pb.st.jj;
-  const int64_t* kk = pb.kk + (int64_t)w * pb.st.kk;
   const int n_chunks = wp.hdr->n_chunks;
   const int nw = (pb.F + 31) / 32;
   const int t0 = pb.t0, t1 = pb.t1;
@@ -228,8 +226,8 @@ __global__ void __launch_bounds__(256) plan_cells_kernel(Problem pb) {
     __syncthreads();
     const int eb = sch.edge_begin, ee = sch.edge_end, kbase = sch.kbase, fi = sch.frame;
     for (int pos = eb + tid; pos < ee; pos += T) {
-      const int n = wp.perm[pos];
-      const int k = (int)kk[n] - kbase, j = (int)jj[n];
+      const int4 rec = wp.perm[pos];
+      const int k = rec.z - kbase, j = rec.y;
       atomicOr(&pflag[k >> 5], 1u << (k & 31));
       atomicOr(&jflag[j >> 5], 1u << (j & 31));
     }
@@ -293,8 +291,8 @@ __global__ void __launch_bounds__(256) plan_cells_kernel(Problem pb) {
         wp.slots[sch.slot_base + jpref[f >> 5] + __popc(jflag[f >> 5] & ((1u << (f & 31)) - 1u))] = f;
     __syncthreads();
     for (int pos = eb + tid; pos < ee; pos += T) {
-      const int n = wp.perm[pos];
-      const int k = (int)kk[n] - kbase, j = (int)jj[n];
+      const int4 rec = wp.perm[pos];
+      const int n = rec.x, k = rec.z - kbase, j = rec.y;
       const int p = ppref[k >> 5] + __popc(pflag[k >> 5] & ((1u << (k & 31)) - 1u));
       const int s = jpref[j >> 5] + __popc(jflag[j >> 5] & ((1u << (j & 31)) - 1u));
       const int old = atomicCAS(&cells[p * ns + s], -1, n);

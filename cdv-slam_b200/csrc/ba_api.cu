@@ -8,8 +8,8 @@
 
 namespace pgba {
 void launch_plan(const Problem& pb, int64_t batch, cudaStream_t stream);
-cudaError_t launch_iteration(const Problem& pb, int64_t batch, cudaStream_t stream, cudaEvent_t* ev, bool more);
-void launch_linearize(const Problem& pb, int64_t batch, cudaStream_t stream);
+cudaError_t launch_iteration(const Problem& pb, int64_t batch, cudaStream_t stream, cudaEvent_t* ev, bool first, bool more);
+void launch_linearize(const Problem& pb, int64_t batch, cudaStream_t stream, bool fuse_update);
 void launch_solve(const Problem& pb, int64_t batch, cudaStream_t stream);
 void launch_update(const Problem& pb, int64_t batch, cudaStream_t stream);
 bool solve_supported(int N);
@@ -194,7 +194,7 @@ int pgba_ba_solve_batched(float* poses, float* patches, const float* intrinsics,
   if (e != cudaSuccess) return (int)e;
   launch_plan(pb, batch, s);
   for (int it = 0; it < iterations; ++it) {
-    e = launch_iteration(pb, batch, s, nullptr, it + 1 < iterations);
+    e = launch_iteration(pb, batch, s, nullptr, it == 0, it + 1 < iterations);
     if (e != cudaSuccess) return (int)e;
   }
   return (int)cudaGetLastError();
@@ -219,7 +219,7 @@ int pgba_ba_solve_profiled(float* poses, float* patches, const float* intrinsics
   cudaError_t e = clear_workspace(pb, batch, s);
   launch_plan(pb, batch, s);
   cudaEventRecord(ev[1], s);
-  for (int it = 0; it < iterations && e == cudaSuccess; ++it) e = launch_iteration(pb, batch, s, ev + 2 + 4 * it, it + 1 < iterations);
+  for (int it = 0; it < iterations && e == cudaSuccess; ++it) e = launch_iteration(pb, batch, s, ev + 2 + 4 * it, it == 0, it + 1 < iterations);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);
   if (e == cudaSuccess) {
     cudaEventElapsedTime(&stage_ms[0], ev[0], ev[1]);
@@ -259,7 +259,7 @@ int pgba_ba_linearize_debug(const float* poses, const float* patches, const floa
   cudaError_t e = clear_workspace(pb, 1, s);
   if (e != cudaSuccess) return (int)e;
   launch_plan(pb, 1, s);
-  launch_linearize(pb, 1, s);
+  launch_linearize(pb, 1, s, false);
   launch_k(export_debug_kernel, dim3(256), dim3(256), 0, s, pb, S, y, nullptr, patch_ids, C, u, Q, nullptr, n_unique, nullptr);   // before the solve
   count_launch();
   launch_solve(pb, 1, s);

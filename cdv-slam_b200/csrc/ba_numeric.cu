@@ -112,8 +112,12 @@ __device__ __forceinline__ void red_add2(float* p, float a, float b) {       // 
   atomicAdd(reinterpret_cast<float2*>(p), make_float2(a, b));
 }
 
-// grid = (gx, batch), block = 256, dynamic smem = lin_smem_bytes(pc, ebudget)
-__global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb, int ebudget) {
+__device__ __forceinline__ void chunk_depth_update(const Problem& pb, const WinPtrs& wp, const Chunk& ch, float* patches,
+                                                   float* sdx, bool apply);
+
+// grid = (gx, batch), block = 256, dynamic smem = lin_smem_bytes(pc, ebudget).  fuse_update: first apply the previous
+// iteration's back-substitution + depth retraction to the chunk's patches (saves the separate update launch).
+__global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb, int ebudget, int fuse_update) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ float smem[];
@@ -153,6 +157,7 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
     const bool i_free = ch.icol >= 0;
     const int* cells = wp.cells + ch.cell_base;
     const int* kx = wp.kx + ch.patch_base;
+    if (fuse_update) chunk_depth_update(pb, wp, ch, pb.patches + (int64_t)w * pb.st.patches, s.sHw, true);
     // ---- per-slot relative poses, zero the H accumulators
     for (int sl = tid; sl < ns; sl += 256) {
       const int fj = wp.slots[ch.slot_base + sl];
@@ -612,76 +617,84 @@ __global__ void __launch_bounds__(256, 1) solve_small_kernel(Problem pb) {
 // Back-substitution dZ = Q (u - E^T dX) and inverse-depth retraction (ba_cuda.cu:592, 209-229; block_e.cu:253-283)
 // grid = (gx, batch), block = 256: one warp per patch, lanes over the E row.  apply = 0 only computes dZ.
 // ---------------------------------------------------------------------------------------------------------------
+// Per-chunk back-substitution + depth retraction by the whole CTA (256 threads).  sdx: >= (SMAX + 1) * 6 floats of
+// shared memory, 8-byte aligned.  Ends with a __syncthreads().
+__device__ __forceinline__ void chunk_depth_update(const Problem& pb, const WinPtrs& wp, const Chunk& ch, float* patches,
+                                                   float* sdx, bool apply) {
+  const int tid = threadIdx.x;
+  const int N = pb.t1 - pb.t0, t0 = pb.t0;
+  const int PP = pb.P * pb.P, pstride = 3 * PP;
+  const int ncols = (N > 0 && pb.with_schur != 0) ? ch.ncols : 0;
+  for (int x = tid; x < ncols * 6; x += 256) {
+    const int col = x / 6, a = x - col * 6;
+    const int f = (col < ch.n_free) ? wp.slots[ch.slot_base + ch.first_free + col] : ch.frame;
+    sdx[x] = wp.dX[6 * (f - t0) + a];
+  }
+  __syncthreads();
+  const int len2 = ncols * 3;
+  const float2* dx2 = reinterpret_cast<const float2*>(sdx);
+  if (pb.L.pc > 32) {
+    // large chunks: one thread per patch, its E row (ncols * 6 floats, 8-byte aligned) is read with independent
+    // 8-byte loads (no shuffles; consecutive threads read consecutive rows)
+    for (int p = tid; p < ch.n_patches; p += 256) {
+      const float2* eg = reinterpret_cast<const float2*>(wp.ecells + 6 * ((int64_t)ch.ecell_base + (int64_t)p * ch.ncols));
+      float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 4
+      for (int x = 0; x < len2; ++x) {
+        const float2 e = eg[x], d = dx2[x];
+        acc0 += e.x * d.x;
+        acc1 += e.y * d.y;
+      }
+      const float dz = wp.Q[ch.patch_base + p] * (wp.u[ch.patch_base + p] - (acc0 + acc1));
+      wp.dZ[ch.patch_base + p] = dz;
+      if (apply) {
+        float* pr = patches + (int64_t)wp.kx[ch.patch_base + p] * pstride + 2 * PP;
+        float d = pr[0] + dz;                   // reads [2][0][0] (ba_cuda.cu:218)
+        d = (d > 20.f) ? 1.0f : d;
+        d = fmaxf(d, 1e-4f);
+        for (int x = 0; x < PP; ++x) pr[x] = d;
+      }
+    }
+  } else {
+    // small chunks (single window): one warp per patch, lanes over the E row
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int p = warp; p < ch.n_patches; p += 8) {
+      const float2* eg = reinterpret_cast<const float2*>(wp.ecells + 6 * ((int64_t)ch.ecell_base + (int64_t)p * ch.ncols));
+      float acc = 0.f;
+      for (int x = lane; x < len2; x += 32) {
+        const float2 e = eg[x], d = dx2[x];
+        acc += e.x * d.x + e.y * d.y;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      const float dz = wp.Q[ch.patch_base + p] * (wp.u[ch.patch_base + p] - acc);
+      if (lane == 0) wp.dZ[ch.patch_base + p] = dz;
+      if (apply) {
+        float* pr = patches + (int64_t)wp.kx[ch.patch_base + p] * pstride + 2 * PP;
+        float d = pr[0] + dz;
+        d = (d > 20.f) ? 1.0f : d;
+        d = fmaxf(d, 1e-4f);
+        __syncwarp();
+        for (int x = lane; x < PP; x += 32) pr[x] = d;
+      }
+    }
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(256) update_kernel(Problem pb) {
   pdl_wait();
   pdl_trigger();
   __shared__ __align__(8) float sdx[(SMAX + 1) * 6];
-  const int w = blockIdx.y, tid = threadIdx.x;
+  const int w = blockIdx.y;
   const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
   float* patches = pb.patches + (int64_t)w * pb.st.patches;
-  const int N = pb.t1 - pb.t0, t0 = pb.t0;
-  const int PP = pb.P * pb.P, pstride = 3 * PP;
   const int n_chunks = wp.hdr->n_chunks;
-  const bool schur = pb.with_schur != 0;
   for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
     const Chunk ch = wp.chunks[c];
     if (ch.n_patches == 0) continue;
     __syncthreads();
-    const int ncols = (N > 0 && schur) ? ch.ncols : 0;
-    for (int x = tid; x < ncols * 6; x += 256) {
-      const int col = x / 6, a = x - col * 6;
-      const int f = (col < ch.n_free) ? wp.slots[ch.slot_base + ch.first_free + col] : ch.frame;
-      sdx[x] = wp.dX[6 * (f - t0) + a];
-    }
-    __syncthreads();
-    const int len2 = ncols * 3;
-    const float2* dx2 = reinterpret_cast<const float2*>(sdx);
-    if (pb.L.pc > 32) {
-      // large chunks: one thread per patch, its E row (ncols * 6 floats, 8-byte aligned) is read with independent
-      // 8-byte loads (no shuffles; consecutive threads read consecutive rows)
-      for (int p = tid; p < ch.n_patches; p += 256) {
-        const float2* eg = reinterpret_cast<const float2*>(wp.ecells + 6 * ((int64_t)ch.ecell_base + (int64_t)p * ch.ncols));
-        float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll 4
-        for (int x = 0; x < len2; ++x) {
-          const float2 e = eg[x], d = dx2[x];
-          acc0 += e.x * d.x;
-          acc1 += e.y * d.y;
-        }
-        const float dz = wp.Q[ch.patch_base + p] * (wp.u[ch.patch_base + p] - (acc0 + acc1));
-        wp.dZ[ch.patch_base + p] = dz;
-        if (pb.apply) {
-          float* pr = patches + (int64_t)wp.kx[ch.patch_base + p] * pstride + 2 * PP;
-          float d = pr[0] + dz;                   // reads [2][0][0] (ba_cuda.cu:218)
-          d = (d > 20.f) ? 1.0f : d;
-          d = fmaxf(d, 1e-4f);
-          for (int x = 0; x < PP; ++x) pr[x] = d;
-        }
-      }
-    } else {
-      // small chunks (single window): one warp per patch, lanes over the E row
-      const int lane = tid & 31, warp = tid >> 5;
-      for (int p = warp; p < ch.n_patches; p += 8) {
-        const float2* eg = reinterpret_cast<const float2*>(wp.ecells + 6 * ((int64_t)ch.ecell_base + (int64_t)p * ch.ncols));
-        float acc = 0.f;
-        for (int x = lane; x < len2; x += 32) {
-          const float2 e = eg[x], d = dx2[x];
-          acc += e.x * d.x + e.y * d.y;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        const float dz = wp.Q[ch.patch_base + p] * (wp.u[ch.patch_base + p] - acc);
-        if (lane == 0) wp.dZ[ch.patch_base + p] = dz;
-        if (pb.apply) {
-          float* pr = patches + (int64_t)wp.kx[ch.patch_base + p] * pstride + 2 * PP;
-          float d = pr[0] + dz;
-          d = (d > 20.f) ? 1.0f : d;
-          d = fmaxf(d, 1e-4f);
-          __syncwarp();
-          for (int x = lane; x < PP; x += 32) pr[x] = d;
-        }
-      }
-    }
+    chunk_depth_update(pb, wp, ch, patches, sdx, pb.apply != 0);
   }
 }
 
@@ -699,12 +712,12 @@ int lin_ebudget(const Problem& pb) {
 
 cudaError_t launch_big_solve(const Problem& pb, int64_t batch, cudaStream_t stream);
 
-void launch_linearize(const Problem& pb, int64_t batch, cudaStream_t stream) {
+void launch_linearize(const Problem& pb, int64_t batch, cudaStream_t stream, bool fuse_update) {
   const int gx = chunk_grid(pb, batch);
   const int ebudget = lin_ebudget(pb);
   const size_t lsm = lin_smem_bytes(pb.L.pc, ebudget);
   cudaFuncSetAttribute(linearize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm);
-  launch_k(linearize_kernel, dim3((unsigned)gx, (unsigned)batch), dim3(256), lsm, stream, pb, ebudget);
+  launch_k(linearize_kernel, dim3((unsigned)gx, (unsigned)batch), dim3(256), lsm, stream, pb, ebudget, fuse_update ? 1 : 0);
   count_launch();
 }
 
@@ -737,14 +750,19 @@ cudaError_t clear_big_system(const Problem& pb, int64_t batch, cudaStream_t stre
   return e;
 }
 
+// One Gauss-Newton iteration.  The back-substitution + depth retraction of iteration k is fused into the linearisation
+// of iteration k + 1 (`first` = false); only the last iteration (`more` = false) launches update_kernel.
 // ev (optional): 4 events recorded before linearize / solve / update and after update
-cudaError_t launch_iteration(const Problem& pb, int64_t batch, cudaStream_t stream, cudaEvent_t* ev, bool more) {
+cudaError_t launch_iteration(const Problem& pb, int64_t batch, cudaStream_t stream, cudaEvent_t* ev, bool first, bool more) {
+  // fusing pays in the latency-bound single-window regime (small chunks); with large chunks (batched windows) the
+  // separate, fully parallel update kernel measured faster
+  const bool fuse = pb.L.pc <= 32;
   if (ev) cudaEventRecord(ev[0], stream);
-  launch_linearize(pb, batch, stream);
+  launch_linearize(pb, batch, stream, fuse && !first);
   if (ev) cudaEventRecord(ev[1], stream);
   launch_solve(pb, batch, stream);
   if (ev) cudaEventRecord(ev[2], stream);
-  launch_update(pb, batch, stream);
+  if (!fuse || !more) launch_update(pb, batch, stream);
   if (pb.L.big && more) {
     cudaError_t e = clear_big_system(pb, batch, stream);
     if (e != cudaSuccess) return e;

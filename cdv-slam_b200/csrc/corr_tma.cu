@@ -1,0 +1,463 @@
+// Patch correlation lookup, production shape (fp16 features, C in {24, 32}, P = 3, radius = 3), sm_100a:
+// channel-last maps + TMA region tiles + tensor-core contraction + fused blend.
+//
+// Reference semantics: cdvslam/altcorr/correlation_kernel.cu:83-136 (window dot products, zero outside the map) and
+// :193-233 (4-tap bilinear blend, permute); two-level form of cdvslam/slam.py:316-323.
+//
+//   to_nhwc_kernel     fmap2 [B*F, C, H, W] -> [B*F, H, W, C]: every map pixel becomes one contiguous 2C-byte record,
+//                      so the (<= 12 x 12)-pixel region that contains the nine 8x8 windows of an edge is a dense box.
+//   corr_tma_kernel    one WARP per edge (both pyramid levels), persistent CTAs.  Per (edge, level): the region box is
+//                      fetched by ONE TMA tile load (cp.async.bulk.tensor.4d, out-of-map pixels zero-filled by the
+//                      hardware, completion on a per-warp mbarrier), issued one half-task ahead.  The contraction
+//                      D[region pixel, patch pixel] = sum_c region[px][c] * patch[p][c] runs on the tensor cores
+//                      (mma.sync m16n8k16 / m16n8k8, fp16 in, fp32 accumulate; operands by ldmatrix).  Each 16-pixel
+//                      tile of D is written back IN PLACE over the region records it was computed from (9 floats fit a
+//                      2C-byte record), then the per-pixel window selection + 4-tap blend + permute are done from
+//                      shared memory and the result is stored once, in the final layout (levels interleaved).
+//                      Edges whose nine windows do not fit one region (strong zoom) take a per-tap path in the kernel.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pcorr.h"
+
+namespace pgba { void count_launch(); }
+
+namespace pcorr_tma {
+
+constexpr int R = 3, D = 8, Do = 7, PP = 9;
+constexpr int RG = 12, RPX = RG * RG;       // region: 12 x 12 pixels
+constexpr int NOUT = (Do * Do * PP + 31) / 32;   // 14 outputs per lane
+constexpr int WARPS = 4;
+
+template <int C> struct __align__(128) WarpSmem {
+  unsigned char reg[2][RPX * C * 2];   // TMA destinations; the region volume overwrites the records in place
+  __half a[16 * C];                    // patch features [p][c] (rows 9..15 stay zero)
+  float4 wgt[2][12];                   // bilinear weights of pixel p: (1-dx)(1-dy), dx(1-dy), (1-dx)dy, dx dy
+  int vbase[2][12];                    // float offset of pixel p's window origin inside the volume (+ p)
+  unsigned long long bar[2];
+};
+
+struct Params {
+  const __half* fmap1;                 // [B, K, C, 3, 3]
+  const __half* nhwc[2];               // [B*F, H, W, C] per level
+  int H[2], W[2];
+  const float* coords;                 // [B, E, 2, 3, 3]
+  const int64_t* us; const int64_t* vs;
+  int B; int64_t E, K, F;
+  __half* out;                         // [B, E, 7, 7, 3, 3, NLEV]
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// box [C, RG, RG, 1] at (0, x, y, frame) of the 4-D map [C, W, H, B*F]; elements outside the map arrive as zeros
+__device__ __forceinline__ void tma_load_region(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int x, int y, int f) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(dst), "l"((uint64_t)tm), "r"(bar), "r"(0), "r"(x), "r"(y), "r"(f) : "memory");
+}
+
+__device__ __forceinline__ void ldsm_x4(unsigned& r0, unsigned& r1, unsigned& r2, unsigned& r3, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void ldsm_x2(unsigned& r0, unsigned& r1, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void mma_k16(float d[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0,
+                                        unsigned b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma_k8(float d[4], unsigned a0, unsigned a1, unsigned b0) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(b0));
+}
+
+__device__ __forceinline__ int safe_floor(float v) {     // far-out / non-finite -> "entirely outside the map"
+  const float f = floorf(v);
+  return (f > -1e6f && f < 1e6f) ? (int)f : -1000000;
+}
+
+// [B*F, C, HW] -> [B*F, HW, C]; thread = (pixel, group of 8 channels): 8 coalesced 2-byte reads, one 16-byte store
+__global__ void __launch_bounds__(256) to_nhwc_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int C,
+                                                      int HW) {
+  const int px = blockIdx.x * 256 + threadIdx.x;
+  if (px >= HW) return;
+  const int64_t bf = blockIdx.y;
+  const int c0 = blockIdx.z * 8;
+  const __half* s = src + (bf * C + c0) * (int64_t)HW + px;
+  unsigned short v[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = __half_as_ushort(__ldg(s + (int64_t)k * HW));
+  uint4 o;
+  o.x = v[0] | ((unsigned)v[1] << 16); o.y = v[2] | ((unsigned)v[3] << 16);
+  o.z = v[4] | ((unsigned)v[5] << 16); o.w = v[6] | ((unsigned)v[7] << 16);
+  *reinterpret_cast<uint4*>(dst + (bf * HW + px) * (int64_t)C + c0) = o;
+}
+
+template <int C, int NLEV>
+__global__ void __launch_bounds__(32 * WARPS) corr_tma_kernel(const __grid_constant__ CUtensorMap tm0,
+                                                              const __grid_constant__ CUtensorMap tm1, Params P) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  static_assert(C % 8 == 0 && 2 * C >= 4 * PP, "a 2C-byte pixel record must hold the 9 volume values");
+  constexpr int SLOT = C / 2;                           // floats per pixel record
+  constexpr int K16 = C / 16, K8 = (C % 16) / 8;
+  constexpr uint32_t TX_BYTES = RPX * C * 2;
+  constexpr int NA4 = C * PP / 8;                        // uint4 per patch-feature record
+  constexpr int NAV = (NA4 + 31) / 32;
+  using WS = WarpSmem<C>;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  WS& S = reinterpret_cast<WS*>(smraw)[warp];
+  const uint32_t bar0 = smem_u32(&S.bar[0]);
+  const uint32_t reg0 = smem_u32(&S.reg[0][0]);
+  const uint32_t sa = smem_u32(&S.a[0]);
+
+  if (lane == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async();
+  }
+  for (int x = lane; x < 7 * C / 2; x += 32) reinterpret_cast<unsigned*>(&S.a[PP * C])[x] = 0u;   // rows 9..15
+  __syncwarp();
+
+  // output o = lane + 32 t -> (p, yo, xo), the same for every task: p | ((yo * RG + xo) * SLOT) << 4 | (yo*8+xo) << 20
+  int odec[NOUT];
+#pragma unroll
+  for (int t = 0; t < NOUT; ++t) {
+    const int o = lane + 32 * t;
+    const int p = o % 9, yo = (o / 9) % 7, xo = o / 63;
+    odec[t] = p | (((yo * RG + xo) * SLOT) << 4) | ((yo * 8 + xo) << 20);
+  }
+  // ldmatrix lane offsets (bytes).  A operand = region records: matrices (rows 0-7 | 8-15) x (ch 0-7 | 8-15)
+  const uint32_t a_off4 = (uint32_t)((((lane >> 3) & 1) * 8 + (lane & 7)) * (2 * C) + (lane >> 4) * 16);
+  const uint32_t a_off2 = (uint32_t)((((lane >> 3) & 1) * 8 + (lane & 7)) * (2 * C) + K16 * 32);
+  const int g = lane >> 2, tq = lane & 3;
+
+  const int64_t total = (int64_t)P.B * P.E;
+  const int64_t ustride = (int64_t)gridDim.x * WARPS;
+  const int64_t u_first = (int64_t)blockIdx.x * WARPS + warp;
+  if (u_first >= total) return;
+  const int64_t n_units = (total - u_first + ustride - 1) / ustride;
+  const int64_t n_half = n_units * NLEV;
+
+  // ---- pipeline state
+  float ux = 0.f, uy = 0.f;          // lanes 0..8: level-0 coordinates of the unit of the NEXT half-task
+  int ujx = 0;                       // its target frame (b * F + jj)
+  int64_t uf1 = 0;                   // element offset of its patch-feature record in fmap1
+  uint4 apre[NAV];                   // prefetched patch features of the next unit
+  bool fits_cur = false, fits_nxt = false;
+  uint32_t phase = 0;                // bit b: parity to wait for on buffer b
+  unsigned bf0[K16 * 2 + K8], bf1[K16 * 2 + K8];    // B operand (patch features), n-tiles p 0-7 / 8-15
+  unsigned hold[NOUT / 2];           // level-0 results (packed halfs) until level 1 is done
+
+  auto load_unit_raw = [&](int64_t unit) {
+    const float* cg = P.coords + unit * (2 * PP);
+    if (lane < PP) { ux = __ldg(cg + lane); uy = __ldg(cg + PP + lane); }
+    const int64_t b = (P.B == 1) ? 0 : unit / P.E;
+    const int64_t m = unit - b * P.E;
+    ujx = (int)(b * P.F + __ldg(P.vs + m));
+    uf1 = (b * P.K + __ldg(P.us + m)) * (int64_t)(C * PP);
+  };
+  auto prefetch_a = [&]() {
+    const uint4* f1 = reinterpret_cast<const uint4*>(P.fmap1 + uf1);
+#pragma unroll
+    for (int k = 0; k < NAV; ++k)
+      if (lane + 32 * k < NA4) apre[k] = __ldg(f1 + lane + 32 * k);
+  };
+  // geometry of half-task (lev, buffer slot) from the raw coordinates; issues the region load
+  auto prepare = [&](int lev, int slot) -> bool {
+    const float x = (lev == 0) ? ux : ux * 0.25f;     // level 1: coords / 4 in fp32 (slam.py:322)
+    const float y = (lev == 0) ? uy : uy * 0.25f;
+    const int fxp = safe_floor(x), fyp = safe_floor(y);
+    const int xmin = __reduce_min_sync(0xffffffffu, lane < PP ? fxp : 0x7fffffff);
+    const int xmax = __reduce_max_sync(0xffffffffu, lane < PP ? fxp : -0x7fffffff);
+    const int ymin = __reduce_min_sync(0xffffffffu, lane < PP ? fyp : 0x7fffffff);
+    const int ymax = __reduce_max_sync(0xffffffffu, lane < PP ? fyp : -0x7fffffff);
+    const bool fits = (xmax - xmin + D <= RG) && (ymax - ymin + D <= RG);
+    if (lane < PP) {
+      const float dx = x - floorf(x), dy = y - floorf(y);
+      S.wgt[slot][lane] = make_float4((1.f - dx) * (1.f - dy), dx * (1.f - dy), (1.f - dx) * dy, dx * dy);
+      S.vbase[slot][lane] = fits ? ((fyp - ymin) * RG + (fxp - xmin)) * SLOT + lane : lane;
+    }
+    __syncwarp();
+    if (fits && lane == 0) {
+      const int H = lev == 0 ? P.H[0] : P.H[1], W = lev == 0 ? P.W[0] : P.W[1];
+      // a region entirely outside the map may be fetched from any outside position (all zeros either way)
+      const int x0 = min(max(xmin - R, -RG), W), y0 = min(max(ymin - R, -RG), H);
+      fence_proxy_async();                    // generic-proxy accesses of this buffer precede the async-proxy write
+      mbar_expect_tx(bar0 + 8 * slot, TX_BYTES);
+      tma_load_region(reg0 + slot * TX_BYTES, lev == 0 ? &tm0 : &tm1, bar0 + 8 * slot, x0, y0, ujx);
+    }
+    return fits;
+  };
+
+  // ---- prologue: half-task 0
+  load_unit_raw(u_first);
+  prefetch_a();
+  fits_cur = prepare(0, 0);
+
+  for (int64_t s = 0; s < n_half; ++s) {
+    const int lev = (NLEV == 1) ? 0 : (int)(s & 1);
+    const int slot = (int)(s & 1);
+    const int64_t unit = u_first + (s / NLEV) * ustride;
+    const bool have_next = s + 1 < n_half;
+    const int lev_n = (NLEV == 1) ? 0 : (int)((s + 1) & 1);
+    const int64_t unit_n = u_first + ((s + 1) / NLEV) * ustride;
+    const int cur_jx = ujx;                              // frame of the current half-task (slow path)
+
+    // ---- (1) raw loads of the next half-task's unit (latency hidden behind the contraction)
+    if (lev == 0) {                                      // new unit: its patch features to shared memory, B fragments
+#pragma unroll
+      for (int k = 0; k < NAV; ++k) {
+        const int i4 = lane + 32 * k;
+        if (i4 < NA4) {
+          const unsigned w[4] = {apre[k].x, apre[k].y, apre[k].z, apre[k].w};
+          int c = (i4 * 8) / PP, p = (i4 * 8) - c * PP;            // element x = c * 9 + p  ->  a[p][c]
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const unsigned short h = (unsigned short)((e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xffffu));
+            reinterpret_cast<unsigned short*>(&S.a[0])[p * C + c] = h;
+            if (++p == PP) { p = 0; ++c; }
+          }
+        }
+      }
+      __syncwarp();
+      // B fragments: matrices of 8 patch pixels x 8 channels, rows = patch pixels (k contiguous)
+#pragma unroll
+      for (int ks = 0; ks < K16; ++ks) {
+        // x4: (p 0-7, ch 16ks..+7), (p 0-7, ch +8..+15), (p 8-15, ch ..+7), (p 8-15, ch +8..+15)
+        const uint32_t off = (uint32_t)((((lane >> 4) & 1) * 8 + (lane & 7)) * (2 * C) + ((lane >> 3) & 1) * 16 + ks * 32);
+        ldsm_x4(bf0[2 * ks], bf0[2 * ks + 1], bf1[2 * ks], bf1[2 * ks + 1], sa + off);
+      }
+      if (K8) {
+        const uint32_t off = (uint32_t)((((lane >> 3) & 1) * 8 + (lane & 7)) * (2 * C) + K16 * 32);
+        ldsm_x2(bf0[2 * K16], bf1[2 * K16], sa + off);
+      }
+    }
+    if (have_next && lev_n == 0) load_unit_raw(unit_n);
+
+    // ---- (2) contraction of the current half-task, volume written in place
+    float* vol = reinterpret_cast<float*>(&S.reg[slot][0]);
+    if (fits_cur) {
+      mbar_wait(bar0 + 8 * slot, (phase >> slot) & 1u);
+      phase ^= 1u << slot;
+      const uint32_t rb = reg0 + slot * TX_BYTES;
+#pragma unroll
+      for (int mt = 0; mt < RPX / 16; ++mt) {
+        float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
+        const uint32_t tb = rb + mt * 16 * (2 * C);
+#pragma unroll
+        for (int ks = 0; ks < K16; ++ks) {
+          unsigned a0, a1, a2, a3;
+          ldsm_x4(a0, a1, a2, a3, tb + a_off4 + ks * 32);
+          mma_k16(d0, a0, a1, a2, a3, bf0[2 * ks], bf0[2 * ks + 1]);
+          mma_k16(d1, a0, a1, a2, a3, bf1[2 * ks], bf1[2 * ks + 1]);
+        }
+        if (K8) {
+          unsigned a0, a1;
+          ldsm_x2(a0, a1, tb + a_off2);
+          mma_k8(d0, a0, a1, bf0[2 * K16]);
+          mma_k8(d1, a0, a1, bf1[2 * K16]);
+        }
+        // D[px = 16 mt + g (+8)][p = 2 tq, 2 tq + 1] and p = 8 from the second n-tile (tq == 0)
+        float* v0 = vol + (mt * 16 + g) * SLOT;
+        *reinterpret_cast<float2*>(v0 + 2 * tq) = make_float2(d0[0], d0[1]);
+        *reinterpret_cast<float2*>(v0 + 8 * SLOT + 2 * tq) = make_float2(d0[2], d0[3]);
+        if (tq == 0) { v0[8] = d1[0]; v0[8 * SLOT + 8] = d1[2]; }
+      }
+    } else {
+      // per-tap path (windows too far apart for one region): vol[(io * 8 + jo)][p]
+      const int H = lev == 0 ? P.H[0] : P.H[1], W = lev == 0 ? P.W[0] : P.W[1];
+      const __half* f2 = (lev == 0 ? P.nhwc[0] : P.nhwc[1]) + (int64_t)cur_jx * H * W * C;
+      const float* cg = P.coords + unit * (2 * PP);
+      for (int o = lane; o < PP * D * D; o += 32) {
+        const int p = o / (D * D), pos = o - p * (D * D);
+        const int io = pos / D, jo = pos - io * D;
+        const float xs = (lev == 0) ? cg[p] : cg[p] * 0.25f, ys = (lev == 0) ? cg[PP + p] : cg[PP + p] * 0.25f;
+        const int i1 = safe_floor(ys) + (io - R), j1 = safe_floor(xs) + (jo - R);
+        float acc = 0.f;
+        if (i1 >= 0 && i1 < H && j1 >= 0 && j1 < W) {
+          const __half* src = f2 + ((int64_t)i1 * W + j1) * C;
+          for (int c = 0; c < C; ++c) acc += __half2float(S.a[p * C + c]) * __half2float(src[c]);
+        }
+        vol[pos * SLOT + p] = acc;
+      }
+    }
+    __syncwarp();
+
+    // ---- (3) geometry + region load of the next half-task (its buffer was released by the previous epilogue)
+    if (have_next) {
+      fits_nxt = prepare(lev_n, slot ^ 1);
+      if (lev_n == 0) prefetch_a();
+    }
+
+    // ---- (4) window selection + bilinear blend + permute: out[xo][yo][p] (correlation_kernel.cu:221-232)
+    {
+      const int rs = fits_cur ? RG * SLOT : D * SLOT;          // float stride of one volume row
+      __half* og = P.out + unit * (int64_t)(Do * Do * PP) * NLEV;
+#pragma unroll
+      for (int t = 0; t < NOUT; ++t) {
+        const int o = lane + 32 * t;
+        float r = 0.f;
+        if (o < Do * Do * PP) {
+          const int p = odec[t] & 15;
+          const float4 wg = S.wgt[slot][p];
+          const int off = fits_cur ? ((odec[t] >> 4) & 0xffff) : ((odec[t] >> 20) * SLOT);
+          const float* v = vol + S.vbase[slot][p] + off;
+          r = wg.x * v[0] + wg.y * v[SLOT] + wg.z * v[rs] + wg.w * v[rs + SLOT];
+        }
+        if (NLEV == 1) {
+          if (o < Do * Do * PP) og[o] = __float2half_rn(r);
+        } else {
+          const unsigned short h = __half_as_ushort(__float2half_rn(r));
+          if (lev == 0) {
+            if (t & 1) hold[t >> 1] |= (unsigned)h << 16; else hold[t >> 1] = h;
+          } else if (o < Do * Do * PP) {
+            const unsigned h0 = (t & 1) ? (hold[t >> 1] >> 16) : (hold[t >> 1] & 0xffffu);
+            reinterpret_cast<unsigned*>(og)[o] = h0 | ((unsigned)h << 16);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    fits_cur = fits_nxt;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+static int make_map(CUtensorMap* tm, const void* base, int C, int W, int H, int64_t frames) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return PCORR_ERR_UNSUPPORTED;
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)frames};
+  const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  const cuuint32_t box[4] = {(cuuint32_t)C, RG, RG, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? PCORR_OK : PCORR_ERR_UNSUPPORTED;
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+template <int C, int NLEV>
+static int launch(const CUtensorMap& tm0, const CUtensorMap& tm1, const Params& P, cudaStream_t s) {
+  auto kern = corr_tma_kernel<C, NLEV>;
+  const size_t smem = sizeof(WarpSmem<C>) * WARPS;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int64_t units = (int64_t)P.B * P.E;
+  int64_t grid = (units + WARPS - 1) / WARPS;
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  if (per_sm > 4) per_sm = 4;
+  if (per_sm < 1) per_sm = 1;
+  if (grid > 148 * per_sm) grid = 148 * per_sm;
+  kern<<<(unsigned)grid, 32 * WARPS, smem, s>>>(tm0, tm1, P);
+  pgba::count_launch();
+  return (int)cudaGetLastError();
+}
+
+}  // namespace pcorr_tma
+
+using namespace pcorr_tma;
+
+extern "C" {
+
+int pcorr_tma_supported(int C, int P, int radius, int dtype) {
+  return (dtype == PCORR_F16 && P == 3 && radius == 3 && (C == 24 || C == 32)) ? 1 : 0;
+}
+
+int pcorr_tma_workspace_bytes(int nlev, int B, int64_t F, int C, int H0, int W0, int H1, int W1, size_t* bytes) {
+  if (!bytes) return PCORR_ERR_NULL;
+  if (nlev < 1 || nlev > 2 || B <= 0 || F <= 0 || C <= 0 || H0 <= 0 || W0 <= 0 || (nlev == 2 && (H1 <= 0 || W1 <= 0)))
+    return PCORR_ERR_SHAPE;
+  size_t n = align256((size_t)B * F * H0 * W0 * C * 2);
+  if (nlev == 2) n += align256((size_t)B * F * H1 * W1 * C * 2);
+  *bytes = n;
+  return PCORR_OK;
+}
+
+int pcorr_forward_tma(const void* fmap1, const void* fmap2_l0, const void* fmap2_l1, const float* coords,
+                      const int64_t* ii, const int64_t* jj, int nlev, int B, int64_t E, int64_t K, int64_t F, int C,
+                      int H0, int W0, int H1, int W1, int P, int radius, int dtype, void* out, void* workspace,
+                      size_t workspace_bytes, pcorr_stream_t stream) {
+  if (E == 0 || B == 0) return PCORR_OK;
+  if (!fmap1 || !fmap2_l0 || (nlev == 2 && !fmap2_l1) || !coords || !ii || !jj || !out || !workspace) return PCORR_ERR_NULL;
+  if (nlev < 1 || nlev > 2 || B < 0 || E < 0 || K <= 0 || F <= 0 || H0 <= 0 || W0 <= 0) return PCORR_ERR_SHAPE;
+  if (!pcorr_tma_supported(C, P, radius, dtype)) return PCORR_ERR_UNSUPPORTED;
+  if ((int64_t)B * F >= ((int64_t)1 << 31) || (int64_t)B * F > 65535 || ((uintptr_t)workspace & 255)) return PCORR_ERR_UNSUPPORTED;
+  size_t need = 0;
+  int rc = pcorr_tma_workspace_bytes(nlev, B, F, C, H0, W0, H1, W1, &need);
+  if (rc) return rc;
+  if (need > workspace_bytes) return PCORR_ERR_SHAPE;
+  cudaStream_t s = (cudaStream_t)stream;
+  __half* n0 = (__half*)workspace;
+  __half* n1 = (__half*)((char*)workspace + align256((size_t)B * F * H0 * W0 * C * 2));
+  {
+    const int HW = H0 * W0;
+    to_nhwc_kernel<<<dim3((unsigned)((HW + 255) / 256), (unsigned)(B * F), (unsigned)(C / 8)), 256, 0, s>>>(
+        (const __half*)fmap2_l0, n0, C, HW);
+    pgba::count_launch();
+  }
+  if (nlev == 2) {
+    const int HW = H1 * W1;
+    to_nhwc_kernel<<<dim3((unsigned)((HW + 255) / 256), (unsigned)(B * F), (unsigned)(C / 8)), 256, 0, s>>>(
+        (const __half*)fmap2_l1, n1, C, HW);
+    pgba::count_launch();
+  }
+  CUtensorMap tm0, tm1;
+  rc = make_map(&tm0, n0, C, W0, H0, (int64_t)B * F);
+  if (rc) return rc;
+  if (nlev == 2) rc = make_map(&tm1, n1, C, W1, H1, (int64_t)B * F);
+  else tm1 = tm0;
+  if (rc) return rc;
+  Params Pm{};
+  Pm.fmap1 = (const __half*)fmap1;
+  Pm.nhwc[0] = n0; Pm.nhwc[1] = n1;
+  Pm.H[0] = H0; Pm.W[0] = W0; Pm.H[1] = H1; Pm.W[1] = W1;
+  Pm.coords = coords; Pm.us = ii; Pm.vs = jj;
+  Pm.B = B; Pm.E = E; Pm.K = K; Pm.F = F;
+  Pm.out = (__half*)out;
+  if (C == 24) return nlev == 2 ? launch<24, 2>(tm0, tm1, Pm, s) : launch<24, 1>(tm0, tm1, Pm, s);
+  return nlev == 2 ? launch<32, 2>(tm0, tm1, Pm, s) : launch<32, 1>(tm0, tm1, Pm, s);
+}
+
+}  // extern "C"

@@ -49,6 +49,33 @@ def _tiled(fmap1, maps, coords, ii, jj, radius, out):
     return True
 
 
+def _tma(fmap1, maps, coords, ii, jj, radius, out):
+    """Default path of the production shape (fp16, C in {24, 32}, P = 3, R = 3): channel-last maps + TMA region tiles +
+    tensor cores (corr_tma.cu); returns False when the shape does not qualify.  PCORR_TMA=0 disables it (A/B runs)."""
+    if os.environ.get("PCORR_TMA", "1") == "0":
+        return False
+    L = native.lib()
+    B, E, _, P, _ = coords.shape
+    K, C = fmap1.shape[1], fmap1.shape[2]
+    F = maps[0].shape[1]
+    if fmap1.dtype not in _DT or not L.pcorr_tma_supported(C, P, int(radius), _DT[fmap1.dtype]) or E == 0:
+        return False
+    nlev = len(maps)
+    H0, W0 = maps[0].shape[3], maps[0].shape[4]
+    H1, W1 = (maps[1].shape[3], maps[1].shape[4]) if nlev == 2 else (0, 0)
+    nbytes = ctypes.c_size_t(0)
+    native.check(L.pcorr_tma_workspace_bytes(nlev, B, F, C, H0, W0, H1, W1, ctypes.byref(nbytes)),
+                 "pcorr_tma_workspace_bytes")
+    with torch.cuda.device(fmap1.device):
+        ws = native.workspace(nbytes.value, fmap1.device, pool="corr_tma")
+        rc = L.pcorr_forward_tma(fmap1.data_ptr(), maps[0].data_ptr(), maps[1].data_ptr() if nlev == 2 else None,
+                                 coords.data_ptr(), ii.data_ptr(), jj.data_ptr(), nlev, B, E, K, F, C, H0, W0, H1, W1,
+                                 P, int(radius), _DT[fmap1.dtype], out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                 native.stream_ptr(fmap1.device))
+    native.check(rc, "pcorr_forward_tma")
+    return True
+
+
 def forward(fmap1, fmap2, coords, ii, jj, radius):
     """cuda_corr.forward (correlation.cpp:28-35 -> corr_cuda_forward, correlation_kernel.cu:193-233).
     Returns [corr] with corr [B, E, 2R+1 (x-off), 2R+1 (y-off), P, P] in fmap1's dtype."""
@@ -63,7 +90,7 @@ def forward(fmap1, fmap2, coords, ii, jj, radius):
     F, H2, W2 = fmap2.shape[1], fmap2.shape[3], fmap2.shape[4]
     D = 2 * radius + 1
     out = torch.empty((B, E, D, D, P, P), dtype=fmap1.dtype, device=fmap1.device)
-    if _tiled(fmap1, [fmap2], coords, ii, jj, radius, out):
+    if _tiled(fmap1, [fmap2], coords, ii, jj, radius, out) or _tma(fmap1, [fmap2], coords, ii, jj, radius, out):
         return [out]
     with torch.cuda.device(fmap1.device):
         rc = native.lib().pcorr_forward(fmap1.data_ptr(), fmap2.data_ptr(), coords.data_ptr(), ii.data_ptr(),
@@ -85,7 +112,9 @@ def forward_pyramid2(fmap1, fmap2_l0, fmap2_l1, coords, ii, jj, radius):
     F = fmap2_l0.shape[1]
     D = 2 * radius + 1
     out = torch.empty((B, E, D, D, P, P, 2), dtype=fmap1.dtype, device=fmap1.device)
-    if fmap2_l1.dtype == fmap1.dtype == fmap2_l0.dtype and _tiled(fmap1, [fmap2_l0, fmap2_l1], coords, ii, jj, radius, out):
+    if fmap2_l1.dtype == fmap1.dtype == fmap2_l0.dtype and (
+            _tiled(fmap1, [fmap2_l0, fmap2_l1], coords, ii, jj, radius, out) or
+            _tma(fmap1, [fmap2_l0, fmap2_l1], coords, ii, jj, radius, out)):
         return out
     with torch.cuda.device(fmap1.device):
         rc = native.lib().pcorr_forward_pyramid2(fmap1.data_ptr(), fmap2_l0.data_ptr(), fmap2_l1.data_ptr(),

@@ -55,6 +55,21 @@ int pcorr_forward_tiled(const void* fmap1, const void* fmap2_l0, const void* fma
                         int H0, int W0, int H1, int W1, int P, int radius, int dtype, void* out, void* workspace,
                         size_t workspace_bytes, pcorr_stream_t stream);
 
+/* TMA + tensor-core lookup for the production shape (fp16 features, C in {24, 32}, P = 3, radius = 3) -- the default
+ * path of cuda_corr.forward for that shape.  The frame maps are first copied to a channel-last layout in the
+ * caller-owned, 256-byte aligned workspace (pcorr_tma_workspace_bytes()), then one warp per edge fetches its region
+ * of fmap2[jj] with one TMA tile load per pyramid level (out-of-map pixels are zero-filled by the hardware), contracts
+ * it with the patch features on the tensor cores (fp32 accumulate) and writes the blended, permuted result once.
+ * Same results layout as pcorr_forward (nlev = 1; fmap2_l1 may be NULL) / pcorr_forward_pyramid2 (nlev = 2).
+ * The host builds two CUtensorMap descriptors per call (no allocation, no synchronisation; graph-capturable). */
+int pcorr_tma_supported(int C, int P, int radius, int dtype);
+int pcorr_tma_workspace_bytes(int nlev, int B, int64_t F, int C, int H0, int W0, int H1, int W1,
+                              size_t* bytes /* host, out */);
+int pcorr_forward_tma(const void* fmap1, const void* fmap2_l0, const void* fmap2_l1, const float* coords,
+                      const int64_t* ii, const int64_t* jj, int nlev, int B, int64_t E, int64_t K, int64_t F, int C,
+                      int H0, int W0, int H1, int W1, int P, int radius, int dtype, void* out, void* workspace,
+                      size_t workspace_bytes, pcorr_stream_t stream);
+
 /* Gradient of pcorr_forward w.r.t. fmap1 and fmap2.  Replaces cuda_corr.backward == corr_cuda_backward()
  * (reference: correlation_kernel.cu:140-190, 236-286).  grad is the gradient of `out` in out's layout, f32;
  * fmap1_grad / fmap2_grad have the shapes and dtype of fmap1 / fmap2 and must be zero-filled by the caller. */

@@ -175,3 +175,75 @@ def test_corr_fp16_tiled_c2_shape_matches_staged_fp32(tiled):
     err = (got - ref).abs()
     assert bool((err <= 2.0 ** -11 * ref.abs() + 1e-4).all())
     assert ref.abs().max() > 0.1
+
+
+@pytest.mark.parametrize("C", [24, 32])
+def test_corr_fp16_tma_path(C, monkeypatch):
+    """fp16, C in {24, 32}, P = 3, R = 3 takes the TMA + tensor-core path (corr_tma.cu) by default: both levels, windows
+    across the map border, far outside the map, on exact integers, windows too far apart for one region (per-tap path);
+    the fused two-level call must equal the two single-level calls bit for bit, and the staged kernel (PCORR_TMA=0)
+    must agree to output rounding."""
+    p, gmap, pyr, coords = _setup(C, np.float16, seed=3, F=8, M=24, n_mem=8)
+    coords[0, 40:44] += 5000.0                       # far outside: all-zero windows
+    coords[0, 44:46, :, 0, 0] += 9.0                 # windows too far apart for one region: per-tap path
+    coords[0, 46, 0, 1, 1] = np.float32("nan")       # non-finite coordinate: that pixel's window is all zeros
+    dev = "cuda"
+    g = torch.as_tensor(gmap, device=dev)[None]
+    maps = [torch.as_tensor(x, device=dev)[None] for x in pyr]
+    ii = torch.as_tensor(p.kk, device=dev); jj = torch.as_tensor(p.jj, device=dev)
+    c = torch.as_tensor(coords, device=dev)
+    finite = np.isfinite(coords).all(axis=(2,))[0]                      # [E, 3, 3]
+    outs = []
+    for lvl, scale in ((0, 1.0), (1, 4.0)):
+        cl = (coords / np.float32(scale)).astype(np.float32)
+        got = altcorr.corr(g, maps[lvl], torch.as_tensor(cl, device=dev), ii, jj, 3)
+        want = corr_oracle.corr(gmap[None], pyr[lvl][None], np.nan_to_num(cl, nan=-1e7), p.kk, p.jj, 3)
+        assert got.dtype == torch.float16 and got.shape == (1, p.E, 7, 7, 3, 3)
+        gotn = got.float().cpu().numpy()
+        err = np.abs(gotn - want)
+        ok = np.broadcast_to(finite[None, :, None, None], err.shape)
+        assert (err[ok] <= 2.0 ** -11 * np.abs(want[ok]) + 1e-4).all()
+        assert np.abs(want).max() > 0.05
+        monkeypatch.setenv("PCORR_TMA", "0")
+        staged = altcorr.corr(g, maps[lvl], torch.as_tensor(cl, device=dev), ii, jj, 3)
+        monkeypatch.delenv("PCORR_TMA")
+        d = (got.float() - staged.float()).abs().cpu().numpy()
+        assert (d[ok] <= 2.0 ** -10 * np.abs(want[ok]) + 1e-4).all()
+        outs.append(got)
+    fused = altcorr.corr_pyramid2(g, maps, c, ii, jj, 3)
+    both = torch.stack(outs, -1).view(1, p.E, -1)
+    okf = torch.as_tensor(np.broadcast_to(finite[None, :, None, None, :, :, None], (1, p.E, 7, 7, 3, 3, 2)).reshape(1, p.E, -1).copy(), device=dev)
+    assert torch.equal(fused[okf], both[okf])
+
+
+def test_corr_fp16_tma_batch2():
+    """B = 2: per-batch maps and coordinates, shared edge lists (the reference's [B, ...] layout)."""
+    p, gmap, pyr, coords = _setup(24, np.float16, seed=4, F=6, M=16, n_mem=6)
+    rng = np.random.default_rng(11)
+    gm = np.stack([gmap, rng.permutation(gmap.reshape(-1)).reshape(gmap.shape)])
+    m0 = np.stack([pyr[0], pyr[0][::-1].copy()])
+    cc = np.concatenate([coords, coords + rng.uniform(-2, 2, coords.shape).astype(np.float32)], 0)
+    dev = "cuda"
+    got = altcorr.corr(torch.as_tensor(gm, device=dev), torch.as_tensor(m0, device=dev), torch.as_tensor(cc, device=dev),
+                       torch.as_tensor(p.kk, device=dev), torch.as_tensor(p.jj, device=dev), 3)
+    want = corr_oracle.corr(gm, m0, cc, p.kk, p.jj, 3)
+    err = np.abs(got.float().cpu().numpy() - want)
+    assert (err <= 2.0 ** -11 * np.abs(want) + 1e-4).all()
+
+
+def test_corr_fp16_tma_c2_shape_matches_staged_fp32():
+    """Production shape (c2 graph, 120x160 + 30x40 maps, C = 24): default (TMA) fp16 result vs the fp32 staged kernel run
+    on the same (fp16-representable) inputs: differences are output rounding only."""
+    p = synth.config_c2()
+    gmap, pyr = synth.make_fmaps(p, C=24, dtype=np.float16)
+    dev = "cuda"
+    d = to_dev(p)
+    from cdvslam_b200 import fastba
+    coords = fastba.reproject(d["poses"], d["patches"], d["intrinsics"], d["ii"], d["jj"], d["kk"])
+    g16 = torch.as_tensor(gmap, device=dev)[None]
+    m16 = [torch.as_tensor(x, device=dev)[None] for x in pyr]
+    got = altcorr.corr_pyramid2(g16, m16, coords, d["kk"], d["jj"], 3).float()
+    ref = altcorr.corr_pyramid2(g16.float(), [m.float() for m in m16], coords, d["kk"], d["jj"], 3)
+    err = (got - ref).abs()
+    assert bool((err <= 2.0 ** -11 * ref.abs() + 1e-4).all())
+    assert ref.abs().max() > 0.1

@@ -28,7 +28,6 @@ namespace pcorr_tma {
 
 constexpr int R = 3, D = 8, Do = 7, PP = 9;
 constexpr int RG = 12, RPX = RG * RG;       // region: 12 x 12 pixels
-constexpr int NOUT = (Do * Do * PP + 31) / 32;   // 14 outputs per lane
 constexpr int WARPS = 4;
 
 template <int C> struct __align__(128) WarpSmem {
@@ -96,21 +95,65 @@ __device__ __forceinline__ int safe_floor(float v) {     // far-out / non-finite
   return (f > -1e6f && f < 1e6f) ? (int)f : -1000000;
 }
 
-// [B*F, C, HW] -> [B*F, HW, C]; thread = (pixel, group of 8 channels): 8 coalesced 2-byte reads, one 16-byte store
-__global__ void __launch_bounds__(256) to_nhwc_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int C,
-                                                      int HW) {
+// [B*F, C, HW] -> [B*F, HW, C]; thread = pixel (all channels): C coalesced 2-byte reads, C/8 16-byte stores that are
+// contiguous across the warp (whole sectors are written at once)
+template <int C>
+__global__ void __launch_bounds__(256) to_nhwc_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int HW) {
   const int px = blockIdx.x * 256 + threadIdx.x;
   if (px >= HW) return;
   const int64_t bf = blockIdx.y;
-  const int c0 = blockIdx.z * 8;
-  const __half* s = src + (bf * C + c0) * (int64_t)HW + px;
-  unsigned short v[8];
+  const __half* s = src + bf * C * (int64_t)HW + px;
+  unsigned short v[C];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) v[k] = __half_as_ushort(__ldg(s + (int64_t)k * HW));
-  uint4 o;
-  o.x = v[0] | ((unsigned)v[1] << 16); o.y = v[2] | ((unsigned)v[3] << 16);
-  o.z = v[4] | ((unsigned)v[5] << 16); o.w = v[6] | ((unsigned)v[7] << 16);
-  *reinterpret_cast<uint4*>(dst + (bf * HW + px) * (int64_t)C + c0) = o;
+  for (int k = 0; k < C; ++k) v[k] = __half_as_ushort(__ldg(s + (int64_t)k * HW));
+  uint4* d = reinterpret_cast<uint4*>(dst + (bf * HW + px) * (int64_t)C);
+#pragma unroll
+  for (int q = 0; q < C / 8; ++q) {
+    uint4 o;
+    o.x = v[8 * q + 0] | ((unsigned)v[8 * q + 1] << 16); o.y = v[8 * q + 2] | ((unsigned)v[8 * q + 3] << 16);
+    o.z = v[8 * q + 4] | ((unsigned)v[8 * q + 5] << 16); o.w = v[8 * q + 6] | ((unsigned)v[8 * q + 7] << 16);
+    d[q] = o;
+  }
+}
+
+// Window selection + 4-tap bilinear blend + permute of one (edge, level) from its volume in shared memory
+// (correlation_kernel.cu:221-232).  Lane-task lt = yo * 9 + p (63 of them, two rounds of 32 lanes): the lane reads the
+// two volume rows yo, yo + 1 of patch pixel p (8 + 8 taps) and produces the 7 x-offsets; for a fixed xo the 63 results
+// are contiguous in the output (o = xo * 63 + lt).  RS: records per volume row, SLOT: floats per record.
+template <int RS, int SLOT, int NLEV>
+__device__ __forceinline__ void blend_store(const float* vol, const float4* wgt, const int* vbase, int lane, int lev,
+                                            __half* og, unsigned (&hold)[7]) {
+#pragma unroll
+  for (int rd = 0; rd < 2; ++rd) {
+    const int lt = lane + 32 * rd;
+    const bool on = lt < 63;
+    const int yo = lt / 9, p = lt - yo * 9;
+    float a[8], b[8];
+    float4 wg = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (on) {
+      wg = wgt[p];
+      const float* v = vol + vbase[p] + yo * (RS * SLOT);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { a[j] = v[j * SLOT]; b[j] = v[(RS + j) * SLOT]; }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { a[j] = 0.f; b[j] = 0.f; }
+    }
+#pragma unroll
+    for (int xo = 0; xo < 7; ++xo) {
+      const float r = wg.x * a[xo] + wg.y * a[xo + 1] + wg.z * b[xo] + wg.w * b[xo + 1];
+      const unsigned short h = __half_as_ushort(__float2half_rn(r));
+      const int t = rd * 7 + xo;
+      if (NLEV == 1) {
+        if (on) reinterpret_cast<unsigned short*>(og)[xo * 63 + lt] = h;
+      } else if (lev == 0) {
+        if (t & 1) hold[t >> 1] |= (unsigned)h << 16; else hold[t >> 1] = h;
+      } else if (on) {
+        const unsigned h0 = (t & 1) ? (hold[t >> 1] >> 16) : (hold[t >> 1] & 0xffffu);
+        reinterpret_cast<unsigned*>(og)[xo * 63 + lt] = h0 | ((unsigned)h << 16);
+      }
+    }
+  }
 }
 
 template <int C, int NLEV>
@@ -139,14 +182,6 @@ __global__ void __launch_bounds__(32 * WARPS) corr_tma_kernel(const __grid_const
   for (int x = lane; x < 7 * C / 2; x += 32) reinterpret_cast<unsigned*>(&S.a[PP * C])[x] = 0u;   // rows 9..15
   __syncwarp();
 
-  // output o = lane + 32 t -> (p, yo, xo), the same for every task: p | ((yo * RG + xo) * SLOT) << 4 | (yo*8+xo) << 20
-  int odec[NOUT];
-#pragma unroll
-  for (int t = 0; t < NOUT; ++t) {
-    const int o = lane + 32 * t;
-    const int p = o % 9, yo = (o / 9) % 7, xo = o / 63;
-    odec[t] = p | (((yo * RG + xo) * SLOT) << 4) | ((yo * 8 + xo) << 20);
-  }
   // ldmatrix lane offsets (bytes).  A operand = region records: matrices (rows 0-7 | 8-15) x (ch 0-7 | 8-15)
   const uint32_t a_off4 = (uint32_t)((((lane >> 3) & 1) * 8 + (lane & 7)) * (2 * C) + (lane >> 4) * 16);
   const uint32_t a_off2 = (uint32_t)((((lane >> 3) & 1) * 8 + (lane & 7)) * (2 * C) + K16 * 32);
@@ -159,40 +194,45 @@ __global__ void __launch_bounds__(32 * WARPS) corr_tma_kernel(const __grid_const
   const int64_t n_units = (total - u_first + ustride - 1) / ustride;
   const int64_t n_half = n_units * NLEV;
 
-  // ---- pipeline state
-  float ux = 0.f, uy = 0.f;          // lanes 0..8: level-0 coordinates of the unit of the NEXT half-task
-  int ujx = 0;                       // its target frame (b * F + jj)
-  int64_t uf1 = 0;                   // element offset of its patch-feature record in fmap1
+  // ---- pipeline state.  Raw per-unit values are loaded two units ahead and only used (arithmetic) one unit later, so
+  //      no global-load latency sits on the warp's in-order instruction stream.
+  struct Raw { float x, y; int jx, ix; };   // lanes 0..8: level-0 coordinates; all lanes: vs[m], us[m]
+  Raw ra{0.f, 0.f, 0, 0}, rb{0.f, 0.f, 0, 0};
+  int64_t ka = 0;                    // ordinal of the unit held by ra (unit = u_first + ka * ustride)
   uint4 apre[NAV];                   // prefetched patch features of the next unit
   bool fits_cur = false, fits_nxt = false;
+  int frame_cur = 0, frame_nxt = 0;  // b * F + jj of the current / next half-task
   uint32_t phase = 0;                // bit b: parity to wait for on buffer b
   unsigned bf0[K16 * 2 + K8], bf1[K16 * 2 + K8];    // B operand (patch features), n-tiles p 0-7 / 8-15
-  unsigned hold[NOUT / 2];           // level-0 results (packed halfs) until level 1 is done
+  unsigned hold[7];                  // level-0 results (packed halfs) until level 1 is done
 
-  auto load_unit_raw = [&](int64_t unit) {
+  auto load_raw = [&](Raw& r, int64_t k) {
+    const int64_t unit = u_first + k * ustride;
+    const int64_t m = (P.B == 1) ? unit : unit % P.E;
     const float* cg = P.coords + unit * (2 * PP);
-    if (lane < PP) { ux = __ldg(cg + lane); uy = __ldg(cg + PP + lane); }
-    const int64_t b = (P.B == 1) ? 0 : unit / P.E;
-    const int64_t m = unit - b * P.E;
-    ujx = (int)(b * P.F + __ldg(P.vs + m));
-    uf1 = (b * P.K + __ldg(P.us + m)) * (int64_t)(C * PP);
+    if (lane < PP) { r.x = __ldg(cg + lane); r.y = __ldg(cg + PP + lane); }
+    r.jx = (int)__ldg(P.vs + m);
+    r.ix = (int)__ldg(P.us + m);
   };
-  auto prefetch_a = [&]() {
-    const uint4* f1 = reinterpret_cast<const uint4*>(P.fmap1 + uf1);
+  auto prefetch_a = [&]() {          // patch features of the unit held by ra
+    const int64_t b = (P.B == 1) ? 0 : (u_first + ka * ustride) / P.E;
+    const uint4* f1 = reinterpret_cast<const uint4*>(P.fmap1 + (b * P.K + ra.ix) * (int64_t)(C * PP));
 #pragma unroll
     for (int k = 0; k < NAV; ++k)
       if (lane + 32 * k < NA4) apre[k] = __ldg(f1 + lane + 32 * k);
   };
-  // geometry of half-task (lev, buffer slot) from the raw coordinates; issues the region load
-  auto prepare = [&](int lev, int slot) -> bool {
-    const float x = (lev == 0) ? ux : ux * 0.25f;     // level 1: coords / 4 in fp32 (slam.py:322)
-    const float y = (lev == 0) ? uy : uy * 0.25f;
+  // geometry of the half-task (lev, buffer slot) of the unit held by ra; issues the region load
+  auto prepare = [&](int lev, int slot, int& frame) -> bool {
+    const float x = (lev == 0) ? ra.x : ra.x * 0.25f;     // level 1: coords / 4 in fp32 (slam.py:322)
+    const float y = (lev == 0) ? ra.y : ra.y * 0.25f;
     const int fxp = safe_floor(x), fyp = safe_floor(y);
     const int xmin = __reduce_min_sync(0xffffffffu, lane < PP ? fxp : 0x7fffffff);
     const int xmax = __reduce_max_sync(0xffffffffu, lane < PP ? fxp : -0x7fffffff);
     const int ymin = __reduce_min_sync(0xffffffffu, lane < PP ? fyp : 0x7fffffff);
     const int ymax = __reduce_max_sync(0xffffffffu, lane < PP ? fyp : -0x7fffffff);
     const bool fits = (xmax - xmin + D <= RG) && (ymax - ymin + D <= RG);
+    const int b = (P.B == 1) ? 0 : (int)((u_first + ka * ustride) / P.E);
+    frame = b * (int)P.F + ra.jx;
     if (lane < PP) {
       const float dx = x - floorf(x), dy = y - floorf(y);
       S.wgt[slot][lane] = make_float4((1.f - dx) * (1.f - dy), dx * (1.f - dy), (1.f - dx) * dy, dx * dy);
@@ -205,15 +245,23 @@ __global__ void __launch_bounds__(32 * WARPS) corr_tma_kernel(const __grid_const
       const int x0 = min(max(xmin - R, -RG), W), y0 = min(max(ymin - R, -RG), H);
       fence_proxy_async();                    // generic-proxy accesses of this buffer precede the async-proxy write
       mbar_expect_tx(bar0 + 8 * slot, TX_BYTES);
-      tma_load_region(reg0 + slot * TX_BYTES, lev == 0 ? &tm0 : &tm1, bar0 + 8 * slot, x0, y0, ujx);
+      tma_load_region(reg0 + slot * TX_BYTES, lev == 0 ? &tm0 : &tm1, bar0 + 8 * slot, x0, y0, frame);
     }
     return fits;
   };
+  // after the last level of ra's unit has been prepared: ra <- rb, start loading the unit after that
+  auto advance = [&]() {
+    ra = rb;
+    ++ka;
+    if (ka + 1 < n_units) load_raw(rb, ka + 1);
+  };
 
   // ---- prologue: half-task 0
-  load_unit_raw(u_first);
+  load_raw(ra, 0);
+  if (n_units > 1) load_raw(rb, 1);
   prefetch_a();
-  fits_cur = prepare(0, 0);
+  fits_cur = prepare(0, 0, frame_cur);
+  if (NLEV == 1) advance();
 
   for (int64_t s = 0; s < n_half; ++s) {
     const int lev = (NLEV == 1) ? 0 : (int)(s & 1);
@@ -221,11 +269,9 @@ __global__ void __launch_bounds__(32 * WARPS) corr_tma_kernel(const __grid_const
     const int64_t unit = u_first + (s / NLEV) * ustride;
     const bool have_next = s + 1 < n_half;
     const int lev_n = (NLEV == 1) ? 0 : (int)((s + 1) & 1);
-    const int64_t unit_n = u_first + ((s + 1) / NLEV) * ustride;
-    const int cur_jx = ujx;                              // frame of the current half-task (slow path)
 
-    // ---- (1) raw loads of the next half-task's unit (latency hidden behind the contraction)
-    if (lev == 0) {                                      // new unit: its patch features to shared memory, B fragments
+    // ---- (0) new unit: its patch features to shared memory, B fragments
+    if (lev == 0) {
 #pragma unroll
       for (int k = 0; k < NAV; ++k) {
         const int i4 = lane + 32 * k;
@@ -253,18 +299,25 @@ __global__ void __launch_bounds__(32 * WARPS) corr_tma_kernel(const __grid_const
         ldsm_x2(bf0[2 * K16], bf1[2 * K16], sa + off);
       }
     }
-    if (have_next && lev_n == 0) load_unit_raw(unit_n);
+
+    // ---- (1) geometry + region load of the next half-task (its buffer was released by the previous epilogue), patch
+    //      features of the next unit, raw values of the unit after it
+    if (have_next) {
+      fits_nxt = prepare(lev_n, slot ^ 1, frame_nxt);
+      if (lev_n == 0) prefetch_a();
+      if (lev_n == NLEV - 1) advance();
+    }
 
     // ---- (2) contraction of the current half-task, volume written in place
     float* vol = reinterpret_cast<float*>(&S.reg[slot][0]);
     if (fits_cur) {
       mbar_wait(bar0 + 8 * slot, (phase >> slot) & 1u);
       phase ^= 1u << slot;
-      const uint32_t rb = reg0 + slot * TX_BYTES;
+      const uint32_t rb_ = reg0 + slot * TX_BYTES;
 #pragma unroll
       for (int mt = 0; mt < RPX / 16; ++mt) {
         float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
-        const uint32_t tb = rb + mt * 16 * (2 * C);
+        const uint32_t tb = rb_ + mt * 16 * (2 * C);
 #pragma unroll
         for (int ks = 0; ks < K16; ++ks) {
           unsigned a0, a1, a2, a3;
@@ -287,7 +340,7 @@ __global__ void __launch_bounds__(32 * WARPS) corr_tma_kernel(const __grid_const
     } else {
       // per-tap path (windows too far apart for one region): vol[(io * 8 + jo)][p]
       const int H = lev == 0 ? P.H[0] : P.H[1], W = lev == 0 ? P.W[0] : P.W[1];
-      const __half* f2 = (lev == 0 ? P.nhwc[0] : P.nhwc[1]) + (int64_t)cur_jx * H * W * C;
+      const __half* f2 = (lev == 0 ? P.nhwc[0] : P.nhwc[1]) + (int64_t)frame_cur * H * W * C;
       const float* cg = P.coords + unit * (2 * PP);
       for (int o = lane; o < PP * D * D; o += 32) {
         const int p = o / (D * D), pos = o - p * (D * D);
@@ -304,42 +357,15 @@ __global__ void __launch_bounds__(32 * WARPS) corr_tma_kernel(const __grid_const
     }
     __syncwarp();
 
-    // ---- (3) geometry + region load of the next half-task (its buffer was released by the previous epilogue)
-    if (have_next) {
-      fits_nxt = prepare(lev_n, slot ^ 1);
-      if (lev_n == 0) prefetch_a();
-    }
-
-    // ---- (4) window selection + bilinear blend + permute: out[xo][yo][p] (correlation_kernel.cu:221-232)
+    // ---- (3) window selection + bilinear blend + permute: out[xo][yo][p]
     {
-      const int rs = fits_cur ? RG * SLOT : D * SLOT;          // float stride of one volume row
       __half* og = P.out + unit * (int64_t)(Do * Do * PP) * NLEV;
-#pragma unroll
-      for (int t = 0; t < NOUT; ++t) {
-        const int o = lane + 32 * t;
-        float r = 0.f;
-        if (o < Do * Do * PP) {
-          const int p = odec[t] & 15;
-          const float4 wg = S.wgt[slot][p];
-          const int off = fits_cur ? ((odec[t] >> 4) & 0xffff) : ((odec[t] >> 20) * SLOT);
-          const float* v = vol + S.vbase[slot][p] + off;
-          r = wg.x * v[0] + wg.y * v[SLOT] + wg.z * v[rs] + wg.w * v[rs + SLOT];
-        }
-        if (NLEV == 1) {
-          if (o < Do * Do * PP) og[o] = __float2half_rn(r);
-        } else {
-          const unsigned short h = __half_as_ushort(__float2half_rn(r));
-          if (lev == 0) {
-            if (t & 1) hold[t >> 1] |= (unsigned)h << 16; else hold[t >> 1] = h;
-          } else if (o < Do * Do * PP) {
-            const unsigned h0 = (t & 1) ? (hold[t >> 1] >> 16) : (hold[t >> 1] & 0xffffu);
-            reinterpret_cast<unsigned*>(og)[o] = h0 | ((unsigned)h << 16);
-          }
-        }
-      }
+      if (fits_cur) blend_store<RG, SLOT, NLEV>(vol, S.wgt[slot], S.vbase[slot], lane, lev, og, hold);
+      else blend_store<D, SLOT, NLEV>(vol, S.wgt[slot], S.vbase[slot], lane, lev, og, hold);
     }
     __syncwarp();
     fits_cur = fits_nxt;
+    frame_cur = frame_nxt;
   }
 }
 
@@ -395,6 +421,12 @@ static int launch(const CUtensorMap& tm0, const CUtensorMap& tm1, const Params& 
   return (int)cudaGetLastError();
 }
 
+static void transpose_maps(int C, const __half* src, __half* dst, int HW, int frames, cudaStream_t s) {
+  const dim3 grid((unsigned)((HW + 255) / 256), (unsigned)frames);
+  if (C == 24) to_nhwc_kernel<24><<<grid, 256, 0, s>>>(src, dst, HW);
+  else to_nhwc_kernel<32><<<grid, 256, 0, s>>>(src, dst, HW);
+}
+
 }  // namespace pcorr_tma
 
 using namespace pcorr_tma;
@@ -433,14 +465,12 @@ int pcorr_forward_tma(const void* fmap1, const void* fmap2_l0, const void* fmap2
   __half* n1 = (__half*)((char*)workspace + align256((size_t)B * F * H0 * W0 * C * 2));
   {
     const int HW = H0 * W0;
-    to_nhwc_kernel<<<dim3((unsigned)((HW + 255) / 256), (unsigned)(B * F), (unsigned)(C / 8)), 256, 0, s>>>(
-        (const __half*)fmap2_l0, n0, C, HW);
+    transpose_maps(C, (const __half*)fmap2_l0, n0, HW, B * (int)F, s);
     pgba::count_launch();
   }
   if (nlev == 2) {
     const int HW = H1 * W1;
-    to_nhwc_kernel<<<dim3((unsigned)((HW + 255) / 256), (unsigned)(B * F), (unsigned)(C / 8)), 256, 0, s>>>(
-        (const __half*)fmap2_l1, n1, C, HW);
+    transpose_maps(C, (const __half*)fmap2_l1, n1, HW, B * (int)F, s);
     pgba::count_launch();
   }
   CUtensorMap tm0, tm1;

@@ -7,7 +7,7 @@
 //   to_nhwc_kernel     fmap2 [B*F, C, H, W] -> [B*F, H, W, C]: every map pixel becomes one contiguous 2C-byte record,
 //                      so the (<= 12 x 12)-pixel region that contains the nine 8x8 windows of an edge is a dense box.
 //   corr_tma_kernel    one WARP per edge (both pyramid levels), persistent CTAs.  Per (edge, level): the region box is
-//                      fetched by ONE TMA tile load (cp.async.bulk.tensor.4d, out-of-map pixels zero-filled by the
+//                      fetched by ONE TMA tile load (cp.async.bulk.tensor.3d, out-of-map pixels zero-filled by the
 //                      hardware, completion on a per-warp mbarrier), issued one half-task ahead.  The contraction
 //                      D[region pixel, patch pixel] = sum_c region[px][c] * patch[p][c] runs on the tensor cores
 //                      (mma.sync m16n8k16 / m16n8k8, fp16 in, fp32 accumulate; operands by ldmatrix).  Each 16-pixel
@@ -35,6 +35,7 @@ template <int C> struct __align__(128) WarpSmem {
   __half a[16 * C];                    // patch features [p][c] (rows 9..15 stay zero)
   float4 wgt[2][12];                   // bilinear weights of pixel p: (1-dx)(1-dy), dx(1-dy), (1-dx)dy, dx dy
   int vbase[2][12];                    // float offset of pixel p's window origin inside the volume (+ p)
+  __half stage[7 * 136];               // blended results of the unit, [xo][yo * 9 + p][level] with padded rows
   unsigned long long bar[2];
 };
 
@@ -65,10 +66,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// box [C, RG, RG, 1] at (0, x, y, frame) of the 4-D map [C, W, H, B*F]; elements outside the map arrive as zeros
-__device__ __forceinline__ void tma_load_region(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int x, int y, int f) {
-  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-               ::"r"(dst), "l"((uint64_t)tm), "r"(bar), "r"(0), "r"(x), "r"(y), "r"(f) : "memory");
+// box [RG * C / 2, RG, 1] at (xw, y, frame) of the 3-D map [W * C / 2 (32-bit words), H, B*F]: the x and channel axes
+// are merged so that one region row is ONE contiguous 24C-byte chunk (a [C, W, H, F] box would be fetched as 144 chunks of
+// 2C bytes and is bound by the TMA unit's chunk rate).  Words outside the map arrive as zeros; pixel borders are word
+// borders, so this is exactly "taps outside the map contribute 0".
+__device__ __forceinline__ void tma_load_region(uint32_t dst, uint64_t tm, uint32_t bar, int xw, int y, int f) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(dst), "l"(tm), "r"(bar), "r"(xw), "r"(y), "r"(f) : "memory");
 }
 
 __device__ __forceinline__ void ldsm_x4(unsigned& r0, unsigned& r1, unsigned& r2, unsigned& r3, uint32_t addr) {
@@ -80,12 +84,12 @@ __device__ __forceinline__ void ldsm_x2(unsigned& r0, unsigned& r1, uint32_t add
 }
 __device__ __forceinline__ void mma_k16(float d[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0,
                                         unsigned b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ void mma_k8(float d[4], unsigned a0, unsigned a1, unsigned b0) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a0), "r"(a1), "r"(b0));
 }
@@ -116,41 +120,34 @@ __global__ void __launch_bounds__(256) to_nhwc_kernel(const __half* __restrict__
   }
 }
 
-// Window selection + 4-tap bilinear blend + permute of one (edge, level) from its volume in shared memory
-// (correlation_kernel.cu:221-232).  Lane-task lt = yo * 9 + p (63 of them, two rounds of 32 lanes): the lane reads the
-// two volume rows yo, yo + 1 of patch pixel p (8 + 8 taps) and produces the 7 x-offsets; for a fixed xo the 63 results
-// are contiguous in the output (o = xo * 63 + lt).  RS: records per volume row, SLOT: floats per record.
-template <int RS, int SLOT, int NLEV>
-__device__ __forceinline__ void blend_store(const float* vol, const float4* wgt, const int* vbase, int lane, int lev,
-                                            __half* og, unsigned (&hold)[7]) {
+// Window selection + 4-tap bilinear blend of one (edge, level) from its volume in shared memory
+// (correlation_kernel.cu:221-230).  Lane = (p & 3, x tap j): for a group of four patch pixels the lane reads the taps
+// (iy, j) and (iy, j + 1) of all 8 window rows -- record addresses are 12 X + 16 Y + p (mod 32 banks), so the 4 x 8
+// lanes of one load always hit 32 different banks whatever the per-pixel window origins are -- and produces the outputs
+// (xo = j, yo = 0..6).  Results go to a small staging buffer [xo][yo * 9 + p][level] (row stride chosen so that these
+// stores are conflict-free as well) from which the unit's output is written with fully coalesced stores.
+// RS: records per volume row, SLOT: floats per record, SROW: halfs per staging row.
+template <int RS, int SLOT, int NLEV, int SROW>
+__device__ __forceinline__ void blend_stage(const float* vol, const float4* wgt, const int* vbase, int lane, int lev,
+                                            __half* stage) {
+  const int p_lo = lane & 3, j = lane >> 2;
+  const int j1 = min(j + 1, 7);
 #pragma unroll
-  for (int rd = 0; rd < 2; ++rd) {
-    const int lt = lane + 32 * rd;
-    const bool on = lt < 63;
-    const int yo = lt / 9, p = lt - yo * 9;
-    float a[8], b[8];
-    float4 wg = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (on) {
-      wg = wgt[p];
-      const float* v = vol + vbase[p] + yo * (RS * SLOT);
+  for (int pg = 0; pg < 3; ++pg) {
+    const int p = 4 * pg + p_lo;
+    if (p < PP) {
+      const float4 wg = wgt[p];
+      const float* v = vol + vbase[p];
+      float t0[8], t1[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { a[j] = v[j * SLOT]; b[j] = v[(RS + j) * SLOT]; }
-    } else {
+      for (int iy = 0; iy < 8; ++iy) { t0[iy] = v[(iy * RS + j) * SLOT]; t1[iy] = v[(iy * RS + j1) * SLOT]; }
+      if (j < 7) {
+        __half* st = stage + j * SROW + p * NLEV + lev;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { a[j] = 0.f; b[j] = 0.f; }
-    }
-#pragma unroll
-    for (int xo = 0; xo < 7; ++xo) {
-      const float r = wg.x * a[xo] + wg.y * a[xo + 1] + wg.z * b[xo] + wg.w * b[xo + 1];
-      const unsigned short h = __half_as_ushort(__float2half_rn(r));
-      const int t = rd * 7 + xo;
-      if (NLEV == 1) {
-        if (on) reinterpret_cast<unsigned short*>(og)[xo * 63 + lt] = h;
-      } else if (lev == 0) {
-        if (t & 1) hold[t >> 1] |= (unsigned)h << 16; else hold[t >> 1] = h;
-      } else if (on) {
-        const unsigned h0 = (t & 1) ? (hold[t >> 1] >> 16) : (hold[t >> 1] & 0xffffu);
-        reinterpret_cast<unsigned*>(og)[xo * 63 + lt] = h0 | ((unsigned)h << 16);
+        for (int yo = 0; yo < 7; ++yo) {
+          const float r = wg.x * t0[yo] + wg.y * t1[yo] + wg.z * t0[yo + 1] + wg.w * t1[yo + 1];
+          st[yo * 9 * NLEV] = __float2half_rn(r);
+        }
       }
     }
   }
@@ -183,9 +180,14 @@ __global__ void __launch_bounds__(32 * WARPS) corr_tma_kernel(const __grid_const
   __syncwarp();
 
   // ldmatrix lane offsets (bytes).  A operand = region records: matrices (rows 0-7 | 8-15) x (ch 0-7 | 8-15)
-  const uint32_t a_off4 = (uint32_t)((((lane >> 3) & 1) * 8 + (lane & 7)) * (2 * C) + (lane >> 4) * 16);
-  const uint32_t a_off2 = (uint32_t)((((lane >> 3) & 1) * 8 + (lane & 7)) * (2 * C) + K16 * 32);
+  // Row r of an 8-row fragment block is region record perm(r) = 0,2,4,6,1,3,5,7 of the block: with 12-float records
+  // the D stores of lanes g = 0..3 (and 4..7) then fall into disjoint banks.
+  const int rperm = (((lane & 7) & 3) << 1) | ((lane & 7) >> 2);
+  const uint32_t a_off4 = (uint32_t)((((lane >> 3) & 1) * 8 + rperm) * (2 * C) + (lane >> 4) * 16);
+  const uint32_t a_off2 = (uint32_t)((((lane >> 3) & 1) * 8 + rperm) * (2 * C) + K16 * 32);
   const int g = lane >> 2, tq = lane & 3;
+  const int gperm = ((g & 3) << 1) | (g >> 2);
+  const uint64_t tma0 = (uint64_t)&tm0, tma1 = (uint64_t)&tm1;
 
   const int64_t total = (int64_t)P.B * P.E;
   const int64_t ustride = (int64_t)gridDim.x * WARPS;
@@ -204,7 +206,6 @@ __global__ void __launch_bounds__(32 * WARPS) corr_tma_kernel(const __grid_const
   int frame_cur = 0, frame_nxt = 0;  // b * F + jj of the current / next half-task
   uint32_t phase = 0;                // bit b: parity to wait for on buffer b
   unsigned bf0[K16 * 2 + K8], bf1[K16 * 2 + K8];    // B operand (patch features), n-tiles p 0-7 / 8-15
-  unsigned hold[7];                  // level-0 results (packed halfs) until level 1 is done
 
   auto load_raw = [&](Raw& r, int64_t k) {
     const int64_t unit = u_first + k * ustride;
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(32 * WARPS) corr_tma_kernel(const __grid_const
       const int x0 = min(max(xmin - R, -RG), W), y0 = min(max(ymin - R, -RG), H);
       fence_proxy_async();                    // generic-proxy accesses of this buffer precede the async-proxy write
       mbar_expect_tx(bar0 + 8 * slot, TX_BYTES);
-      tma_load_region(reg0 + slot * TX_BYTES, lev == 0 ? &tm0 : &tm1, bar0 + 8 * slot, x0, y0, frame);
+      tma_load_region(reg0 + slot * TX_BYTES, lev == 0 ? tma0 : tma1, bar0 + 8 * slot, x0 * (C / 2), y0, frame);
     }
     return fits;
   };
@@ -314,28 +315,43 @@ __global__ void __launch_bounds__(32 * WARPS) corr_tma_kernel(const __grid_const
       mbar_wait(bar0 + 8 * slot, (phase >> slot) & 1u);
       phase ^= 1u << slot;
       const uint32_t rb_ = reg0 + slot * TX_BYTES;
+      // three 16-pixel tiles at a time: their fragment loads, MMAs and in-place stores form independent chains
 #pragma unroll
-      for (int mt = 0; mt < RPX / 16; ++mt) {
-        float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
-        const uint32_t tb = rb_ + mt * 16 * (2 * C);
+      for (int mg = 0; mg < RPX / 48; ++mg) {
+        unsigned af[3][K16 * 4 + K8 * 2];
+        float d0[3][4], d1[3][4];
 #pragma unroll
-        for (int ks = 0; ks < K16; ++ks) {
-          unsigned a0, a1, a2, a3;
-          ldsm_x4(a0, a1, a2, a3, tb + a_off4 + ks * 32);
-          mma_k16(d0, a0, a1, a2, a3, bf0[2 * ks], bf0[2 * ks + 1]);
-          mma_k16(d1, a0, a1, a2, a3, bf1[2 * ks], bf1[2 * ks + 1]);
+        for (int q = 0; q < 3; ++q) {
+          const uint32_t tb = rb_ + (mg * 3 + q) * 16 * (2 * C);
+#pragma unroll
+          for (int ks = 0; ks < K16; ++ks)
+            ldsm_x4(af[q][4 * ks], af[q][4 * ks + 1], af[q][4 * ks + 2], af[q][4 * ks + 3], tb + a_off4 + ks * 32);
+          if (K8) ldsm_x2(af[q][4 * K16], af[q][4 * K16 + 1], tb + a_off2);
+#pragma unroll
+          for (int x = 0; x < 4; ++x) { d0[q][x] = 0.f; d1[q][x] = 0.f; }
         }
+#pragma unroll
+        for (int ks = 0; ks < K16; ++ks)
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            mma_k16(d0[q], af[q][4 * ks], af[q][4 * ks + 1], af[q][4 * ks + 2], af[q][4 * ks + 3], bf0[2 * ks], bf0[2 * ks + 1]);
+            mma_k16(d1[q], af[q][4 * ks], af[q][4 * ks + 1], af[q][4 * ks + 2], af[q][4 * ks + 3], bf1[2 * ks], bf1[2 * ks + 1]);
+          }
         if (K8) {
-          unsigned a0, a1;
-          ldsm_x2(a0, a1, tb + a_off2);
-          mma_k8(d0, a0, a1, bf0[2 * K16]);
-          mma_k8(d1, a0, a1, bf1[2 * K16]);
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            mma_k8(d0[q], af[q][4 * K16], af[q][4 * K16 + 1], bf0[2 * K16]);
+            mma_k8(d1[q], af[q][4 * K16], af[q][4 * K16 + 1], bf1[2 * K16]);
+          }
         }
-        // D[px = 16 mt + g (+8)][p = 2 tq, 2 tq + 1] and p = 8 from the second n-tile (tq == 0)
-        float* v0 = vol + (mt * 16 + g) * SLOT;
-        *reinterpret_cast<float2*>(v0 + 2 * tq) = make_float2(d0[0], d0[1]);
-        *reinterpret_cast<float2*>(v0 + 8 * SLOT + 2 * tq) = make_float2(d0[2], d0[3]);
-        if (tq == 0) { v0[8] = d1[0]; v0[8 * SLOT + 8] = d1[2]; }
+        // D[px = 16 mt + perm(g) (+8)][p = 2 tq, 2 tq + 1] and p = 8 from the second n-tile (tq == 0)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          float* v0 = vol + ((mg * 3 + q) * 16 + gperm) * SLOT;
+          *reinterpret_cast<float2*>(v0 + 2 * tq) = make_float2(d0[q][0], d0[q][1]);
+          *reinterpret_cast<float2*>(v0 + 8 * SLOT + 2 * tq) = make_float2(d0[q][2], d0[q][3]);
+          if (tq == 0) { v0[8] = d1[q][0]; v0[8 * SLOT + 8] = d1[q][2]; }
+        }
       }
     } else {
       // per-tap path (windows too far apart for one region): vol[(io * 8 + jo)][p]
@@ -357,13 +373,28 @@ __global__ void __launch_bounds__(32 * WARPS) corr_tma_kernel(const __grid_const
     }
     __syncwarp();
 
-    // ---- (3) window selection + bilinear blend + permute: out[xo][yo][p]
+    // ---- (3) window selection + bilinear blend into the staging buffer; after the unit's last level: permuted,
+    //      level-interleaved output out[xo][yo][p][lev] (correlation_kernel.cu:232, slam.py:323), coalesced
     {
-      __half* og = P.out + unit * (int64_t)(Do * Do * PP) * NLEV;
-      if (fits_cur) blend_store<RG, SLOT, NLEV>(vol, S.wgt[slot], S.vbase[slot], lane, lev, og, hold);
-      else blend_store<D, SLOT, NLEV>(vol, S.wgt[slot], S.vbase[slot], lane, lev, og, hold);
+      constexpr int SROW = (NLEV == 2) ? 136 : 72;          // halfs per staging row: 68 words (2 levels) / 36 words
+      if (fits_cur) blend_stage<RG, SLOT, NLEV, SROW>(vol, S.wgt[slot], S.vbase[slot], lane, lev, S.stage);
+      else blend_stage<D, SLOT, NLEV, SROW>(vol, S.wgt[slot], S.vbase[slot], lane, lev, S.stage);
+      __syncwarp();
+      if (lev == NLEV - 1) {
+        __half* og = P.out + unit * (int64_t)(Do * Do * PP) * NLEV;
+#pragma unroll
+        for (int t = 0; t < (Do * Do * PP + 31) / 32; ++t) {
+          const int o = lane + 32 * t;
+          if (o < Do * Do * PP) {
+            const int xo = (o * 1041) >> 16;                // o / 63 for o < 441
+            const int r = o - xo * 63;
+            if (NLEV == 2) reinterpret_cast<unsigned*>(og)[o] = reinterpret_cast<const unsigned*>(S.stage)[xo * (SROW / 2) + r];
+            else og[o] = S.stage[xo * SROW + r];
+          }
+        }
+        __syncwarp();
+      }
     }
-    __syncwarp();
     fits_cur = fits_nxt;
     frame_cur = frame_nxt;
   }
@@ -393,12 +424,12 @@ static EncodeTiledFn encode_fn() {
 static int make_map(CUtensorMap* tm, const void* base, int C, int W, int H, int64_t frames) {
   EncodeTiledFn enc = encode_fn();
   if (!enc) return PCORR_ERR_UNSUPPORTED;
-  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)frames};
-  const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  const cuuint32_t box[4] = {(cuuint32_t)C, RG, RG, 1};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
-  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+  const cuuint64_t dims[3] = {(cuuint64_t)W * C / 2, (cuuint64_t)H, (cuuint64_t)frames};
+  const cuuint64_t strides[2] = {(cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  const cuuint32_t box[3] = {(cuuint32_t)(RG * C / 2), RG, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? PCORR_OK : PCORR_ERR_UNSUPPORTED;
 }

@@ -30,7 +30,11 @@ def main():
             fn = lambda: altcorr.corr_pyramid2(g, [f0, f1], coords, d["kk"], d["jj"], 3)
             for _ in range(3):
                 fn()
-            res["C%d_tma%s_ms" % (C, mode)] = bench.timed_events(fn, 20, before=flush.zero_)
+            res["C%d_tma%s_eager_ms" % (C, mode)] = bench.timed_events(fn, 20, before=flush.zero_)
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                fn()
+            res["C%d_tma%s_graph_ms" % (C, mode)] = bench.timed_events(gr.replay, 20, before=flush.zero_)
     print(json.dumps(res))
 
 

@@ -32,7 +32,7 @@ constexpr int WARPS = 4;
 
 template <int C> struct __align__(128) WarpSmem {
   unsigned char reg[2][RPX * C * 2];   // TMA destinations; the region volume overwrites the records in place
-  __half a[16 * C];                    // patch features [p][c] (rows 9..15 stay zero)
+  __half a[16 * C];                    // patch-feature record of the unit, [c][p] as in fmap1 (9C halfs used)
   float4 wgt[2][12];                   // bilinear weights of pixel p: (1-dx)(1-dy), dx(1-dy), (1-dx)dy, dx dy
   int vbase[2][12];                    // float offset of pixel p's window origin inside the volume (+ p)
   __half stage[7 * 136];               // blended results of the unit, [xo][yo * 9 + p][level] with padded rows
@@ -99,30 +99,46 @@ __device__ __forceinline__ int safe_floor(float v) {     // far-out / non-finite
   return (f > -1e6f && f < 1e6f) ? (int)f : -1000000;
 }
 
-// [B*F, C, HW] -> [B*F, HW, C]; thread = pixel (all channels): C coalesced 2-byte reads, C/8 16-byte stores that are
-// contiguous across the warp (whole sectors are written at once)
-template <int C>
-__global__ void __launch_bounds__(256) to_nhwc_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int HW) {
-  const int px = blockIdx.x * 256 + threadIdx.x;
-  if (px >= HW) return;
-  const int64_t bf = blockIdx.y;
-  const __half* s = src + bf * C * (int64_t)HW + px;
-  unsigned short v[C];
+// Channel-last copy of the frame maps of up to two pyramid levels in ONE launch: [B*F, C, HW] -> [B*F, HW, C].
+// A block handles 512 consecutive pixels of one frame: every thread reads two adjacent pixels of each channel (4-byte
+// loads, coalesced), the [512][C] tile is transposed through shared memory and written with contiguous 16-byte stores.
+// blockIdx.x enumerates (level, frame, pixel block).  HW must be even (the host falls back to scalar loads otherwise).
+struct NhwcJob { const __half* src; __half* dst; int HW; int blocks_per_frame; int first_block; };
+
+template <int C, bool PAIR>
+__global__ void __launch_bounds__(256) to_nhwc_kernel(NhwcJob j0, NhwcJob j1) {
+  __shared__ __align__(16) __half tile[512 * C];
+  const bool second = (int)blockIdx.x >= j1.first_block;
+  const NhwcJob J = second ? j1 : j0;
+  const int blk = (int)blockIdx.x - J.first_block;
+  const int frame = blk / J.blocks_per_frame;
+  const int px0 = (blk - frame * J.blocks_per_frame) * 512;
+  const int npx = min(512, J.HW - px0);
+  const __half* s = J.src + (int64_t)frame * C * J.HW + px0;
+  const int t = threadIdx.x;
+  if (PAIR) {
+    if (2 * t < npx) {
 #pragma unroll
-  for (int k = 0; k < C; ++k) v[k] = __half_as_ushort(__ldg(s + (int64_t)k * HW));
-  uint4* d = reinterpret_cast<uint4*>(dst + (bf * HW + px) * (int64_t)C);
+      for (int c = 0; c < C; ++c) {
+        const __half2 v = *reinterpret_cast<const __half2*>(s + (int64_t)c * J.HW + 2 * t);
+        tile[(2 * t) * C + c] = __low2half(v);
+        tile[(2 * t + 1) * C + c] = __high2half(v);
+      }
+    }
+  } else {
+    for (int px = t; px < npx; px += 256)
 #pragma unroll
-  for (int q = 0; q < C / 8; ++q) {
-    uint4 o;
-    o.x = v[8 * q + 0] | ((unsigned)v[8 * q + 1] << 16); o.y = v[8 * q + 2] | ((unsigned)v[8 * q + 3] << 16);
-    o.z = v[8 * q + 4] | ((unsigned)v[8 * q + 5] << 16); o.w = v[8 * q + 6] | ((unsigned)v[8 * q + 7] << 16);
-    d[q] = o;
+      for (int c = 0; c < C; ++c) tile[px * C + c] = s[(int64_t)c * J.HW + px];
   }
+  __syncthreads();
+  uint4* d = reinterpret_cast<uint4*>(J.dst + ((int64_t)frame * J.HW + px0) * C);
+  const uint4* t4 = reinterpret_cast<const uint4*>(tile);
+  for (int x = t; x < npx * C / 8; x += 256) d[x] = t4[x];
 }
 
 // Window selection + 4-tap bilinear blend of one (edge, level) from its volume in shared memory
 // (correlation_kernel.cu:221-230).  Lane = (p & 3, x tap j): for a group of four patch pixels the lane reads the taps
-// (iy, j) and (iy, j + 1) of all 8 window rows -- record addresses are 12 X + 16 Y + p (mod 32 banks), so the 4 x 8
+// (iy, j) of all 8 window rows (tap (iy, j + 1) comes from the neighbouring lane) -- record addresses are 12 X + 16 Y + p (mod 32 banks), so the 4 x 8
 // lanes of one load always hit 32 different banks whatever the per-pixel window origins are -- and produces the outputs
 // (xo = j, yo = 0..6).  Results go to a small staging buffer [xo][yo * 9 + p][level] (row stride chosen so that these
 // stores are conflict-free as well) from which the unit's output is written with fully coalesced stores.
@@ -131,23 +147,23 @@ template <int RS, int SLOT, int NLEV, int SROW>
 __device__ __forceinline__ void blend_stage(const float* vol, const float4* wgt, const int* vbase, int lane, int lev,
                                             __half* stage) {
   const int p_lo = lane & 3, j = lane >> 2;
-  const int j1 = min(j + 1, 7);
 #pragma unroll
   for (int pg = 0; pg < 3; ++pg) {
     const int p = 4 * pg + p_lo;
-    if (p < PP) {
-      const float4 wg = wgt[p];
-      const float* v = vol + vbase[p];
-      float t0[8], t1[8];
+    const int pc = min(p, PP - 1);                 // lanes beyond the last pixel repeat it (same address: broadcast)
+    const float4 wg = wgt[pc];
+    const float* v = vol + vbase[pc] + j * SLOT;
+    float t0[8], t1[8];
 #pragma unroll
-      for (int iy = 0; iy < 8; ++iy) { t0[iy] = v[(iy * RS + j) * SLOT]; t1[iy] = v[(iy * RS + j1) * SLOT]; }
-      if (j < 7) {
-        __half* st = stage + j * SROW + p * NLEV + lev;
+    for (int iy = 0; iy < 8; ++iy) t0[iy] = v[iy * RS * SLOT];
 #pragma unroll
-        for (int yo = 0; yo < 7; ++yo) {
-          const float r = wg.x * t0[yo] + wg.y * t1[yo] + wg.z * t0[yo + 1] + wg.w * t1[yo + 1];
-          st[yo * 9 * NLEV] = __float2half_rn(r);
-        }
+    for (int iy = 0; iy < 8; ++iy) t1[iy] = __shfl_down_sync(0xffffffffu, t0[iy], 4);      // tap (iy, j + 1)
+    if (p < PP && j < 7) {
+      __half* st = stage + j * SROW + p * NLEV + lev;
+#pragma unroll
+      for (int yo = 0; yo < 7; ++yo) {
+        const float r = wg.x * t0[yo] + wg.y * t1[yo] + wg.z * t0[yo + 1] + wg.w * t1[yo + 1];
+        st[yo * 9 * NLEV] = __float2half_rn(r);
       }
     }
   }
@@ -168,7 +184,6 @@ __global__ void __launch_bounds__(32 * WARPS) corr_tma_kernel(const __grid_const
   WS& S = reinterpret_cast<WS*>(smraw)[warp];
   const uint32_t bar0 = smem_u32(&S.bar[0]);
   const uint32_t reg0 = smem_u32(&S.reg[0][0]);
-  const uint32_t sa = smem_u32(&S.a[0]);
 
   if (lane == 0) {
     mbar_init(bar0, 1);
@@ -176,7 +191,6 @@ __global__ void __launch_bounds__(32 * WARPS) corr_tma_kernel(const __grid_const
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_proxy_async();
   }
-  for (int x = lane; x < 7 * C / 2; x += 32) reinterpret_cast<unsigned*>(&S.a[PP * C])[x] = 0u;   // rows 9..15
   __syncwarp();
 
   // ldmatrix lane offsets (bytes).  A operand = region records: matrices (rows 0-7 | 8-15) x (ch 0-7 | 8-15)
@@ -271,33 +285,19 @@ __global__ void __launch_bounds__(32 * WARPS) corr_tma_kernel(const __grid_const
     const bool have_next = s + 1 < n_half;
     const int lev_n = (NLEV == 1) ? 0 : (int)((s + 1) & 1);
 
-    // ---- (0) new unit: its patch features to shared memory, B fragments
+    // ---- (0) new unit: its patch-feature record [c][p] to shared memory as it is (one 16-byte store per lane), then
+    //      the B fragments (8 patch pixels x 8 channels, k contiguous) by 16-bit loads: b(k = c, n = p) = a[c * 9 + p]
     if (lev == 0) {
 #pragma unroll
-      for (int k = 0; k < NAV; ++k) {
-        const int i4 = lane + 32 * k;
-        if (i4 < NA4) {
-          const unsigned w[4] = {apre[k].x, apre[k].y, apre[k].z, apre[k].w};
-          int c = (i4 * 8) / PP, p = (i4 * 8) - c * PP;            // element x = c * 9 + p  ->  a[p][c]
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const unsigned short h = (unsigned short)((e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xffffu));
-            reinterpret_cast<unsigned short*>(&S.a[0])[p * C + c] = h;
-            if (++p == PP) { p = 0; ++c; }
-          }
-        }
-      }
+      for (int k = 0; k < NAV; ++k)
+        if (lane + 32 * k < NA4) reinterpret_cast<uint4*>(&S.a[0])[lane + 32 * k] = apre[k];
       __syncwarp();
-      // B fragments: matrices of 8 patch pixels x 8 channels, rows = patch pixels (k contiguous)
+      const unsigned short* ar = reinterpret_cast<const unsigned short*>(&S.a[0]);
 #pragma unroll
-      for (int ks = 0; ks < K16; ++ks) {
-        // x4: (p 0-7, ch 16ks..+7), (p 0-7, ch +8..+15), (p 8-15, ch ..+7), (p 8-15, ch +8..+15)
-        const uint32_t off = (uint32_t)((((lane >> 4) & 1) * 8 + (lane & 7)) * (2 * C) + ((lane >> 3) & 1) * 16 + ks * 32);
-        ldsm_x4(bf0[2 * ks], bf0[2 * ks + 1], bf1[2 * ks], bf1[2 * ks + 1], sa + off);
-      }
-      if (K8) {
-        const uint32_t off = (uint32_t)((((lane >> 3) & 1) * 8 + (lane & 7)) * (2 * C) + K16 * 32);
-        ldsm_x2(bf0[2 * K16], bf1[2 * K16], sa + off);
+      for (int x = 0; x < K16 * 2 + K8; ++x) {
+        const int c = 8 * x + 2 * tq;
+        bf0[x] = (unsigned)ar[c * PP + g] | ((unsigned)ar[(c + 1) * PP + g] << 16);
+        bf1[x] = (g == 0) ? ((unsigned)ar[c * PP + 8] | ((unsigned)ar[(c + 1) * PP + 8] << 16)) : 0u;
       }
     }
 
@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(32 * WARPS) corr_tma_kernel(const __grid_const
         float acc = 0.f;
         if (i1 >= 0 && i1 < H && j1 >= 0 && j1 < W) {
           const __half* src = f2 + ((int64_t)i1 * W + j1) * C;
-          for (int c = 0; c < C; ++c) acc += __half2float(S.a[p * C + c]) * __half2float(src[c]);
+          for (int c = 0; c < C; ++c) acc += __half2float(S.a[c * PP + p]) * __half2float(src[c]);
         }
         vol[pos * SLOT + p] = acc;
       }
@@ -452,10 +452,21 @@ static int launch(const CUtensorMap& tm0, const CUtensorMap& tm1, const Params& 
   return (int)cudaGetLastError();
 }
 
-static void transpose_maps(int C, const __half* src, __half* dst, int HW, int frames, cudaStream_t s) {
-  const dim3 grid((unsigned)((HW + 255) / 256), (unsigned)frames);
-  if (C == 24) to_nhwc_kernel<24><<<grid, 256, 0, s>>>(src, dst, HW);
-  else to_nhwc_kernel<32><<<grid, 256, 0, s>>>(src, dst, HW);
+static void transpose_maps(int C, int nlev, const __half* src0, __half* dst0, int HW0, const __half* src1, __half* dst1,
+                           int HW1, int frames, cudaStream_t s) {
+  NhwcJob j0{src0, dst0, HW0, (HW0 + 511) / 512, 0};
+  NhwcJob j1{src1, dst1, HW1, (HW1 + 511) / 512, j0.blocks_per_frame * frames};
+  int blocks = j1.first_block + (nlev == 2 ? j1.blocks_per_frame * frames : 0);
+  if (nlev == 1) j1.first_block = 0x7fffffff;
+  const bool pair = (HW0 % 2 == 0) && (nlev == 1 || HW1 % 2 == 0);
+  if (C == 24) {
+    if (pair) to_nhwc_kernel<24, true><<<blocks, 256, 0, s>>>(j0, j1);
+    else to_nhwc_kernel<24, false><<<blocks, 256, 0, s>>>(j0, j1);
+  } else {
+    if (pair) to_nhwc_kernel<32, true><<<blocks, 256, 0, s>>>(j0, j1);
+    else to_nhwc_kernel<32, false><<<blocks, 256, 0, s>>>(j0, j1);
+  }
+  pgba::count_launch();
 }
 
 }  // namespace pcorr_tma
@@ -494,16 +505,8 @@ int pcorr_forward_tma(const void* fmap1, const void* fmap2_l0, const void* fmap2
   cudaStream_t s = (cudaStream_t)stream;
   __half* n0 = (__half*)workspace;
   __half* n1 = (__half*)((char*)workspace + align256((size_t)B * F * H0 * W0 * C * 2));
-  {
-    const int HW = H0 * W0;
-    transpose_maps(C, (const __half*)fmap2_l0, n0, HW, B * (int)F, s);
-    pgba::count_launch();
-  }
-  if (nlev == 2) {
-    const int HW = H1 * W1;
-    transpose_maps(C, (const __half*)fmap2_l1, n1, HW, B * (int)F, s);
-    pgba::count_launch();
-  }
+  transpose_maps(C, nlev, (const __half*)fmap2_l0, n0, H0 * W0, (const __half*)fmap2_l1, n1, nlev == 2 ? H1 * W1 : 0,
+                 B * (int)F, s);
   CUtensorMap tm0, tm1;
   rc = make_map(&tm0, n0, C, W0, H0, (int64_t)B * F);
   if (rc) return rc;

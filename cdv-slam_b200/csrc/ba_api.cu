@@ -13,6 +13,10 @@ void launch_linearize(const Problem& pb, int64_t batch, cudaStream_t stream, boo
 void launch_solve(const Problem& pb, int64_t batch, cudaStream_t stream);
 void launch_update(const Problem& pb, int64_t batch, cudaStream_t stream);
 bool solve_supported(int N);
+bool plan_clears_workspace(const Problem& pb, int64_t batch);
+#ifdef PGBA_PLAN_TIMING
+void plan_timestamps(unsigned long long* out);
+#endif
 
 bool pdl_enabled() {
   static int v = -1;
@@ -127,6 +131,7 @@ static Problem make_problem(float* poses, float* patches, const float* intrinsic
 
 // one memset for the zero regions of all windows (headers, frame statistics, chunk counters, S, y)
 static cudaError_t clear_workspace(const Problem& pb, int64_t batch, cudaStream_t s) {
+  if (plan_clears_workspace(pb, batch)) return cudaSuccess;          // done by the first phase of plan_cluster_kernel
   return cudaMemsetAsync(pb.ws, 0, pb.L.zero_bytes * (size_t)batch, s);
 }
 }  // namespace pgba
@@ -231,6 +236,10 @@ int pgba_ba_solve_profiled(float* poses, float* patches, const float* intrinsics
 }
 
 long long pgba_launch_count(void) { return launch_count(); }
+
+#ifdef PGBA_PLAN_TIMING
+void pgba_debug_plan_timestamps(unsigned long long* out16) { pgba::plan_timestamps(out16); }
+#endif
 
 int pgba_ba_solve(float* poses, float* patches, const float* intrinsics, const float* target, const float* weight,
                   const float* lmbda, const int64_t* ii, const int64_t* jj, const int64_t* kk, int64_t n_edges,

@@ -44,6 +44,8 @@ struct Chunk {          // 64 bytes
   int pad0, pad1;
 };
 
+static_assert(sizeof(Chunk) == 64, "Chunk is written as four 16-byte words");
+
 struct DupEdge { int chunk, p, s, n; };
 
 struct Layout {         // host-computed

@@ -10,7 +10,12 @@
 //   plan_count_kernel    edges per chunk                        -> epilogue: chunk edge ranges
 //   plan_scatter_kernel  counting-sort scatter of the edge ids by chunk (perm)
 //   plan_cells_kernel    per chunk: compact patch list, sorted target-frame slots, cell table cells[p][s] = edge
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
 #include "ba_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace pgba {
 
@@ -305,6 +310,218 @@ __global__ void __launch_bounds__(256) plan_cells_kernel(Problem pb) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Single-launch form of memset + plan_frames + plan_count + plan_scatter for windows whose dense system is small
+// (everything except the global BA): ONE thread-block cluster of 8 CTAs x 1024 threads per window (blockIdx.y = window),
+// the grid-wide dependencies of the three passes become hardware cluster barriers.  Every thread keeps its (up to 8)
+// edges in registers across the passes, so the index arrays are read once (larger windows re-read the remainder).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int PLAN_CL = 8, PLAN_T = 1024, PLAN_KEEP = 8;
+
+#ifdef PGBA_PLAN_TIMING
+__device__ unsigned long long g_plan_ts[16];
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define PLAN_TS(i) do { if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) g_plan_ts[i] = gtimer(); } while (0)
+#else
+#define PLAN_TS(i) do { } while (0)
+#endif
+
+constexpr int PLAN_CMAX = 8192;          // chunk counts scanned in shared memory up to this many chunks
+
+size_t plan_cluster_smem(int F) { return sizeof(int) * ((size_t)2 * ((F + 31) & ~31) + PLAN_CMAX + 32); }
+
+__global__ void __launch_bounds__(PLAN_T, 1) plan_cluster_kernel(Problem pb) {
+  pdl_wait();
+  pdl_trigger();
+  PLAN_TS(0);
+  extern __shared__ int psm[];
+  __shared__ int scratch[40];
+  cg::cluster_group cl = cg::this_cluster();
+  const int w = blockIdx.y, tid = threadIdx.x, lane = tid & 31, T = PLAN_T;
+  const int rank = blockIdx.x;                       // the cluster spans the x dimension of the grid
+  const int gt = rank * PLAN_T + tid, GT = PLAN_CL * PLAN_T;
+  const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
+  const int64_t* ii = pb.ii + (int64_t)w * pb.st.ii;
+  const int64_t* jj = pb.jj + (int64_t)w * pb.st.jj;
+  const int64_t* kk = pb.kk + (int64_t)w * pb.st.kk;
+  const int E = window_edges(pb, w);
+  const int pc = pb.L.pc, F = pb.F;
+  int* s_fb = psm;                                   // [F]  first chunk of every source frame
+  int* s_km = psm + ((F + 31) & ~31);                // [F]  smallest patch id of every source frame
+  int* s_cb = s_km + ((F + 31) & ~31);               // [n_chunks + 1]  first edge position of every chunk
+
+  // ---- P0: clear the window's zero region (header, frame statistics, chunk counters, y, S)
+  {
+    uint4* z = reinterpret_cast<uint4*>((char*)pb.ws + (size_t)w * pb.L.zero_bytes);
+    const int n16 = (int)(pb.L.zero_bytes >> 4);
+    for (int x = gt; x < n16; x += GT) z[x] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  // edges of this thread (loads are independent of P0)
+  EdgeIdx keep[PLAN_KEEP];
+  int bad = 0;
+#pragma unroll
+  for (int q = 0; q < PLAN_KEEP; ++q) {
+    const int e = gt + q * GT;
+    keep[q] = load_edge(pb, ii, jj, kk, e, E);
+    if (e < E && !keep[q].ok) bad = 1;
+  }
+  const int e_rest = PLAN_KEEP * GT + (gt - lane);     // warp-uniform start of the part that is re-read
+  PLAN_TS(1);
+  cl.sync();
+  PLAN_TS(2);
+
+  // ---- P1: per source frame min / max patch id
+#pragma unroll
+  for (int q = 0; q < PLAN_KEEP; ++q) {
+    const EdgeIdx x = keep[q];
+    const unsigned grp = __match_any_sync(0xffffffffu, x.i);
+    const int kmn = __reduce_min_sync(grp, x.k), kmx = __reduce_max_sync(grp, x.k);
+    if (x.ok && lane == __ffs(grp) - 1) {
+      atomicMax(&wp.fmaxinv[x.i], 0x7fffffff - kmn);
+      atomicMax(&wp.fkmax1[x.i], kmx + 1);
+    }
+  }
+  for (int e0 = e_rest; e0 < E; e0 += GT) {
+    const int e = e0 + lane;
+    const EdgeIdx x = load_edge(pb, ii, jj, kk, e, E);
+    if (e < E && !x.ok) bad = 1;
+    const unsigned grp = __match_any_sync(0xffffffffu, x.i);
+    const int kmn = __reduce_min_sync(grp, x.k), kmx = __reduce_max_sync(grp, x.k);
+    if (x.ok && lane == __ffs(grp) - 1) {
+      atomicMax(&wp.fmaxinv[x.i], 0x7fffffff - kmn);
+      atomicMax(&wp.fkmax1[x.i], kmx + 1);
+    }
+  }
+  if (bad) atomicOr(&wp.hdr->status, PGBA_ST_INDEX_RANGE);
+  PLAN_TS(3);
+  cl.sync();
+  PLAN_TS(4);
+
+  // ---- P2 (every CTA, in its own shared memory; CTA 0 also writes the global copies): chunk table
+  for (int f = tid; f < F; f += T) {
+    const int mx1 = __ldcg(&wp.fkmax1[f]);
+    const int kmin = 0x7fffffff - __ldcg(&wp.fmaxinv[f]);
+    s_km[f] = kmin;
+    s_fb[f] = mx1 > 0 ? ((mx1 - 1) - kmin) / pc + 1 : 0;
+  }
+  PLAN_TS(12);
+  __syncthreads();
+  int n_chunks = block_exclusive_scan(s_fb, F, scratch);
+  PLAN_TS(13);
+  if (n_chunks > (int)pb.L.ch_max) {     // cannot happen when every patch has one source frame; stay memory-safe anyway
+    if (rank == 0 && tid == 0) atomicOr(&wp.hdr->status, PGBA_ST_CAPACITY);
+    n_chunks = 0;
+  }
+  if (rank == 0) {
+    for (int f = tid; f < F; f += T) wp.fbase[f] = s_fb[f];
+    // one thread per chunk: its source frame is the last f with s_fb[f] <= c (frames without patches repeat the offset)
+    for (int c = tid; c < n_chunks; c += T) {
+      int lo = 0, hi = F - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (s_fb[mid] <= c) lo = mid; else hi = mid - 1;
+      }
+      uint4* dst = reinterpret_cast<uint4*>(&wp.chunks[c]);
+      dst[0] = make_uint4((unsigned)lo, (unsigned)(s_km[lo] + (c - s_fb[lo]) * pc), 0u, 0u);   // frame, kbase, -, -
+      dst[1] = make_uint4(0u, 0u, 0u, 0u);
+      dst[2] = make_uint4(0u, 0u, 0u, 0u);
+      dst[3] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    PLAN_TS(14);
+    if (tid == 0) wp.hdr->n_chunks = n_chunks;
+  }
+  PLAN_TS(5);
+  PLAN_TS(6);
+  if (n_chunks == 0) return;               // uniform over the cluster
+
+  // ---- P3: edges per chunk
+  int ck[PLAN_KEEP];
+#pragma unroll
+  for (int q = 0; q < PLAN_KEEP; ++q) {
+    const EdgeIdx x = keep[q];
+    const int c = x.ok ? s_fb[x.i] + (x.k - s_km[x.i]) / pc : -1;
+    ck[q] = c;
+    const unsigned grp = __match_any_sync(0xffffffffu, c);
+    if (x.ok && lane == __ffs(grp) - 1) atomicAdd(&wp.ccnt[c], __popc(grp));
+  }
+  for (int e0 = e_rest; e0 < E; e0 += GT) {
+    const EdgeIdx x = load_edge(pb, ii, jj, kk, e0 + lane, E);
+    const int c = x.ok ? s_fb[x.i] + (x.k - s_km[x.i]) / pc : -1;
+    const unsigned grp = __match_any_sync(0xffffffffu, c);
+    if (x.ok && lane == __ffs(grp) - 1) atomicAdd(&wp.ccnt[c], __popc(grp));
+  }
+  PLAN_TS(7);
+  cl.sync();
+  PLAN_TS(8);
+
+  // ---- P4: exclusive scan of the chunk counts -> edge ranges.  Small chunk tables (the normal case): every CTA scans
+  //      its own copy in shared memory, and the scatter takes its tickets from the UPPER 16 bits of the same counters
+  //      (a CTA that is still reading the counts masks them off), so no further cluster barrier is needed.  Large
+  //      tables, or windows with >= 65536 edges (a count might not fit 16 bits): CTA 0 scans in global memory and one
+  //      more barrier separates the passes.
+  const bool small = n_chunks <= PLAN_CMAX && E < 65536;
+  if (small) {
+    for (int c = tid; c < n_chunks; c += T) s_cb[c] = (int)((unsigned)__ldcg(&wp.ccnt[c]) & 0xffffu);
+    __syncthreads();
+  }
+  if (small) {
+    const int n_valid = block_exclusive_scan(s_cb, n_chunks, scratch);
+    if (tid == 0) s_cb[n_chunks] = n_valid;
+    __syncthreads();
+    if (rank == 0) {
+      for (int c = tid; c < n_chunks; c += T) {
+        wp.chunks[c].edge_begin = s_cb[c];
+        wp.chunks[c].edge_end = s_cb[c + 1];
+      }
+      if (tid == 0) wp.hdr->n_valid_edges = n_valid;
+    }
+  } else {
+    if (rank == 0) {
+      int* ccur = wp.ccur;
+      for (int c = tid; c < n_chunks; c += T) ccur[c] = __ldcg(&wp.ccnt[c]);
+      __syncthreads();
+      const int n_valid = block_exclusive_scan(ccur, n_chunks, scratch);
+      for (int c = tid; c < n_chunks; c += T) {
+        wp.chunks[c].edge_begin = ccur[c];
+        wp.chunks[c].edge_end = ccur[c] + __ldcg(&wp.ccnt[c]);
+      }
+      if (tid == 0) wp.hdr->n_valid_edges = n_valid;
+    }
+    cl.sync();
+  }
+  PLAN_TS(9);
+  PLAN_TS(10);
+
+  // ---- P5: counting-sort scatter of (edge, target frame, patch id) records by chunk
+  auto ticket = [&](int c, int n) -> int {        // first position of n records of chunk c
+    if (small) return s_cb[c] + (int)(atomicAdd(reinterpret_cast<unsigned*>(&wp.ccnt[c]), (unsigned)n << 16) >> 16);
+    return atomicAdd(&wp.ccur[c], n);
+  };
+#pragma unroll
+  for (int q = 0; q < PLAN_KEEP; ++q) {
+    const EdgeIdx x = keep[q];
+    const int c = ck[q];
+    const unsigned grp = __match_any_sync(0xffffffffu, c);
+    const int leader = __ffs(grp) - 1;
+    int base = 0;
+    if (x.ok && lane == leader) base = ticket(c, __popc(grp));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (x.ok) wp.perm[base + __popc(grp & ((1u << lane) - 1u))] = make_int4(gt + q * GT, x.j, x.k, 0);
+  }
+  for (int e0 = e_rest; e0 < E; e0 += GT) {
+    const int e = e0 + lane;
+    const EdgeIdx x = load_edge(pb, ii, jj, kk, e, E);
+    const int c = x.ok ? s_fb[x.i] + (x.k - s_km[x.i]) / pc : -1;
+    const unsigned grp = __match_any_sync(0xffffffffu, c);
+    const int leader = __ffs(grp) - 1;
+    int base = 0;
+    if (x.ok && lane == leader) base = ticket(c, __popc(grp));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (x.ok) wp.perm[base + __popc(grp & ((1u << lane) - 1u))] = make_int4(e, x.j, x.k, 0);
+  }
+  PLAN_TS(11);
+}
+
 static int edge_grid(int64_t E, int64_t batch) {
   int64_t g = (E + 255) / 256;
   const int64_t cap = batch > 1 ? (148 * 8 + batch - 1) / batch : 148 * 4;
@@ -319,17 +536,49 @@ int chunk_grid(const Problem& pb, int64_t batch) {
   return (int)(g < 1 ? 1 : g);
 }
 
+static bool plan_cluster_enabled() {           // PGBA_PLAN_CLUSTER=0: grid-wide multi-kernel plan (A/B runs, tests)
+  const char* e = getenv("PGBA_PLAN_CLUSTER");
+  return !(e && e[0] == '0');
+}
+
+// true: the cluster kernel also clears the zero region (no memset needed)
+// The cluster form pays for single windows / small batches (latency: 5 launches + memset become 2); with many windows per
+// call the grid-wide kernels fill the machine better (measured on c5: 116 us vs 134 us for 64 windows).
+bool plan_clears_workspace(const Problem& pb, int64_t batch) { return plan_cluster_enabled() && !pb.L.big && batch <= 8; }
+
 void launch_plan(const Problem& pb, int64_t batch, cudaStream_t stream) {
-  const int ge = edge_grid(pb.E, batch);
-  const dim3 grid((unsigned)ge, (unsigned)batch);
-  launch_k(plan_frames_kernel, dim3(grid), dim3(256), 0, stream, pb);
-  count_launch();
-  launch_k(plan_count_kernel, dim3(grid), dim3(256), 0, stream, pb);
-  count_launch();
-  launch_k(plan_scatter_kernel, dim3(grid), dim3(256), 0, stream, pb);
-  count_launch();
+  if (plan_clears_workspace(pb, batch)) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(PLAN_CL, (unsigned)batch);
+    cfg.blockDim = dim3(PLAN_T);
+    cfg.dynamicSmemBytes = plan_cluster_smem(pb.F);
+    cfg.stream = stream;
+    cudaFuncSetAttribute(plan_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = PLAN_CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    cudaLaunchKernelEx(&cfg, plan_cluster_kernel, pb);
+    count_launch();
+  } else {
+    const int ge = edge_grid(pb.E, batch);
+    const dim3 grid((unsigned)ge, (unsigned)batch);
+    launch_k(plan_frames_kernel, dim3(grid), dim3(256), 0, stream, pb);
+    count_launch();
+    launch_k(plan_count_kernel, dim3(grid), dim3(256), 0, stream, pb);
+    count_launch();
+    launch_k(plan_scatter_kernel, dim3(grid), dim3(256), 0, stream, pb);
+    count_launch();
+  }
   launch_k(plan_cells_kernel, dim3((unsigned)chunk_grid(pb, batch), (unsigned)batch), dim3(256), 0, stream, pb);
   count_launch();
 }
+
+#ifdef PGBA_PLAN_TIMING
+void plan_timestamps(unsigned long long* out) { cudaMemcpyFromSymbol(out, g_plan_ts, sizeof(unsigned long long) * 16); }
+#endif
 
 }  // namespace pgba

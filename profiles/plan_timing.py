@@ -1,0 +1,25 @@
+"""Phase timestamps (globaltimer, ns) of plan_cluster_kernel on the c2 window; needs a -DPGBA_PLAN_TIMING build:
+    PGBA_LIB=cdv-slam_b200/lib/libpgba_timing.so python profiles/plan_timing.py"""
+import ctypes, os, sys
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [REPO, os.path.join(REPO, "cdv-slam_b200")]
+import numpy as np
+import torch
+import bench
+from cdvslam_b200 import native
+
+dev = torch.device("cuda", 0)
+arm = bench.GpuArm(bench.make_workload(sys.argv[1] if len(sys.argv) > 1 else "c2", 0, 64), dev)
+L = native.lib()
+acc = []
+for it in range(8):
+    arm.restore(); arm.flush_l2(); torch.cuda.synchronize()
+    arm.call(); torch.cuda.synchronize()
+    buf = (ctypes.c_ulonglong * 16)()
+    L.pgba_debug_plan_timestamps(buf)
+    t = np.array(list(buf)[:16], dtype=np.float64)
+    acc.append(t - t[0])
+acc = np.median(np.array(acc[2:]), axis=0)
+names = ["start", "zero+load issued", "sync0", "P1 frames", "sync1", "P2 table", "sync2", "P3 count", "sync3", "P4 scan", "sync4", "P5 scatter", "P2a loads", "P2b scan", "P2c table", "-"]
+for n, a, d in zip(names, acc, np.diff(np.concatenate([[0], acc]))):
+    print("%-18s t=%8.0f ns  (+%6.0f)" % (n, a, d))

@@ -262,3 +262,15 @@ def test_global_ba_c4_full_size():
     assert np.abs(d_g - d_o).max() < 5 * TOL
     np.testing.assert_array_equal(patches[:, 2], np.broadcast_to(patches[:, 2, :1, :1], patches[:, 2].shape))
     np.testing.assert_array_equal(patches[:, :2], np.asarray(p.patches, np.float32)[:, :2].astype(np.float64))
+
+
+@pytest.mark.parametrize("cluster", ["1", "0"])
+def test_window_with_more_than_65535_edges(cluster, monkeypatch):
+    """A window of ~80k edges: the single-launch (cluster) plan re-reads the edges beyond its register-resident part and
+    uses the unpacked scatter tickets; PGBA_PLAN_CLUSTER=0 is the grid-wide multi-kernel plan.  Both against the oracle."""
+    monkeypatch.setenv("PGBA_PLAN_CLUSTER", cluster)
+    p = synth.make_problem("w80k", 40, synth.window_edges(40, 96), 30, 40, 5, 96)
+    assert p.E > 65536
+    poses, patches = _run_gpu(p, 2)
+    o_poses, o_patches = _oracle(p, 2)
+    _check_state(p, poses, patches, o_poses, o_patches)

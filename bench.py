@@ -290,7 +290,11 @@ def extra_corr_c3(dev, peak, flush):
         fn = lambda: altcorr.corr_pyramid2(g, [f0, f1], coords, kk, jj, 3)
         for _ in range(3):
             fn()
-        ms = timed_events(fn, 20, before=flush)
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            fn()
+        ms = timed_events(gr.replay, 20, before=flush)
         E, K, Fj = p.E, gmap.shape[0], len(np.unique(p.jj))
         alg = sum(E * 88 + K * 9 * C * s + Fj * C * h * w * s + E * 441 * s for (h, w) in ((120, 160), (30, 40))) - E * 88 - K * 9 * C * s
         out["C%d_%s" % (C, str(dt).split(".")[-1])] = {
@@ -299,6 +303,49 @@ def extra_corr_c3(dev, peak, flush):
                          "frac": alg / (ms * 1e-3) / 1e9 / peak}}
         del g, f0, f1
     return {"workload": "c3: fused 2-level altcorr.corr on the c2 graph (37824 edges), radius 3, L2 flushed", **out}
+
+
+def extra_update_loop(dev, flush, n_updates=12):
+    """BASELINE config c3: the per-update hot path of slam.py:316-337, 470-496 on the c2 graph -- reproject -> two-level
+    correlation lookup (C = 24 fp16, radius 3) -> synthetic network output (delta ~ N(0,1), weight ~ U(0,1)) -> BA, 2
+    iterations -- captured as one CUDA graph and replayed `n_updates` times (the initialisation loop, slam.py:715-716)."""
+    from cdvslam_b200 import synth, fastba, altcorr
+    p = synth.config_c2()
+    d = synth.to_torch(p, dev)
+    gmap, pyr = synth.make_fmaps(p, C=24)
+    g = torch.as_tensor(gmap, device=dev)[None].half()
+    f0 = torch.as_tensor(pyr[0], device=dev)[None].half()
+    f1 = torch.as_tensor(pyr[1], device=dev)[None].half()
+    gen = torch.Generator(device=dev).manual_seed(1234)
+    delta = torch.randn((1, p.E, 2), device=dev, generator=gen)
+    weight = torch.rand((1, p.E, 2), device=dev, generator=gen)
+    p0, q0 = d["poses"].clone(), d["patches"].clone()
+    corr_out = {}
+
+    def update():
+        coords = fastba.reproject(d["poses"], d["patches"], d["intrinsics"], d["ii"], d["jj"], d["kk"], clamp_depth=True)
+        corr_out["c"] = altcorr.corr_pyramid2(g, [f0, f1], coords, d["kk"], d["jj"], 3)
+        target = coords[:, :, :, 1, 1] + delta                         # slam.py:493
+        fastba.BA(d["poses"], d["patches"], d["intrinsics"], target, weight, d["lmbda"], d["ii"], d["jj"], d["kk"],
+                  p.t0, p.t1, M=p.M, iterations=ITERATIONS, eff_impl=False)
+
+    def reset():
+        d["poses"].copy_(p0); d["patches"].copy_(q0); flush()
+    for _ in range(2):
+        reset(); update()
+    torch.cuda.synchronize()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        update()
+
+    def loop():
+        for _ in range(n_updates):
+            gr.replay()
+    ms = timed_events(loop, 5, before=reset)
+    return {"workload": "c3: reproject -> corr (2 levels, C=24 fp16, r=3) -> BA (2 iterations) on the c2 graph, "
+                        "%d updates per step, one CUDA graph per update, L2 flushed before each step" % n_updates,
+            "ms_per_update": ms / n_updates, "updates_per_s": n_updates / (ms * 1e-3),
+            "edges_per_s": p.E * n_updates / (ms * 1e-3)}
 
 
 def extra_c4(dev, flush):
@@ -470,6 +517,7 @@ def main():
         flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
         try:
             line["corr_c3"] = extra_corr_c3(dev, peak, flush_buf.zero_)
+            line["update_loop_c3"] = extra_update_loop(dev, flush_buf.zero_)
             line["global_c4"] = extra_c4(dev, flush_buf.zero_)
         except Exception as e:            # extras must never cost the headline line
             line["extras_error"] = repr(e)[:200]

@@ -515,13 +515,6 @@ size_t solve_small_smem_bytes(int n) {
   return sizeof(double) * ((size_t)(n + 1) * ld + n + 8);
 }
 
-#ifdef PGBA_SOLVE_TIMING
-__device__ long long g_solve_ts[64];
-#define SOLVE_TS(i) do { if (threadIdx.x == 0 && blockIdx.x == 0 && (i) < 64) g_solve_ts[i] = clock64(); } while (0)
-#else
-#define SOLVE_TS(i) do { } while (0)
-#endif
-
 __global__ void __launch_bounds__(256, 1) solve_small_kernel(Problem pb) {
   pdl_wait();
   pdl_trigger();
@@ -575,16 +568,23 @@ __global__ void __launch_bounds__(256, 1) solve_small_kernel(Problem pb) {
     double* xv = A + n * ld;
     for (int kb = n - 6; kb >= 0; kb -= 6) {
       if (lane == 0) {
-        double x[6];
+        // L11^T x = v, right-looking: x[c] = v[c] / L[c][c], then v[e] -= L[c][e] x[c] for e < c
+        double v[6], l[6][6];
 #pragma unroll
-        for (int c = 5; c >= 0; --c) {
-          double v = xv[kb + c];
+        for (int c = 0; c < 6; ++c) {
+          v[c] = xv[kb + c];
 #pragma unroll
-          for (int e = c + 1; e < 6; ++e) v -= A[(kb + e) * ld + kb + c] * x[e];
-          x[c] = v * rd[kb + c];
+          for (int e = 0; e < c; ++e) l[c][e] = A[(kb + c) * ld + kb + e];
         }
 #pragma unroll
-        for (int c = 0; c < 6; ++c) xv[kb + c] = x[c];
+        for (int c = 5; c >= 0; --c) {
+          const double x = v[c] * rd[kb + c];
+          v[c] = x;
+#pragma unroll
+          for (int e = 0; e < c; ++e) v[e] -= l[c][e] * x;
+        }
+#pragma unroll
+        for (int c = 0; c < 6; ++c) xv[kb + c] = v[c];
       }
       __syncwarp();
       for (int c = lane; c < kb; c += 32) {

@@ -5,7 +5,7 @@
 #include <vector>
 #include <cmath>
 #include "../../cdv-slam_b200/csrc/ba_numeric.cu"
-namespace pgba { void count_launch() {} long long launch_count() { return 0; } int chunk_grid(const Problem&, int64_t) { return 1; } }
+namespace pgba { void count_launch() {} long long launch_count() { return 0; } int chunk_grid(const Problem&, int64_t) { return 1; } bool pdl_enabled() { return false; } cudaError_t launch_big_solve(const Problem&, int64_t, cudaStream_t) { return cudaSuccess; } }
 using namespace pgba;
 int main(int argc, char** argv) {
   const int N = argc > 1 ? atoi(argv[1]) : 10, n = 6 * N, F = N + 12, batch = argc > 2 ? atoi(argv[2]) : 1;

@@ -222,6 +222,40 @@ class GpuArm:
         d2h = sum(v.numel() * v.element_size() for v in self.out_h.values())
         return [a.elapsed_time(b) for a, b in evs], h2d, d2h
 
+    def timed_e2e_host(self, steps, use_graph):
+        """Host-buffer entry point (fastba.BA_host -> pgba_ba_solve_host): pinned host tensors in, results written back
+        into them; H2D of every input and D2H of poses / patches are inside the call.  The state is not reset between
+        steps (the in-place host tensors keep being refined; the work per call does not depend on the values)."""
+        from cdvslam_b200 import fastba
+        p = self.p0
+        hh = {k: v.clone().pin_memory() for k, v in self.h.items()}
+
+        def call():
+            fastba.BA_host(hh["poses"], hh["patches"], hh["intrinsics"], hh["target"], hh["weight"], hh["lmbda"],
+                           hh["ii"][0], hh["jj"][0], hh["kk"][0], p.t0, p.t1, M=p.M, iterations=ITERATIONS,
+                           eff_impl=False, device=self.dev)
+        for _ in range(3):
+            call()
+        torch.cuda.synchronize()
+        run = call
+        if use_graph:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                call()
+            run = g.replay
+        evs = []
+        for _ in range(steps):
+            self.flush_l2()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            run()
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        h2d = sum(hh[k].numel() * hh[k].element_size() for k in hh if k != "intrinsics") + 16
+        d2h = hh["poses"].numel() * 4 + hh["patches"].numel() * 4
+        return [a.elapsed_time(b) for a, b in evs], h2d, d2h
+
     def profiled(self, steps):
         """Per-stage device times of the same launch sequence (events between the kernels, library hook)."""
         native, d, p = self.native, self.d, self.p0
@@ -456,7 +490,17 @@ def main():
     ms = arm.timed_resident(graph, args.steps)
     barrier()
     total_ms = max_over_ranks(sum(ms))
+    e2e_modes = {}
     e2e_ms, h2d, d2h = arm.timed_e2e(args.steps)
+    e2e_modes["device_api_with_torch_copies"] = sum(e2e_ms) / args.steps
+    e2e_mode = "device_api_with_torch_copies"
+    if arm.B == 1:
+        for use_graph in (False, True):
+            ms_h, h2d_h, d2h_h = arm.timed_e2e_host(args.steps, use_graph)
+            name = "host_api_graph_replay" if use_graph else "host_api_eager"
+            e2e_modes[name] = sum(ms_h) / args.steps
+            if sum(ms_h) < sum(e2e_ms):
+                e2e_ms, h2d, d2h, e2e_mode = ms_h, h2d_h, d2h_h, name
     barrier()
     e2e_total = max_over_ranks(sum(e2e_ms))
     stages = arm.profiled(min(args.steps, 50))
@@ -478,7 +522,8 @@ def main():
                            timing="CUDA events around a CUDA-graph replay of the public API call, max over ranks"),
             "edges_per_s": probs[0].E * value,
             "e2e": {"value": its / (e2e_total * 1e-3), "unit": "BA iterations/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_total / args.steps},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_total / args.steps, "mode": e2e_mode,
+                    "ms_per_step_by_mode": e2e_modes},
             "gpu_launches": int(arm.launches_per_step * args.steps),
             "launches_per_step": int(arm.launches_per_step),
             "roofline": {"bound": "hbm", "kernel": "linearize_kernel (residual+Jacobian+assembly+Schur)",

@@ -9,3 +9,11 @@ def BA(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, t0, t1, M,
     """In-place patch-graph bundle adjustment; signature of cdvslam/fastba/ba.py:7-8."""
     return cuda_ba.forward(poses.data, patches, intrinsics, target, weight, lmbda, ii, jj, kk, M, t0, t1, iterations,
                            eff_impl)
+
+
+def BA_host(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, t0, t1, M, iterations, eff_impl=False,
+            device=None):
+    """Extension: BA() for tensors that live in (pinned) host memory -- same argument order and in-place semantics;
+    upload, solve and download are enqueued on the current CUDA stream of `device`."""
+    return cuda_ba.forward_host(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, M, t0, t1, iterations,
+                                eff_impl, device=device)

@@ -31,6 +31,9 @@ SIGNATURES = {
                                            c_vp]),
     "pgba_ba_solve_batched": (c_int, [c_vp] * 10 + [ctypes.POINTER(Strides), c_i64, c_i64, c_i64, c_i64, c_int, c_int,
                                                      c_int, c_int, c_int, c_int, c_vp, c_sz, c_vp]),
+    "pgba_ba_host_staging_bytes": (c_int, [c_i64, c_i64, c_i64, c_int, ctypes.POINTER(c_sz)]),
+    "pgba_ba_solve_host": (c_int, [c_vp] * 9 + [c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_sz,
+                                                c_vp, c_sz, c_vp, c_vp]),
     "pgba_ba_linearize_debug": (c_int, [c_vp] * 9 + [c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int] + [c_vp] * 10 +
                                 [c_vp, c_sz, c_vp]),
     "pgba_ba_solve_profiled": (c_int, [c_vp] * 9 + [ctypes.POINTER(Strides), c_i64, c_i64, c_i64, c_i64, c_int, c_int,

@@ -251,6 +251,106 @@ int pgba_ba_solve(float* poses, float* patches, const float* intrinsics, const f
                                workspace_bytes, stream);
 }
 
+// ---- host-buffer entry point -------------------------------------------------------------------------------------
+namespace {
+struct HostStage { size_t poses, patches, intr, target, weight, lmbda, ii, jj, kk, total; };
+HostStage host_stage(int64_t E, int64_t F, int64_t K, int P) {
+  HostStage h{};
+  size_t o = 0;
+  h.poses = o;   o = align256(o + sizeof(float) * 7 * (size_t)F);
+  h.patches = o; o = align256(o + sizeof(float) * 3 * P * P * (size_t)K);
+  h.intr = o;    o = align256(o + sizeof(float) * 4);
+  h.target = o;  o = align256(o + sizeof(float) * 2 * (size_t)E);
+  h.weight = o;  o = align256(o + sizeof(float) * 2 * (size_t)E);
+  h.lmbda = o;   o = align256(o + sizeof(float));
+  h.ii = o;      o = align256(o + sizeof(int64_t) * (size_t)E);
+  h.jj = o;      o = align256(o + sizeof(int64_t) * (size_t)E);
+  h.kk = o;      o = align256(o + sizeof(int64_t) * (size_t)E);
+  h.total = o;
+  return h;
+}
+// fork / join events, created once per device (never destroyed: they live as long as the library)
+cudaEvent_t* stage_events() {
+  static cudaEvent_t ev[64][2];
+  static bool made[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!made[dev]) {
+    if (cudaEventCreateWithFlags(&ev[dev][0], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&ev[dev][1], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    made[dev] = true;
+  }
+  return ev[dev];
+}
+}  // namespace
+
+int pgba_ba_host_staging_bytes(int64_t n_edges, int64_t n_pose_rows, int64_t n_patch_rows, int P, size_t* bytes) {
+  if (!bytes) return PGBA_ERR_NULL;
+  if (n_edges < 0 || n_pose_rows <= 0 || n_patch_rows <= 0 || P < 2) return PGBA_ERR_SHAPE;
+  *bytes = host_stage(n_edges, n_pose_rows, n_patch_rows, P).total;
+  return PGBA_OK;
+}
+
+int pgba_ba_solve_host(float* poses_h, float* patches_h, const float* intrinsics_h, const float* target_h,
+                       const float* weight_h, const float* lmbda_h, const int64_t* ii_h, const int64_t* jj_h,
+                       const int64_t* kk_h, int64_t n_edges, int64_t n_pose_rows, int64_t n_patch_rows, int P, int ppf,
+                       int t0, int t1, int iterations, int eff_impl, void* staging, size_t staging_bytes,
+                       void* workspace, size_t workspace_bytes, pgba_stream_t stream, pgba_stream_t aux_stream) {
+  (void)ppf; (void)eff_impl;
+  if (iterations < 0) return PGBA_ERR_SHAPE;
+  if (!staging || ((uintptr_t)staging & 255)) return PGBA_ERR_WORKSPACE;
+  int rc = check_common(poses_h, patches_h, intrinsics_h, target_h, weight_h, lmbda_h, ii_h, jj_h, kk_h, n_edges,
+                        n_pose_rows, n_patch_rows, P, t0, t1);
+  if (rc) return rc;
+  const HostStage h = host_stage(n_edges, n_pose_rows, n_patch_rows, P);
+  if (h.total > staging_bytes) return PGBA_ERR_WORKSPACE;
+  char* sb = (char*)staging;
+  float* d_poses = (float*)(sb + h.poses);
+  float* d_patches = (float*)(sb + h.patches);
+  Problem pb;
+  pgba_strides st{};
+  rc = prepare(pb, d_poses, d_patches, (const float*)(sb + h.intr), (const float*)(sb + h.target),
+               (const float*)(sb + h.weight), (const float*)(sb + h.lmbda), (const int64_t*)(sb + h.ii),
+               (const int64_t*)(sb + h.jj), (const int64_t*)(sb + h.kk), nullptr, &st, 1, n_edges, n_pose_rows,
+               n_patch_rows, P, t0, t1, workspace, workspace_bytes);
+  if (rc) return rc;
+  if (iterations == 0 || n_edges == 0) return PGBA_OK;
+  cudaStream_t s = (cudaStream_t)stream, a = (cudaStream_t)aux_stream;
+  cudaEvent_t* ev = stage_events();
+  if (!ev) return PGBA_ERR_UNSUPPORTED;
+  const size_t E = (size_t)n_edges;
+  const bool fork = a != s;
+  cudaError_t e = cudaSuccess;
+#define PGBA_TRY(x) do { if (e == cudaSuccess) e = (x); } while (0)
+  if (fork) {                                  // aux joins the capture / ordering of the main stream
+    PGBA_TRY(cudaEventRecord(ev[0], s));
+    PGBA_TRY(cudaStreamWaitEvent(a, ev[0], 0));
+  }
+  PGBA_TRY(cudaMemcpyAsync(sb + h.ii, ii_h, 8 * E, cudaMemcpyHostToDevice, s));
+  PGBA_TRY(cudaMemcpyAsync(sb + h.jj, jj_h, 8 * E, cudaMemcpyHostToDevice, s));
+  PGBA_TRY(cudaMemcpyAsync(sb + h.kk, kk_h, 8 * E, cudaMemcpyHostToDevice, s));
+  PGBA_TRY(cudaMemcpyAsync(sb + h.target, target_h, 8 * E, cudaMemcpyHostToDevice, a));
+  PGBA_TRY(cudaMemcpyAsync(sb + h.weight, weight_h, 8 * E, cudaMemcpyHostToDevice, a));
+  PGBA_TRY(cudaMemcpyAsync(d_patches, patches_h, sizeof(float) * 3 * P * P * (size_t)n_patch_rows, cudaMemcpyHostToDevice, a));
+  PGBA_TRY(cudaMemcpyAsync(d_poses, poses_h, sizeof(float) * 7 * (size_t)n_pose_rows, cudaMemcpyHostToDevice, a));
+  PGBA_TRY(cudaMemcpyAsync(sb + h.intr, intrinsics_h, sizeof(float) * 4, cudaMemcpyHostToDevice, a));
+  PGBA_TRY(cudaMemcpyAsync(sb + h.lmbda, lmbda_h, sizeof(float), cudaMemcpyHostToDevice, a));
+  if (e != cudaSuccess) return (int)e;
+  e = clear_workspace(pb, 1, s);
+  if (e != cudaSuccess) return (int)e;
+  launch_plan(pb, 1, s);
+  if (fork) {
+    PGBA_TRY(cudaEventRecord(ev[1], a));
+    PGBA_TRY(cudaStreamWaitEvent(s, ev[1], 0));
+  }
+  for (int it = 0; it < iterations && e == cudaSuccess; ++it) e = launch_iteration(pb, 1, s, nullptr, it == 0, it + 1 < iterations);
+  PGBA_TRY(cudaMemcpyAsync(poses_h, d_poses, sizeof(float) * 7 * (size_t)n_pose_rows, cudaMemcpyDeviceToHost, s));
+  PGBA_TRY(cudaMemcpyAsync(patches_h, d_patches, sizeof(float) * 3 * P * P * (size_t)n_patch_rows, cudaMemcpyDeviceToHost, s));
+#undef PGBA_TRY
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaGetLastError();
+}
+
 int pgba_ba_linearize_debug(const float* poses, const float* patches, const float* intrinsics, const float* target,
                             const float* weight, const float* lmbda, const int64_t* ii, const int64_t* jj,
                             const int64_t* kk, int64_t n_edges, int64_t n_pose_rows, int64_t n_patch_rows, int P,

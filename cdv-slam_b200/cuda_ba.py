@@ -54,6 +54,49 @@ def forward(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, PPF, 
     return []
 
 
+_aux_streams = {}
+
+
+def forward_host(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, PPF, t0, t1, iterations,
+                 eff_impl=False, device=None):
+    """Extension: cuda_ba.forward for HOST tensors (pinned memory for asynchronous copies).  Uploads the inputs, runs
+    the same kernels and writes the updated `poses` / `patches` back into the host tensors, all enqueued on the
+    current stream of `device` (plus an auxiliary stream: the upload of everything but ii/jj/kk overlaps the graph
+    analysis).  Asynchronous like every CUDA op: synchronise the stream before reading the host tensors."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    tens = dict(poses=poses, patches=patches, intrinsics=intrinsics, target=target, weight=weight, lmbda=lmbda)
+    for name, t in tens.items():
+        if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            raise RuntimeError("cuda_ba.forward_host: %s must be a contiguous float32 CPU tensor" % name)
+    for name, t in dict(ii=ii, jj=jj, kk=kk).items():
+        if t.is_cuda or t.dtype != torch.int64 or not t.is_contiguous():
+            raise RuntimeError("cuda_ba.forward_host: %s must be a contiguous int64 CPU tensor" % name)
+    P = patches.shape[-1]
+    F = poses.numel() // 7
+    K = patches.numel() // (3 * P * P)
+    E = ii.numel()
+    if target.numel() != 2 * E or weight.numel() != 2 * E or jj.numel() != E or kk.numel() != E:
+        raise RuntimeError("cuda_ba.forward_host: target/weight/ii/jj/kk sizes disagree")
+    L = native.lib()
+    nws, nst = ctypes.c_size_t(0), ctypes.c_size_t(0)
+    native.check(L.pgba_ba_workspace_bytes(E, F, K, int(t0), int(t1), 1, ctypes.byref(nws)), "pgba_ba_workspace_bytes")
+    native.check(L.pgba_ba_host_staging_bytes(E, F, K, P, ctypes.byref(nst)), "pgba_ba_host_staging_bytes")
+    with torch.cuda.device(dev):
+        ws = native.workspace(nws.value, dev)
+        stg = native.workspace(nst.value, dev, pool="ba_host_staging")
+        key = dev.index if dev.index is not None else torch.cuda.current_device()
+        aux = _aux_streams.get(key)
+        if aux is None:
+            aux = _aux_streams[key] = torch.cuda.Stream(device=dev)
+        rc = L.pgba_ba_solve_host(poses.data_ptr(), patches.data_ptr(), intrinsics.data_ptr(), target.data_ptr(),
+                                  weight.data_ptr(), lmbda.data_ptr(), ii.data_ptr(), jj.data_ptr(), kk.data_ptr(),
+                                  E, F, K, P, int(PPF), int(t0), int(t1), int(iterations), int(bool(eff_impl)),
+                                  stg.data_ptr(), stg.numel(), ws.data_ptr(), ws.numel(), native.stream_ptr(dev),
+                                  aux.cuda_stream)
+    native.check(rc, "pgba_ba_solve_host")
+    return []
+
+
 def reproject(poses, patches, intrinsics, ii, jj, kk, clamp_depth=False):
     """cuda_ba.reproject (ba.cpp:48-56 -> cuda_reproject(), ba_cuda.cu:614-645): coords f32 [1, E, 2, P, P]."""
     poses = _prep(poses, torch.float32, "poses")

@@ -81,6 +81,27 @@ int pgba_ba_solve_batched(float* poses, float* patches, const float* intrinsics,
                           int t0, int t1, int iterations, int eff_impl, void* workspace, size_t workspace_bytes,
                           pgba_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * The same operator for a caller whose tensors live in HOST memory (pinned for asynchronous copies): all pointers
+ * marked _h are host pointers in the layouts of pgba_ba_solve; `lmbda_h` points to one float.  The call enqueues, and
+ * returns without synchronising:
+ *     stream      : H2D ii, jj, kk -> graph analysis (plan)          | wait for aux | iterations -> D2H poses, patches
+ *     aux_stream  : H2D poses, patches, intrinsics[0], target, weight, lmbda |
+ * i.e. the upload of everything the plan does not need overlaps the plan; `poses_h` rows t0..t1-1 and channel 2 of
+ * `patches_h` hold the result once `stream` has been synchronised (in-place semantics of cuda_ba.forward, on the host
+ * tensors).  `staging` is a caller-owned DEVICE buffer of pgba_ba_host_staging_bytes() (256-byte aligned), `workspace`
+ * as for pgba_ba_solve.  aux_stream may equal stream (no overlap).  The two cudaEvents used for the fork / join are
+ * created once per device and cached by the library; everything is capturable into a CUDA graph from `stream`.
+ * ------------------------------------------------------------------------------------------------------------- */
+int pgba_ba_host_staging_bytes(int64_t n_edges, int64_t n_pose_rows, int64_t n_patch_rows, int P,
+                               size_t* bytes /* host, out */);
+
+int pgba_ba_solve_host(float* poses_h, float* patches_h, const float* intrinsics_h, const float* target_h,
+                       const float* weight_h, const float* lmbda_h, const int64_t* ii_h, const int64_t* jj_h,
+                       const int64_t* kk_h, int64_t n_edges, int64_t n_pose_rows, int64_t n_patch_rows, int P, int ppf,
+                       int t0, int t1, int iterations, int eff_impl, void* staging, size_t staging_bytes,
+                       void* workspace, size_t workspace_bytes, pgba_stream_t stream, pgba_stream_t aux_stream);
+
 /* Measurement hooks (used by bench.py only).  pgba_ba_solve_profiled runs exactly the launch sequence of
  * pgba_ba_solve_batched with cudaEvents between the stages, SYNCHRONISES the stream and fills the host array
  * stage_ms [1 + 3*iterations]: workspace clear + plan, then per iteration {linearize+Schur, solve + pose

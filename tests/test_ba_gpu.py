@@ -274,3 +274,23 @@ def test_window_with_more_than_65535_edges(cluster, monkeypatch):
     poses, patches = _run_gpu(p, 2)
     o_poses, o_patches = _oracle(p, 2)
     _check_state(p, poses, patches, o_poses, o_patches)
+
+
+@pytest.mark.parametrize("maker", [lambda: synth.small_problem(seed=4, F=7, M=12, t0=2, lifetime=4), synth.config_c2])
+def test_host_buffer_entry_matches_device_entry_and_oracle(maker):
+    """pgba_ba_solve_host (pinned host tensors in, results written back in place) == the device-tensor call, bit for
+    bit up to the order of the floating-point reductions, and both match the oracle."""
+    p = maker()
+    h = to_dev(p, device="cpu")
+    h = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in h.items()}
+    fastba.BA_host(h["poses"], h["patches"], h["intrinsics"], h["target"], h["weight"], h["lmbda"], h["ii"], h["jj"],
+                   h["kk"], p.t0, p.t1, M=p.M, iterations=2)
+    torch.cuda.synchronize()
+    poses, patches = h["poses"][0].numpy().astype(np.float64), h["patches"][0].numpy().astype(np.float64)
+    o_poses, o_patches = _oracle(p, 2)
+    _check_state(p, poses, patches, o_poses, o_patches)
+    d_poses, d_patches = _run_gpu(p, 2)
+    assert rel_err(poses, d_poses) < 1e-5 and rel_err(patches[:, 2], d_patches[:, 2]) < 1e-5
+    with pytest.raises(RuntimeError):
+        fastba.BA_host(h["poses"].cuda(), h["patches"], h["intrinsics"], h["target"], h["weight"], h["lmbda"], h["ii"],
+                       h["jj"], h["kk"], p.t0, p.t1, M=p.M, iterations=2)

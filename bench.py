@@ -222,13 +222,20 @@ class GpuArm:
         d2h = sum(v.numel() * v.element_size() for v in self.out_h.values())
         return [a.elapsed_time(b) for a, b in evs], h2d, d2h
 
-    def timed_e2e_host(self, steps, use_graph):
+    def timed_e2e_host(self, steps, use_graph, arena=False):
         """Host-buffer entry point (fastba.BA_host -> pgba_ba_solve_host): pinned host tensors in, results written back
         into them; H2D of every input and D2H of poses / patches are inside the call.  The state is not reset between
         steps (the in-place host tensors keep being refined; the work per call does not depend on the values)."""
         from cdvslam_b200 import fastba
         p = self.p0
-        hh = {k: v.clone().pin_memory() for k, v in self.h.items()}
+        if arena:       # the nine tensors as views of one pinned allocation (native.host_arena): 2 uploads + 1 download
+            hh = self.native.host_arena(self.h["ii"].shape[-1], self.h["poses"].shape[1], self.h["patches"].shape[1],
+                                        self.h["patches"].shape[-1])
+            for k, v in self.h.items():
+                hh[k].view(-1).copy_(v.reshape(-1)) if k not in ("ii", "jj", "kk") else hh[k].copy_(v[0])
+            hh = {k: (v[None] if k in ("ii", "jj", "kk") else v) for k, v in hh.items()}
+        else:
+            hh = {k: v.clone().pin_memory() for k, v in self.h.items()}
 
         def call():
             fastba.BA_host(hh["poses"], hh["patches"], hh["intrinsics"], hh["target"], hh["weight"], hh["lmbda"],
@@ -252,7 +259,8 @@ class GpuArm:
             b.record()
             evs.append((a, b))
         torch.cuda.synchronize()
-        h2d = sum(hh[k].numel() * hh[k].element_size() for k in hh if k != "intrinsics") + 16
+        h2d = sum(hh[k].numel() * hh[k].element_size() for k in hh if k not in ("intrinsics", "_arena")) + \
+            (hh["intrinsics"].numel() * 4 if arena else 16)
         d2h = hh["poses"].numel() * 4 + hh["patches"].numel() * 4
         return [a.elapsed_time(b) for a, b in evs], h2d, d2h
 
@@ -495,9 +503,9 @@ def main():
     e2e_modes["device_api_with_torch_copies"] = sum(e2e_ms) / args.steps
     e2e_mode = "device_api_with_torch_copies"
     if arm.B == 1:
-        for use_graph in (False, True):
-            ms_h, h2d_h, d2h_h = arm.timed_e2e_host(args.steps, use_graph)
-            name = "host_api_graph_replay" if use_graph else "host_api_eager"
+        for use_graph, arena in ((False, False), (True, False), (False, True), (True, True)):
+            ms_h, h2d_h, d2h_h = arm.timed_e2e_host(args.steps, use_graph, arena)
+            name = ("host_api_arena" if arena else "host_api") + ("_graph_replay" if use_graph else "_eager")
             e2e_modes[name] = sum(ms_h) / args.steps
             if sum(ms_h) < sum(e2e_ms):
                 e2e_ms, h2d, d2h, e2e_mode = ms_h, h2d_h, d2h_h, name

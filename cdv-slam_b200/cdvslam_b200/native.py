@@ -32,6 +32,7 @@ SIGNATURES = {
     "pgba_ba_solve_batched": (c_int, [c_vp] * 10 + [ctypes.POINTER(Strides), c_i64, c_i64, c_i64, c_i64, c_int, c_int,
                                                      c_int, c_int, c_int, c_int, c_vp, c_sz, c_vp]),
     "pgba_ba_host_staging_bytes": (c_int, [c_i64, c_i64, c_i64, c_int, ctypes.POINTER(c_sz)]),
+    "pgba_ba_host_arena_offsets": (c_int, [c_i64, c_i64, c_i64, c_int, ctypes.POINTER(c_sz), ctypes.POINTER(c_sz)]),
     "pgba_ba_solve_host": (c_int, [c_vp] * 9 + [c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_sz,
                                                 c_vp, c_sz, c_vp, c_vp]),
     "pgba_ba_linearize_debug": (c_int, [c_vp] * 9 + [c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int] + [c_vp] * 10 +
@@ -117,3 +118,23 @@ def workspace(nbytes, device, pool="ba"):
         buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
         _workspaces[key] = buf
     return buf
+
+
+def host_arena(n_edges, n_pose_rows, n_patch_rows, P=3):
+    """One pinned host allocation holding the nine input tensors of fastba.BA_host at the offsets of
+    pgba_ba_host_arena_offsets (views with the reference's shapes, leading batch dim of 1).  BA_host then moves the
+    problem with two uploads and one download instead of nine + two."""
+    offs = (c_sz * 9)()
+    total = c_sz(0)
+    check(lib().pgba_ba_host_arena_offsets(n_edges, n_pose_rows, n_patch_rows, P, offs, ctypes.byref(total)),
+          "pgba_ba_host_arena_offsets")
+    buf = torch.zeros(total.value, dtype=torch.uint8).pin_memory()
+    E, F, K = n_edges, n_pose_rows, n_patch_rows
+
+    def view(i, dtype, shape):
+        n = int(torch.tensor(shape).prod().item()) * torch.empty((), dtype=dtype).element_size()
+        return buf[offs[i]:offs[i] + n].view(dtype).view(shape)
+    return dict(_arena=buf, poses=view(0, torch.float32, (1, F, 7)), patches=view(1, torch.float32, (1, K, 3, P, P)),
+                intrinsics=view(2, torch.float32, (1, F, 4)), target=view(3, torch.float32, (1, E, 2)),
+                weight=view(4, torch.float32, (1, E, 2)), lmbda=view(5, torch.float32, (1,)),
+                ii=view(6, torch.int64, (E,)), jj=view(7, torch.int64, (E,)), kk=view(8, torch.int64, (E,)))

@@ -259,7 +259,7 @@ HostStage host_stage(int64_t E, int64_t F, int64_t K, int P) {
   size_t o = 0;
   h.poses = o;   o = align256(o + sizeof(float) * 7 * (size_t)F);
   h.patches = o; o = align256(o + sizeof(float) * 3 * P * P * (size_t)K);
-  h.intr = o;    o = align256(o + sizeof(float) * 4);
+  h.intr = o;    o = align256(o + sizeof(float) * 4 * (size_t)F);
   h.target = o;  o = align256(o + sizeof(float) * 2 * (size_t)E);
   h.weight = o;  o = align256(o + sizeof(float) * 2 * (size_t)E);
   h.lmbda = o;   o = align256(o + sizeof(float));
@@ -288,6 +288,17 @@ int pgba_ba_host_staging_bytes(int64_t n_edges, int64_t n_pose_rows, int64_t n_p
   if (!bytes) return PGBA_ERR_NULL;
   if (n_edges < 0 || n_pose_rows <= 0 || n_patch_rows <= 0 || P < 2) return PGBA_ERR_SHAPE;
   *bytes = host_stage(n_edges, n_pose_rows, n_patch_rows, P).total;
+  return PGBA_OK;
+}
+
+int pgba_ba_host_arena_offsets(int64_t n_edges, int64_t n_pose_rows, int64_t n_patch_rows, int P, size_t* offsets9,
+                               size_t* bytes) {
+  if (!offsets9 || !bytes) return PGBA_ERR_NULL;
+  if (n_edges < 0 || n_pose_rows <= 0 || n_patch_rows <= 0 || P < 2) return PGBA_ERR_SHAPE;
+  const HostStage h = host_stage(n_edges, n_pose_rows, n_patch_rows, P);
+  const size_t o[9] = {h.poses, h.patches, h.intr, h.target, h.weight, h.lmbda, h.ii, h.jj, h.kk};
+  for (int i = 0; i < 9; ++i) offsets9[i] = o[i];
+  *bytes = h.total;
   return PGBA_OK;
 }
 
@@ -326,15 +337,27 @@ int pgba_ba_solve_host(float* poses_h, float* patches_h, const float* intrinsics
     PGBA_TRY(cudaEventRecord(ev[0], s));
     PGBA_TRY(cudaStreamWaitEvent(a, ev[0], 0));
   }
-  PGBA_TRY(cudaMemcpyAsync(sb + h.ii, ii_h, 8 * E, cudaMemcpyHostToDevice, s));
-  PGBA_TRY(cudaMemcpyAsync(sb + h.jj, jj_h, 8 * E, cudaMemcpyHostToDevice, s));
-  PGBA_TRY(cudaMemcpyAsync(sb + h.kk, kk_h, 8 * E, cudaMemcpyHostToDevice, s));
-  PGBA_TRY(cudaMemcpyAsync(sb + h.target, target_h, 8 * E, cudaMemcpyHostToDevice, a));
-  PGBA_TRY(cudaMemcpyAsync(sb + h.weight, weight_h, 8 * E, cudaMemcpyHostToDevice, a));
-  PGBA_TRY(cudaMemcpyAsync(d_patches, patches_h, sizeof(float) * 3 * P * P * (size_t)n_patch_rows, cudaMemcpyHostToDevice, a));
-  PGBA_TRY(cudaMemcpyAsync(d_poses, poses_h, sizeof(float) * 7 * (size_t)n_pose_rows, cudaMemcpyHostToDevice, a));
-  PGBA_TRY(cudaMemcpyAsync(sb + h.intr, intrinsics_h, sizeof(float) * 4, cudaMemcpyHostToDevice, a));
-  PGBA_TRY(cudaMemcpyAsync(sb + h.lmbda, lmbda_h, sizeof(float), cudaMemcpyHostToDevice, a));
+  // arena mode: the caller's tensors are views of ONE host allocation laid out like the staging buffer
+  // (pgba_ba_host_arena_offsets): two uploads (indices | everything else) and one download instead of nine + two
+  const char* hb = (const char*)poses_h - h.poses;
+  const bool arena = (const char*)patches_h == hb + h.patches && (const char*)intrinsics_h == hb + h.intr &&
+                     (const char*)target_h == hb + h.target && (const char*)weight_h == hb + h.weight &&
+                     (const char*)lmbda_h == hb + h.lmbda && (const char*)ii_h == hb + h.ii &&
+                     (const char*)jj_h == hb + h.jj && (const char*)kk_h == hb + h.kk;
+  if (arena) {
+    PGBA_TRY(cudaMemcpyAsync(sb + h.ii, hb + h.ii, h.total - h.ii, cudaMemcpyHostToDevice, s));
+    PGBA_TRY(cudaMemcpyAsync(sb, hb, h.ii, cudaMemcpyHostToDevice, a));
+  } else {
+    PGBA_TRY(cudaMemcpyAsync(sb + h.ii, ii_h, 8 * E, cudaMemcpyHostToDevice, s));
+    PGBA_TRY(cudaMemcpyAsync(sb + h.jj, jj_h, 8 * E, cudaMemcpyHostToDevice, s));
+    PGBA_TRY(cudaMemcpyAsync(sb + h.kk, kk_h, 8 * E, cudaMemcpyHostToDevice, s));
+    PGBA_TRY(cudaMemcpyAsync(sb + h.target, target_h, 8 * E, cudaMemcpyHostToDevice, a));
+    PGBA_TRY(cudaMemcpyAsync(sb + h.weight, weight_h, 8 * E, cudaMemcpyHostToDevice, a));
+    PGBA_TRY(cudaMemcpyAsync(d_patches, patches_h, sizeof(float) * 3 * P * P * (size_t)n_patch_rows, cudaMemcpyHostToDevice, a));
+    PGBA_TRY(cudaMemcpyAsync(d_poses, poses_h, sizeof(float) * 7 * (size_t)n_pose_rows, cudaMemcpyHostToDevice, a));
+    PGBA_TRY(cudaMemcpyAsync(sb + h.intr, intrinsics_h, sizeof(float) * 4, cudaMemcpyHostToDevice, a));
+    PGBA_TRY(cudaMemcpyAsync(sb + h.lmbda, lmbda_h, sizeof(float), cudaMemcpyHostToDevice, a));
+  }
   if (e != cudaSuccess) return (int)e;
   e = clear_workspace(pb, 1, s);
   if (e != cudaSuccess) return (int)e;
@@ -344,8 +367,12 @@ int pgba_ba_solve_host(float* poses_h, float* patches_h, const float* intrinsics
     PGBA_TRY(cudaStreamWaitEvent(s, ev[1], 0));
   }
   for (int it = 0; it < iterations && e == cudaSuccess; ++it) e = launch_iteration(pb, 1, s, nullptr, it == 0, it + 1 < iterations);
-  PGBA_TRY(cudaMemcpyAsync(poses_h, d_poses, sizeof(float) * 7 * (size_t)n_pose_rows, cudaMemcpyDeviceToHost, s));
-  PGBA_TRY(cudaMemcpyAsync(patches_h, d_patches, sizeof(float) * 3 * P * P * (size_t)n_patch_rows, cudaMemcpyDeviceToHost, s));
+  if (arena) {
+    PGBA_TRY(cudaMemcpyAsync((char*)hb, sb, h.intr, cudaMemcpyDeviceToHost, s));          // poses | patches
+  } else {
+    PGBA_TRY(cudaMemcpyAsync(poses_h, d_poses, sizeof(float) * 7 * (size_t)n_pose_rows, cudaMemcpyDeviceToHost, s));
+    PGBA_TRY(cudaMemcpyAsync(patches_h, d_patches, sizeof(float) * 3 * P * P * (size_t)n_patch_rows, cudaMemcpyDeviceToHost, s));
+  }
 #undef PGBA_TRY
   if (e != cudaSuccess) return (int)e;
   return (int)cudaGetLastError();

@@ -96,6 +96,12 @@ int pgba_ba_solve_batched(float* poses, float* patches, const float* intrinsics,
 int pgba_ba_host_staging_bytes(int64_t n_edges, int64_t n_pose_rows, int64_t n_patch_rows, int P,
                                size_t* bytes /* host, out */);
 
+/* Arena mode: when the nine host tensors are views of ONE allocation at the byte offsets returned here (order: poses,
+ * patches, intrinsics [n_pose_rows, 4], target, weight, lmbda, ii, jj, kk; `bytes` = size of the allocation),
+ * pgba_ba_solve_host uploads it with two copies (indices | everything else) and downloads poses + patches with one. */
+int pgba_ba_host_arena_offsets(int64_t n_edges, int64_t n_pose_rows, int64_t n_patch_rows, int P,
+                               size_t* offsets9 /* host, out */, size_t* bytes /* host, out */);
+
 int pgba_ba_solve_host(float* poses_h, float* patches_h, const float* intrinsics_h, const float* target_h,
                        const float* weight_h, const float* lmbda_h, const int64_t* ii_h, const int64_t* jj_h,
                        const int64_t* kk_h, int64_t n_edges, int64_t n_pose_rows, int64_t n_patch_rows, int P, int ppf,

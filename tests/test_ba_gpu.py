@@ -294,3 +294,22 @@ def test_host_buffer_entry_matches_device_entry_and_oracle(maker):
     with pytest.raises(RuntimeError):
         fastba.BA_host(h["poses"].cuda(), h["patches"], h["intrinsics"], h["target"], h["weight"], h["lmbda"], h["ii"],
                        h["jj"], h["kk"], p.t0, p.t1, M=p.M, iterations=2)
+
+
+def test_host_buffer_entry_arena_mode():
+    """The nine host tensors as views of one pinned allocation (native.host_arena): two uploads + one download; same
+    results as the device-tensor call."""
+    from cdvslam_b200 import native
+    p = synth.small_problem(seed=6, F=9, M=20, t0=3, lifetime=5)
+    h = to_dev(p, device="cpu")
+    a = native.host_arena(p.E, h["poses"].shape[1], h["patches"].shape[1], 3)
+    for k in ("poses", "patches", "intrinsics", "target", "weight", "lmbda", "ii", "jj", "kk"):
+        a[k].copy_(h[k].reshape(a[k].shape))
+    fastba.BA_host(a["poses"], a["patches"], a["intrinsics"], a["target"], a["weight"], a["lmbda"], a["ii"], a["jj"],
+                   a["kk"], p.t0, p.t1, M=p.M, iterations=2)
+    torch.cuda.synchronize()
+    poses, patches = a["poses"][0].numpy().astype(np.float64), a["patches"][0].numpy().astype(np.float64)
+    o_poses, o_patches = _oracle(p, 2)
+    _check_state(p, poses, patches, o_poses, o_patches)
+    np.testing.assert_array_equal(a["ii"].numpy(), np.asarray(p.ii))          # inputs are not disturbed by the download
+    np.testing.assert_array_equal(a["target"][0].numpy(), np.asarray(p.target, np.float32))

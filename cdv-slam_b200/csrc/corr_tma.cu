@@ -100,30 +100,40 @@ __device__ __forceinline__ int safe_floor(float v) {     // far-out / non-finite
 }
 
 // Channel-last copy of the frame maps of up to two pyramid levels in ONE launch: [B*F, C, HW] -> [B*F, HW, C].
-// A block handles 512 consecutive pixels of one frame: every thread reads two adjacent pixels of each channel (4-byte
+// A block handles PXT consecutive pixels of one frame: the threads read pairs of adjacent pixels of a channel (4-byte
 // loads, coalesced), the [512][C] tile is transposed through shared memory and written with contiguous 16-byte stores.
 // blockIdx.x enumerates (level, frame, pixel block).  HW must be even (the host falls back to scalar loads otherwise).
 struct NhwcJob { const __half* src; __half* dst; int HW; int blocks_per_frame; int first_block; };
 
-template <int C, bool PAIR>
+template <int C, bool PAIR, int PXT>
 __global__ void __launch_bounds__(256) to_nhwc_kernel(NhwcJob j0, NhwcJob j1) {
-  __shared__ __align__(16) __half tile[512 * C];
+  __shared__ __align__(16) __half tile[PXT * C];
   const bool second = (int)blockIdx.x >= j1.first_block;
   const NhwcJob J = second ? j1 : j0;
   const int blk = (int)blockIdx.x - J.first_block;
   const int frame = blk / J.blocks_per_frame;
-  const int px0 = (blk - frame * J.blocks_per_frame) * 512;
-  const int npx = min(512, J.HW - px0);
+  const int px0 = (blk - frame * J.blocks_per_frame) * PXT;
+  const int npx = min(PXT, J.HW - px0);
   const __half* s = J.src + (int64_t)frame * C * J.HW + px0;
   const int t = threadIdx.x;
   if (PAIR) {
-    if (2 * t < npx) {
+    // item = (pixel pair, channel): consecutive threads read consecutive pixel pairs of one channel; the trip count is
+    // a compile-time constant, so all loads of a thread are in flight together
+    constexpr int ITEMS = (PXT / 2) * C / 256;
+    static_assert((PXT / 2) * C % 256 == 0, "tile items must divide evenly over the 256 threads");
+    __half2 v[ITEMS];
 #pragma unroll
-      for (int c = 0; c < C; ++c) {
-        const __half2 v = *reinterpret_cast<const __half2*>(s + (int64_t)c * J.HW + 2 * t);
-        tile[(2 * t) * C + c] = __low2half(v);
-        tile[(2 * t + 1) * C + c] = __high2half(v);
-      }
+    for (int i = 0; i < ITEMS; ++i) {
+      const int x = t + 256 * i;
+      const int c = x / (PXT / 2), pp = x - c * (PXT / 2);
+      v[i] = (2 * pp < npx) ? *reinterpret_cast<const __half2*>(s + (int64_t)c * J.HW + 2 * pp) : __half2();
+    }
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      const int x = t + 256 * i;
+      const int c = x / (PXT / 2), pp = x - c * (PXT / 2);
+      tile[(2 * pp) * C + c] = __low2half(v[i]);
+      tile[(2 * pp + 1) * C + c] = __high2half(v[i]);
     }
   } else {
     for (int px = t; px < npx; px += 256)
@@ -134,6 +144,35 @@ __global__ void __launch_bounds__(256) to_nhwc_kernel(NhwcJob j0, NhwcJob j1) {
   uint4* d = reinterpret_cast<uint4*>(J.dst + ((int64_t)frame * J.HW + px0) * C);
   const uint4* t4 = reinterpret_cast<const uint4*>(tile);
   for (int x = t; x < npx * C / 8; x += 256) d[x] = t4[x];
+}
+
+// C a multiple of 16: no shared memory.  Thread = (pixel pair, group of 16 channels): sixteen coalesced 4-byte loads (one
+// per channel plane), then two full 32-byte sectors per pixel are written (16 channels x 2 bytes).
+template <int C>
+__global__ void __launch_bounds__(256) to_nhwc16_kernel(NhwcJob j0, NhwcJob j1) {
+  const bool second = (int)blockIdx.x >= j1.first_block;
+  const NhwcJob J = second ? j1 : j0;
+  const int blk = (int)blockIdx.x - J.first_block;                 // blocks_per_frame = ceil(HW / 2 / 256) here
+  const int frame = blk / J.blocks_per_frame;
+  const int pp = (blk - frame * J.blocks_per_frame) * 256 + threadIdx.x;
+  if (2 * pp >= J.HW) return;
+  const int c0 = blockIdx.y * 16;
+  const __half* s = J.src + ((int64_t)frame * C + c0) * J.HW + 2 * pp;
+  unsigned v[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) v[k] = *reinterpret_cast<const unsigned*>(s + (int64_t)k * J.HW);
+  uint4 a0, a1, b0, b1;                                              // pixel 2pp: low halves; pixel 2pp + 1: high halves
+  a0.x = __byte_perm(v[0], v[1], 0x5410); a0.y = __byte_perm(v[2], v[3], 0x5410);
+  a0.z = __byte_perm(v[4], v[5], 0x5410); a0.w = __byte_perm(v[6], v[7], 0x5410);
+  a1.x = __byte_perm(v[8], v[9], 0x5410); a1.y = __byte_perm(v[10], v[11], 0x5410);
+  a1.z = __byte_perm(v[12], v[13], 0x5410); a1.w = __byte_perm(v[14], v[15], 0x5410);
+  b0.x = __byte_perm(v[0], v[1], 0x7632); b0.y = __byte_perm(v[2], v[3], 0x7632);
+  b0.z = __byte_perm(v[4], v[5], 0x7632); b0.w = __byte_perm(v[6], v[7], 0x7632);
+  b1.x = __byte_perm(v[8], v[9], 0x7632); b1.y = __byte_perm(v[10], v[11], 0x7632);
+  b1.z = __byte_perm(v[12], v[13], 0x7632); b1.w = __byte_perm(v[14], v[15], 0x7632);
+  uint4* d = reinterpret_cast<uint4*>(J.dst + ((int64_t)frame * J.HW + 2 * pp) * C + c0);
+  d[0] = a0; d[1] = a1;
+  d[C / 8] = b0; d[C / 8 + 1] = b1;
 }
 
 // Window selection + 4-tap bilinear blend of one (edge, level) from its volume in shared memory
@@ -401,6 +440,265 @@ __global__ void __launch_bounds__(32 * WARPS) corr_tma_kernel(const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Wide feature maps (C a multiple of 32, e.g. the 128-channel maps of the DPVO-style network, net_dpv.py:99): same
+// scheme, but the channel axis is split into chunks of 32.  Per (edge, level) the 12 x 12 region arrives as C / 32
+// TMA boxes [32 ch, 12, 12] (64-byte pixel records, SWIZZLE_64B so that ldmatrix rows do not collide in the banks) in
+// a ring of WNBUF buffers that is refilled chunk by chunk (two chunks ahead, across half-tasks); the accumulators of the
+// nine region tiles stay in registers across the chunks and are then written to a separate volume buffer with the
+// same 12-float records as the narrow kernel, so the blend / staging / output code is shared.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int WCK = 32;                      // channels per chunk
+constexpr int WNBUF = 2;                     // chunk buffers per warp (ring)
+constexpr int WWARPS = 7;                    // warps per CTA of the wide kernel (one CTA per SM)
+constexpr int WCH_BYTES = RPX * WCK * 2;     // 9216
+
+template <int C> struct __align__(512) WideSmem {
+  unsigned char buf[WNBUF][WCH_BYTES];     // TMA destinations (64B-swizzled pixel records)
+  float vol[RPX * 12];                     // region volume, 12-float records: vol[px * 12 + p]
+  __half a[PP * C];                        // patch-feature record of the unit, [c][p] as in fmap1
+  float4 wgt[2][12];
+  int vbase[2][12];
+  __half stage[7 * 136];
+  unsigned long long bar[WNBUF];
+};
+
+template <int C, int NLEV>
+__global__ void __launch_bounds__(32 * WWARPS, 1) corr_tma_wide_kernel(const __grid_constant__ CUtensorMap tm0,
+                                                                      const __grid_constant__ CUtensorMap tm1, Params P) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  static_assert(C % WCK == 0, "channel count must be a multiple of the chunk size");
+  static_assert((C / WCK) % WNBUF == 0, "the chunk ring must divide the chunks of a half-task");
+  constexpr int NCH = C / WCK;                           // chunks per half-task
+  constexpr int SLOT = 12;
+  constexpr int NA4 = C * PP / 8;
+  constexpr int NAV = (NA4 + 31) / 32;
+  using WS = WideSmem<C>;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // the swizzled TMA destinations need 512-byte alignment: align by hand (the launch adds 1 KB of slack)
+  WS& S = reinterpret_cast<WS*>(smraw + ((512u - (smem_u32(smraw) & 511u)) & 511u))[warp];
+  const uint32_t bar0 = smem_u32(&S.bar[0]);
+  const uint32_t buf0 = smem_u32(&S.buf[0][0]);
+  if (lane == 0) {
+    for (int b = 0; b < WNBUF; ++b) mbar_init(bar0 + 8 * b, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async();
+  }
+  __syncwarp();
+
+  // ldmatrix lane offsets inside a chunk buffer: row = permuted region record of the 8-row block, 16-byte channel
+  // group XOR-swizzled with bits 1..2 of the record index (SWIZZLE_64B of 64-byte records)
+  const int rperm = (((lane & 7) & 3) << 1) | ((lane & 7) >> 2);
+  const int rrow = ((lane >> 3) & 1) * 8 + rperm;                 // record inside the 16-record tile
+  const int sw = (rrow >> 1) & 3;
+  const uint32_t a_off_k0 = (uint32_t)(rrow * 64 + (((0 + (lane >> 4)) ^ sw) << 4));   // channels 0..15 of the chunk
+  const uint32_t a_off_k1 = (uint32_t)(rrow * 64 + (((2 + (lane >> 4)) ^ sw) << 4));   // channels 16..31
+  const int g = lane >> 2, tq = lane & 3;
+  const int gperm = ((g & 3) << 1) | (g >> 2);
+  const uint64_t tma0 = (uint64_t)&tm0, tma1 = (uint64_t)&tm1;
+
+  const int64_t total = (int64_t)P.B * P.E;
+  const int64_t ustride = (int64_t)gridDim.x * WWARPS;
+  const int64_t u_first = (int64_t)blockIdx.x * WWARPS + warp;
+  if (u_first >= total) return;
+  const int64_t n_units = (total - u_first + ustride - 1) / ustride;
+  const int64_t n_half = n_units * NLEV;
+
+  struct Raw { float x, y; int jx, ix; };
+  Raw ra{0.f, 0.f, 0, 0}, rb{0.f, 0.f, 0, 0};
+  int64_t ka = 0;
+  uint4 apre[NAV];
+  struct Geo { int x0, y0, frame, lev; bool fits; };
+  Geo gc{0, 0, 0, 0, false}, gn{0, 0, 0, 0, false};
+  uint32_t phase = 0;
+  unsigned bf0[C / 8], bf1[C / 8];
+
+  auto load_raw = [&](Raw& r, int64_t k) {
+    const int64_t unit = u_first + k * ustride;
+    const int64_t m = (P.B == 1) ? unit : unit % P.E;
+    const float* cg = P.coords + unit * (2 * PP);
+    if (lane < PP) { r.x = __ldg(cg + lane); r.y = __ldg(cg + PP + lane); }
+    r.jx = (int)__ldg(P.vs + m);
+    r.ix = (int)__ldg(P.us + m);
+  };
+  auto prefetch_a = [&]() {
+    const int64_t b = (P.B == 1) ? 0 : (u_first + ka * ustride) / P.E;
+    const uint4* f1 = reinterpret_cast<const uint4*>(P.fmap1 + (b * P.K + ra.ix) * (int64_t)(C * PP));
+#pragma unroll
+    for (int k = 0; k < NAV; ++k)
+      if (lane + 32 * k < NA4) apre[k] = __ldg(f1 + lane + 32 * k);
+  };
+  auto prepare = [&](int lev, int slot) -> Geo {
+    const float x = (lev == 0) ? ra.x : ra.x * 0.25f;
+    const float y = (lev == 0) ? ra.y : ra.y * 0.25f;
+    const int fxp = safe_floor(x), fyp = safe_floor(y);
+    const int xmin = __reduce_min_sync(0xffffffffu, lane < PP ? fxp : 0x7fffffff);
+    const int xmax = __reduce_max_sync(0xffffffffu, lane < PP ? fxp : -0x7fffffff);
+    const int ymin = __reduce_min_sync(0xffffffffu, lane < PP ? fyp : 0x7fffffff);
+    const int ymax = __reduce_max_sync(0xffffffffu, lane < PP ? fyp : -0x7fffffff);
+    Geo gq;
+    gq.fits = (xmax - xmin + D <= RG) && (ymax - ymin + D <= RG);
+    gq.lev = lev;
+    const int b = (P.B == 1) ? 0 : (int)((u_first + ka * ustride) / P.E);
+    gq.frame = b * (int)P.F + ra.jx;
+    const int H = lev == 0 ? P.H[0] : P.H[1], W = lev == 0 ? P.W[0] : P.W[1];
+    gq.x0 = min(max(xmin - R, -RG), W);
+    gq.y0 = min(max(ymin - R, -RG), H);
+    if (lane < PP) {
+      const float dx = x - floorf(x), dy = y - floorf(y);
+      S.wgt[slot][lane] = make_float4((1.f - dx) * (1.f - dy), dx * (1.f - dy), (1.f - dx) * dy, dx * dy);
+      S.vbase[slot][lane] = gq.fits ? ((fyp - ymin) * RG + (fxp - xmin)) * SLOT + lane : lane;
+    }
+    __syncwarp();
+    return gq;
+  };
+  // chunk q of half-task geometry gq into buffer q % WNBUF (the buffer must have been released)
+  auto issue = [&](const Geo& gq, int q) {
+    if (gq.fits && lane == 0) {
+      const int b = q % WNBUF;
+      fence_proxy_async();
+      mbar_expect_tx(bar0 + 8 * b, WCH_BYTES);
+      asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                   ::"r"(buf0 + b * WCH_BYTES), "l"(gq.lev == 0 ? tma0 : tma1), "r"(bar0 + 8 * b), "r"(q * WCK), "r"(gq.x0),
+                     "r"(gq.y0), "r"(gq.frame) : "memory");
+    }
+  };
+  auto advance = [&]() {
+    ra = rb;
+    ++ka;
+    if (ka + 1 < n_units) load_raw(rb, ka + 1);
+  };
+
+  // ---- prologue: half-task 0, all its chunks
+  load_raw(ra, 0);
+  if (n_units > 1) load_raw(rb, 1);
+  prefetch_a();
+  gc = prepare(0, 0);
+#pragma unroll
+  for (int q = 0; q < NCH && q < WNBUF; ++q) issue(gc, q);
+  if (NLEV == 1) advance();
+
+  for (int64_t s = 0; s < n_half; ++s) {
+    const int lev = (NLEV == 1) ? 0 : (int)(s & 1);
+    const int slot = (int)(s & 1);
+    const int64_t unit = u_first + (s / NLEV) * ustride;
+    const bool have_next = s + 1 < n_half;
+    const int lev_n = (NLEV == 1) ? 0 : (int)((s + 1) & 1);
+
+    // ---- (0) new unit: patch-feature record to shared memory, B fragments for all channels
+    if (lev == 0) {
+#pragma unroll
+      for (int k = 0; k < NAV; ++k)
+        if (lane + 32 * k < NA4) reinterpret_cast<uint4*>(&S.a[0])[lane + 32 * k] = apre[k];
+      __syncwarp();
+      const unsigned short* ar = reinterpret_cast<const unsigned short*>(&S.a[0]);
+#pragma unroll
+      for (int x = 0; x < C / 8; ++x) {
+        const int c = 8 * x + 2 * tq;
+        bf0[x] = (unsigned)ar[c * PP + g] | ((unsigned)ar[(c + 1) * PP + g] << 16);
+        bf1[x] = (g == 0) ? ((unsigned)ar[c * PP + 8] | ((unsigned)ar[(c + 1) * PP + 8] << 16)) : 0u;
+      }
+    }
+
+    // ---- (1) geometry of the next half-task, patch features of the next unit, raw values of the unit after it
+    if (have_next) {
+      gn = prepare(lev_n, slot ^ 1);
+      if (lev_n == 0) prefetch_a();
+      if (lev_n == NLEV - 1) advance();
+      if (!gc.fits) {                     // the current half-task holds no buffers: fill them for the next one now
+#pragma unroll
+        for (int q = 0; q < NCH && q < WNBUF; ++q) issue(gn, q);
+      }
+    }
+
+    // ---- (2) contraction, chunk by chunk; every consumed buffer is refilled for the next half-task
+    float* vol = S.vol;
+    if (gc.fits) {
+      float d0[RPX / 16][4], d1[RPX / 16][4];
+#pragma unroll
+      for (int mt = 0; mt < RPX / 16; ++mt)
+#pragma unroll
+        for (int x = 0; x < 4; ++x) { d0[mt][x] = 0.f; d1[mt][x] = 0.f; }
+#pragma unroll
+      for (int q = 0; q < NCH; ++q) {
+        const int b = q % WNBUF;
+        mbar_wait(bar0 + 8 * b, (phase >> b) & 1u);
+        phase ^= 1u << b;
+        const uint32_t cb = buf0 + b * WCH_BYTES;
+#pragma unroll
+        for (int mg = 0; mg < RPX / 48; ++mg) {
+          unsigned af[3][8];
+#pragma unroll
+          for (int t = 0; t < 3; ++t) {
+            const uint32_t tb = cb + (mg * 3 + t) * 16 * 64;
+            ldsm_x4(af[t][0], af[t][1], af[t][2], af[t][3], tb + a_off_k0);
+            ldsm_x4(af[t][4], af[t][5], af[t][6], af[t][7], tb + a_off_k1);
+          }
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+              const int x = 4 * q + 2 * ks;
+              mma_k16(d0[mg * 3 + t], af[t][4 * ks], af[t][4 * ks + 1], af[t][4 * ks + 2], af[t][4 * ks + 3], bf0[x], bf0[x + 1]);
+              mma_k16(d1[mg * 3 + t], af[t][4 * ks], af[t][4 * ks + 1], af[t][4 * ks + 2], af[t][4 * ks + 3], bf1[x], bf1[x + 1]);
+            }
+        }
+        __syncwarp();
+        // buffer b is free: it takes the chunk WNBUF positions further down the stream (this or the next half-task)
+        if (q + WNBUF < NCH) issue(gc, q + WNBUF);
+        else if (have_next) issue(gn, q + WNBUF - NCH);
+      }
+#pragma unroll
+      for (int mt = 0; mt < RPX / 16; ++mt) {
+        float* v0 = vol + (mt * 16 + gperm) * SLOT;
+        *reinterpret_cast<float2*>(v0 + 2 * tq) = make_float2(d0[mt][0], d0[mt][1]);
+        *reinterpret_cast<float2*>(v0 + 8 * SLOT + 2 * tq) = make_float2(d0[mt][2], d0[mt][3]);
+        if (tq == 0) { v0[8] = d1[mt][0]; v0[8 * SLOT + 8] = d1[mt][2]; }
+      }
+    } else {
+      const int H = lev == 0 ? P.H[0] : P.H[1], W = lev == 0 ? P.W[0] : P.W[1];
+      const __half* f2 = (lev == 0 ? P.nhwc[0] : P.nhwc[1]) + (int64_t)gc.frame * H * W * C;
+      const float* cg = P.coords + unit * (2 * PP);
+      for (int o = lane; o < PP * D * D; o += 32) {
+        const int p = o / (D * D), pos = o - p * (D * D);
+        const int io = pos / D, jo = pos - io * D;
+        const float xs = (lev == 0) ? cg[p] : cg[p] * 0.25f, ys = (lev == 0) ? cg[PP + p] : cg[PP + p] * 0.25f;
+        const int i1 = safe_floor(ys) + (io - R), j1 = safe_floor(xs) + (jo - R);
+        float acc = 0.f;
+        if (i1 >= 0 && i1 < H && j1 >= 0 && j1 < W) {
+          const __half* src = f2 + ((int64_t)i1 * W + j1) * C;
+          for (int c = 0; c < C; ++c) acc += __half2float(S.a[c * PP + p]) * __half2float(src[c]);
+        }
+        vol[pos * SLOT + p] = acc;
+      }
+    }
+    __syncwarp();
+
+    // ---- (3) blend into the staging buffer; after the unit's last level: coalesced output
+    {
+      constexpr int SROW = (NLEV == 2) ? 136 : 72;
+      if (gc.fits) blend_stage<RG, SLOT, NLEV, SROW>(vol, S.wgt[slot], S.vbase[slot], lane, lev, S.stage);
+      else blend_stage<D, SLOT, NLEV, SROW>(vol, S.wgt[slot], S.vbase[slot], lane, lev, S.stage);
+      __syncwarp();
+      if (lev == NLEV - 1) {
+        __half* og = P.out + unit * (int64_t)(Do * Do * PP) * NLEV;
+#pragma unroll
+        for (int t = 0; t < (Do * Do * PP + 31) / 32; ++t) {
+          const int o = lane + 32 * t;
+          if (o < Do * Do * PP) {
+            const int xo = (o * 1041) >> 16;
+            const int r = o - xo * 63;
+            if (NLEV == 2) reinterpret_cast<unsigned*>(og)[o] = reinterpret_cast<const unsigned*>(S.stage)[xo * (SROW / 2) + r];
+            else og[o] = S.stage[xo * SROW + r];
+          }
+        }
+        __syncwarp();
+      }
+    }
+    gc = gn;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -434,7 +732,34 @@ static int make_map(CUtensorMap* tm, const void* base, int C, int W, int H, int6
   return r == CUDA_SUCCESS ? PCORR_OK : PCORR_ERR_UNSUPPORTED;
 }
 
+// 4-D map [C, W, H, frames] with box [32, 12, 12, 1] and SWIZZLE_64B (wide maps: one box per channel chunk)
+static int make_map_wide(CUtensorMap* tm, const void* base, int C, int W, int H, int64_t frames) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return PCORR_ERR_UNSUPPORTED;
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)frames};
+  const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  const cuuint32_t box[4] = {WCK, RG, RG, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? PCORR_OK : PCORR_ERR_UNSUPPORTED;
+}
+
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+template <int C, int NLEV>
+static int launch_wide(const CUtensorMap& tm0, const CUtensorMap& tm1, const Params& P, cudaStream_t s) {
+  auto kern = corr_tma_wide_kernel<C, NLEV>;
+  const size_t smem = sizeof(WideSmem<C>) * WWARPS + 1024;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int64_t units = (int64_t)P.B * P.E;
+  int64_t grid = (units + WWARPS - 1) / WWARPS;
+  if (grid > 148) grid = 148;
+  kern<<<(unsigned)grid, 32 * WWARPS, smem, s>>>(tm0, tm1, P);
+  pgba::count_launch();
+  return (int)cudaGetLastError();
+}
 
 template <int C, int NLEV>
 static int launch(const CUtensorMap& tm0, const CUtensorMap& tm1, const Params& P, cudaStream_t s) {
@@ -454,17 +779,29 @@ static int launch(const CUtensorMap& tm0, const CUtensorMap& tm1, const Params& 
 
 static void transpose_maps(int C, int nlev, const __half* src0, __half* dst0, int HW0, const __half* src1, __half* dst1,
                            int HW1, int frames, cudaStream_t s) {
-  NhwcJob j0{src0, dst0, HW0, (HW0 + 511) / 512, 0};
-  NhwcJob j1{src1, dst1, HW1, (HW1 + 511) / 512, j0.blocks_per_frame * frames};
+  const bool pair = (HW0 % 2 == 0) && (nlev == 1 || HW1 % 2 == 0);
+  if (C == 128 && pair) {                       // wide maps: direct copy, grid.y = channel groups of 16
+    NhwcJob j0{src0, dst0, HW0, (HW0 / 2 + 255) / 256, 0};
+    NhwcJob j1{src1, dst1, HW1, (HW1 / 2 + 255) / 256, j0.blocks_per_frame * frames};
+    const int blocks = j1.first_block + (nlev == 2 ? j1.blocks_per_frame * frames : 0);
+    if (nlev == 1) j1.first_block = 0x7fffffff;
+    to_nhwc16_kernel<128><<<dim3((unsigned)blocks, 128 / 16), 256, 0, s>>>(j0, j1);
+    pgba::count_launch();
+    return;
+  }
+  const int pxt = C > 32 ? 128 : 512;
+  NhwcJob j0{src0, dst0, HW0, (HW0 + pxt - 1) / pxt, 0};
+  NhwcJob j1{src1, dst1, HW1, (HW1 + pxt - 1) / pxt, j0.blocks_per_frame * frames};
   int blocks = j1.first_block + (nlev == 2 ? j1.blocks_per_frame * frames : 0);
   if (nlev == 1) j1.first_block = 0x7fffffff;
-  const bool pair = (HW0 % 2 == 0) && (nlev == 1 || HW1 % 2 == 0);
   if (C == 24) {
-    if (pair) to_nhwc_kernel<24, true><<<blocks, 256, 0, s>>>(j0, j1);
-    else to_nhwc_kernel<24, false><<<blocks, 256, 0, s>>>(j0, j1);
+    if (pair) to_nhwc_kernel<24, true, 512><<<blocks, 256, 0, s>>>(j0, j1);
+    else to_nhwc_kernel<24, false, 512><<<blocks, 256, 0, s>>>(j0, j1);
+  } else if (C == 32) {
+    if (pair) to_nhwc_kernel<32, true, 512><<<blocks, 256, 0, s>>>(j0, j1);
+    else to_nhwc_kernel<32, false, 512><<<blocks, 256, 0, s>>>(j0, j1);
   } else {
-    if (pair) to_nhwc_kernel<32, true><<<blocks, 256, 0, s>>>(j0, j1);
-    else to_nhwc_kernel<32, false><<<blocks, 256, 0, s>>>(j0, j1);
+    to_nhwc_kernel<128, false, 128><<<blocks, 256, 0, s>>>(j0, j1);       // odd map sizes only
   }
   pgba::count_launch();
 }
@@ -476,7 +813,7 @@ using namespace pcorr_tma;
 extern "C" {
 
 int pcorr_tma_supported(int C, int P, int radius, int dtype) {
-  return (dtype == PCORR_F16 && P == 3 && radius == 3 && (C == 24 || C == 32)) ? 1 : 0;
+  return (dtype == PCORR_F16 && P == 3 && radius == 3 && (C == 24 || C == 32 || C == 128)) ? 1 : 0;
 }
 
 int pcorr_tma_workspace_bytes(int nlev, int B, int64_t F, int C, int H0, int W0, int H1, int W1, size_t* bytes) {
@@ -508,9 +845,10 @@ int pcorr_forward_tma(const void* fmap1, const void* fmap2_l0, const void* fmap2
   transpose_maps(C, nlev, (const __half*)fmap2_l0, n0, H0 * W0, (const __half*)fmap2_l1, n1, nlev == 2 ? H1 * W1 : 0,
                  B * (int)F, s);
   CUtensorMap tm0, tm1;
-  rc = make_map(&tm0, n0, C, W0, H0, (int64_t)B * F);
+  const bool wide = C > 32;
+  rc = wide ? make_map_wide(&tm0, n0, C, W0, H0, (int64_t)B * F) : make_map(&tm0, n0, C, W0, H0, (int64_t)B * F);
   if (rc) return rc;
-  if (nlev == 2) rc = make_map(&tm1, n1, C, W1, H1, (int64_t)B * F);
+  if (nlev == 2) rc = wide ? make_map_wide(&tm1, n1, C, W1, H1, (int64_t)B * F) : make_map(&tm1, n1, C, W1, H1, (int64_t)B * F);
   else tm1 = tm0;
   if (rc) return rc;
   Params Pm{};
@@ -520,6 +858,7 @@ int pcorr_forward_tma(const void* fmap1, const void* fmap2_l0, const void* fmap2
   Pm.coords = coords; Pm.us = ii; Pm.vs = jj;
   Pm.B = B; Pm.E = E; Pm.K = K; Pm.F = F;
   Pm.out = (__half*)out;
+  if (C == 128) return nlev == 2 ? launch_wide<128, 2>(tm0, tm1, Pm, s) : launch_wide<128, 1>(tm0, tm1, Pm, s);
   if (C == 24) return nlev == 2 ? launch<24, 2>(tm0, tm1, Pm, s) : launch<24, 1>(tm0, tm1, Pm, s);
   return nlev == 2 ? launch<32, 2>(tm0, tm1, Pm, s) : launch<32, 1>(tm0, tm1, Pm, s);
 }

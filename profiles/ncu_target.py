@@ -22,7 +22,7 @@ else:
     from tests.helpers import to_dev
     p = synth.config_c2()
     d = to_dev(p)
-    C, dt = (24, torch.float16) if what == "corr" else (128, torch.float32)
+    C, dt = (24, torch.float16) if what == "corr" else ((128, torch.float16) if what == "corr128h" else (128, torch.float32))
     gmap, pyr = synth.make_fmaps(p, C=C)
     g = torch.as_tensor(gmap, device=dev)[None].to(dt)
     f0 = torch.as_tensor(pyr[0], device=dev)[None].to(dt)

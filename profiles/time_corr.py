@@ -20,7 +20,7 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     coords = fastba.reproject(d["poses"], d["patches"], d["intrinsics"], d["ii"], d["jj"], d["kk"])
     res = {}
-    for C in (24, 32):
+    for C in (24, 32, 128):
         gmap, pyr = synth.make_fmaps(p, C=C)
         g = torch.as_tensor(gmap, device=dev)[None].half()
         f0 = torch.as_tensor(pyr[0], device=dev)[None].half()

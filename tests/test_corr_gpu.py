@@ -177,7 +177,7 @@ def test_corr_fp16_tiled_c2_shape_matches_staged_fp32(tiled):
     assert ref.abs().max() > 0.1
 
 
-@pytest.mark.parametrize("C", [24, 32])
+@pytest.mark.parametrize("C", [24, 32, 128])
 def test_corr_fp16_tma_path(C, monkeypatch):
     """fp16, C in {24, 32}, P = 3, R = 3 takes the TMA + tensor-core path (corr_tma.cu) by default: both levels, windows
     across the map border, far outside the map, on exact integers, windows too far apart for one region (per-tap path);

@@ -146,33 +146,39 @@ __global__ void __launch_bounds__(256) to_nhwc_kernel(NhwcJob j0, NhwcJob j1) {
   for (int x = t; x < npx * C / 8; x += 256) d[x] = t4[x];
 }
 
-// C a multiple of 16: no shared memory.  Thread = (pixel pair, group of 16 channels): sixteen coalesced 4-byte loads (one
-// per channel plane), then two full 32-byte sectors per pixel are written (16 channels x 2 bytes).
+// Wide maps (C = 128): 128-pixel tiles through shared memory with rows padded by one word (conflict-free 4-byte
+// copy-out, 2-way conflicts on the 2-byte transposing stores); reads are 4-byte (pixel pairs) and coalesced per channel
+// plane, writes are 4-byte words, 128 contiguous bytes per warp.  H*W must be even.
 template <int C>
-__global__ void __launch_bounds__(256) to_nhwc16_kernel(NhwcJob j0, NhwcJob j1) {
+__global__ void __launch_bounds__(256) to_nhwc_wide_kernel(NhwcJob j0, NhwcJob j1) {
+  constexpr int PXT = 128, RS = C + 2;                               // tile pixels, row stride in halfs
+  __shared__ __align__(16) __half tile[PXT * RS];
   const bool second = (int)blockIdx.x >= j1.first_block;
   const NhwcJob J = second ? j1 : j0;
-  const int blk = (int)blockIdx.x - J.first_block;                 // blocks_per_frame = ceil(HW / 2 / 256) here
+  const int blk = (int)blockIdx.x - J.first_block;
   const int frame = blk / J.blocks_per_frame;
-  const int pp = (blk - frame * J.blocks_per_frame) * 256 + threadIdx.x;
-  if (2 * pp >= J.HW) return;
-  const int c0 = blockIdx.y * 16;
-  const __half* s = J.src + ((int64_t)frame * C + c0) * J.HW + 2 * pp;
-  unsigned v[16];
-#pragma unroll
-  for (int k = 0; k < 16; ++k) v[k] = *reinterpret_cast<const unsigned*>(s + (int64_t)k * J.HW);
-  uint4 a0, a1, b0, b1;                                              // pixel 2pp: low halves; pixel 2pp + 1: high halves
-  a0.x = __byte_perm(v[0], v[1], 0x5410); a0.y = __byte_perm(v[2], v[3], 0x5410);
-  a0.z = __byte_perm(v[4], v[5], 0x5410); a0.w = __byte_perm(v[6], v[7], 0x5410);
-  a1.x = __byte_perm(v[8], v[9], 0x5410); a1.y = __byte_perm(v[10], v[11], 0x5410);
-  a1.z = __byte_perm(v[12], v[13], 0x5410); a1.w = __byte_perm(v[14], v[15], 0x5410);
-  b0.x = __byte_perm(v[0], v[1], 0x7632); b0.y = __byte_perm(v[2], v[3], 0x7632);
-  b0.z = __byte_perm(v[4], v[5], 0x7632); b0.w = __byte_perm(v[6], v[7], 0x7632);
-  b1.x = __byte_perm(v[8], v[9], 0x7632); b1.y = __byte_perm(v[10], v[11], 0x7632);
-  b1.z = __byte_perm(v[12], v[13], 0x7632); b1.w = __byte_perm(v[14], v[15], 0x7632);
-  uint4* d = reinterpret_cast<uint4*>(J.dst + ((int64_t)frame * J.HW + 2 * pp) * C + c0);
-  d[0] = a0; d[1] = a1;
-  d[C / 8] = b0; d[C / 8 + 1] = b1;
+  const int px0 = (blk - frame * J.blocks_per_frame) * PXT;
+  const int npx = min(PXT, J.HW - px0);
+  const __half* s = J.src + (int64_t)frame * C * J.HW + px0;
+  const int t = threadIdx.x;
+  constexpr int ITEMS = (PXT / 2) * C / 256;                         // 32 for C = 128
+#pragma unroll 8
+  for (int i = 0; i < ITEMS; ++i) {
+    const int x = t + 256 * i;
+    const int c = x / (PXT / 2), pp = x - c * (PXT / 2);
+    if (2 * pp < npx) {
+      const __half2 v = *reinterpret_cast<const __half2*>(s + (int64_t)c * J.HW + 2 * pp);
+      tile[(2 * pp) * RS + c] = __low2half(v);
+      tile[(2 * pp + 1) * RS + c] = __high2half(v);
+    }
+  }
+  __syncthreads();
+  unsigned* d = reinterpret_cast<unsigned*>(J.dst + ((int64_t)frame * J.HW + px0) * C);
+  const unsigned* tw = reinterpret_cast<const unsigned*>(tile);
+  for (int x = t; x < npx * (C / 2); x += 256) {
+    const int px = x / (C / 2), w = x - px * (C / 2);
+    d[x] = tw[px * (RS / 2) + w];
+  }
 }
 
 // Window selection + 4-tap bilinear blend of one (edge, level) from its volume in shared memory
@@ -780,12 +786,12 @@ static int launch(const CUtensorMap& tm0, const CUtensorMap& tm1, const Params& 
 static void transpose_maps(int C, int nlev, const __half* src0, __half* dst0, int HW0, const __half* src1, __half* dst1,
                            int HW1, int frames, cudaStream_t s) {
   const bool pair = (HW0 % 2 == 0) && (nlev == 1 || HW1 % 2 == 0);
-  if (C == 128 && pair) {                       // wide maps: direct copy, grid.y = channel groups of 16
-    NhwcJob j0{src0, dst0, HW0, (HW0 / 2 + 255) / 256, 0};
-    NhwcJob j1{src1, dst1, HW1, (HW1 / 2 + 255) / 256, j0.blocks_per_frame * frames};
+  if (C == 128 && pair) {                       // wide maps
+    NhwcJob j0{src0, dst0, HW0, (HW0 + 127) / 128, 0};
+    NhwcJob j1{src1, dst1, HW1, (HW1 + 127) / 128, j0.blocks_per_frame * frames};
     const int blocks = j1.first_block + (nlev == 2 ? j1.blocks_per_frame * frames : 0);
     if (nlev == 1) j1.first_block = 0x7fffffff;
-    to_nhwc16_kernel<128><<<dim3((unsigned)blocks, 128 / 16), 256, 0, s>>>(j0, j1);
+    to_nhwc_wide_kernel<128><<<blocks, 256, 0, s>>>(j0, j1);
     pgba::count_launch();
     return;
   }
@@ -801,7 +807,7 @@ static void transpose_maps(int C, int nlev, const __half* src0, __half* dst0, in
     if (pair) to_nhwc_kernel<32, true, 512><<<blocks, 256, 0, s>>>(j0, j1);
     else to_nhwc_kernel<32, false, 512><<<blocks, 256, 0, s>>>(j0, j1);
   } else {
-    to_nhwc_kernel<128, false, 128><<<blocks, 256, 0, s>>>(j0, j1);       // odd map sizes only
+    to_nhwc_kernel<128, false, 128><<<blocks, 256, 0, s>>>(j0, j1);       // odd H*W only
   }
   pgba::count_launch();
 }

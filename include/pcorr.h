@@ -55,7 +55,7 @@ int pcorr_forward_tiled(const void* fmap1, const void* fmap2_l0, const void* fma
                         int H0, int W0, int H1, int W1, int P, int radius, int dtype, void* out, void* workspace,
                         size_t workspace_bytes, pcorr_stream_t stream);
 
-/* TMA + tensor-core lookup for the production shape (fp16 features, C in {24, 32}, P = 3, radius = 3) -- the default
+/* TMA + tensor-core lookup for the production shapes (fp16 features, C in {24, 32, 128}, P = 3, radius = 3) -- the default
  * path of cuda_corr.forward for that shape.  The frame maps are first copied to a channel-last layout in the
  * caller-owned, 256-byte aligned workspace (pcorr_tma_workspace_bytes()), then one warp per edge fetches its region
  * of fmap2[jj] with one TMA tile load per pyramid level (out-of-map pixels are zero-filled by the hardware), contracts

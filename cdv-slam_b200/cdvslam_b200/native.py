@@ -108,13 +108,17 @@ def require_cuda(*tensors):
 
 
 _workspaces = {}
+_retired = []          # outgrown buffers stay alive: a CUDA graph captured earlier may still point into them
 
 
 def workspace(nbytes, device, pool="ba"):
-    """Grow-only per-device scratch buffer (the C ABI never allocates)."""
+    """Grow-only per-device scratch buffer (the C ABI never allocates).  When a larger buffer is needed the old one is
+    kept alive, so pointers baked into previously captured CUDA graphs remain valid."""
     key = (pool, device.type, device.index if device.index is not None else torch.cuda.current_device())
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
+        if buf is not None:
+            _retired.append(buf)
         buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
         _workspaces[key] = buf
     return buf

@@ -3,6 +3,7 @@
 #include <stdlib.h>
 
 #include <atomic>
+#include <mutex>
 
 #include "ba_common.cuh"
 
@@ -16,6 +17,9 @@ bool solve_supported(int N);
 bool plan_clears_workspace(const Problem& pb, int64_t batch);
 #ifdef PGBA_PLAN_TIMING
 void plan_timestamps(unsigned long long* out);
+#endif
+#ifdef PGBA_LIN_TIMING
+void lin_timestamps(long long* out);
 #endif
 
 bool pdl_enabled() {
@@ -237,6 +241,9 @@ int pgba_ba_solve_profiled(float* poses, float* patches, const float* intrinsics
 
 long long pgba_launch_count(void) { return launch_count(); }
 
+#ifdef PGBA_LIN_TIMING
+void pgba_debug_lin_timestamps(long long* out32) { pgba::lin_timestamps(out32); }
+#endif
 #ifdef PGBA_PLAN_TIMING
 void pgba_debug_plan_timestamps(unsigned long long* out16) { pgba::plan_timestamps(out16); }
 #endif
@@ -273,8 +280,10 @@ HostStage host_stage(int64_t E, int64_t F, int64_t K, int P) {
 cudaEvent_t* stage_events() {
   static cudaEvent_t ev[64][2];
   static bool made[64] = {};
+  static std::mutex mu;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
   if (!made[dev]) {
     if (cudaEventCreateWithFlags(&ev[dev][0], cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&ev[dev][1], cudaEventDisableTiming) != cudaSuccess) return nullptr;
@@ -339,11 +348,12 @@ int pgba_ba_solve_host(float* poses_h, float* patches_h, const float* intrinsics
   }
   // arena mode: the caller's tensors are views of ONE host allocation laid out like the staging buffer
   // (pgba_ba_host_arena_offsets): two uploads (indices | everything else) and one download instead of nine + two
-  const char* hb = (const char*)poses_h - h.poses;
-  const bool arena = (const char*)patches_h == hb + h.patches && (const char*)intrinsics_h == hb + h.intr &&
-                     (const char*)target_h == hb + h.target && (const char*)weight_h == hb + h.weight &&
-                     (const char*)lmbda_h == hb + h.lmbda && (const char*)ii_h == hb + h.ii &&
-                     (const char*)jj_h == hb + h.jj && (const char*)kk_h == hb + h.kk;
+  const uintptr_t hb0 = (uintptr_t)poses_h - h.poses;              // integer arithmetic: the tensors may be unrelated
+  const bool arena = (uintptr_t)patches_h == hb0 + h.patches && (uintptr_t)intrinsics_h == hb0 + h.intr &&
+                     (uintptr_t)target_h == hb0 + h.target && (uintptr_t)weight_h == hb0 + h.weight &&
+                     (uintptr_t)lmbda_h == hb0 + h.lmbda && (uintptr_t)ii_h == hb0 + h.ii &&
+                     (uintptr_t)jj_h == hb0 + h.jj && (uintptr_t)kk_h == hb0 + h.kk;
+  const char* hb = (const char*)hb0;
   if (arena) {
     PGBA_TRY(cudaMemcpyAsync(sb + h.ii, hb + h.ii, h.total - h.ii, cudaMemcpyHostToDevice, s));
     PGBA_TRY(cudaMemcpyAsync(sb, hb, h.ii, cudaMemcpyHostToDevice, a));

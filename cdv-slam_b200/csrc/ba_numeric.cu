@@ -117,9 +117,17 @@ __device__ __forceinline__ void chunk_depth_update(const Problem& pb, const WinP
 
 // grid = (gx, batch), block = 256, dynamic smem = lin_smem_bytes(pc, ebudget).  fuse_update: first apply the previous
 // iteration's back-substitution + depth retraction to the chunk's patches (saves the separate update launch).
+#ifdef PGBA_LIN_TIMING
+__device__ long long g_lin_ts[32];
+#define LIN_TS(i) do { if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) g_lin_ts[i] = clock64(); } while (0)
+#else
+#define LIN_TS(i) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb, int ebudget, int fuse_update) {
   pdl_wait();
   pdl_trigger();
+  LIN_TS(0);
   extern __shared__ float smem[];
   const int pc = pb.L.pc;
   LinSmem s;
@@ -153,6 +161,7 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
     const Chunk ch = wp.chunks[c];
     if (ch.n_patches == 0) continue;
     __syncthreads();
+    LIN_TS(1);
     const int ns = ch.n_slots, ncols = ch.ncols, fi = ch.frame, np = ch.n_patches;
     const bool i_free = ch.icol >= 0;
     const int* cells = wp.cells + ch.cell_base;
@@ -176,6 +185,7 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
     for (int b0 = 0; b0 < np; b0 += PB) {
       const int b1 = min(b0 + PB, np);
       __syncthreads();
+    LIN_TS(2);
       // ---- stage patch centres, zero the E tile
       for (int p = b0 + tid; p < b1; p += 256) {
         const float* pr = patches + (int64_t)kx[p] * pstride;
@@ -186,6 +196,7 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
       }
       for (int x = tid; x < (b1 - b0) * estride; x += 256) s.sE[x] = 0.f;
       __syncthreads();
+    LIN_TS(3);
 
       // ---- tile loop: lanes <-> slots (DW wide), PW patches per warp step
       for (int sb = 0; sb < ns; sb += 32) {
@@ -282,6 +293,7 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
           for (int x = 0; x < 6; ++x) dst[21 + x] = g[x];
         }
         __syncthreads();
+    LIN_TS(4);
         for (int x = tid; x < ns_here * 27; x += 256) {
           const int sx = x / 27, v = x - sx * 27;
           float acc = 0.f;
@@ -290,6 +302,7 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
           s.sH[(sb + sx) * 28 + v] += acc;
         }
         __syncthreads();
+    LIN_TS(5);
       }
 
       // ---- duplicated (patch, slot) edges: rare slow path, one thread (deterministic, no shared atomics)
@@ -335,6 +348,7 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
         }
       }
       __syncthreads();
+    LIN_TS(6);
       if (N > 0 && schur && ncols > 0) {
         float* eg = wp.ecells + 6 * ((int64_t)ch.ecell_base + (int64_t)b0 * ncols);
         for (int x = tid; x < (b1 - b0) * estride; x += 256) eg[x] = s.sE[x];
@@ -394,7 +408,9 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
         }
       }
     }
+    LIN_TS(7);
     __syncthreads();
+    LIN_TS(8);
 
     // ---- pose blocks of this chunk (ba_cuda.cu:364-398)
     if (N > 0) {
@@ -435,6 +451,7 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
           }
         }
         __syncthreads();
+    LIN_TS(9);
         // B2: B_ii = sum_s AH_s A_s^T ; row a per warp: (AH A^T)[a][:] = A * (AH[a][:])^T
         if (warp < 6) {
           float bi[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -462,6 +479,7 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
           }
         }
         __syncthreads();
+    LIN_TS(10);
       }
       // B3: scatter.  Item = (slot, row a).
       for (int it = tid; it < ns * 6; it += 256) {
@@ -502,8 +520,13 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
         atomicAdd(&wp.y[io + tid], s.sBii[36 + tid]);
       }
     }
+    LIN_TS(11);
   }
 }
+
+#ifdef PGBA_LIN_TIMING
+void lin_timestamps(long long* out) { cudaMemcpyFromSymbol(out, g_lin_ts, sizeof(long long) * 32); }
+#endif
 
 // ---------------------------------------------------------------------------------------------------------------
 // Small dense solve: one CTA per window, fp64 in shared memory, blocked (6 wide) right-looking Cholesky on the

@@ -166,10 +166,31 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
     const bool i_free = ch.icol >= 0;
     const int* cells = wp.cells + ch.cell_base;
     const int* kx = wp.kx + ch.patch_base;
+    const int estride = ncols * 6;
+    const int PB = (estride > 0) ? min(np, max(ebudget / estride, 1)) : np;
+    // ---- early loads.  The chunk's tables are chains of dependent global loads (slot -> pose, patch id -> patch,
+    //      cell -> target / weight); in the single-window regime their round trips are the kernel's critical path, so
+    //      the first link of every chain is issued here, before the fused depth update, and the second links together
+    //      right after it (3 + 1 round trips instead of 6 in sequence).
+    const int e_fj = (tid < ns) ? wp.slots[ch.slot_base + tid] : 0;                       // ns <= SMAX <= 256
+    const int e_np = min(PB, np);                                                         // first patch batch [0, e_np)
+    const int e_kx = (tid < e_np) ? kx[tid] : 0;                                          // e_np <= PMAX <= 256
+    const int e_DW = pow2_ceil(min(32, ns)), e_PW = 32 / e_DW;
+    const bool e_ok = (lane & (e_DW - 1)) < min(32, ns);
+    const int e_p = warp * e_PW + lane / e_DW, e_sl = lane & (e_DW - 1);
+    const int e_n0 = (e_ok && e_p < e_np) ? cells[e_p * ns + e_sl] : -1;
+    const int e_n1 = (e_ok && e_p + 8 * e_PW < e_np) ? cells[(e_p + 8 * e_PW) * ns + e_sl] : -1;
     if (fuse_update) chunk_depth_update(pb, wp, ch, pb.patches + (int64_t)w * pb.st.patches, s.sHw, true);
+    float2 e_tg = make_float2(0.f, 0.f), e_wt = make_float2(0.f, 0.f);
+    if (e_n0 >= 0) { e_tg = __ldg(target + e_n0); e_wt = __ldg(weight + e_n0); }
+    float e_px = 0.f, e_py = 0.f, e_pd = 0.f;
+    if (tid < e_np) {
+      const float* pr = patches + (int64_t)e_kx * pstride;     // after the depth update (it rewrites channel 2)
+      e_px = pr[cidx]; e_py = pr[PP + cidx]; e_pd = pr[2 * PP + cidx];
+    }
     // ---- per-slot relative poses, zero the H accumulators
-    for (int sl = tid; sl < ns; sl += 256) {
-      const int fj = wp.slots[ch.slot_base + sl];
+    if (tid < ns) {
+      const int sl = tid, fj = e_fj;
       s.sFrame[sl] = fj;
       float R[9], t[3];
       rel_pose(poses + 7 * (int64_t)fi, poses + 7 * (int64_t)fj, R, t);
@@ -180,19 +201,25 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
     }
     for (int x = tid; x < ns * 28; x += 256) s.sH[x] = 0.f;
 
-    const int estride = ncols * 6;
-    const int PB = (estride > 0) ? min(np, max(ebudget / estride, 1)) : np;
     for (int b0 = 0; b0 < np; b0 += PB) {
       const int b1 = min(b0 + PB, np);
       __syncthreads();
     LIN_TS(2);
       // ---- stage patch centres, zero the E tile
-      for (int p = b0 + tid; p < b1; p += 256) {
-        const float* pr = patches + (int64_t)kx[p] * pstride;
-        const int q = p - b0;
-        s.sPatch[q * 4 + 0] = (pr[cidx] - cx) / fx;              // ba_cuda.cu:282-283
-        s.sPatch[q * 4 + 1] = (pr[PP + cidx] - cy) / fy;
-        s.sPatch[q * 4 + 2] = pr[2 * PP + cidx];
+      if (b0 == 0) {
+        if (tid < b1) {
+          s.sPatch[tid * 4 + 0] = (e_px - cx) / fx;              // ba_cuda.cu:282-283
+          s.sPatch[tid * 4 + 1] = (e_py - cy) / fy;
+          s.sPatch[tid * 4 + 2] = e_pd;
+        }
+      } else {
+        for (int p = b0 + tid; p < b1; p += 256) {
+          const float* pr = patches + (int64_t)kx[p] * pstride;
+          const int q = p - b0;
+          s.sPatch[q * 4 + 0] = (pr[cidx] - cx) / fx;
+          s.sPatch[q * 4 + 1] = (pr[PP + cidx] - cy) / fy;
+          s.sPatch[q * 4 + 2] = pr[2 * PP + cidx];
+        }
       }
       for (int x = tid; x < (b1 - b0) * estride; x += 256) s.sE[x] = 0.f;
       __syncthreads();
@@ -228,10 +255,15 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
         // step ahead, so the two dependent global loads of an edge are off the critical path
         const int pstep = 8 * PW;
         const int p_first = b0 + warp * PW + pl;
-        int n_cur = (slot_ok && p_first < b1) ? cells[p_first * ns + sl] : -1;
-        int n_nxt = (slot_ok && p_first + pstep < b1) ? cells[(p_first + pstep) * ns + sl] : -1;
+        int n_cur, n_nxt;
         float2 tg_cur = make_float2(0.f, 0.f), wt_cur = make_float2(0.f, 0.f);
-        if (n_cur >= 0) { tg_cur = __ldg(target + n_cur); wt_cur = __ldg(weight + n_cur); }
+        if (b0 == 0 && sb == 0) {                    // loaded early (same DW / PW / lane mapping)
+          n_cur = e_n0; n_nxt = e_n1; tg_cur = e_tg; wt_cur = e_wt;
+        } else {
+          n_cur = (slot_ok && p_first < b1) ? cells[p_first * ns + sl] : -1;
+          n_nxt = (slot_ok && p_first + pstep < b1) ? cells[(p_first + pstep) * ns + sl] : -1;
+          if (n_cur >= 0) { tg_cur = __ldg(target + n_cur); wt_cur = __ldg(weight + n_cur); }
+        }
         for (int p0 = b0 + warp * PW; p0 < b1; p0 += pstep) {
           const int p = p0 + pl;
           const int n = n_cur;

@@ -685,8 +685,22 @@ __device__ __forceinline__ void chunk_depth_update(const Problem& pb, const WinP
     const int f = (col < ch.n_free) ? wp.slots[ch.slot_base + ch.first_free + col] : ch.frame;
     sdx[x] = wp.dX[6 * (f - t0) + a];
   }
-  __syncthreads();
   const int len2 = ncols * 3;
+  // small-chunk path: the first patch of every warp, requested before the barrier
+  float2 pre_e0 = make_float2(0.f, 0.f), pre_e1 = make_float2(0.f, 0.f);
+  float pre_q = 0.f, pre_u = 0.f, pre_d = 0.f;
+  int pre_kx = 0;
+  if (pb.L.pc <= 32 && (tid >> 5) < ch.n_patches) {
+    const int p = tid >> 5, lane = tid & 31;
+    const float2* eg = reinterpret_cast<const float2*>(wp.ecells + 6 * ((int64_t)ch.ecell_base + (int64_t)p * ch.ncols));
+    if (lane < len2) pre_e0 = eg[lane];
+    if (lane + 32 < len2) pre_e1 = eg[lane + 32];
+    pre_q = wp.Q[ch.patch_base + p];
+    pre_u = wp.u[ch.patch_base + p];
+    pre_kx = wp.kx[ch.patch_base + p];
+    if (apply) pre_d = patches[(int64_t)pre_kx * pstride + 2 * PP];       // reads [2][0][0] (ba_cuda.cu:218)
+  }
+  __syncthreads();
   const float2* dx2 = reinterpret_cast<const float2*>(sdx);
   if (pb.L.pc > 32) {
     // large chunks: one thread per patch, its E row (ncols * 6 floats, 8-byte aligned) is read with independent
@@ -711,22 +725,26 @@ __device__ __forceinline__ void chunk_depth_update(const Problem& pb, const WinP
       }
     }
   } else {
-    // small chunks (single window): one warp per patch, lanes over the E row
+    // small chunks (single window): one warp per patch, lanes over the E row.  Latency-bound: everything that does not
+    // depend on dX (E row, Q, u, patch id -> old depth) was requested before the barrier above (pre[] below).
     const int lane = tid & 31, warp = tid >> 5;
     for (int p = warp; p < ch.n_patches; p += 8) {
       const float2* eg = reinterpret_cast<const float2*>(wp.ecells + 6 * ((int64_t)ch.ecell_base + (int64_t)p * ch.ncols));
+      const bool first = p == warp;
       float acc = 0.f;
-      for (int x = lane; x < len2; x += 32) {
-        const float2 e = eg[x], d = dx2[x];
+      for (int x = lane, k = 0; x < len2; x += 32, ++k) {
+        const float2 e = (first && k < 2) ? (k == 0 ? pre_e0 : pre_e1) : eg[x];
+        const float2 d = dx2[x];
         acc += e.x * d.x + e.y * d.y;
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      const float dz = wp.Q[ch.patch_base + p] * (wp.u[ch.patch_base + p] - acc);
+      const float q = first ? pre_q : wp.Q[ch.patch_base + p], u = first ? pre_u : wp.u[ch.patch_base + p];
+      const float dz = q * (u - acc);
       if (lane == 0) wp.dZ[ch.patch_base + p] = dz;
       if (apply) {
-        float* pr = patches + (int64_t)wp.kx[ch.patch_base + p] * pstride + 2 * PP;
-        float d = pr[0] + dz;
+        float* pr = patches + (int64_t)(first ? pre_kx : wp.kx[ch.patch_base + p]) * pstride + 2 * PP;
+        float d = (first ? pre_d : pr[0]) + dz;
         d = (d > 20.f) ? 1.0f : d;
         d = fmaxf(d, 1e-4f);
         __syncwarp();

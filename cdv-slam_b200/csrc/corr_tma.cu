@@ -840,6 +840,8 @@ int pcorr_forward_tma(const void* fmap1, const void* fmap2_l0, const void* fmap2
   if (!fmap1 || !fmap2_l0 || (nlev == 2 && !fmap2_l1) || !coords || !ii || !jj || !out || !workspace) return PCORR_ERR_NULL;
   if (nlev < 1 || nlev > 2 || B < 0 || E < 0 || K <= 0 || F <= 0 || H0 <= 0 || W0 <= 0) return PCORR_ERR_SHAPE;
   if (!pcorr_tma_supported(C, P, radius, dtype)) return PCORR_ERR_UNSUPPORTED;
+  // the TMA box (12 x 12 pixels) must not exceed the map
+  if (H0 < RG || W0 < RG || (nlev == 2 && (H1 < RG || W1 < RG))) return PCORR_ERR_UNSUPPORTED;
   if ((int64_t)B * F >= ((int64_t)1 << 31) || (int64_t)B * F > 65535 || ((uintptr_t)workspace & 255)) return PCORR_ERR_UNSUPPORTED;
   size_t need = 0;
   int rc = pcorr_tma_workspace_bytes(nlev, B, F, C, H0, W0, H1, W1, &need);

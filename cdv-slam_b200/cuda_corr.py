@@ -63,6 +63,8 @@ def _tma(fmap1, maps, coords, ii, jj, radius, out):
     nlev = len(maps)
     H0, W0 = maps[0].shape[3], maps[0].shape[4]
     H1, W1 = (maps[1].shape[3], maps[1].shape[4]) if nlev == 2 else (0, 0)
+    if min(H0, W0) < 12 or (nlev == 2 and min(H1, W1) < 12):        # the 12 x 12 TMA box must fit the map
+        return False
     nbytes = ctypes.c_size_t(0)
     native.check(L.pcorr_tma_workspace_bytes(nlev, B, F, C, H0, W0, H1, W1, ctypes.byref(nbytes)),
                  "pcorr_tma_workspace_bytes")

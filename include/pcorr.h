@@ -61,6 +61,7 @@ int pcorr_forward_tiled(const void* fmap1, const void* fmap2_l0, const void* fma
  * of fmap2[jj] with one TMA tile load per pyramid level (out-of-map pixels are zero-filled by the hardware), contracts
  * it with the patch features on the tensor cores (fp32 accumulate) and writes the blended, permuted result once.
  * Same results layout as pcorr_forward (nlev = 1; fmap2_l1 may be NULL) / pcorr_forward_pyramid2 (nlev = 2).
+ * Maps smaller than 12 x 12 pixels are not supported (PCORR_ERR_UNSUPPORTED; use pcorr_forward).
  * The host builds two CUtensorMap descriptors per call (no allocation, no synchronisation; graph-capturable). */
 int pcorr_tma_supported(int C, int P, int radius, int dtype);
 int pcorr_tma_workspace_bytes(int nlev, int B, int64_t F, int C, int H0, int W0, int H1, int W1,

@@ -247,3 +247,19 @@ def test_corr_fp16_tma_c2_shape_matches_staged_fp32():
     err = (got - ref).abs()
     assert bool((err <= 2.0 ** -11 * ref.abs() + 1e-4).all())
     assert ref.abs().max() > 0.1
+
+
+def test_corr_fp16_tiny_maps_fall_back():
+    """Maps smaller than the 12 x 12 TMA box take the staged kernel; same oracle bound."""
+    rng = np.random.default_rng(3)
+    C, K, F, E = 24, 20, 3, 50
+    gmap = (rng.standard_normal((K, C, 3, 3)) / 4).astype(np.float16)
+    fmap = (rng.standard_normal((F, C, 9, 10)) / 4).astype(np.float16)
+    coords = rng.uniform(-2, 11, (1, E, 2, 3, 3)).astype(np.float32)
+    ii = rng.integers(0, K, E); jj = rng.integers(0, F, E)
+    got = altcorr.corr(torch.as_tensor(gmap, device="cuda")[None], torch.as_tensor(fmap, device="cuda")[None],
+                       torch.as_tensor(coords, device="cuda"), torch.as_tensor(ii, device="cuda"),
+                       torch.as_tensor(jj, device="cuda"), 3)
+    want = corr_oracle.corr(gmap[None], fmap[None], coords, ii, jj, 3)
+    err = np.abs(got.float().cpu().numpy() - want)
+    assert (err <= 2.0 ** -11 * np.abs(want) + 1e-4).all()

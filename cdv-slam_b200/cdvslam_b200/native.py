@@ -41,6 +41,8 @@ SIGNATURES = {
                                                      c_int, c_int, c_vp, c_sz, c_vp, ctypes.POINTER(ctypes.c_float)]),
     "pgba_launch_count": (ctypes.c_longlong, []),
     "pgba_ba_status_ptr": (c_vp, [c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_i64, c_i64]),
+    "pgba_pgo_workspace_bytes": (c_int, [c_i64, ctypes.POINTER(c_sz)]),
+    "pgba_pgo_solve": (c_int, [c_vp] * 5 + [c_i64, c_i64, ctypes.c_float, ctypes.c_float, c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "pgba_reproject": (c_int, [c_vp] * 6 + [c_i64, c_i64, c_i64, c_int, c_int, c_vp, c_vp]),
     "pcorr_forward": (c_int, [c_vp] * 5 + [c_int, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_vp,
                                            c_vp]),

@@ -139,6 +139,30 @@ def neighbors(ii, jj):
 
 
 def solve_system(J_Ginv_i, J_Ginv_j, ii, jj, res, ep, lm, freen):
-    """cuda_ba.solve_system (ba.cpp:120-180): Sim3 pose-graph normal equations + sparse Cholesky on the CPU (Eigen).
-    Only used by the optional classical loop closure; out of scope for this round."""
-    raise NotImplementedError("cuda_ba.solve_system (classical loop-closure PGO) is not part of the B200 hot path yet")
+    """cuda_ba.solve_system (ba.cpp:120-180): pose-graph normal equations A = J^T J (+ lm * diag + ep), b = -J^T res and
+    the double-precision Cholesky solve of the leading 7*freen block (all when freen < 0), on the device (the reference
+    moves everything to the CPU and uses Eigen).  Returns [delta] with delta f32 [n, 7] on res.device."""
+    J_Ginv_i = _prep(J_Ginv_i, torch.float32, "J_Ginv_i")
+    J_Ginv_j = _prep(J_Ginv_j, torch.float32, "J_Ginv_j")
+    res = _prep(res, torch.float32, "res")
+    ii = _prep(ii, torch.int64, "ii")
+    jj = _prep(jj, torch.int64, "jj")
+    r = res.shape[0]
+    if J_Ginv_i.shape != (r, 7, 7) or J_Ginv_j.shape != (r, 7, 7) or res.shape != (r, 7) or ii.numel() != r or jj.numel() != r:
+        raise RuntimeError("cuda_ba.solve_system: expected J_Ginv_i/j [r,7,7], res [r,7], ii/jj [r]")
+    if r == 0:
+        raise RuntimeError("cuda_ba.solve_system: no residuals")
+    if bool((ii == jj).any()):                    # the reference calls exit(1) here (ba.cpp:151-152)
+        raise RuntimeError("cuda_ba.solve_system: self edge (ii[x] == jj[x])")
+    n = int(torch.maximum(ii.max(), jj.max()).item()) + 1          # like the reference (ba.cpp:131), a host sync
+    L = native.lib()
+    nbytes = ctypes.c_size_t(0)
+    native.check(L.pgba_pgo_workspace_bytes(n, ctypes.byref(nbytes)), "pgba_pgo_workspace_bytes")
+    delta = torch.empty((n, 7), dtype=torch.float32, device=res.device)
+    with torch.cuda.device(res.device):
+        ws = native.workspace(nbytes.value, res.device, pool="pgo")
+        rc = L.pgba_pgo_solve(J_Ginv_i.data_ptr(), J_Ginv_j.data_ptr(), ii.data_ptr(), jj.data_ptr(), res.data_ptr(), r, n,
+                              float(ep), float(lm), int(freen), delta.data_ptr(), None, ws.data_ptr(), ws.numel(),
+                              native.stream_ptr(res.device))
+    native.check(rc, "pgba_pgo_solve")
+    return [delta]

@@ -147,6 +147,19 @@ int pgba_reproject(const float* poses, const float* patches, const float* intrin
                    const int64_t* jj, const int64_t* kk, int64_t n_edges, int64_t n_pose_rows, int64_t n_patch_rows,
                    int P, int clamp_depth, float* coords, pgba_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Pose-graph normal equations + solve.  Replaces cuda_ba.solve_system == solve_system() (reference:
+ * cdvslam/fastba/ba.cpp:99-180; caller cdvslam/loop_closure/optim_utils.py:230).  J_Ginv_i, J_Ginv_j f32 [r,7,7];
+ * ii, jj i64 [r] (ii[x] != jj[x]); res f32 [r,7]; delta f32 [n_poses,7] (out).  A = J^T J, b = -J^T res,
+ * A.diag += A.diag*lm + ep, solve the leading 7*freen x 7*freen block (all of A when freen < 0), rest of delta = 0.
+ * Arithmetic in double like the reference (Eigen SimplicialCholesky); `info` (device i32, may be NULL) receives 0 or
+ * 1 + the index of the first non-positive pivot.  Workspace: pgba_pgo_workspace_bytes() (dense 7n x 7n doubles).
+ * ------------------------------------------------------------------------------------------------------------- */
+int pgba_pgo_workspace_bytes(int64_t n_poses, size_t* bytes /* host, out */);
+int pgba_pgo_solve(const float* J_Ginv_i, const float* J_Ginv_j, const int64_t* ii, const int64_t* jj, const float* res,
+                   int64_t n_res, int64_t n_poses, float ep, float lm, int freen, float* delta, int32_t* info,
+                   void* workspace, size_t workspace_bytes, pgba_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -33,14 +33,9 @@ template <typename T> struct BigSys {
 };
 
 // grid = (1, batch), block = 256, dynamic smem: (2*NB) x (NB|1) doubles + NB
-template <typename Sys>
-__global__ void __launch_bounds__(256, 1) big_potf2_kernel(Sys sys, int step) {
-  pdl_wait();
-  pdl_trigger();
-  extern __shared__ double sd[];
-  using T = typename Sys::T;
+template <typename T>
+__device__ __forceinline__ void big_potf2_dev(const BigSys<T>& bp, int step, double* sd) {
   const int tid = threadIdx.x;
-  const BigSys<T> bp = sys.get(blockIdx.y);
   const int n6 = bp.n, kb = step * NB;
   const int nh = min(NB, n6 - kb), ld = NB | 1;
   double* A = sd;                       // rows 0..nh-1: diagonal tile; rows nh..2nh-1: identity (-> L^-T, see below)
@@ -64,21 +59,23 @@ __global__ void __launch_bounds__(256, 1) big_potf2_kernel(Sys sys, int step) {
   if (tid == 0) bp.nact[step] = 0;
 }
 
-// Row "tile" t of the rows below panel `step`: t < ntb -> rows [kb+nh + 48 t, +48) of S; t == ntb -> the rhs row y.
-// grid = (ntb + 1, batch), block = 256
 template <typename Sys>
-__global__ void __launch_bounds__(256) big_trsm_kernel(Sys sys, int step) {
+__global__ void __launch_bounds__(256, 1) big_potf2_kernel(Sys sys, int step) {
   pdl_wait();
   pdl_trigger();
-  using T = typename Sys::T;
-  __shared__ T sA[NB][NB + 1];
-  __shared__ T sW[NB][NB + 1];
+  extern __shared__ double sd[];
+  big_potf2_dev(sys.get(blockIdx.y), step, sd);
+}
+
+// Row "tile" t of the rows below panel `step`: t < ntb -> rows [kb+nh + 48 t, +48) of S; t == ntb -> the rhs row y.
+// grid = (ntb + 1, batch), block = 256
+template <typename T>
+__device__ __forceinline__ void big_trsm_dev(const BigSys<T>& bp, int step, int t, T (*sA)[NB + 1], T (*sW)[NB + 1]) {
   const int tid = threadIdx.x;
-  const BigSys<T> bp = sys.get(blockIdx.y);
   const int n6 = bp.n, kb = step * NB;
   const int nh = min(NB, n6 - kb), r0 = kb + nh;
   const int ntb = (n6 - r0 + NB - 1) / NB;
-  const int t = blockIdx.x;
+  __syncthreads();                               // the tiles may still be in use by the caller's previous item
   const bool rhs = (t == ntb);
   const int rows = rhs ? 1 : min(NB, n6 - (r0 + t * NB));
   T* src = rhs ? (bp.y + kb) : (bp.S + (size_t)(r0 + t * NB) * bp.ld + kb);
@@ -109,8 +106,71 @@ __global__ void __launch_bounds__(256) big_trsm_kernel(Sys sys, int step) {
   }
 }
 
+template <typename Sys>
+__global__ void __launch_bounds__(256) big_trsm_kernel(Sys sys, int step) {
+  pdl_wait();
+  pdl_trigger();
+  using T = typename Sys::T;
+  __shared__ T sA[NB][NB + 1];
+  __shared__ T sW[NB][NB + 1];
+  big_trsm_dev(sys.get(blockIdx.y), step, (int)blockIdx.x, sA, sW);
+}
+
 // Trailing update over pairs (a >= b) of active row tiles of this panel: S[tile a][tile b] -= X_a X_b^T.
 // Persistent grid: grid = (gx, batch), block = 256 (16 x 16 threads, 3 x 3 outputs each).
+template <typename T>
+__device__ __forceinline__ void big_syrk_pair_dev(const BigSys<T>& bp, int step, int ta, int tb, T (*sXa)[NB + 1],
+                                                  T (*sXb)[NB + 1]) {
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int n6 = bp.n, kb = step * NB;
+  const int nh = min(NB, n6 - kb), r0 = kb + nh;
+  if (ta == -1 && tb == -1) return;              // rhs x rhs: nothing to update
+  // order so that "a" is the lower tile (larger row index); the rhs row is below everything
+  if (tb == -1 || (ta != -1 && tb > ta)) { const int s = ta; ta = tb; tb = s; }
+  const bool rhs = (ta == -1);
+  const int ra = rhs ? 0 : r0 + ta * NB, rb = r0 + tb * NB;
+  const int rows_a = rhs ? 1 : min(NB, n6 - ra), rows_b = min(NB, n6 - rb);
+  const T* xa = rhs ? (bp.y + kb) : (bp.S + (size_t)ra * bp.ld + kb);
+  const size_t sa = rhs ? 0 : (size_t)bp.ld;
+  const T* xb = bp.S + (size_t)rb * bp.ld + kb;
+  __syncthreads();
+  for (int x = tid; x < NB * NB; x += 256) {
+    const int r = x / NB, k = x - r * NB;
+    sXa[k][r] = (r < rows_a && k < nh) ? xa[r * sa + k] : (T)0;
+    sXb[k][r] = (r < rows_b && k < nh) ? xb[(size_t)r * bp.ld + k] : (T)0;
+  }
+  __syncthreads();
+  T acc[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  for (int k = 0; k < nh; ++k) {
+    T a[3], b[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { a[i] = sXa[k][ty + 16 * i]; b[i] = sXb[k][tx + 16 * i]; }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) acc[i][j] += a[i] * b[j];
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int r = ty + 16 * i, c = tx + 16 * j;
+      if (r >= rows_a || c >= rows_b) continue;
+      if (rhs) {
+        bp.y[rb + c] -= acc[i][j];
+      } else if (rb + c <= ra + r) {             // lower triangle only
+        bp.S[(size_t)(ra + r) * bp.ld + rb + c] -= acc[i][j];
+      }
+    }
+}
+
+__device__ __forceinline__ void pair_of(int pr, int& ia, int& ib) {
+  ia = (int)((sqrtf(8.f * pr + 1.f) - 1.f) * 0.5f);
+  while (ia * (ia + 1) / 2 > pr) --ia;
+  while ((ia + 1) * (ia + 2) / 2 <= pr) ++ia;
+  ib = pr - ia * (ia + 1) / 2;
+}
+
 template <typename Sys>
 __global__ void __launch_bounds__(256) big_syrk_kernel(Sys sys, int step) {
   pdl_wait();
@@ -118,78 +178,28 @@ __global__ void __launch_bounds__(256) big_syrk_kernel(Sys sys, int step) {
   using T = typename Sys::T;
   __shared__ T sXa[NB][NB + 1];     // [k][row]
   __shared__ T sXb[NB][NB + 1];
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const BigSys<T> bp = sys.get(blockIdx.y);
-  const int n6 = bp.n, kb = step * NB;
-  const int nh = min(NB, n6 - kb), r0 = kb + nh;
   const int na = bp.nact[step];
   const int* act = bp.active + (size_t)step * bp.big_tiles;
   const int npairs = na * (na + 1) / 2;
   for (int pr = blockIdx.x; pr < npairs; pr += gridDim.x) {
-    int ia = (int)((sqrtf(8.f * pr + 1.f) - 1.f) * 0.5f);
-    while (ia * (ia + 1) / 2 > pr) --ia;
-    while ((ia + 1) * (ia + 2) / 2 <= pr) ++ia;
-    const int ib = pr - ia * (ia + 1) / 2;
-    int ta = act[ia], tb = act[ib];
-    if (ta == -1 && tb == -1) continue;            // rhs x rhs: nothing to update
-    // order so that "a" is the lower tile (larger row index); the rhs row is below everything
-    if (tb == -1 || (ta != -1 && tb > ta)) { const int s = ta; ta = tb; tb = s; }
-    const bool rhs = (ta == -1);
-    const int ra = rhs ? 0 : r0 + ta * NB, rb = r0 + tb * NB;
-    const int rows_a = rhs ? 1 : min(NB, n6 - ra), rows_b = min(NB, n6 - rb);
-    const T* xa = rhs ? (bp.y + kb) : (bp.S + (size_t)ra * bp.ld + kb);
-    const size_t sa = rhs ? 0 : (size_t)bp.ld;
-    const T* xb = bp.S + (size_t)rb * bp.ld + kb;
-    __syncthreads();
-    for (int x = tid; x < NB * NB; x += 256) {
-      const int r = x / NB, k = x - r * NB;
-      sXa[k][r] = (r < rows_a && k < nh) ? xa[r * sa + k] : (T)0;
-      sXb[k][r] = (r < rows_b && k < nh) ? xb[(size_t)r * bp.ld + k] : (T)0;
-    }
-    __syncthreads();
-    T acc[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-    for (int k = 0; k < nh; ++k) {
-      T a[3], b[3];
-#pragma unroll
-      for (int i = 0; i < 3; ++i) { a[i] = sXa[k][ty + 16 * i]; b[i] = sXb[k][tx + 16 * i]; }
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) acc[i][j] += a[i] * b[j];
-    }
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const int r = ty + 16 * i, c = tx + 16 * j;
-        if (r >= rows_a || c >= rows_b) continue;
-        if (rhs) {
-          bp.y[rb + c] -= acc[i][j];
-        } else if (rb + c <= ra + r) {             // lower triangle only
-          bp.S[(size_t)(ra + r) * bp.ld + rb + c] -= acc[i][j];
-        }
-      }
+    int ia, ib;
+    pair_of(pr, ia, ib);
+    big_syrk_pair_dev(bp, step, act[ia], act[ib], sXa, sXb);
   }
 }
 
 // Backward substitution, panel `step` (launched for step = last .. 0): x_k = L11^-T (y_k - sum_below L[r][k]^T x[r]).
 // grid = (gx, batch), block = 256.  The active row tiles of this panel are the only rows with non-zero L[r][k].
-template <typename Sys>
-__global__ void __launch_bounds__(256) big_back_kernel(Sys sys, int step) {
-  pdl_wait();
-  pdl_trigger();
-  using T = typename Sys::T;
-  __shared__ T spart[5][NB];
-  __shared__ T sz[NB];
-  __shared__ int s_last;
+template <typename T>
+__device__ __forceinline__ void big_back_partial_dev(const BigSys<T>& bp, int step, int first, int stride, T (*spart)[NB]) {
   const int tid = threadIdx.x;
-  const BigSys<T> bp = sys.get(blockIdx.y);
   const int n6 = bp.n, kb = step * NB;
   const int nh = min(NB, n6 - kb), r0 = kb + nh;
   const int na = bp.nact[step];
   const int* act = bp.active + (size_t)step * bp.big_tiles;
   const int c = tid % NB, grp = tid / NB;          // 5 row groups x 48 columns (threads 240..255 idle)
-  for (int ia = blockIdx.x; ia < na; ia += gridDim.x) {
+  for (int ia = first; ia < na; ia += stride) {
     const int t = act[ia];
     if (t == -1) continue;
     const int ra = r0 + t * NB, rows = min(NB, n6 - ra);
@@ -201,17 +211,17 @@ __global__ void __launch_bounds__(256) big_back_kernel(Sys sys, int step) {
     __syncthreads();
     if (tid < nh) atomicAdd(&bp.tbuf[tid], spart[0][tid] + spart[1][tid] + spart[2][tid] + spart[3][tid] + spart[4][tid]);
   }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) s_last = (atomicAdd(bp.ticket, 1) == (int)gridDim.x - 1);
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
+}
+
+template <typename T>
+__device__ __forceinline__ void big_back_finish_dev(const BigSys<T>& bp, int step, T* sz) {
+  const int tid = threadIdx.x;
+  const int n6 = bp.n, kb = step * NB;
+  const int nh = min(NB, n6 - kb);
   if (tid < nh) {
     sz[tid] = bp.y[kb + tid] - __ldcg(&bp.tbuf[tid]);
     bp.tbuf[tid] = 0;
   }
-  if (tid == 0) *bp.ticket = 0;
   __syncthreads();
   if (tid < nh) {                                   // x[c] = sum_{e >= c} W[c][e] z[e]
     const T* W = bp.winv + (size_t)step * NB * NB + tid * NB;
@@ -219,6 +229,27 @@ __global__ void __launch_bounds__(256) big_back_kernel(Sys sys, int step) {
     for (int e = tid; e < nh; ++e) acc += W[e] * sz[e];
     bp.y[kb + tid] = acc;
   }
+}
+
+template <typename Sys>
+__global__ void __launch_bounds__(256) big_back_kernel(Sys sys, int step) {
+  pdl_wait();
+  pdl_trigger();
+  using T = typename Sys::T;
+  __shared__ T spart[5][NB];
+  __shared__ T sz[NB];
+  __shared__ int s_last;
+  const int tid = threadIdx.x;
+  const BigSys<T> bp = sys.get(blockIdx.y);
+  big_back_partial_dev(bp, step, (int)blockIdx.x, (int)gridDim.x, spart);
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(bp.ticket, 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (tid == 0) *bp.ticket = 0;
+  big_back_finish_dev(bp, step, sz);
 }
 
 // Host: factorisation + both substitutions of `batch` systems of order n (the damping has been applied by the caller).

@@ -19,8 +19,14 @@ for r in rows:
     if hdr and len(r) > 10 and r[0].strip().isdigit():
         col = {h: i for i, h in enumerate(hdr)}
         num = lambda k: float(r[col[k]].replace(",", "") or 0) if r[col[k]] not in ("-", "") else 0.0
-        s, inst = num("# Samples"), num("Instructions Executed")
-        stalls = {k: num(k) for k in hdr if k.startswith("stall_") and "Not Issued" not in k}
+        try:
+            s, inst = num("# Samples"), num("Instructions Executed")
+        except ValueError:          # a source line with embedded quotes (inline asm) breaks the CSV row: skip it
+            continue
+        try:
+            stalls = {k: num(k) for k in hdr if k.startswith("stall_") and "Not Issued" not in k}
+        except ValueError:
+            continue
         out.append((s, inst, (cur_file or "?").split("/")[-1], r[0], r[1].strip()[:88], stalls))
 tot = sum(o[0] for o in out) or 1
 print("total samples %d, total warp insts %d" % (tot, sum(o[1] for o in out)))

@@ -313,3 +313,23 @@ def test_host_buffer_entry_arena_mode():
     _check_state(p, poses, patches, o_poses, o_patches)
     np.testing.assert_array_equal(a["ii"].numpy(), np.asarray(p.ii))          # inputs are not disturbed by the download
     np.testing.assert_array_equal(a["target"][0].numpy(), np.asarray(p.target, np.float32))
+
+
+@pytest.mark.parametrize("pc,mma,plm", [("128", "0", "0"), ("64", "0", "0"), ("32", "0", "0"), ("128", "1", "0"),
+                                        ("8", "1", "0"), ("128", "0", "1"), ("64", "1", "1")])
+def test_forced_chunk_size_and_kernel_variants(pc, mma, plm):
+    """The chunk size (PGBA_PC, normally a heuristic of the edge count), the Schur implementation (PGBA_SCHUR_MMA: 3xTF32
+    tensor-core contraction instead of FFMA2) and the edge-loop mapping (PGBA_PATCH_LANES: lanes <-> patches instead of
+    lanes <-> target frames) are read from the environment once per process, so every combination is checked in its own
+    interpreter: normal equations (B, v, S, y, C, u, dX, dZ), end states, edge cases and the batched entry against the
+    oracle at the same 1e-4 tolerance."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PGBA_PC=pc, PGBA_SCHUR_MMA=mma, PGBA_PATCH_LANES=plm)
+    res = subprocess.run([sys.executable, "-m", "pytest", "tests/test_ba_gpu.py", "-x", "-q", "-m", "gpu", "-k",
+                          "test_normal_equations or test_ba_matches_oracle or test_batched_equals_single or "
+                          "test_edge_cases or test_global_ba_matches_oracle or test_depth_guards or test_structure_only"],
+                         cwd=root, env=env, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]

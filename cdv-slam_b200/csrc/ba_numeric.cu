@@ -116,8 +116,17 @@ __device__ __forceinline__ void red_add2(float* p, float a, float b) {       // 
   atomicAdd(reinterpret_cast<float2*>(p), make_float2(a, b));
 }
 
+// Everything the back-substitution of a chunk needs that does NOT depend on dX, requested ahead of time (small-chunk
+// path: the first patch of every warp): E row, Q, u, patch id -> old depth, and the index of the thread's dX entry.
+struct UpdPre {
+  float2 e0, e1;
+  float q, u, d;
+  int kx, dxi;
+};
+__device__ __forceinline__ UpdPre upd_prefetch(const Problem& pb, const WinPtrs& wp, const Chunk& ch, const float* patches,
+                                               bool apply);
 __device__ __forceinline__ void chunk_depth_update(const Problem& pb, const WinPtrs& wp, const Chunk& ch, float* patches,
-                                                   float* sdx, bool apply);
+                                                   float* sdx, bool apply, const UpdPre& pre, float* s_depth);
 
 // ---------------------------------------------------------------------------------------------------------------
 // Schur update of one patch batch on the tensor cores (chunks with many patches: batched windows, global BA).
@@ -303,13 +312,20 @@ __device__ long long g_lin_ts[32];
 #define CTA_TS(k, f) do { } while (0)
 #endif
 
-template <bool PLM>
+template <bool PLM, bool FUSE>
 __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb, int ebudget, int flags) {
   CTA_TS((flags & 1) ? 3 : 0, 0);
-  pdl_wait();
-  pdl_trigger();
-  CTA_TS((flags & 1) ? 3 : 0, 1);
-  LIN_TS(0);
+  // flags & 8 (second and later linearisations of a call, small solve in between): the previous kernel is the solve,
+  // which lets this kernel start only after its own pdl_wait(), i.e. after the previous linearisation and the plan have
+  // completed.  Only dX and the poses are still being produced; the chunk tables, cells, targets / weights, patch
+  // coordinates and the inputs of the fused back-substitution are final and are requested BEFORE pdl_wait().
+  bool waited = (flags & 8) == 0;
+  if (waited) {
+    pdl_wait();
+    pdl_trigger();
+    CTA_TS((flags & 1) ? 3 : 0, 1);
+    LIN_TS(0);
+  }
   extern __shared__ __align__(16) float smem[];
   const int pc = pb.L.pc;
   LinSmem s;
@@ -338,7 +354,8 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
   const int n_chunks = wp.hdr->n_chunks;
   const int n_dups = wp.hdr->n_dups;
   const bool schur = pb.with_schur != 0;
-  const bool fuse_update = (flags & 1) != 0, use_mma = (flags & 2) != 0;
+  constexpr bool fuse_update = FUSE;
+  const bool use_mma = (flags & 2) != 0;
   constexpr bool plm = PLM;
 
   for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
@@ -365,12 +382,33 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
     const int e_p = warp * e_PW + lane / e_DW, e_sl = lane & (e_DW - 1);
     const int e_n0 = (!plm && e_ok && e_p < e_np) ? cells[e_p * ns + e_sl] : -1;
     const int e_n1 = (!plm && e_ok && e_p + 8 * e_PW < e_np) ? cells[(e_p + 8 * e_PW) * ns + e_sl] : -1;
-    if (fuse_update) chunk_depth_update(pb, wp, ch, pb.patches + (int64_t)w * pb.st.patches, s.sHw, true);
+    UpdPre upre;
+    if (fuse_update) upre = upd_prefetch(pb, wp, ch, patches, true);
+    float e_px = 0.f, e_py = 0.f, e_pd = 0.f;                  // x, y never change; the depth is rewritten by the update
+    if (FUSE && tid < e_np) {
+      const float* pr = patches + (int64_t)e_kx * pstride;
+      e_px = pr[cidx]; e_py = pr[PP + cidx];
+    }
+    if (!waited) {
+      pdl_wait();
+      pdl_trigger();
+      waited = true;
+      CTA_TS((flags & 1) ? 3 : 0, 1);
+      LIN_TS(0);
+    }
+    float Pi[7], Pj[7];                                         // pose rows: requested before the depth update
+    if (FUSE && tid < ns) {
+#pragma unroll
+      for (int x = 0; x < 7; ++x) { Pi[x] = poses[7 * (int64_t)fi + x]; Pj[x] = poses[7 * (int64_t)e_fj + x]; }
+    }
+    if (fuse_update) {
+      chunk_depth_update(pb, wp, ch, pb.patches + (int64_t)w * pb.st.patches, s.sHw, true, upre, s.sQ);
+      if (tid < e_np) e_pd = s.sQ[tid];                         // the retracted depth, straight from the update
+    }
     float2 e_tg = make_float2(0.f, 0.f), e_wt = make_float2(0.f, 0.f);
     if (e_n0 >= 0) { e_tg = __ldg(target + e_n0); e_wt = __ldg(weight + e_n0); }
-    float e_px = 0.f, e_py = 0.f, e_pd = 0.f;
-    if (tid < e_np) {
-      const float* pr = patches + (int64_t)e_kx * pstride;     // after the depth update (it rewrites channel 2)
+    if (!FUSE && tid < e_np) {
+      const float* pr = patches + (int64_t)e_kx * pstride;
       e_px = pr[cidx]; e_py = pr[PP + cidx]; e_pd = pr[2 * PP + cidx];
     }
     // ---- per-slot relative poses, zero the H accumulators
@@ -378,7 +416,11 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
       const int sl = tid, fj = e_fj;
       s.sFrame[sl] = fj;
       float R[9], t[3];
-      rel_pose(poses + 7 * (int64_t)fi, poses + 7 * (int64_t)fj, R, t);
+      if (!FUSE) {
+#pragma unroll
+        for (int x = 0; x < 7; ++x) { Pi[x] = poses[7 * (int64_t)fi + x]; Pj[x] = poses[7 * (int64_t)fj + x]; }
+      }
+      rel_pose(Pi, Pj, R, t);
 #pragma unroll
       for (int x = 0; x < 9; ++x) s.sRt[sl * 12 + x] = R[x];
 #pragma unroll
@@ -829,6 +871,11 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
     }
     LIN_TS(11);
   }
+  if (!waited) {                                                // a CTA without a chunk still has to release its dependents
+    pdl_wait();
+    pdl_trigger();
+    CTA_TS((flags & 1) ? 3 : 0, 1);
+  }
   CTA_TS((flags & 1) ? 3 : 0, 2);
 }
 
@@ -954,32 +1001,51 @@ __global__ void __launch_bounds__(256, 1) solve_small_kernel(Problem pb) {
 // ---------------------------------------------------------------------------------------------------------------
 // Per-chunk back-substitution + depth retraction by the whole CTA (256 threads).  sdx: >= (SMAX + 1) * 6 floats of
 // shared memory, 8-byte aligned.  Ends with a __syncthreads().
+__device__ __forceinline__ UpdPre upd_prefetch(const Problem& pb, const WinPtrs& wp, const Chunk& ch, const float* patches,
+                                               bool apply) {
+  const int tid = threadIdx.x;
+  const int N = pb.t1 - pb.t0;
+  const int PP = pb.P * pb.P, pstride = 3 * PP;
+  const int ncols = (N > 0 && pb.with_schur != 0) ? ch.ncols : 0;
+  const int len2 = ncols * 3;
+  UpdPre pre;
+  pre.e0 = make_float2(0.f, 0.f); pre.e1 = make_float2(0.f, 0.f);
+  pre.q = 0.f; pre.u = 0.f; pre.d = 0.f; pre.kx = 0; pre.dxi = -1;
+  if (tid < ncols * 6) {
+    const int col = tid / 6, a = tid - col * 6;
+    const int f = (col < ch.n_free) ? wp.slots[ch.slot_base + ch.first_free + col] : ch.frame;
+    pre.dxi = 6 * (f - pb.t0) + a;
+  }
+  if (pb.L.pc <= 32 && (tid >> 5) < ch.n_patches) {
+    const int p = tid >> 5, lane = tid & 31;
+    const float2* eg = reinterpret_cast<const float2*>(wp.ecells + 6 * ((int64_t)ch.ecell_base + (int64_t)p * ch.ncols));
+    if (lane < len2) pre.e0 = eg[lane];
+    if (lane + 32 < len2) pre.e1 = eg[lane + 32];
+    pre.q = wp.Q[ch.patch_base + p];
+    pre.u = wp.u[ch.patch_base + p];
+    pre.kx = wp.kx[ch.patch_base + p];
+    if (apply) pre.d = patches[(int64_t)pre.kx * pstride + 2 * PP];       // reads [2][0][0] (ba_cuda.cu:218)
+  }
+  return pre;
+}
+
+// s_depth (optional, shared memory, >= n_patches floats): receives the retracted inverse depth of every patch of the chunk.
 __device__ __forceinline__ void chunk_depth_update(const Problem& pb, const WinPtrs& wp, const Chunk& ch, float* patches,
-                                                   float* sdx, bool apply) {
+                                                   float* sdx, bool apply, const UpdPre& pre, float* s_depth) {
   const int tid = threadIdx.x;
   const int N = pb.t1 - pb.t0, t0 = pb.t0;
   const int PP = pb.P * pb.P, pstride = 3 * PP;
   const int ncols = (N > 0 && pb.with_schur != 0) ? ch.ncols : 0;
-  for (int x = tid; x < ncols * 6; x += 256) {
+  if (pre.dxi >= 0) sdx[tid] = wp.dX[pre.dxi];
+  for (int x = tid + 256; x < ncols * 6; x += 256) {
     const int col = x / 6, a = x - col * 6;
     const int f = (col < ch.n_free) ? wp.slots[ch.slot_base + ch.first_free + col] : ch.frame;
     sdx[x] = wp.dX[6 * (f - t0) + a];
   }
   const int len2 = ncols * 3;
-  // small-chunk path: the first patch of every warp, requested before the barrier
-  float2 pre_e0 = make_float2(0.f, 0.f), pre_e1 = make_float2(0.f, 0.f);
-  float pre_q = 0.f, pre_u = 0.f, pre_d = 0.f;
-  int pre_kx = 0;
-  if (pb.L.pc <= 32 && (tid >> 5) < ch.n_patches) {
-    const int p = tid >> 5, lane = tid & 31;
-    const float2* eg = reinterpret_cast<const float2*>(wp.ecells + 6 * ((int64_t)ch.ecell_base + (int64_t)p * ch.ncols));
-    if (lane < len2) pre_e0 = eg[lane];
-    if (lane + 32 < len2) pre_e1 = eg[lane + 32];
-    pre_q = wp.Q[ch.patch_base + p];
-    pre_u = wp.u[ch.patch_base + p];
-    pre_kx = wp.kx[ch.patch_base + p];
-    if (apply) pre_d = patches[(int64_t)pre_kx * pstride + 2 * PP];       // reads [2][0][0] (ba_cuda.cu:218)
-  }
+  const float2 pre_e0 = pre.e0, pre_e1 = pre.e1;
+  const float pre_q = pre.q, pre_u = pre.u, pre_d = pre.d;
+  const int pre_kx = pre.kx;
   __syncthreads();
   const float2* dx2 = reinterpret_cast<const float2*>(sdx);
   if (pb.L.pc > 32) {
@@ -1002,6 +1068,7 @@ __device__ __forceinline__ void chunk_depth_update(const Problem& pb, const WinP
         d = (d > 20.f) ? 1.0f : d;
         d = fmaxf(d, 1e-4f);
         for (int x = 0; x < PP; ++x) pr[x] = d;
+        if (s_depth) s_depth[p] = d;
       }
     }
   } else {
@@ -1029,17 +1096,20 @@ __device__ __forceinline__ void chunk_depth_update(const Problem& pb, const WinP
         d = fmaxf(d, 1e-4f);
         __syncwarp();
         for (int x = lane; x < PP; x += 32) pr[x] = d;
+        if (s_depth && lane == 0) s_depth[p] = d;
       }
     }
   }
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) update_kernel(Problem pb) {
+// early != 0: the kernel before this one is the small solve, which passes its own pdl_wait() -- i.e. the linearisation
+// that wrote E, Q, u has completed -- before it lets this kernel start.  Everything except dX (chunk table, E rows, Q, u,
+// old depths) is then final when the CTA begins and is requested BEFORE pdl_wait(), while the solve is still running.
+__global__ void __launch_bounds__(256) update_kernel(Problem pb, int early) {
   CTA_TS(2, 0);
-  pdl_wait();
-  pdl_trigger();
-  CTA_TS(2, 1);
+  bool waited = early == 0;
+  if (waited) { pdl_wait(); pdl_trigger(); CTA_TS(2, 1); }
   __shared__ __align__(8) float sdx[(SMAX + 1) * 6];
   const int w = blockIdx.y;
   const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
@@ -1049,8 +1119,11 @@ __global__ void __launch_bounds__(256) update_kernel(Problem pb) {
     const Chunk ch = wp.chunks[c];
     if (ch.n_patches == 0) continue;
     __syncthreads();
-    chunk_depth_update(pb, wp, ch, patches, sdx, pb.apply != 0);
+    const UpdPre pre = upd_prefetch(pb, wp, ch, patches, pb.apply != 0);
+    if (!waited) { pdl_wait(); pdl_trigger(); waited = true; CTA_TS(2, 1); }
+    chunk_depth_update(pb, wp, ch, patches, sdx, pb.apply != 0, pre, nullptr);
   }
+  if (!waited) { pdl_wait(); pdl_trigger(); CTA_TS(2, 1); }
   CTA_TS(2, 2);
 }
 
@@ -1082,6 +1155,16 @@ static bool schur_on_tensor_cores(int pc) {
   return forced > 0;
 }
 
+// Loads ahead of pdl_wait() in the second linearisation / the update kernel (PGBA_EARLY=0 disables, for A/B runs).
+static bool early_loads_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PGBA_EARLY");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
 // Edge loop with lanes <-> patches (linearize_kernel<true>): opt-in (PGBA_PATCH_LANES=1).  Measured on the B200 (c5): every
 // lane carries an edge (the slot-lane loop runs at ~18 of 32 lanes) and the per-patch shuffles disappear, but target /
 // weight become 32-sector gathers, H / g need a 27-value warp reduction per slot and the per-warp partials one more
@@ -1101,13 +1184,16 @@ void launch_linearize(const Problem& pb, int64_t batch, cudaStream_t stream, boo
   const int gx = chunk_grid(pb, batch);
   const int ebudget = lin_ebudget(pb);
   const size_t lsm = lin_smem_bytes(pb.L.pc, ebudget);
-  const int flags = (fuse_update ? 1 : 0) | (schur_on_tensor_cores(pb.L.pc) ? 2 : 0);
+  const bool early = fuse_update && pb.t1 > pb.t0 && !pb.L.big && early_loads_enabled();
+  const int flags = (fuse_update ? 1 : 0) | (schur_on_tensor_cores(pb.L.pc) ? 2 : 0) | (early ? 8 : 0);
+  auto go = [&](auto kern) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm);
+    launch_k(kern, dim3((unsigned)gx, (unsigned)batch), dim3(256), lsm, stream, pb, ebudget, flags);
+  };
   if (patch_lanes(pb.L.pc)) {
-    cudaFuncSetAttribute(linearize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm);
-    launch_k(linearize_kernel<true>, dim3((unsigned)gx, (unsigned)batch), dim3(256), lsm, stream, pb, ebudget, flags);
+    if (fuse_update) go(linearize_kernel<true, true>); else go(linearize_kernel<true, false>);
   } else {
-    cudaFuncSetAttribute(linearize_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm);
-    launch_k(linearize_kernel<false>, dim3((unsigned)gx, (unsigned)batch), dim3(256), lsm, stream, pb, ebudget, flags);
+    if (fuse_update) go(linearize_kernel<false, true>); else go(linearize_kernel<false, false>);
   }
   count_launch();
 }
@@ -1129,7 +1215,8 @@ void launch_solve(const Problem& pb, int64_t batch, cudaStream_t stream) {
 
 void launch_update(const Problem& pb, int64_t batch, cudaStream_t stream) {
   const int gx = chunk_grid(pb, batch);
-  launch_k(update_kernel, dim3((unsigned)gx, (unsigned)batch), dim3(256), 0, stream, pb);
+  const int N = pb.t1 - pb.t0;
+  launch_k(update_kernel, dim3((unsigned)gx, (unsigned)batch), dim3(256), 0, stream, pb, (N > 0 && !pb.L.big && early_loads_enabled()) ? 1 : 0);
   count_launch();
 }
 

@@ -21,6 +21,7 @@ void plan_timestamps(unsigned long long* out);
 #ifdef PGBA_LIN_TIMING
 void lin_timestamps(long long* out);
 void cta_timestamps(unsigned long long* out);
+void plan_cta_timestamps(unsigned long long* out);
 #endif
 
 bool pdl_enabled() {
@@ -245,6 +246,7 @@ long long pgba_launch_count(void) { return launch_count(); }
 #ifdef PGBA_LIN_TIMING
 void pgba_debug_lin_timestamps(long long* out32) { pgba::lin_timestamps(out32); }
 void pgba_debug_cta_timestamps(unsigned long long* out6144) { pgba::cta_timestamps(out6144); }
+void pgba_debug_plan_cta_timestamps(unsigned long long* out3072) { pgba::plan_cta_timestamps(out3072); }
 #endif
 #ifdef PGBA_PLAN_TIMING
 void pgba_debug_plan_timestamps(unsigned long long* out16) { pgba::plan_timestamps(out16); }

@@ -19,6 +19,22 @@ namespace cg = cooperative_groups;
 
 namespace pgba {
 
+#ifdef PGBA_LIN_TIMING
+// per-CTA wall-clock trace (globaltimer, ns) of the plan kernels: [0 plan_cluster, 1 plan_cells][entry / after pdl_wait /
+// exit][flattened CTA index < 512]   (profiles/cta_trace.py)
+__device__ unsigned long long g_plan_cta_ts[2][3][512];
+__device__ __forceinline__ unsigned long long plan_gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define PCTA_TS(k, f) do { if (threadIdx.x == 0) { const int b_ = blockIdx.x + gridDim.x * blockIdx.y; \
+                           if (b_ < 512) g_plan_cta_ts[k][f][b_] = plan_gtime_ns(); } } while (0)
+void plan_cta_timestamps(unsigned long long* out) { cudaMemcpyFromSymbol(out, g_plan_cta_ts, sizeof(unsigned long long) * 2 * 3 * 512); }
+#else
+#define PCTA_TS(k, f) do { } while (0)
+#endif
+
 // In-place exclusive scan of a[0..n) by the whole block; returns the total.  scratch: >= 33 ints of shared memory.
 __device__ int block_exclusive_scan(int* a, int n, int* scratch) {
   const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -209,8 +225,10 @@ __global__ void __launch_bounds__(256) plan_scatter_kernel(Problem pb) {
 
 // grid = (gx, batch), block = 256, static smem.  Chunks are taken round-robin by blockIdx.x.
 __global__ void __launch_bounds__(256) plan_cells_kernel(Problem pb) {
+  PCTA_TS(1, 0);
   pdl_wait();
   pdl_trigger();
+  PCTA_TS(1, 1);
   __shared__ unsigned pflag[PMAX / 32];
   __shared__ int ppref[PMAX / 32 + 1];
   __shared__ unsigned jflag[PGBA_MAX_POSE_ROWS / 32];
@@ -308,6 +326,7 @@ __global__ void __launch_bounds__(256) plan_cells_kernel(Problem pb) {
       }
     }
   }
+  PCTA_TS(1, 2);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -316,7 +335,7 @@ __global__ void __launch_bounds__(256) plan_cells_kernel(Problem pb) {
 // the grid-wide dependencies of the three passes become hardware cluster barriers.  Every thread keeps its (up to 8)
 // edges in registers across the passes, so the index arrays are read once (larger windows re-read the remainder).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int PLAN_CL = 8, PLAN_T = 1024, PLAN_KEEP = 8;
+constexpr int PLAN_T = 1024, PLAN_KEEP = 8;    // cluster size: template parameter (8 portable, 16 opt-in)
 
 #ifdef PGBA_PLAN_TIMING
 __device__ unsigned long long g_plan_ts[16];
@@ -330,9 +349,12 @@ constexpr int PLAN_CMAX = 8192;          // chunk counts scanned in shared memor
 
 size_t plan_cluster_smem(int F) { return sizeof(int) * ((size_t)2 * ((F + 31) & ~31) + PLAN_CMAX + 32); }
 
+template <int PLAN_CL>
 __global__ void __launch_bounds__(PLAN_T, 1) plan_cluster_kernel(Problem pb) {
+  PCTA_TS(0, 0);
   pdl_wait();
   pdl_trigger();
+  PCTA_TS(0, 1);
   PLAN_TS(0);
   extern __shared__ int psm[];
   __shared__ int scratch[40];
@@ -362,7 +384,7 @@ __global__ void __launch_bounds__(PLAN_T, 1) plan_cluster_kernel(Problem pb) {
 #pragma unroll
   for (int q = 0; q < PLAN_KEEP; ++q) {
     const int e = gt + q * GT;
-    keep[q] = load_edge(pb, ii, jj, kk, e, E);
+    keep[q] = load_edge(pb, ii, jj, kk, e, E);        // slots with q * GT >= E: ok = false, skipped below
     if (e < E && !keep[q].ok) bad = 1;
   }
   const int e_rest = PLAN_KEEP * GT + (gt - lane);     // warp-uniform start of the part that is re-read
@@ -373,6 +395,7 @@ __global__ void __launch_bounds__(PLAN_T, 1) plan_cluster_kernel(Problem pb) {
   // ---- P1: per source frame min / max patch id
 #pragma unroll
   for (int q = 0; q < PLAN_KEEP; ++q) {
+    if (q * GT >= E) break;                          // uniform: no edges in this register slot
     const EdgeIdx x = keep[q];
     const unsigned grp = __match_any_sync(0xffffffffu, x.i);
     const int kmn = __reduce_min_sync(grp, x.k), kmx = __reduce_max_sync(grp, x.k);
@@ -438,6 +461,7 @@ __global__ void __launch_bounds__(PLAN_T, 1) plan_cluster_kernel(Problem pb) {
   int ck[PLAN_KEEP];
 #pragma unroll
   for (int q = 0; q < PLAN_KEEP; ++q) {
+    if (q * GT >= E) break;                          // uniform: no edges in this register slot
     const EdgeIdx x = keep[q];
     const int c = x.ok ? s_fb[x.i] + (x.k - s_km[x.i]) / pc : -1;
     ck[q] = c;
@@ -499,6 +523,7 @@ __global__ void __launch_bounds__(PLAN_T, 1) plan_cluster_kernel(Problem pb) {
   };
 #pragma unroll
   for (int q = 0; q < PLAN_KEEP; ++q) {
+    if (q * GT >= E) break;                          // uniform: no edges in this register slot
     const EdgeIdx x = keep[q];
     const int c = ck[q];
     const unsigned grp = __match_any_sync(0xffffffffu, c);
@@ -520,6 +545,7 @@ __global__ void __launch_bounds__(PLAN_T, 1) plan_cluster_kernel(Problem pb) {
     if (x.ok) wp.perm[base + __popc(grp & ((1u << lane) - 1u))] = make_int4(e, x.j, x.k, 0);
   }
   PLAN_TS(11);
+  PCTA_TS(0, 2);
 }
 
 static int edge_grid(int64_t E, int64_t batch) {
@@ -548,20 +574,31 @@ bool plan_clears_workspace(const Problem& pb, int64_t batch) { return plan_clust
 
 void launch_plan(const Problem& pb, int64_t batch, cudaStream_t stream) {
   if (plan_clears_workspace(pb, batch)) {
+    // single windows: a 16-CTA (non-portable) cluster -- 16 SMs pull the index arrays and every per-edge phase is half as
+    // long; small batches: 8 CTAs per window.  PGBA_PLAN_CL=8 / 16 forces the size (A/B runs).
+    const char* cl_env = getenv("PGBA_PLAN_CL");
+    const int forced_cl = cl_env ? atoi(cl_env) : 0;
+    const int cl_size = (forced_cl == 8 || forced_cl == 16) ? forced_cl : (batch == 1 ? 16 : 8);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(PLAN_CL, (unsigned)batch);
+    cfg.gridDim = dim3((unsigned)cl_size, (unsigned)batch);
     cfg.blockDim = dim3(PLAN_T);
     cfg.dynamicSmemBytes = plan_cluster_smem(pb.F);
     cfg.stream = stream;
-    cudaFuncSetAttribute(plan_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
     cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = PLAN_CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[0].val.clusterDim.x = (unsigned)cl_size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    cudaLaunchKernelEx(&cfg, plan_cluster_kernel, pb);
+    if (cl_size == 16) {
+      cudaFuncSetAttribute(plan_cluster_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
+      cudaFuncSetAttribute(plan_cluster_kernel<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      cudaLaunchKernelEx(&cfg, plan_cluster_kernel<16>, pb);
+    } else {
+      cudaFuncSetAttribute(plan_cluster_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
+      cudaLaunchKernelEx(&cfg, plan_cluster_kernel<8>, pb);
+    }
     count_launch();
   } else {
     const int ge = edge_grid(pb.E, batch);

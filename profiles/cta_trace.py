@@ -15,16 +15,22 @@ g = arm.capture()
 rows = []
 for it in range(6):
     arm.restore(); arm.flush_l2(); torch.cuda.synchronize()
-    g.replay(); torch.cuda.synchronize()
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ea.record(); g.replay(); eb.record(); torch.cuda.synchronize()
     buf = (ctypes.c_ulonglong * (4 * 3 * 512))()
     L.pgba_debug_cta_timestamps(buf)
-    rows.append(np.array(list(buf), dtype=np.float64).reshape(4, 3, 512))
+    buf2 = (ctypes.c_ulonglong * (2 * 3 * 512))()
+    L.pgba_debug_plan_cta_timestamps(buf2)
+    rows.append(np.concatenate([np.array(list(buf2), dtype=np.float64).reshape(2, 3, 512),
+                                np.array(list(buf), dtype=np.float64).reshape(4, 3, 512)]))
+    ev_us = 1e3 * ea.elapsed_time(eb)
 t = rows[-1]
-names = {0: "linearize #1", 1: "solve (last)", 2: "update", 3: "linearize #2 (fused update)"}
+names = {0: "plan_cluster", 1: "plan_cells", 2: "linearize #1", 3: "solve (last)", 4: "update", 5: "linearize #2 (fused update)"}
 valid = t > 0
 t0 = t[valid].min()
+print("event-timed graph replay of this call: %.1f us" % ev_us)
 print("all times in us relative to the first traced CTA entry; n = CTAs traced (<= 512)")
-for k in (0, 1, 3, 2):
+for k in (0, 1, 2, 3, 5, 4):
     m = valid[k, 0] & valid[k, 2]
     if not m.any():
         continue

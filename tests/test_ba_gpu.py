@@ -81,9 +81,11 @@ def test_normal_equations(maker):
     assert np.abs(S - S.T).max() <= 1e-6 * np.abs(S).max()
 
 
+@pytest.mark.parametrize("plan_cl", ["16", "8"])
 @pytest.mark.parametrize("iterations", [1, 2])
 @pytest.mark.parametrize("maker", [lambda: synth.small_problem(seed=3, F=6, M=8, t0=2, lifetime=4), synth.config_c2])
-def test_ba_matches_oracle(maker, iterations):
+def test_ba_matches_oracle(maker, iterations, plan_cl, monkeypatch):
+    monkeypatch.setenv("PGBA_PLAN_CL", plan_cl)       # thread-block cluster size of the single-launch plan
     p = maker()
     o_poses, o_patches = _oracle(p, iterations)
     poses, patches = _run_gpu(p, iterations)
@@ -264,11 +266,14 @@ def test_global_ba_c4_full_size():
     np.testing.assert_array_equal(patches[:, :2], np.asarray(p.patches, np.float32)[:, :2].astype(np.float64))
 
 
-@pytest.mark.parametrize("cluster", ["1", "0"])
+@pytest.mark.parametrize("cluster", ["16", "8", "0"])
 def test_window_with_more_than_65535_edges(cluster, monkeypatch):
-    """A window of ~80k edges: the single-launch (cluster) plan re-reads the edges beyond its register-resident part and
-    uses the unpacked scatter tickets; PGBA_PLAN_CLUSTER=0 is the grid-wide multi-kernel plan.  Both against the oracle."""
-    monkeypatch.setenv("PGBA_PLAN_CLUSTER", cluster)
+    """A window of ~80k edges: the single-launch (cluster) plan uses the unpacked scatter tickets and, with the 8-CTA
+    cluster, re-reads the edges beyond its register-resident part (the 16-CTA cluster keeps them all);
+    PGBA_PLAN_CLUSTER=0 is the grid-wide multi-kernel plan.  All against the oracle."""
+    monkeypatch.setenv("PGBA_PLAN_CLUSTER", "0" if cluster == "0" else "1")
+    if cluster != "0":
+        monkeypatch.setenv("PGBA_PLAN_CL", cluster)
     p = synth.make_problem("w80k", 40, synth.window_edges(40, 96), 30, 40, 5, 96)
     assert p.E > 65536
     poses, patches = _run_gpu(p, 2)

@@ -72,6 +72,7 @@ __device__ int block_exclusive_scan(int* a, int n, int* scratch) {
 }
 
 struct EdgeIdx { int i, j, k; bool ok; };
+constexpr int EDGE_U = 4;                 // edges in flight per thread in the grid-wide passes
 
 __device__ __forceinline__ EdgeIdx load_edge(const Problem& pb, const int64_t* ii, const int64_t* jj,
                                              const int64_t* kk, int e, int E) {
@@ -115,15 +116,24 @@ __global__ void __launch_bounds__(256) plan_frames_kernel(Problem pb) {
   const int E = window_edges(pb, w);
   const int stride = gridDim.x * blockDim.x;
   int bad = 0;
-  for (int e0 = blockIdx.x * blockDim.x; e0 < E; e0 += stride) {     // warp-uniform trip count
-    const int e = e0 + tid;
-    const EdgeIdx x = load_edge(pb, ii, jj, kk, e, E);
-    if (e < E && !x.ok) bad = 1;
-    const unsigned grp = __match_any_sync(0xffffffffu, x.i);
-    const int kmn = __reduce_min_sync(grp, x.k), kmx = __reduce_max_sync(grp, x.k);
-    if (x.ok && lane == __ffs(grp) - 1) {
-      atomicMax(&wp.fmaxinv[x.i], 0x7fffffff - kmn);      // zero-initialised "min": stores max of (INT_MAX - k)
-      atomicMax(&wp.fkmax1[x.i], kmx + 1);
+  // EDGE_U edges per thread and trip: the index loads (three dependent-free 8-byte loads per edge, cold in DRAM) are all
+  // issued before the first warp vote, otherwise every trip pays a full memory round trip
+  for (int e0 = blockIdx.x * blockDim.x; e0 < E; e0 += stride * EDGE_U) {     // warp-uniform trip count
+    EdgeIdx xs[EDGE_U];
+#pragma unroll
+    for (int u = 0; u < EDGE_U; ++u) xs[u] = load_edge(pb, ii, jj, kk, e0 + u * stride + tid, E);
+#pragma unroll
+    for (int u = 0; u < EDGE_U; ++u) {
+      if (e0 + u * stride >= E) break;
+      const int e = e0 + u * stride + tid;
+      const EdgeIdx x = xs[u];
+      if (e < E && !x.ok) bad = 1;
+      const unsigned grp = __match_any_sync(0xffffffffu, x.i);
+      const int kmn = __reduce_min_sync(grp, x.k), kmx = __reduce_max_sync(grp, x.k);
+      if (x.ok && lane == __ffs(grp) - 1) {
+        atomicMax(&wp.fmaxinv[x.i], 0x7fffffff - kmn);      // zero-initialised "min": stores max of (INT_MAX - k)
+        atomicMax(&wp.fkmax1[x.i], kmx + 1);
+      }
     }
   }
   if (bad) atomicOr(&wp.hdr->status, PGBA_ST_INDEX_RANGE);
@@ -176,11 +186,19 @@ __global__ void __launch_bounds__(256) plan_count_kernel(Problem pb) {
   const int n_chunks = wp.hdr->n_chunks;
   const int stride = gridDim.x * blockDim.x;
   if (n_chunks > 0) {
-    for (int e0 = blockIdx.x * blockDim.x; e0 < E; e0 += stride) {
-      const EdgeIdx x = load_edge(pb, ii, jj, kk, e0 + tid, E);
-      const int c = x.ok ? chunk_of(wp, x, pb.L.pc) : -1;
-      const unsigned grp = __match_any_sync(0xffffffffu, c);
-      if (x.ok && lane == __ffs(grp) - 1) atomicAdd(&wp.ccnt[c], __popc(grp));
+    for (int e0 = blockIdx.x * blockDim.x; e0 < E; e0 += stride * EDGE_U) {
+      EdgeIdx xs[EDGE_U];
+#pragma unroll
+      for (int u = 0; u < EDGE_U; ++u) xs[u] = load_edge(pb, ii, jj, kk, e0 + u * stride + tid, E);
+      int cs[EDGE_U];
+#pragma unroll
+      for (int u = 0; u < EDGE_U; ++u) cs[u] = xs[u].ok ? chunk_of(wp, xs[u], pb.L.pc) : -1;
+#pragma unroll
+      for (int u = 0; u < EDGE_U; ++u) {
+        if (e0 + u * stride >= E) break;
+        const unsigned grp = __match_any_sync(0xffffffffu, cs[u]);
+        if (xs[u].ok && lane == __ffs(grp) - 1) atomicAdd(&wp.ccnt[cs[u]], __popc(grp));
+      }
     }
   }
   if (!last_block_done(&wp.hdr->ticket[1])) return;
@@ -210,16 +228,28 @@ __global__ void __launch_bounds__(256) plan_scatter_kernel(Problem pb) {
   const int E = window_edges(pb, w);
   if (wp.hdr->n_chunks == 0) return;
   const int stride = gridDim.x * blockDim.x;
-  for (int e0 = blockIdx.x * blockDim.x; e0 < E; e0 += stride) {
-    const int e = e0 + tid;
-    const EdgeIdx x = load_edge(pb, ii, jj, kk, e, E);
-    const int c = x.ok ? chunk_of(wp, x, pb.L.pc) : -1;
-    const unsigned grp = __match_any_sync(0xffffffffu, c);
-    const int leader = __ffs(grp) - 1;
-    int base = 0;
-    if (x.ok && lane == leader) base = atomicAdd(&wp.ccur[c], __popc(grp));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (x.ok) wp.perm[base + __popc(grp & ((1u << lane) - 1u))] = make_int4(e, x.j, x.k, 0);
+  for (int e0 = blockIdx.x * blockDim.x; e0 < E; e0 += stride * EDGE_U) {
+    EdgeIdx xs[EDGE_U];
+#pragma unroll
+    for (int u = 0; u < EDGE_U; ++u) xs[u] = load_edge(pb, ii, jj, kk, e0 + u * stride + tid, E);
+    int cs[EDGE_U], base[EDGE_U];
+    unsigned grps[EDGE_U];
+#pragma unroll
+    for (int u = 0; u < EDGE_U; ++u) cs[u] = xs[u].ok ? chunk_of(wp, xs[u], pb.L.pc) : -1;
+#pragma unroll
+    for (int u = 0; u < EDGE_U; ++u) {                       // tickets of all EDGE_U groups in flight together
+      grps[u] = 0u; base[u] = 0;
+      if (e0 + u * stride >= E) break;
+      grps[u] = __match_any_sync(0xffffffffu, cs[u]);
+      if (xs[u].ok && lane == __ffs(grps[u]) - 1) base[u] = atomicAdd(&wp.ccur[cs[u]], __popc(grps[u]));
+    }
+#pragma unroll
+    for (int u = 0; u < EDGE_U; ++u) {
+      if (e0 + u * stride >= E) break;
+      const int b = __shfl_sync(0xffffffffu, base[u], __ffs(grps[u]) - 1);
+      if (xs[u].ok)
+        wp.perm[b + __popc(grps[u] & ((1u << lane) - 1u))] = make_int4(e0 + u * stride + tid, xs[u].j, xs[u].k, 0);
+    }
   }
 }
 
@@ -248,11 +278,27 @@ __global__ void __launch_bounds__(256) plan_cells_kernel(Problem pb) {
     for (int x = tid; x < nw; x += T) jflag[x] = 0;
     __syncthreads();
     const int eb = sch.edge_begin, ee = sch.edge_end, kbase = sch.kbase, fi = sch.frame;
-    for (int pos = eb + tid; pos < ee; pos += T) {
-      const int4 rec = wp.perm[pos];
-      const int k = rec.z - kbase, j = rec.y;
-      atomicOr(&pflag[k >> 5], 1u << (k & 31));
-      atomicOr(&jflag[j >> 5], 1u << (j & 31));
+    // presence bits of the chunk's patches / target frames.  All edges of a chunk hit the same few words, so the bits are
+    // first OR-ed over the warp (one shared-memory atomic per distinct word and warp instead of one per edge: same-address
+    // shared atomics serialise, 2 x 1700 of them per chunk was the bulk of this kernel on the batched shape)
+    for (int pos0 = eb; pos0 < ee; pos0 += T) {                  // warp-uniform trip count
+      const int pos = pos0 + tid;
+      const bool in = pos < ee;
+      int k = 0, j = 0;
+      if (in) {
+        const int4 rec = wp.perm[pos];
+        k = rec.z - kbase; j = rec.y;
+      }
+      const int lane = tid & 31;
+      const unsigned kbit = in ? 1u << (k & 31) : 0u, jbit = in ? 1u << (j & 31) : 0u;
+#pragma unroll
+      for (int wd = 0; wd < PMAX / 32; ++wd) {
+        const unsigned m = __reduce_or_sync(0xffffffffu, (k >> 5) == wd ? kbit : 0u);
+        if (m && lane == wd) atomicOr(&pflag[wd], m);
+      }
+      const unsigned grp = __match_any_sync(0xffffffffu, in ? (j >> 5) : -1);
+      const unsigned m = __reduce_or_sync(grp, jbit);
+      if (in && lane == __ffs(grp) - 1) atomicOr(&jflag[j >> 5], m);
     }
     __syncthreads();
     for (int x = tid; x < nw; x += T) jpref[x] = __popc(jflag[x]);

@@ -56,6 +56,10 @@ __device__ __forceinline__ void chol6_smem(double* A, double* rd, int n, int las
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   __syncthreads();
   if (tid == 0) factor_diag6(A, rd, ld, 0);
+  int la_r = 0, la_c = lane;                       // look-ahead warp: lane -> entry (r, c), c <= r < 6, of the next block
+  if (warp == LA_WARP) {
+    while (la_c > la_r) { la_c -= la_r + 1; ++la_r; }
+  }
   __syncthreads();
   for (int kb = 0; kb < n; kb += 6) {
     const int tsb = (kb == 0) ? 10 : (kb == 24 ? 20 : 100);
@@ -93,12 +97,15 @@ __device__ __forceinline__ void chol6_smem(double* A, double* rd, int n, int las
       SOLVE_TS_LA(tsb + 5);
       // look-ahead: update and factor the next diagonal block while the other warps update the rest
       if (lane < 21) {
-        int r = 0, c = lane;
-        while (c > r) { c -= r + 1; ++r; }          // lane -> (r, c), c <= r < 6
-        double acc = 0.0;
+        const double* pr = A + (nb + la_r) * ld + kb;
+        const double* pc = A + (nb + la_c) * ld + kb;
+        double acc0 = 0.0, acc1 = 0.0;              // two chains of three
 #pragma unroll
-        for (int a = 0; a < 6; ++a) acc += A[(nb + r) * ld + kb + a] * A[(nb + c) * ld + kb + a];
-        A[(nb + r) * ld + nb + c] -= acc;
+        for (int a = 0; a < 6; a += 2) {
+          acc0 += pr[a] * pc[a];
+          acc1 += pr[a + 1] * pc[a + 1];
+        }
+        A[(nb + la_r) * ld + nb + la_c] -= acc0 + acc1;
       }
       __syncwarp();
       SOLVE_TS_LA(tsb + 6);
@@ -112,9 +119,19 @@ __device__ __forceinline__ void chol6_smem(double* A, double* rd, int n, int las
       const int nrows = last_row + 1 - rb0;
       const int npair = (nrows + 1) >> 1;
       const int nblk = (n - nb) / 6;                // column blocks nb, nb+6, ..., n-6
-      for (int it = (warp < LA_WARP ? tid : tid - 32); it < npair * nblk; it += 224) {
-        const int rp = it / nblk;
-        const int r0 = rb0 + 2 * rp, r1 = r0 + 1, cb = nb + 6 * (it - rp * nblk);
+      // only the items of the lower block triangle are enumerated: column block cbi (cb = nb + 6 cbi) pairs with the row
+      // pairs rp >= max(0, 3 cbi - 3); at n = 60 the first step has 141 such items for the 224 threads (one round; the
+      // rectangular enumeration gave thread 0 two items and made the early steps trailing-bound)
+      const int mb = nblk - 1;
+      const int total = npair * nblk - 3 * ((mb * (mb - 1)) >> 1);    // npair >= 3 (nblk - 1): no column is empty
+      for (int it = (warp < LA_WARP ? tid : tid - 32); it < total; it += 224) {
+        int cbi = 0, rem = it, cnt = npair;
+        if (rem >= cnt) {
+          rem -= cnt; cbi = 1;
+          while (rem >= cnt && cbi < mb) { rem -= cnt; cnt -= 3; ++cbi; }
+        }
+        const int rp = max(0, 3 * cbi - 3) + rem;
+        const int r0 = rb0 + 2 * rp, r1 = r0 + 1, cb = nb + 6 * cbi;
         const bool p0 = cb <= r0, p1 = r1 <= last_row && cb <= r1;
         if (!p0 && !p1) continue;
         double l0[6], l1[6];

@@ -338,3 +338,44 @@ def test_forced_chunk_size_and_kernel_variants(pc, mma, plm):
                           "test_edge_cases or test_global_ba_matches_oracle or test_depth_guards or test_structure_only"],
                          cwd=root, env=env, capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
+
+
+def test_patch_centre_and_depth_cell_conventions():
+    """the projection reads the patch centre [1][1] (x, y AND inverse depth), the depth update reads
+    [2][0][0] and writes all P x P cells (ba_cuda.cu:218,223-227,282-285).  A patch whose depth channel is not constant
+    tells the two apart."""
+    p = synth.small_problem(seed=8, F=6, M=10, t0=2, lifetime=4)
+    rng = np.random.default_rng(1)
+    p.patches[:, 2] *= rng.uniform(0.9, 1.1, p.patches[:, 2].shape)       # nine different inverse depths per patch
+    assert np.abs(p.patches[:, 2, 1, 1] - p.patches[:, 2, 0, 0]).min() > 0
+    for iterations in (1, 2):
+        o_poses, o_patches = _oracle(p, iterations)
+        poses, patches = _run_gpu(p, iterations)
+        _check_state(p, poses, patches, o_poses, o_patches, tol=2e-4)
+
+
+def test_only_the_first_intrinsics_row_is_used():
+    """every edge is projected with intrinsics[0] (ba_cuda.cu:253-259), whatever the other rows hold."""
+    p = synth.small_problem(seed=9, F=6, M=10, t0=2, lifetime=4)
+    d = to_dev(p)
+    d["intrinsics"][0, 1:] = torch.tensor([123.0, 45.0, 6.0, 7.0], device="cuda")
+    fastba.BA(d["poses"], d["patches"], d["intrinsics"], d["target"], d["weight"], d["lmbda"], d["ii"], d["jj"], d["kk"],
+              p.t0, p.t1, M=p.M, iterations=2)
+    torch.cuda.synchronize()
+    o_poses, o_patches = _oracle(p, 2)
+    _check_state(p, d["poses"][0].cpu().numpy().astype(np.float64), d["patches"][0].cpu().numpy().astype(np.float64),
+                 o_poses, o_patches)
+
+
+def test_zero_residual_takes_the_small_angle_branches():
+    """at the exact solution (ground-truth state, noise-free targets) dX ~ 1e-7, so the retraction runs
+    through the Taylor branch of expSO3 (theta^2 < 1e-8) and the tau-only branch of expSE3 (theta <= 1e-4)
+    (ba_cuda.cu:97-103,140-152): the state must stay finite and move by less than 1e-5 (no 0/0)."""
+    p = synth.small_problem(seed=10, F=6, M=10, t0=2, lifetime=4, noise_px=0.0)
+    p.poses = p.gt_poses.copy()
+    p.patches = p.gt_patches.copy()
+    o_poses, o_patches = _oracle(p, 2)
+    poses, patches = _run_gpu(p, 2)
+    assert np.isfinite(poses).all() and np.isfinite(patches).all()
+    assert np.abs(poses - np.asarray(p.poses, np.float32)).max() < 1e-5
+    _check_state(p, poses, patches, o_poses, o_patches)

@@ -112,6 +112,18 @@ __device__ __forceinline__ int pow2_ceil(int x) {
   return p;
 }
 
+// Width of the next block of target-frame slots in the edge loop.  Lanes <-> slots wastes (pow2 - width) / pow2 of every
+// warp step, so with many patches per chunk (split == true: >= 64, i.e. several steps per block) 17..27 remaining slots
+// are taken as 16 + the rest and 9 as 8 + 1 (the extra block costs about one step: fold + two barriers); small chunks
+// (single window, one step per block) always take min(32, rem).
+__device__ __forceinline__ int slot_block_width(int rem, bool split) {
+  if (rem >= 32) return 32;
+  if (!split) return rem;
+  if (rem > 16) return rem >= 28 ? rem : 16;
+  if (rem == 9) return 8;
+  return rem;
+}
+
 __device__ __forceinline__ void red_add2(float* p, float a, float b) {       // p 8-byte aligned
   atomicAdd(reinterpret_cast<float2*>(p), make_float2(a, b));
 }
@@ -377,8 +389,10 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
     const int e_fj = (tid < ns) ? wp.slots[ch.slot_base + tid] : 0;                       // ns <= SMAX <= 256
     const int e_np = min(PB, np);                                                         // first patch batch [0, e_np)
     const int e_kx = (tid < e_np) ? kx[tid] : 0;                                          // e_np <= PMAX <= 256
-    const int e_DW = pow2_ceil(min(32, ns)), e_PW = 32 / e_DW;
-    const bool e_ok = (lane & (e_DW - 1)) < min(32, ns);
+    const bool split_slots = pc >= 64;
+    const int e_w = slot_block_width(ns, split_slots);                                    // width of the first slot block
+    const int e_DW = pow2_ceil(e_w), e_PW = 32 / e_DW;
+    const bool e_ok = (lane & (e_DW - 1)) < e_w;
     const int e_p = warp * e_PW + lane / e_DW, e_sl = lane & (e_DW - 1);
     const int e_n0 = (!plm && e_ok && e_p < e_np) ? cells[e_p * ns + e_sl] : -1;
     const int e_n1 = (!plm && e_ok && e_p + 8 * e_PW < e_np) ? cells[(e_p + 8 * e_PW) * ns + e_sl] : -1;
@@ -538,8 +552,8 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
     LIN_TS(5);
       }
       // ---- tile loop: lanes <-> slots (DW wide), PW patches per warp step
-      for (int sb = 0; sb < (PLM ? 0 : ns); sb += 32) {
-        const int ns_here = min(32, ns - sb);
+      for (int sb = 0, ns_here = 0; sb < (PLM ? 0 : ns); sb += ns_here) {
+        ns_here = slot_block_width(ns - sb, split_slots);
         const int DW = pow2_ceil(ns_here), PW = 32 / DW;
         const int sl = sb + (lane & (DW - 1));
         const int pl = lane / DW;

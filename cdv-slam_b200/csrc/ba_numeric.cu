@@ -715,6 +715,93 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
           schur_mma(s, ch, wp, b1 - b0, ncols, fi, t0, n6);
           continue;
         }
+        if (split_slots) {
+          // ---- large chunks: the phase below is bound by shared-memory wavefronts (5 loads per 12 FMAs).  Here a QUAD of
+          //      lanes owns a whole 6 x 6 block (ca >= cb), each lane takes every fourth patch (7 loads per 36 FMAs, 18
+          //      FFMA2), the quad is summed with two butterfly steps and its lanes share the 18 vector reductions.  The
+          //      gradient term y runs the same way on the quads at the top of the block.
+          const int npairs = ncols * (ncols + 1) / 2;
+          const int nq = b1 - b0;
+          const int qs = tid & 3, quad = tid >> 2;
+          const unsigned qmask = 0xFu << (lane & 28);        // the quads of a warp have different trip counts
+          for (int pr = quad; pr < npairs; pr += 64) {
+            int ca = (int)((sqrtf(8.f * pr + 1.f) - 1.f) * 0.5f);
+            while (ca * (ca + 1) / 2 > pr) --ca;
+            while ((ca + 1) * (ca + 2) / 2 <= pr) ++ca;
+            const int cb = pr - ca * (ca + 1) / 2;
+            float2 acc[6][3];
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+              for (int k = 0; k < 3; ++k) acc[a][k] = make_float2(0.f, 0.f);
+            const float* ea = s.sE + ca * 6;
+            const float* eb = s.sE + cb * 6;
+            for (int q = qs; q < nq; q += 4) {
+              const float Q = s.sQ[q];
+              const float2* pa = reinterpret_cast<const float2*>(ea + q * estride);
+              const float2* pb2 = reinterpret_cast<const float2*>(eb + q * estride);
+              const float2 a01 = pa[0], a23 = pa[1], a45 = pa[2];
+              const float2 bk[3] = {pb2[0], pb2[1], pb2[2]};
+              const float va[6] = {Q * a01.x, Q * a01.y, Q * a23.x, Q * a23.y, Q * a45.x, Q * a45.y};
+#pragma unroll
+              for (int a = 0; a < 6; ++a) {
+                const float2 v = make_float2(va[a], va[a]);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) acc[a][k] = __ffma2_rn(v, bk[k], acc[a][k]);
+              }
+            }
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+              for (int k = 0; k < 3; ++k) {
+                float x = acc[a][k].x, y2 = acc[a][k].y;
+                x += __shfl_xor_sync(qmask, x, 1); y2 += __shfl_xor_sync(qmask, y2, 1);
+                x += __shfl_xor_sync(qmask, x, 2); y2 += __shfl_xor_sync(qmask, y2, 2);
+                acc[a][k] = make_float2(x, y2);
+              }
+            const int fa = ((ca < ch.n_free) ? s.sFrame[ch.first_free + ca] : fi) - t0;
+            const int fb = ((cb < ch.n_free) ? s.sFrame[ch.first_free + cb] : fi) - t0;
+            if (fa >= fb) {                       // block (fa, fb): row a, column pair k
+              float* dst = wp.S + (size_t)(6 * fa) * n6 + 6 * fb;
+#pragma unroll
+              for (int a = 0; a < 6; ++a)
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                  if (((a * 3 + k) & 3) == qs) red_add2(dst + (size_t)a * n6 + 2 * k, -acc[a][k].x, -acc[a][k].y);
+            } else {                              // transposed into block (fb, fa): row b, column pair (a, a + 1)
+              float* dst = wp.S + (size_t)(6 * fb) * n6 + 6 * fa;
+#pragma unroll
+              for (int a2 = 0; a2 < 3; ++a2)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                  if (((a2 * 6 + 2 * k) & 3) == qs)
+                    red_add2(dst + (size_t)(2 * k) * n6 + 2 * a2, -acc[2 * a2][k].x, -acc[2 * a2 + 1][k].x);
+                  if (((a2 * 6 + 2 * k + 1) & 3) == qs)
+                    red_add2(dst + (size_t)(2 * k + 1) * n6 + 2 * a2, -acc[2 * a2][k].y, -acc[2 * a2 + 1][k].y);
+                }
+            }
+          }
+          for (int ca = 63 - quad; ca < ncols; ca += 64) {          // y[ca] -= sum_p Q_p u_p E_p[ca]
+            float2 g01 = make_float2(0.f, 0.f), g23 = g01, g45 = g01;
+            for (int q = qs; q < nq; q += 4) {
+              const float w = s.sQ[q] * s.sPQ[q * PQS + 1];
+              const float2* pa = reinterpret_cast<const float2*>(s.sE + q * estride + ca * 6);
+              const float2 v = make_float2(w, w);
+              g01 = __ffma2_rn(v, pa[0], g01); g23 = __ffma2_rn(v, pa[1], g23); g45 = __ffma2_rn(v, pa[2], g45);
+            }
+            float gv[6] = {g01.x, g01.y, g23.x, g23.y, g45.x, g45.y};
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+              gv[a] += __shfl_xor_sync(qmask, gv[a], 1);
+              gv[a] += __shfl_xor_sync(qmask, gv[a], 2);
+            }
+            const int fa = ((ca < ch.n_free) ? s.sFrame[ch.first_free + ca] : fi) - t0;
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+              if ((a & 3) == qs) atomicAdd(&wp.y[6 * fa + a], -gv[a]);
+          }
+          continue;
+        }
         // ---- Schur update of this batch.  Item = (column pair ca >= cb, row pair 2*a2, 2*a2+1): twelve sums over
         //      the patches, as packed fp32x2 FMAs (FFMA2).  M = sum_p Q_p E_p[ca] E_p[cb]^T is block (ca, cb); it
         //      lands at (frame(ca), frame(cb)) or transposed.

@@ -616,15 +616,36 @@ static bool plan_cluster_enabled() {           // PGBA_PLAN_CLUSTER=0: grid-wide
 // true: the cluster kernel also clears the zero region (no memset needed)
 // The cluster form pays for single windows / small batches (latency: 5 launches + memset become 2); with many windows per
 // call the grid-wide kernels fill the machine better (measured on c5: 116 us vs 134 us for 64 windows).
-bool plan_clears_workspace(const Problem& pb, int64_t batch) { return plan_cluster_enabled() && !pb.L.big && batch <= 8; }
+// Cluster size of the single-launch plan: the largest of 16 (single window only) / 8 / 4 / 2 CTAs per window with which
+// all windows of the call are co-resident (one 1024-thread CTA per SM); 0 = more windows than that: grid-wide kernels.
+// Measured on c5 (64 windows): 2 CTAs per window 91.6 us, 4: 94.9 (two waves), 8: 116, grid-wide kernels 101.7.
+// PGBA_PLAN_CL=8 / 16 forces the single-window size, PGBA_PLAN_BATCH_CL=0 / 2 / 4 / 8 the size for batches > 8 (A/B runs).
+static int plan_cluster_size(int64_t batch) {
+  if (batch <= 8) {
+    const char* e = getenv("PGBA_PLAN_CL");
+    const int forced = e ? atoi(e) : 0;
+    if (forced == 8 || forced == 16) return forced;
+    return batch == 1 ? 16 : 8;
+  }
+  const char* e = getenv("PGBA_PLAN_BATCH_CL");
+  if (e) {
+    const int v = atoi(e);
+    return (v == 2 || v == 4 || v == 8) ? v : 0;
+  }
+  if (8 * batch <= 148) return 8;
+  if (4 * batch <= 148) return 4;
+  if (2 * batch <= 148) return 2;
+  return 0;
+}
+bool plan_clears_workspace(const Problem& pb, int64_t batch) {
+  return plan_cluster_enabled() && !pb.L.big && plan_cluster_size(batch) != 0;
+}
 
 void launch_plan(const Problem& pb, int64_t batch, cudaStream_t stream) {
   if (plan_clears_workspace(pb, batch)) {
     // single windows: a 16-CTA (non-portable) cluster -- 16 SMs pull the index arrays and every per-edge phase is half as
-    // long; small batches: 8 CTAs per window.  PGBA_PLAN_CL=8 / 16 forces the size (A/B runs).
-    const char* cl_env = getenv("PGBA_PLAN_CL");
-    const int forced_cl = cl_env ? atoi(cl_env) : 0;
-    const int cl_size = (forced_cl == 8 || forced_cl == 16) ? forced_cl : (batch == 1 ? 16 : 8);
+    // long as with 8; batches: see plan_cluster_size
+    const int cl_size = plan_cluster_size(batch);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)cl_size, (unsigned)batch);
     cfg.blockDim = dim3(PLAN_T);
@@ -641,6 +662,12 @@ void launch_plan(const Problem& pb, int64_t batch, cudaStream_t stream) {
       cudaFuncSetAttribute(plan_cluster_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
       cudaFuncSetAttribute(plan_cluster_kernel<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
       cudaLaunchKernelEx(&cfg, plan_cluster_kernel<16>, pb);
+    } else if (cl_size == 2) {
+      cudaFuncSetAttribute(plan_cluster_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
+      cudaLaunchKernelEx(&cfg, plan_cluster_kernel<2>, pb);
+    } else if (cl_size == 4) {
+      cudaFuncSetAttribute(plan_cluster_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
+      cudaLaunchKernelEx(&cfg, plan_cluster_kernel<4>, pb);
     } else {
       cudaFuncSetAttribute(plan_cluster_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
       cudaLaunchKernelEx(&cfg, plan_cluster_kernel<8>, pb);

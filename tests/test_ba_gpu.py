@@ -170,9 +170,11 @@ def test_depth_guards():
     _check_state(p, poses, patches, o_poses, o_patches, tol=2e-4)
 
 
-def test_batched_equals_single():
-    """BA_batched over 5 different windows == 5 separate BA calls (bitwise up to atomics order -> 1e-5)."""
-    probs = [synth.small_problem(seed=20 + s, F=8, M=16, t0=3, lifetime=5) for s in range(5)]
+@pytest.mark.parametrize("n_windows", [5, 20, 40, 80])
+def test_batched_equals_single(n_windows):
+    """BA_batched over n different windows == n separate BA calls (bitwise up to atomics order -> 1e-5).  The plan runs
+    as one thread-block cluster per window (8 / 4 / 2 CTAs for 5 / 20 / 40 windows) or as grid-wide kernels (80)."""
+    probs = [synth.small_problem(seed=20 + s, F=8, M=16, t0=3, lifetime=5) for s in range(n_windows)]
     ds = [to_dev(p) for p in probs]
     cat = lambda k: torch.cat([d[k] for d in ds], 0).contiguous()
     bp, bq = cat("poses"), cat("patches")

@@ -1228,6 +1228,87 @@ __global__ void __launch_bounds__(256) update_kernel(Problem pb, int early) {
   CTA_TS(2, 2);
 }
 
+// Back-substitution + depth retraction for large chunks (batched windows): one thread per patch.  The chunk's E tile
+// (n_patches x ncols x 6 floats, contiguous) is staged in shared memory with coalesced loads, and Q, u, the patch id and
+// the old depth are fetched, BEFORE pdl_wait() when the previous kernel is the small solve (early != 0, see
+// update_kernel): on the batched shape the solve occupies one SM per window for ~20 us, during which the other SMs
+// pull the whole E matrix on chip; after the wait only dX is loaded.
+// dynamic smem: tile_floats (E tile) + (SMAX + 1) * 6 (dX of the chunk's columns)
+__global__ void __launch_bounds__(256) update_large_kernel(Problem pb, int early, int tile_floats) {
+  CTA_TS(2, 0);
+  extern __shared__ __align__(16) float usm[];
+  float* sE = usm;
+  float* sdx = usm + tile_floats;
+  bool waited = early == 0;
+  if (waited) { pdl_wait(); pdl_trigger(); CTA_TS(2, 1); }
+  const int w = blockIdx.y, tid = threadIdx.x;
+  const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
+  float* patches = pb.patches + (int64_t)w * pb.st.patches;
+  const int N = pb.t1 - pb.t0, t0 = pb.t0;
+  const int PP = pb.P * pb.P, pstride = 3 * PP;
+  const bool apply = pb.apply != 0;
+  const int n_chunks = wp.hdr->n_chunks;
+  // the grid is sized for the worst-case chunk count: a CTA without a chunk leaves at once (an exiting CTA needs no wait,
+  // and while it sat at pdl_wait() it would hold a slot that a CTA with a tile to prefetch could use)
+  if ((int)blockIdx.x >= n_chunks) return;
+  for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    const Chunk ch = wp.chunks[c];
+    if (ch.n_patches == 0) continue;
+    __syncthreads();
+    const int np = ch.n_patches;
+    const int ncols = (N > 0 && pb.with_schur != 0) ? ch.ncols : 0;
+    const int len2 = ncols * 3;                                      // float2 per E row
+    {
+      const float2* eg = reinterpret_cast<const float2*>(wp.ecells + 6 * (int64_t)ch.ecell_base);
+      float2* dst = reinterpret_cast<float2*>(sE);
+      for (int x = tid; x < np * len2; x += 256) dst[x] = eg[x];
+    }
+    float q = 0.f, u = 0.f, d_old = 0.f;
+    int kx = 0, dxi = -1;
+    if (tid < np) {
+      q = wp.Q[ch.patch_base + tid];
+      u = wp.u[ch.patch_base + tid];
+      kx = wp.kx[ch.patch_base + tid];
+      if (apply) d_old = patches[(int64_t)kx * pstride + 2 * PP];    // reads [2][0][0] (ba_cuda.cu:218)
+    }
+    if (tid < ncols * 6) {
+      const int col = tid / 6, a = tid - col * 6;
+      const int f = (col < ch.n_free) ? wp.slots[ch.slot_base + ch.first_free + col] : ch.frame;
+      dxi = 6 * (f - t0) + a;
+    }
+    if (!waited) { pdl_wait(); pdl_trigger(); waited = true; CTA_TS(2, 1); }
+    if (dxi >= 0) sdx[tid] = wp.dX[dxi];
+    for (int x = tid + 256; x < ncols * 6; x += 256) {
+      const int col = x / 6, a = x - col * 6;
+      const int f = (col < ch.n_free) ? wp.slots[ch.slot_base + ch.first_free + col] : ch.frame;
+      sdx[x] = wp.dX[6 * (f - t0) + a];
+    }
+    __syncthreads();
+    for (int p = tid; p < np; p += 256) {                            // np <= PMAX <= 256: one trip
+      const float2* er = reinterpret_cast<const float2*>(sE) + p * len2;
+      const float2* dx2 = reinterpret_cast<const float2*>(sdx);
+      float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 4
+      for (int x = 0; x < len2; ++x) {
+        const float2 e = er[x], d = dx2[x];
+        acc0 += e.x * d.x;
+        acc1 += e.y * d.y;
+      }
+      const float dz = q * (u - (acc0 + acc1));
+      wp.dZ[ch.patch_base + p] = dz;
+      if (apply) {
+        float* pr = patches + (int64_t)kx * pstride + 2 * PP;
+        float d = d_old + dz;
+        d = (d > 20.f) ? 1.0f : d;
+        d = fmaxf(d, 1e-4f);
+        for (int x = 0; x < PP; ++x) pr[x] = d;
+      }
+    }
+  }
+  if (!waited) { pdl_wait(); pdl_trigger(); CTA_TS(2, 1); }
+  CTA_TS(2, 2);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Host-side launch sequence of one Gauss-Newton iteration
 // ---------------------------------------------------------------------------------------------------------------
@@ -1317,7 +1398,21 @@ void launch_solve(const Problem& pb, int64_t batch, cudaStream_t stream) {
 void launch_update(const Problem& pb, int64_t batch, cudaStream_t stream) {
   const int gx = chunk_grid(pb, batch);
   const int N = pb.t1 - pb.t0;
-  launch_k(update_kernel, dim3((unsigned)gx, (unsigned)batch), dim3(256), 0, stream, pb, (N > 0 && !pb.L.big && early_loads_enabled()) ? 1 : 0);
+  const int early = (N > 0 && !pb.L.big && early_loads_enabled()) ? 1 : 0;
+  const int64_t cols = (N < SMAX ? N : SMAX) + 1;
+  const int64_t tile_floats = (int64_t)pb.L.pc * cols * 6;
+  static int large_on = -1;                        // PGBA_UPDATE_LARGE=0: the generic kernel for every chunk size (A/B runs)
+  if (large_on < 0) {
+    const char* e = getenv("PGBA_UPDATE_LARGE");
+    large_on = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (large_on && pb.L.pc > 32 && tile_floats * 4 <= 48 * 1024) {
+    const size_t smem = sizeof(float) * ((size_t)tile_floats + (SMAX + 1) * 6);
+    cudaFuncSetAttribute(update_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    launch_k(update_large_kernel, dim3((unsigned)gx, (unsigned)batch), dim3(256), smem, stream, pb, early, (int)tile_floats);
+  } else {
+    launch_k(update_kernel, dim3((unsigned)gx, (unsigned)batch), dim3(256), 0, stream, pb, early);
+  }
   count_launch();
 }
 

@@ -10,7 +10,7 @@
 namespace pgba {
 void launch_plan(const Problem& pb, int64_t batch, cudaStream_t stream);
 cudaError_t launch_iteration(const Problem& pb, int64_t batch, cudaStream_t stream, cudaEvent_t* ev, bool first, bool more);
-void launch_linearize(const Problem& pb, int64_t batch, cudaStream_t stream, bool fuse_update);
+void launch_linearize(const Problem& pb, int64_t batch, cudaStream_t stream, bool fuse_update, bool first);
 void launch_solve(const Problem& pb, int64_t batch, cudaStream_t stream);
 void launch_update(const Problem& pb, int64_t batch, cudaStream_t stream);
 bool solve_supported(int N);
@@ -409,7 +409,7 @@ int pgba_ba_linearize_debug(const float* poses, const float* patches, const floa
   cudaError_t e = clear_workspace(pb, 1, s);
   if (e != cudaSuccess) return (int)e;
   launch_plan(pb, 1, s);
-  launch_linearize(pb, 1, s, false);
+  launch_linearize(pb, 1, s, false, true);
   launch_k(export_debug_kernel, dim3(256), dim3(256), 0, s, pb, S, y, nullptr, patch_ids, C, u, Q, nullptr, n_unique, nullptr);   // before the solve
   count_launch();
   launch_solve(pb, 1, s);

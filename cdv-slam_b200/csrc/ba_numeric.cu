@@ -20,6 +20,7 @@
 #include <stdlib.h>
 
 #include "ba_common.cuh"
+#include "ba_cells.cuh"
 #include "ba_chol.cuh"
 
 namespace pgba {
@@ -324,8 +325,11 @@ __device__ long long g_lin_ts[32];
 #define CTA_TS(k, f) do { } while (0)
 #endif
 
-template <bool PLM, bool FUSE>
+// CELLS: the first linearisation of a call in the single-window regime also builds the cell tables of its chunk
+// (build_chunk_cells, otherwise plan_cells_kernel's job): one kernel and its dependent round trips less per call.
+template <bool PLM, bool FUSE, bool CELLS>
 __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb, int ebudget, int flags) {
+  __shared__ CellScratch csc;
   CTA_TS((flags & 1) ? 3 : 0, 0);
   // flags & 8 (second and later linearisations of a call, small solve in between): the previous kernel is the solve,
   // which lets this kernel start only after its own pdl_wait(), i.e. after the previous linearisation and the plan have
@@ -371,8 +375,17 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
   constexpr bool plm = PLM;
 
   for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
-    const Chunk ch = wp.chunks[c];
-    if (ch.n_patches == 0) continue;
+    Chunk ch_;
+    if constexpr (CELLS) {
+      const bool built = build_chunk_cells(pb, wp, c, csc);
+      __syncthreads();                                           // cell table, kx, slots written; csc.sch final
+      ch_ = csc.sch;
+      if (!built) continue;
+    } else {
+      ch_ = wp.chunks[c];
+      if (ch_.n_patches == 0) continue;
+    }
+    const Chunk& ch = ch_;
     __syncthreads();
     LIN_TS(1);
     const int ns = ch.n_slots, ncols = ch.ncols, fi = ch.frame, np = ch.n_patches;
@@ -663,20 +676,19 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
     LIN_TS(5);
       }
 
-      // ---- duplicated (patch, slot) edges: rare slow path, one thread (deterministic, no shared atomics)
-      if (n_dups > 0) {
+      // ---- duplicated (patch, slot) edges: rare slow path, one thread (deterministic, no shared atomics).  With the
+      //      plan's global list, or (CELLS: the list is still being written by other CTAs) by re-scanning the chunk's own
+      //      edges: a duplicate is an edge that does not own its cell.
+      if (CELLS ? (csc.has_dup != 0) : (n_dups > 0)) {
         if (tid == 0) {
-          for (int dix = 0; dix < n_dups; ++dix) {
-            const DupEdge de = wp.dups[dix];
-            if (de.chunk != c || de.p < b0 || de.p >= b1) continue;
-            const int q = de.p - b0, sl = de.s;
+          auto process_dup = [&](int q, int sl, int n) {
             float R[9], t[3], H[21], g[6], e[6], ei[6], ck, uk;
             for (int x = 0; x < 9; ++x) R[x] = s.sRt[sl * 12 + x];
             for (int x = 0; x < 3; ++x) t[x] = s.sRt[sl * 12 + 9 + x];
             for (int x = 0; x < 21; ++x) H[x] = 0.f;
             for (int x = 0; x < 6; ++x) g[x] = 0.f;
             edge_terms(s.sPatch[q * 4], s.sPatch[q * 4 + 1], s.sPatch[q * 4 + 2], fx, fy, cx, cy, R, t,
-                       __ldg(target + de.n), __ldg(weight + de.n), H, g, e, ck, uk);
+                       __ldg(target + n), __ldg(weight + n), H, g, e, ck, uk);
             const int col = sl - ch.first_free;
             if (col >= 0 && col < ch.n_free && schur)
               for (int a = 0; a < 6; ++a) s.sE[q * estride + col * 6 + a] += e[a];
@@ -688,6 +700,20 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
             s.sPQ[q * PQS + 1] += uk;
             for (int x = 0; x < 21; ++x) s.sH[sl * 28 + x] += H[x];
             for (int x = 0; x < 6; ++x) s.sH[sl * 28 + 21 + x] += g[x];
+          };
+          if constexpr (CELLS) {
+            for (int pos = ch.edge_begin; pos < ch.edge_end; ++pos) {
+              const int4 rec = wp.perm[pos];
+              const int p = cell_patch_rank(csc, rec.z - ch.kbase), sl = cell_slot_rank(csc, rec.y);
+              if (__ldcg(&cells[p * ns + sl]) == rec.x || p < b0 || p >= b1) continue;
+              process_dup(p - b0, sl, rec.x);
+            }
+          } else {
+            for (int dix = 0; dix < n_dups; ++dix) {
+              const DupEdge de = wp.dups[dix];
+              if (de.chunk != c || de.p < b0 || de.p >= b1) continue;
+              process_dup(de.p - b0, de.s, de.n);
+            }
           }
         }
         __syncthreads();
@@ -1362,7 +1388,18 @@ static bool patch_lanes(int pc) {
   return forced > 0;
 }
 
-void launch_linearize(const Problem& pb, int64_t batch, cudaStream_t stream, bool fuse_update) {
+// Opt-in (PGBA_FUSE_CELLS=1), single-window regime (<= 32 patches per chunk): the first linearisation of a call builds the
+// cell tables of its chunks itself and launch_plan skips plan_cells_kernel.  Measured on the B200 (c2, same box): 90.0 us
+// against 86.0 us with the separate kernel -- the per-chunk build is a chain of dependent round trips either way, and inside
+// the linearisation its CTA body grows from 7.4 + 9.7 us (two kernels) to 20.7 us (median, profiles/cta_trace.py).
+// Kept, parity-tested, for the A/B record.
+bool cells_in_linearize(const Problem& pb, int64_t batch) {
+  (void)batch;
+  const char* e = getenv("PGBA_FUSE_CELLS");
+  return pb.L.pc <= 32 && !patch_lanes(pb.L.pc) && (e && e[0] == '1');
+}
+
+void launch_linearize(const Problem& pb, int64_t batch, cudaStream_t stream, bool fuse_update, bool first) {
   const int gx = chunk_grid(pb, batch);
   const int ebudget = lin_ebudget(pb);
   const size_t lsm = lin_smem_bytes(pb.L.pc, ebudget);
@@ -1373,9 +1410,11 @@ void launch_linearize(const Problem& pb, int64_t batch, cudaStream_t stream, boo
     launch_k(kern, dim3((unsigned)gx, (unsigned)batch), dim3(256), lsm, stream, pb, ebudget, flags);
   };
   if (patch_lanes(pb.L.pc)) {
-    if (fuse_update) go(linearize_kernel<true, true>); else go(linearize_kernel<true, false>);
+    if (fuse_update) go(linearize_kernel<true, true, false>); else go(linearize_kernel<true, false, false>);
+  } else if (first && cells_in_linearize(pb, batch)) {
+    go(linearize_kernel<false, false, true>);
   } else {
-    if (fuse_update) go(linearize_kernel<false, true>); else go(linearize_kernel<false, false>);
+    if (fuse_update) go(linearize_kernel<false, true, false>); else go(linearize_kernel<false, false, false>);
   }
   count_launch();
 }
@@ -1432,7 +1471,7 @@ cudaError_t launch_iteration(const Problem& pb, int64_t batch, cudaStream_t stre
   // separate, fully parallel update kernel measured faster
   const bool fuse = pb.L.pc <= 32;
   if (ev) cudaEventRecord(ev[0], stream);
-  launch_linearize(pb, batch, stream, fuse && !first);
+  launch_linearize(pb, batch, stream, fuse && !first, first);
   if (ev) cudaEventRecord(ev[1], stream);
   launch_solve(pb, batch, stream);
   if (ev) cudaEventRecord(ev[2], stream);

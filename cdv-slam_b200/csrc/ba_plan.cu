@@ -14,6 +14,7 @@
 #include <stdlib.h>
 
 #include "ba_common.cuh"
+#include "ba_cells.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -34,42 +35,6 @@ void plan_cta_timestamps(unsigned long long* out) { cudaMemcpyFromSymbol(out, g_
 #else
 #define PCTA_TS(k, f) do { } while (0)
 #endif
-
-// In-place exclusive scan of a[0..n) by the whole block; returns the total.  scratch: >= 33 ints of shared memory.
-__device__ int block_exclusive_scan(int* a, int n, int* scratch) {
-  const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int per = (n + T - 1) / T;
-  const int b = min(tid * per, n), e = min(b + per, n);
-  int s = 0;
-  for (int i = b; i < e; ++i) s += a[i];
-  int x = s;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int y = __shfl_up_sync(0xffffffffu, x, o);
-    if (lane >= o) x += y;
-  }
-  if (lane == 31) scratch[wid] = x;
-  __syncthreads();
-  if (wid == 0) {
-    int w = (lane < (T >> 5)) ? scratch[lane] : 0;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int y = __shfl_up_sync(0xffffffffu, w, o);
-      if (lane >= o) w += y;
-    }
-    scratch[lane] = w;
-  }
-  __syncthreads();
-  int run = (wid > 0 ? scratch[wid - 1] : 0) + x - s;
-  const int total = scratch[(T >> 5) - 1];
-  for (int i = b; i < e; ++i) {
-    int v = a[i];
-    a[i] = run;
-    run += v;
-  }
-  __syncthreads();
-  return total;
-}
 
 struct EdgeIdx { int i, j, k; bool ok; };
 constexpr int EDGE_U = 4;                 // edges in flight per thread in the grid-wide passes
@@ -259,119 +224,11 @@ __global__ void __launch_bounds__(256) plan_cells_kernel(Problem pb) {
   pdl_wait();
   pdl_trigger();
   PCTA_TS(1, 1);
-  __shared__ unsigned pflag[PMAX / 32];
-  __shared__ int ppref[PMAX / 32 + 1];
-  __shared__ unsigned jflag[PGBA_MAX_POSE_ROWS / 32];
-  __shared__ int jpref[PGBA_MAX_POSE_ROWS / 32 + 1];
-  __shared__ int scratch[40];
-  __shared__ Chunk sch;
-  const int w = blockIdx.y, tid = threadIdx.x, T = blockDim.x;
+  __shared__ CellScratch sc;
+  const int w = blockIdx.y;
   const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
   const int n_chunks = wp.hdr->n_chunks;
-  const int nw = (pb.F + 31) / 32;
-  const int t0 = pb.t0, t1 = pb.t1;
-
-  for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
-    __syncthreads();
-    if (tid == 0) sch = wp.chunks[c];
-    if (tid < PMAX / 32) pflag[tid] = 0;
-    for (int x = tid; x < nw; x += T) jflag[x] = 0;
-    __syncthreads();
-    const int eb = sch.edge_begin, ee = sch.edge_end, kbase = sch.kbase, fi = sch.frame;
-    // presence bits of the chunk's patches / target frames.  All edges of a chunk hit the same few words, so the bits are
-    // first OR-ed over the warp (one shared-memory atomic per distinct word and warp instead of one per edge: same-address
-    // shared atomics serialise, 2 x 1700 of them per chunk was the bulk of this kernel on the batched shape)
-    for (int pos0 = eb; pos0 < ee; pos0 += T) {                  // warp-uniform trip count
-      const int pos = pos0 + tid;
-      const bool in = pos < ee;
-      int k = 0, j = 0;
-      if (in) {
-        const int4 rec = wp.perm[pos];
-        k = rec.z - kbase; j = rec.y;
-      }
-      const int lane = tid & 31;
-      const unsigned kbit = in ? 1u << (k & 31) : 0u, jbit = in ? 1u << (j & 31) : 0u;
-#pragma unroll
-      for (int wd = 0; wd < PMAX / 32; ++wd) {
-        const unsigned m = __reduce_or_sync(0xffffffffu, (k >> 5) == wd ? kbit : 0u);
-        if (m && lane == wd) atomicOr(&pflag[wd], m);
-      }
-      const unsigned grp = __match_any_sync(0xffffffffu, in ? (j >> 5) : -1);
-      const unsigned m = __reduce_or_sync(grp, jbit);
-      if (in && lane == __ffs(grp) - 1) atomicOr(&jflag[j >> 5], m);
-    }
-    __syncthreads();
-    for (int x = tid; x < nw; x += T) jpref[x] = __popc(jflag[x]);
-    if (tid == 0) {
-      int run = 0;
-      for (int x = 0; x < PMAX / 32; ++x) { ppref[x] = run; run += __popc(pflag[x]); }
-      ppref[PMAX / 32] = run;
-    }
-    __syncthreads();
-    const int n_slots = block_exclusive_scan(jpref, nw, scratch);
-    if (tid == 0) {
-      const int n_patches = ppref[PMAX / 32];
-      auto rank_j = [&](int f) {   // number of present frames < f
-        if (f <= 0) return 0;
-        if (f >= pb.F) return n_slots;
-        return jpref[f >> 5] + __popc(jflag[f >> 5] & ((1u << (f & 31)) - 1u));
-      };
-      const int first_free = rank_j(t0);
-      const int n_free = max(rank_j(t1) - first_free, 0);
-      const bool i_free = (fi >= t0 && fi < t1);
-      const bool i_is_slot = (jflag[fi >> 5] >> (fi & 31)) & 1u;
-      int icol = -1, ncols = n_free;
-      if (i_free) {
-        if (i_is_slot) icol = rank_j(fi) - first_free;
-        else { icol = n_free; ncols = n_free + 1; }
-      }
-      Chunk ch = sch;
-      ch.n_patches = n_patches; ch.n_slots = n_slots; ch.first_free = first_free; ch.n_free = n_free;
-      ch.icol = icol; ch.ncols = ncols;
-      int st = 0;
-      if (n_slots > SMAX) st |= PGBA_ST_TOO_MANY_SLOTS;
-      if (!st) {
-        ch.patch_base = atomicAdd(&wp.hdr->n_patches, n_patches);
-        ch.slot_base = atomicAdd(&wp.hdr->n_slots, n_slots);
-        ch.cell_base = atomicAdd(&wp.hdr->n_cells, n_patches * n_slots);
-        ch.ecell_base = (pb.t1 > pb.t0) ? atomicAdd(&wp.hdr->n_ecells, n_patches * ncols) : 0;
-        if ((int64_t)ch.patch_base + n_patches > pb.L.patch_max || (int64_t)ch.slot_base + n_slots > pb.L.slot_max ||
-            (int64_t)ch.cell_base + (int64_t)n_patches * n_slots > pb.L.cell_cap ||
-            (int64_t)ch.ecell_base + (int64_t)n_patches * ncols > pb.L.ecell_cap)
-          st |= PGBA_ST_CAPACITY;
-      }
-      if (st) {
-        atomicOr(&wp.hdr->status, st);
-        ch.n_patches = 0; ch.n_slots = 0; ch.ncols = 0; ch.n_free = 0;
-      }
-      sch = ch;
-      wp.chunks[c] = ch;
-    }
-    __syncthreads();
-    const int n_patches = sch.n_patches, ns = sch.n_slots;
-    if (n_patches == 0) continue;
-    int* cells = wp.cells + sch.cell_base;
-    for (int x = tid; x < n_patches * ns; x += T) cells[x] = -1;
-    for (int b = tid; b < PMAX; b += T)
-      if ((pflag[b >> 5] >> (b & 31)) & 1u)
-        wp.kx[sch.patch_base + ppref[b >> 5] + __popc(pflag[b >> 5] & ((1u << (b & 31)) - 1u))] = kbase + b;
-    for (int f = tid; f < pb.F; f += T)
-      if ((jflag[f >> 5] >> (f & 31)) & 1u)
-        wp.slots[sch.slot_base + jpref[f >> 5] + __popc(jflag[f >> 5] & ((1u << (f & 31)) - 1u))] = f;
-    __syncthreads();
-    for (int pos = eb + tid; pos < ee; pos += T) {
-      const int4 rec = wp.perm[pos];
-      const int n = rec.x, k = rec.z - kbase, j = rec.y;
-      const int p = ppref[k >> 5] + __popc(pflag[k >> 5] & ((1u << (k & 31)) - 1u));
-      const int s = jpref[j >> 5] + __popc(jflag[j >> 5] & ((1u << (j & 31)) - 1u));
-      const int old = atomicCAS(&cells[p * ns + s], -1, n);
-      if (old != -1) {      // duplicated (patch, target frame) edge: handled by the slow path of the linearizer
-        const int d = atomicAdd(&wp.hdr->n_dups, 1);
-        DupEdge de; de.chunk = c; de.p = p; de.s = s; de.n = n;
-        wp.dups[d] = de;
-      }
-    }
-  }
+  for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) build_chunk_cells(pb, wp, c, sc);
   PCTA_TS(1, 2);
 }
 
@@ -601,6 +458,8 @@ static int edge_grid(int64_t E, int64_t batch) {
   return (int)(g < 1 ? 1 : g);
 }
 
+bool cells_in_linearize(const Problem& pb, int64_t batch);
+
 int chunk_grid(const Problem& pb, int64_t batch) {
   int64_t g = pb.L.ch_max;
   const int64_t cap = batch > 1 ? (148 * 16 + batch - 1) / batch : 148 * 8;
@@ -683,6 +542,7 @@ void launch_plan(const Problem& pb, int64_t batch, cudaStream_t stream) {
     launch_k(plan_scatter_kernel, dim3(grid), dim3(256), 0, stream, pb);
     count_launch();
   }
+  if (cells_in_linearize(pb, batch)) return;          // the first linearisation builds the cell tables of its chunks
   launch_k(plan_cells_kernel, dim3((unsigned)chunk_grid(pb, batch), (unsigned)batch), dim3(256), 0, stream, pb);
   count_launch();
 }

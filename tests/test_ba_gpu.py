@@ -322,19 +322,20 @@ def test_host_buffer_entry_arena_mode():
     np.testing.assert_array_equal(a["target"][0].numpy(), np.asarray(p.target, np.float32))
 
 
-@pytest.mark.parametrize("pc,mma,plm", [("128", "0", "0"), ("64", "0", "0"), ("32", "0", "0"), ("128", "1", "0"),
-                                        ("8", "1", "0"), ("128", "0", "1"), ("64", "1", "1")])
-def test_forced_chunk_size_and_kernel_variants(pc, mma, plm):
+@pytest.mark.parametrize("pc,mma,plm,cells", [("128", "0", "0", "0"), ("64", "0", "0", "0"), ("32", "0", "0", "0"),
+                                              ("128", "1", "0", "0"), ("8", "1", "0", "0"), ("128", "0", "1", "0"),
+                                              ("64", "1", "1", "0"), ("8", "0", "0", "1"), ("32", "0", "0", "1")])
+def test_forced_chunk_size_and_kernel_variants(pc, mma, plm, cells):
     """The chunk size (PGBA_PC, normally a heuristic of the edge count), the Schur implementation (PGBA_SCHUR_MMA: 3xTF32
     tensor-core contraction instead of FFMA2) and the edge-loop mapping (PGBA_PATCH_LANES: lanes <-> patches instead of
-    lanes <-> target frames) are read from the environment once per process, so every combination is checked in its own
+    lanes <-> target frames; PGBA_FUSE_CELLS: cell tables built by the first linearisation) are read from the environment, so every combination is checked in its own
     interpreter: normal equations (B, v, S, y, C, u, dX, dZ), end states, edge cases and the batched entry against the
     oracle at the same 1e-4 tolerance."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, PGBA_PC=pc, PGBA_SCHUR_MMA=mma, PGBA_PATCH_LANES=plm)
+    env = dict(os.environ, PGBA_PC=pc, PGBA_SCHUR_MMA=mma, PGBA_PATCH_LANES=plm, PGBA_FUSE_CELLS=cells)
     res = subprocess.run([sys.executable, "-m", "pytest", "tests/test_ba_gpu.py", "-x", "-q", "-m", "gpu", "-k",
                           "test_normal_equations or test_ba_matches_oracle or test_batched_equals_single or "
                           "test_edge_cases or test_global_ba_matches_oracle or test_depth_guards or test_structure_only"],

@@ -66,10 +66,17 @@ struct Layout {         // host-computed
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 inline int choose_pc(int64_t E, int64_t batch) {
-  // aim at >= ~1.5 CTAs per SM for the chunk-parallel kernels, assuming ~24 edges per patch
+  // throughput regime (batched windows, global BA): aim at >= ~1.5 CTAs per SM for the chunk-parallel kernels, assuming
+  // ~24 edges per patch
   int64_t want = (E * batch) / (148 * 3 / 2 * 24);
   int pc = 8;
   while (pc * 2 <= want && pc < PMAX) pc *= 2;
+  if (pc >= 32) return pc;
+  // latency regime (single window): about one chunk per SM -- the power of two nearest to E / (148 * 16), at most 32.
+  // Measured on c2 (37 824 edges, same box): pc = 8 (264 chunks) 86.0 us, 16 (132 chunks) 84.0 us, 32 (66 chunks) 92.1 us.
+  want = (E * batch) / (148 * 16);
+  pc = 8;
+  while (pc * 2 * 1000 <= want * 1414 && pc < 32) pc *= 2;
   return pc;
 }
 

@@ -500,11 +500,40 @@ bool plan_clears_workspace(const Problem& pb, int64_t batch) {
   return plan_cluster_enabled() && !pb.L.big && plan_cluster_size(batch) != 0;
 }
 
+// The 16-CTA cluster is a non-portable size: it needs a GPC with 16 SMs that can each hold a 1024-thread CTA.  Asked once
+// (occupancy query, no stream work); a part without such a GPC falls back to the portable 8-CTA cluster.
+static bool cluster16_available(size_t smem) {
+  static int cached = -1;
+  if (cached >= 0) return cached != 0;
+  cudaFuncSetAttribute(plan_cluster_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (cudaFuncSetAttribute(plan_cluster_kernel<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return (cached = 0) != 0;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(16, 1);
+  cfg.blockDim = dim3(PLAN_T);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 16; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, plan_cluster_kernel<16>, &cfg) != cudaSuccess) {
+    (void)cudaGetLastError();
+    n = 0;
+  }
+  cached = n > 0 ? 1 : 0;
+  return cached != 0;
+}
+
 void launch_plan(const Problem& pb, int64_t batch, cudaStream_t stream) {
   if (plan_clears_workspace(pb, batch)) {
     // single windows: a 16-CTA (non-portable) cluster -- 16 SMs pull the index arrays and every per-edge phase is half as
     // long as with 8; batches: see plan_cluster_size
-    const int cl_size = plan_cluster_size(batch);
+    int cl_size = plan_cluster_size(batch);
+    if (cl_size == 16 && !cluster16_available(plan_cluster_smem(pb.F))) cl_size = 8;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)cl_size, (unsigned)batch);
     cfg.blockDim = dim3(PLAN_T);

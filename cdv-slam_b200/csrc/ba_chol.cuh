@@ -63,6 +63,7 @@ __device__ __forceinline__ void chol6_smem(double* A, double* rd, int n, int las
   __syncthreads();
   for (int kb = 0; kb < n; kb += 6) {
     const int tsb = (kb == 0) ? 10 : (kb == 24 ? 20 : 100);
+    (void)tsb;                                        // only used by the PGBA_SOLVE_TIMING build
     SOLVE_TS(tsb);
     // panel: rows below: x L11^T = a (right-looking over the 6 columns: chain = one multiply + one FMA per column)
     if (kb + 6 + tid <= last_row) {

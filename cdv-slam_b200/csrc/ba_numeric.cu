@@ -131,10 +131,11 @@ __device__ __forceinline__ void red_add2(float* p, float a, float b) {       // 
 
 // Everything the back-substitution of a chunk needs that does NOT depend on dX, requested ahead of time (small-chunk
 // path: the first patch of every warp): E row, Q, u, patch id -> old depth, and the index of the thread's dX entry.
+constexpr int UPD_PRE = 2;     // patches per warp fetched ahead (16 patches per chunk in the single-window regime = 2 per warp)
 struct UpdPre {
-  float2 e0, e1;
-  float q, u, d;
-  int kx, dxi;
+  float2 e0[UPD_PRE], e1[UPD_PRE];
+  float q[UPD_PRE], u[UPD_PRE], d[UPD_PRE];
+  int kx[UPD_PRE], dxi;
 };
 __device__ __forceinline__ UpdPre upd_prefetch(const Problem& pb, const WinPtrs& wp, const Chunk& ch, const float* patches,
                                                bool apply);
@@ -1136,22 +1137,26 @@ __device__ __forceinline__ UpdPre upd_prefetch(const Problem& pb, const WinPtrs&
   const int ncols = (N > 0 && pb.with_schur != 0) ? ch.ncols : 0;
   const int len2 = ncols * 3;
   UpdPre pre;
-  pre.e0 = make_float2(0.f, 0.f); pre.e1 = make_float2(0.f, 0.f);
-  pre.q = 0.f; pre.u = 0.f; pre.d = 0.f; pre.kx = 0; pre.dxi = -1;
+  pre.dxi = -1;
   if (tid < ncols * 6) {
     const int col = tid / 6, a = tid - col * 6;
     const int f = (col < ch.n_free) ? wp.slots[ch.slot_base + ch.first_free + col] : ch.frame;
     pre.dxi = 6 * (f - pb.t0) + a;
   }
-  if (pb.L.pc <= 32 && (tid >> 5) < ch.n_patches) {
-    const int p = tid >> 5, lane = tid & 31;
-    const float2* eg = reinterpret_cast<const float2*>(wp.ecells + 6 * ((int64_t)ch.ecell_base + (int64_t)p * ch.ncols));
-    if (lane < len2) pre.e0 = eg[lane];
-    if (lane + 32 < len2) pre.e1 = eg[lane + 32];
-    pre.q = wp.Q[ch.patch_base + p];
-    pre.u = wp.u[ch.patch_base + p];
-    pre.kx = wp.kx[ch.patch_base + p];
-    if (apply) pre.d = patches[(int64_t)pre.kx * pstride + 2 * PP];       // reads [2][0][0] (ba_cuda.cu:218)
+#pragma unroll
+  for (int r = 0; r < UPD_PRE; ++r) {
+    pre.e0[r] = make_float2(0.f, 0.f); pre.e1[r] = make_float2(0.f, 0.f);
+    pre.q[r] = 0.f; pre.u[r] = 0.f; pre.d[r] = 0.f; pre.kx[r] = 0;
+    const int p = (tid >> 5) + 8 * r, lane = tid & 31;
+    if (pb.L.pc <= 32 && p < ch.n_patches) {
+      const float2* eg = reinterpret_cast<const float2*>(wp.ecells + 6 * ((int64_t)ch.ecell_base + (int64_t)p * ch.ncols));
+      if (lane < len2) pre.e0[r] = eg[lane];
+      if (lane + 32 < len2) pre.e1[r] = eg[lane + 32];
+      pre.q[r] = wp.Q[ch.patch_base + p];
+      pre.u[r] = wp.u[ch.patch_base + p];
+      pre.kx[r] = wp.kx[ch.patch_base + p];
+      if (apply) pre.d[r] = patches[(int64_t)pre.kx[r] * pstride + 2 * PP];       // reads [2][0][0] (ba_cuda.cu:218)
+    }
   }
   return pre;
 }
@@ -1170,9 +1175,6 @@ __device__ __forceinline__ void chunk_depth_update(const Problem& pb, const WinP
     sdx[x] = wp.dX[6 * (f - t0) + a];
   }
   const int len2 = ncols * 3;
-  const float2 pre_e0 = pre.e0, pre_e1 = pre.e1;
-  const float pre_q = pre.q, pre_u = pre.u, pre_d = pre.d;
-  const int pre_kx = pre.kx;
   __syncthreads();
   const float2* dx2 = reinterpret_cast<const float2*>(sdx);
   if (pb.L.pc > 32) {
@@ -1202,23 +1204,30 @@ __device__ __forceinline__ void chunk_depth_update(const Problem& pb, const WinP
     // small chunks (single window): one warp per patch, lanes over the E row.  Latency-bound: everything that does not
     // depend on dX (E row, Q, u, patch id -> old depth) was requested before the barrier above (pre[] below).
     const int lane = tid & 31, warp = tid >> 5;
-    for (int p = warp; p < ch.n_patches; p += 8) {
+    int r = 0;
+    for (int p = warp; p < ch.n_patches; p += 8, ++r) {
       const float2* eg = reinterpret_cast<const float2*>(wp.ecells + 6 * ((int64_t)ch.ecell_base + (int64_t)p * ch.ncols));
-      const bool first = p == warp;
+      const bool first = r < UPD_PRE;                  // fetched ahead (upd_prefetch)
+      float2 pe0 = make_float2(0.f, 0.f), pe1 = pe0;
+      float pq = 0.f, pu = 0.f, pd = 0.f;
+      int pkx = 0;
+#pragma unroll
+      for (int rr = 0; rr < UPD_PRE; ++rr)
+        if (rr == r) { pe0 = pre.e0[rr]; pe1 = pre.e1[rr]; pq = pre.q[rr]; pu = pre.u[rr]; pd = pre.d[rr]; pkx = pre.kx[rr]; }
       float acc = 0.f;
       for (int x = lane, k = 0; x < len2; x += 32, ++k) {
-        const float2 e = (first && k < 2) ? (k == 0 ? pre_e0 : pre_e1) : eg[x];
+        const float2 e = (first && k < 2) ? (k == 0 ? pe0 : pe1) : eg[x];
         const float2 d = dx2[x];
         acc += e.x * d.x + e.y * d.y;
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      const float q = first ? pre_q : wp.Q[ch.patch_base + p], u = first ? pre_u : wp.u[ch.patch_base + p];
+      const float q = first ? pq : wp.Q[ch.patch_base + p], u = first ? pu : wp.u[ch.patch_base + p];
       const float dz = q * (u - acc);
       if (lane == 0) wp.dZ[ch.patch_base + p] = dz;
       if (apply) {
-        float* pr = patches + (int64_t)(first ? pre_kx : wp.kx[ch.patch_base + p]) * pstride + 2 * PP;
-        float d = (first ? pre_d : pr[0]) + dz;
+        float* pr = patches + (int64_t)(first ? pkx : wp.kx[ch.patch_base + p]) * pstride + 2 * PP;
+        float d = (first ? pd : pr[0]) + dz;
         d = (d > 20.f) ? 1.0f : d;
         d = fmaxf(d, 1e-4f);
         __syncwarp();

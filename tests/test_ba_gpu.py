@@ -382,3 +382,28 @@ def test_zero_residual_takes_the_small_angle_branches():
     assert np.isfinite(poses).all() and np.isfinite(patches).all()
     assert np.abs(poses - np.asarray(p.poses, np.float32)).max() < 1e-5
     _check_state(p, poses, patches, o_poses, o_patches)
+
+
+def test_cuda_graph_replay_matches_oracle():
+    """The whole call is CUDA-graph capturable (no host synchronisation, caller-owned workspace), and the kernels' loads
+    ahead of pdl_wait() rely on the order of programmatic dependencies, which a captured graph must preserve: replay the
+    captured call on freshly restored inputs (L2 flushed in between) and compare with the oracle."""
+    p = synth.config_c2()
+    d = to_dev(p)
+    pristine = {k: d[k].clone() for k in ("poses", "patches")}
+    call = lambda: fastba.BA(d["poses"], d["patches"], d["intrinsics"], d["target"], d["weight"], d["lmbda"], d["ii"],
+                             d["jj"], d["kk"], p.t0, p.t1, M=p.M, iterations=2)
+    call()                                            # warm-up (lazy initialisation outside the capture)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        call()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    o_poses, o_patches = _oracle(p, 2)
+    for _ in range(3):
+        d["poses"].copy_(pristine["poses"]); d["patches"].copy_(pristine["patches"])
+        flush.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        _check_state(p, d["poses"][0].cpu().numpy().astype(np.float64), d["patches"][0].cpu().numpy().astype(np.float64),
+                     o_poses, o_patches)

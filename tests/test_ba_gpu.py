@@ -407,3 +407,37 @@ def test_cuda_graph_replay_matches_oracle():
         torch.cuda.synchronize()
         _check_state(p, d["poses"][0].cpu().numpy().astype(np.float64), d["patches"][0].cpu().numpy().astype(np.float64),
                      o_poses, o_patches)
+
+
+def test_batched_large_chunks_graph_replay_equals_eager_and_oracle():
+    """16 EuRoC-shaped windows in one call (64 patches per chunk: batched linearisation, update_large_kernel with its tile
+    prefetch ahead of pdl_wait()): CUDA-graph replay == eager call (up to the order of the atomics), window 0 and 15
+    against the oracle."""
+    probs = [synth.config_c5_window(s) for s in range(16)]
+    ds = [to_dev(q) for q in probs]
+    cat = lambda k: torch.cat([x[k] for x in ds], 0).contiguous()
+    idx = lambda k: torch.stack([x[k] for x in ds], 0).contiguous()
+    bp, bq, bi, bt, bw = cat("poses"), cat("patches"), cat("intrinsics"), cat("target"), cat("weight")
+    ii, jj, kk = idx("ii"), idx("jj"), idx("kk")
+    p0 = probs[0]
+    pristine = (bp.clone(), bq.clone())
+    call = lambda: fastba.BA_batched(bp, bq, bi, bt, bw, ds[0]["lmbda"], ii, jj, kk, p0.t0, p0.t1, M=p0.M, iterations=2)
+    call()
+    torch.cuda.synchronize()
+    eager = (bp.clone(), bq.clone())
+    for s in (0, 15):
+        o_poses, o_patches = _oracle(probs[s], 2)
+        _check_state(probs[s], eager[0][s].cpu().numpy().astype(np.float64), eager[1][s].cpu().numpy().astype(np.float64),
+                     o_poses, o_patches, tol=2e-4)
+    g = torch.cuda.CUDAGraph()
+    bp.copy_(pristine[0]); bq.copy_(pristine[1])
+    with torch.cuda.graph(g):
+        call()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for _ in range(2):
+        bp.copy_(pristine[0]); bq.copy_(pristine[1])
+        flush.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        assert rel_err(bp.cpu().numpy(), eager[0].cpu().numpy()) < 1e-5
+        assert rel_err(bq[:, :, 2].cpu().numpy(), eager[1][:, :, 2].cpu().numpy()) < 1e-5

@@ -1,72 +1,56 @@
-"""Mirror of the reference's cdvslam/altcorr/correlation.py: same classes, functions, signatures and modes."""
+"""Host-side mirror of the reference's cdvslam/altcorr/correlation.py: the names a caller imports (CorrLayer, PatchLayer,
+patchify, corr) with the reference's signatures; all arithmetic is in libpgba.so (cuda_corr -> include/pcorr.h)."""
 import torch
 
 import cuda_corr
 
 
 class CorrLayer(torch.autograd.Function):
-    """correlation.py:4-30"""
+    """Correlation lookup with gradients w.r.t. both feature tensors (reference: correlation.py:4-30).  `dropout` < 1
+    back-propagates through a random subset of the edges only, as the reference does."""
 
     @staticmethod
     def forward(ctx, fmap1, fmap2, coords, ii, jj, radius, dropout):
         ctx.save_for_backward(fmap1, fmap2, coords, ii, jj)
-        ctx.radius = radius
-        ctx.dropout = dropout
-        corr, = cuda_corr.forward(fmap1, fmap2, coords, ii, jj, radius)
-        return corr
+        ctx.cfg = (radius, dropout)
+        return cuda_corr.forward(fmap1, fmap2, coords, ii, jj, radius)[0]
 
     @staticmethod
     def backward(ctx, grad):
         fmap1, fmap2, coords, ii, jj = ctx.saved_tensors
-        if ctx.dropout < 1:
-            perm = torch.rand(len(ii), device=ii.device) < ctx.dropout
-            coords = coords[:, perm]
-            grad = grad[:, perm]
-            ii = ii[perm]
-            jj = jj[perm]
-        fmap1_grad, fmap2_grad = cuda_corr.backward(fmap1, fmap2, coords, ii, jj, grad, ctx.radius)
-        return fmap1_grad, fmap2_grad, None, None, None, None, None
+        radius, dropout = ctx.cfg
+        if dropout < 1:
+            keep = torch.rand(len(ii), device=ii.device) < dropout
+            coords, grad, ii, jj = coords[:, keep], grad[:, keep], ii[keep], jj[keep]
+        g1, g2 = cuda_corr.backward(fmap1, fmap2, coords, ii, jj, grad, radius)
+        return g1, g2, None, None, None, None, None
 
 
 class PatchLayer(torch.autograd.Function):
-    """correlation.py:33-49"""
+    """Patch gather with a gradient w.r.t. the map (reference: correlation.py:33-49).  `mode` (extension, default raw
+    window) selects the fused blend / crop of cuda_corr.patchify_mode_forward."""
 
     @staticmethod
-    def forward(ctx, net, coords, radius):
-        ctx.radius = radius
+    def forward(ctx, net, coords, radius, mode=0):
         ctx.save_for_backward(net, coords)
-        patches, = cuda_corr.patchify_forward(net, coords, radius)
-        return patches
+        ctx.cfg = (radius, mode)
+        return cuda_corr.patchify_mode_forward(net, coords, radius, mode)
 
     @staticmethod
     def backward(ctx, grad):
         net, coords = ctx.saved_tensors
-        grad, = cuda_corr.patchify_backward(net, coords, grad, ctx.radius)
-        return grad, None, None
+        radius, mode = ctx.cfg
+        return cuda_corr.patchify_mode_backward(net, coords, grad, radius, mode), None, None, None
 
 
 def patchify(net, coords, radius, mode='bilinear'):
-    """extract patches (correlation.py:51-71)"""
-    patches = PatchLayer.apply(net, coords, radius)
-
-    if mode == 'bilinear':
-        offset = (coords - coords.floor()).to(net.device)
-        dx, dy = offset[:, :, None, None, None].unbind(dim=-1)
-        d = 2 * radius + 1
-        x00 = (1 - dy) * (1 - dx) * patches[..., :d, :d]
-        x01 = (1 - dy) * (dx) * patches[..., :d, 1:]
-        x10 = (dy) * (1 - dx) * patches[..., 1:, :d]
-        x11 = (dy) * (dx) * patches[..., 1:, 1:]
-        return x00 + x01 + x10 + x11
-
-    elif mode == 'upperleft':
-        return patches[..., :1, :1]
-
-    return patches
+    """Extract (2R+1)^2 bilinear / 1x1 upper-left / raw (2R+2)^2 patches around coords (reference: correlation.py:51-71).
+    One kernel per call; any other mode string returns the raw window like the reference."""
+    return PatchLayer.apply(net, coords, radius, cuda_corr.PATCH_MODES.get(mode, 0))
 
 
 def corr(fmap1, fmap2, coords, ii, jj, radius=1, dropout=1):
-    """correlation.py:74-75"""
+    """reference: correlation.py:74-75"""
     return CorrLayer.apply(fmap1, fmap2, coords, ii, jj, radius, dropout)
 
 

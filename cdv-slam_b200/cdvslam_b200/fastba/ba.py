@@ -1,6 +1,8 @@
 """Mirror of the reference's cdvslam/fastba/ba.py (same names, same argument order)."""
 import cuda_ba
+from cdvslam_b200 import native
 
+last_status = native.last_ba_status     # extension: PGBA_ST_* bits of the most recent BA call (0 = every edge processed)
 neighbors = cuda_ba.neighbors
 reproject = cuda_ba.reproject
 

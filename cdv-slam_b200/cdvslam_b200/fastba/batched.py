@@ -44,6 +44,7 @@ def BA_batched(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, t0
                                      P, int(M), int(t0), int(t1), int(iterations), int(bool(eff_impl)), ws.data_ptr(),
                                      ws.numel(), native.stream_ptr(poses.device))
     native.check(rc, "pgba_ba_solve_batched")
+    native.note_ba_call(ws, poses.device, E, F, K, t0, t1, B)
     return []
 
 

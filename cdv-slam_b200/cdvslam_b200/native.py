@@ -43,16 +43,13 @@ SIGNATURES = {
     "pgba_ba_status_ptr": (c_vp, [c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_i64, c_i64]),
     "pgba_pgo_workspace_bytes": (c_int, [c_i64, ctypes.POINTER(c_sz)]),
     "pgba_pgo_solve": (c_int, [c_vp] * 5 + [c_i64, c_i64, ctypes.c_float, ctypes.c_float, c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "pgba_neighbors_workspace_bytes": (c_int, [c_i64, ctypes.POINTER(c_sz)]),
+    "pgba_neighbors": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "pgba_reproject": (c_int, [c_vp] * 6 + [c_i64, c_i64, c_i64, c_int, c_int, c_vp, c_vp]),
     "pcorr_forward": (c_int, [c_vp] * 5 + [c_int, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_vp,
                                            c_vp]),
     "pcorr_forward_pyramid2": (c_int, [c_vp] * 6 + [c_int, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int,
                                                     c_int, c_int, c_int, c_vp, c_vp]),
-    "pcorr_tiled_supported": (c_int, [c_int, c_int, c_int, c_int]),
-    "pcorr_tiled_workspace_bytes": (c_int, [c_int, c_int, c_i64, c_i64, c_int, c_int, c_int, c_int,
-                                            ctypes.POINTER(c_sz)]),
-    "pcorr_forward_tiled": (c_int, [c_vp] * 6 + [c_int, c_int, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int,
-                                                 c_int, c_int, c_int, c_vp, c_vp, c_sz, c_vp]),
     "pcorr_tma_supported": (c_int, [c_int, c_int, c_int, c_int]),
     "pcorr_tma_workspace_bytes": (c_int, [c_int, c_int, c_i64, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_sz)]),
     "pcorr_forward_tma": (c_int, [c_vp] * 6 + [c_int, c_int, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int,
@@ -61,6 +58,8 @@ SIGNATURES = {
                                             c_vp, c_vp]),
     "pcorr_patchify_forward": (c_int, [c_vp, c_vp, c_int, c_i64, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "pcorr_patchify_backward": (c_int, [c_vp, c_vp, c_int, c_i64, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "pcorr_patchify_mode_forward": (c_int, [c_vp, c_vp, c_int, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "pcorr_patchify_mode_backward": (c_int, [c_vp, c_vp, c_int, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
 }
 
 _lib = None
@@ -114,9 +113,13 @@ _retired = []          # outgrown buffers stay alive: a CUDA graph captured earl
 
 
 def workspace(nbytes, device, pool="ba"):
-    """Grow-only per-device scratch buffer (the C ABI never allocates).  When a larger buffer is needed the old one is
-    kept alive, so pointers baked into previously captured CUDA graphs remain valid."""
-    key = (pool, device.type, device.index if device.index is not None else torch.cuda.current_device())
+    """Grow-only scratch buffer per (pool, device, current stream) -- the C ABI never allocates.  Keyed by the stream as
+    well: two streams calling BA concurrently (or a captured graph replayed on a side stream while eager calls run on
+    another) must not share S, y and the plan tables, as the reference's temporaries do not (stream-aware caching
+    allocator).  When a larger buffer is needed the old one is kept alive, so pointers baked into previously captured
+    CUDA graphs remain valid."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    key = (pool, device.type, idx, torch.cuda.current_stream(device).cuda_stream)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
         if buf is not None:
@@ -124,6 +127,49 @@ def workspace(nbytes, device, pool="ba"):
         buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
         _workspaces[key] = buf
     return buf
+
+
+_last_ba = {}          # device index -> (workspace tensor, E, F, K, t0, t1, batch) of the most recent BA call
+
+
+def note_ba_call(ws, device, E, F, K, t0, t1, batch):
+    """Remember where the status words of the call just enqueued live; with PGBA_CHECK_STATUS=1 synchronise and raise when
+    a window could not be processed completely (the reference has no such limits, so a partial update must not pass
+    silently).  Default: asynchronous; poll with last_ba_status()."""
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    _last_ba[key] = (ws, int(E), int(F), int(K), int(t0), int(t1), int(batch))
+    if os.environ.get("PGBA_CHECK_STATUS", "0") == "1":
+        st = last_ba_status(device)
+        if st:
+            raise RuntimeError("fastba.BA: status 0x%x -- %s; the update is partial or missing (limits: INTEGRATION.md)"
+                               % (st, ", ".join(n for b, n in STATUS_BITS if st & b)))
+
+
+STATUS_BITS = ((1, "an ii/jj/kk index is outside the pose / patch buffers (edge skipped)"),
+               (2, "a chunk sees more than 128 distinct target frames (its edges were dropped)"),
+               (4, "internal table capacity exceeded (chunk dropped or whole solve skipped)"),
+               (8, "a patch id appears with two source frames"))
+
+
+def last_ba_status(device=None):
+    """OR of the device-side status words (PGBA_ST_* of include/pgba.h) of every window of the most recent BA call on
+    `device`; synchronises that device's current stream.  0 = every edge was processed."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    rec = _last_ba.get(key)
+    if rec is None:
+        return 0
+    ws, E, F, K, t0, t1, batch = rec
+    torch.cuda.current_stream(dev).synchronize()
+    L = lib()
+    st = 0
+    for b in range(batch):
+        ptr = L.pgba_ba_status_ptr(ws.data_ptr(), E, F, K, t0, t1, batch, b)
+        if not ptr:
+            continue
+        off = ptr - ws.data_ptr()
+        st |= int(ws[off:off + 4].view(torch.int32).item())
+    return st
 
 
 def host_arena(n_edges, n_pose_rows, n_patch_rows, P=3):

@@ -4,6 +4,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <vector>
 
 #include "ba_common.cuh"
 
@@ -37,8 +38,12 @@ static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
-// all PxP pixels of every edge's patch, frame ii -> jj  (reference: cdvslam/fastba/ba_cuda.cu:408-458)
-// one thread per (edge, pixel); coords [E, 2, P, P]
+// all PxP pixels of every edge's patch, frame ii -> jj; one thread per (edge, pixel); coords [E, 2, P, P]
+//   clamp_depth == 0: the reference's reproject kernel (cdvslam/fastba/ba_cuda.cu:408-458): intrinsics row 0 for every
+//                     edge, unguarded X / Z
+//   clamp_depth != 0: pops.transform as slam.py:328 calls it (cdvslam/projective_ops.py:19-68): back-projection with the
+//                     intrinsics of the SOURCE frame (intrinsics[:, ii], :57), projection with those of the TARGET frame
+//                     (intrinsics[:, jj], :68) and d = 1 / Z.clamp(min=0.1) (:43)
 __global__ void reproject_kernel(const float* __restrict__ poses, const float* __restrict__ patches,
                                  const float* __restrict__ intr, const int64_t* __restrict__ ii,
                                  const int64_t* __restrict__ jj, const int64_t* __restrict__ kk, int64_t E, int P,
@@ -50,16 +55,19 @@ __global__ void reproject_kernel(const float* __restrict__ poses, const float* _
   if (idx >= E * PP) return;
   const int64_t n = idx / PP;
   const int px = (int)(idx - n * PP);
-  const float fx = intr[0], fy = intr[1], cx = intr[2], cy = intr[3];
+  const int64_t fi = ii[n], fj = jj[n];
+  const float* ki = clamp_depth ? intr + 4 * fi : intr;
+  const float* kj = clamp_depth ? intr + 4 * fj : intr;
   float R[9], t[3];
-  rel_pose(poses + 7 * ii[n], poses + 7 * jj[n], R, t);
+  rel_pose(poses + 7 * fi, poses + 7 * fj, R, t);
   const float* pr = patches + kk[n] * 3 * PP;
-  const float xi0 = (pr[px] - cx) / fx, xi1 = (pr[PP + px] - cy) / fy, pd = pr[2 * PP + px];
+  const float xi0 = (pr[px] - ki[2]) / ki[0], xi1 = (pr[PP + px] - ki[3]) / ki[1], pd = pr[2 * PP + px];
   const float X = R[0] * xi0 + R[1] * xi1 + R[2] + pd * t[0];
   const float Y = R[3] * xi0 + R[4] * xi1 + R[5] + pd * t[1];
   const float Z = R[6] * xi0 + R[7] * xi1 + R[8] + pd * t[2];
+  const float fx = kj[0], fy = kj[1], cx = kj[2], cy = kj[3];
   float u, v;
-  if (clamp_depth) {                       // projective_ops.proj: d = 1 / Z.clamp(min=0.1)  (projective_ops.py:43)
+  if (clamp_depth) {
     const float d = 1.0f / fmaxf(Z, 0.1f);
     u = fx * (d * X) + cx;
     v = fy * (d * Y) + cy;
@@ -280,20 +288,26 @@ HostStage host_stage(int64_t E, int64_t F, int64_t K, int P) {
   h.total = o;
   return h;
 }
-// fork / join events, created once per device (never destroyed: they live as long as the library)
-cudaEvent_t* stage_events() {
-  static cudaEvent_t ev[64][2];
-  static bool made[64] = {};
+// fork / join events: one pair per (device, main stream), created on first use and never destroyed (they live as long as
+// the library).  Callers on different streams therefore never share an event, so their record / wait pairs cannot
+// interleave; two host threads driving the SAME stream concurrently are the caller's race, as with any stream.
+struct StageEvents { int dev; cudaStream_t stream; cudaEvent_t ev[2]; };
+cudaEvent_t* stage_events(cudaStream_t s) {
   static std::mutex mu;
+  static std::vector<StageEvents*> cache;
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
   std::lock_guard<std::mutex> lock(mu);
-  if (!made[dev]) {
-    if (cudaEventCreateWithFlags(&ev[dev][0], cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&ev[dev][1], cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    made[dev] = true;
+  for (StageEvents* c : cache)
+    if (c->dev == dev && c->stream == s) return c->ev;
+  StageEvents* c = new StageEvents{dev, s, {nullptr, nullptr}};
+  if (cudaEventCreateWithFlags(&c->ev[0], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev[1], cudaEventDisableTiming) != cudaSuccess) {
+    delete c;
+    return nullptr;
   }
-  return ev[dev];
+  cache.push_back(c);
+  return c->ev;
 }
 }  // namespace
 
@@ -340,7 +354,7 @@ int pgba_ba_solve_host(float* poses_h, float* patches_h, const float* intrinsics
   if (rc) return rc;
   if (iterations == 0 || n_edges == 0) return PGBA_OK;
   cudaStream_t s = (cudaStream_t)stream, a = (cudaStream_t)aux_stream;
-  cudaEvent_t* ev = stage_events();
+  cudaEvent_t* ev = stage_events(s);
   if (!ev) return PGBA_ERR_UNSUPPORTED;
   const size_t E = (size_t)n_edges;
   const bool fork = a != s;
@@ -372,14 +386,16 @@ int pgba_ba_solve_host(float* poses_h, float* patches_h, const float* intrinsics
     PGBA_TRY(cudaMemcpyAsync(sb + h.intr, intrinsics_h, sizeof(float) * 4, cudaMemcpyHostToDevice, a));
     PGBA_TRY(cudaMemcpyAsync(sb + h.lmbda, lmbda_h, sizeof(float), cudaMemcpyHostToDevice, a));
   }
-  if (e != cudaSuccess) return (int)e;
-  e = clear_workspace(pb, 1, s);
-  if (e != cudaSuccess) return (int)e;
-  launch_plan(pb, 1, s);
+  // from here on the auxiliary stream is forked off the main one: whatever fails, it is joined again before returning
+  // (an unjoined fork would invalidate a stream capture in progress)
+  PGBA_TRY(clear_workspace(pb, 1, s));
+  if (e == cudaSuccess) launch_plan(pb, 1, s);
   if (fork) {
-    PGBA_TRY(cudaEventRecord(ev[1], a));
-    PGBA_TRY(cudaStreamWaitEvent(s, ev[1], 0));
+    cudaError_t ej = cudaEventRecord(ev[1], a);
+    if (ej == cudaSuccess) ej = cudaStreamWaitEvent(s, ev[1], 0);
+    if (e == cudaSuccess) e = ej;
   }
+  if (e != cudaSuccess) return (int)e;
   for (int it = 0; it < iterations && e == cudaSuccess; ++it) e = launch_iteration(pb, 1, s, nullptr, it == 0, it + 1 < iterations);
   if (arena) {
     PGBA_TRY(cudaMemcpyAsync((char*)hb, sb, h.intr, cudaMemcpyDeviceToHost, s));          // poses | patches

@@ -20,7 +20,6 @@
 #include <stdlib.h>
 
 #include "ba_common.cuh"
-#include "ba_cells.cuh"
 #include "ba_chol.cuh"
 
 namespace pgba {
@@ -86,7 +85,6 @@ __device__ __forceinline__ void edge_terms(float xi0, float xi1, float pd, float
 #ifndef LIN_MIN_CTAS
 #define LIN_MIN_CTAS 2
 #endif
-constexpr int PLM_QS = 116;                          // 8 * 8 * 116 floats = the sHw region
 constexpr int PQS = 9;                              // stride of the per-patch records sPQ
 constexpr int HW_STRIDE = 29;                       // odd stride: conflict-free per-lane rows
 constexpr int LIN_FIXED_FLOATS = SMAX * 12 + SMAX * 28 + 8 * 32 * HW_STRIDE + 48 + SMAX;
@@ -142,167 +140,6 @@ __device__ __forceinline__ UpdPre upd_prefetch(const Problem& pb, const WinPtrs&
 __device__ __forceinline__ void chunk_depth_update(const Problem& pb, const WinPtrs& wp, const Chunk& ch, float* patches,
                                                    float* sdx, bool apply, const UpdPre& pre, float* s_depth);
 
-// ---------------------------------------------------------------------------------------------------------------
-// Schur update of one patch batch on the tensor cores (chunks with many patches: batched windows, global BA).
-// M = sum_q Q_q E_q^T E_q is a [6 ncols x nq] x [nq x 6 ncols] contraction; with nq = 64..128 it is the largest single
-// term of the chunk (132 of ~280 FMAs per edge) and, as scalar FMAs out of shared memory, bound by shared-memory
-// wavefronts.  Here: mma.sync m16n8k8 TF32 with the 3xTF32 split (x = hi + lo, hi*hi + hi*lo + lo*hi, fp32
-// accumulate: error ~2^-21 relative, inside the 1e-4 parity budget; plain TF32 would not be).
-//   A (row-major, M x K) : A[m][q] = Q_q E_q[m]  for m < estride; row m == estride is Q_q u_q, so the same product
-//                          also yields the gradient term y -= sum_q Q_q u_q E_q (last output row)
-//   B (K x N)            : B[q][n] = E_q[n]
-// Output rows are tiled from the END (the last tile holds the y row and needs every column; the first, partial tile
-// only the first blocks), only tiles that touch the lower block triangle are computed.  Work item = (row tile, group
-// of <= SCHUR_G column tiles sharing the A fragments); items round-robin over the 8 warps.
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int SCHUR_G = 5;
-
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  hi = to_tf32(x);
-  lo = to_tf32(x - __uint_as_float(hi));
-}
-__device__ __forceinline__ void mma_tf32(float d[4], const uint32_t a[4], uint32_t b0, uint32_t b1) {
-  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-__device__ __forceinline__ void schur_mma(const LinSmem& s, const Chunk& ch, const WinPtrs& wp, int nq, int ncols, int fi,
-                                          int t0, int n6) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int g = lane >> 2, t = lane & 3;
-  const int estride = ncols * 6;
-  const int rows = estride + 1;                       // + the y row
-  const int n_mt = (rows + 15) >> 4;
-  const int first_len = rows - 16 * (n_mt - 1);       // valid rows of tile 0 (tiles are aligned to the end)
-  const int ksteps = (nq + 7) >> 3;
-  int item = 0;
-  for (int mt = 0; mt < n_mt; ++mt) {
-    const int m0 = (mt == 0) ? 0 : rows - 16 * (n_mt - mt);
-    const int m_hi = (mt == 0) ? first_len - 1 : m0 + 15;                 // last valid row of the tile
-    const int n_end = (m_hi >= estride) ? estride : min(estride, 6 * (m_hi / 6 + 1));
-    const int n_nt = (n_end + 7) >> 3;
-    const int groups = (n_nt + SCHUR_G - 1) / SCHUR_G;
-    const int gsz = (n_nt + groups - 1) / groups;
-    for (int nt0 = 0; nt0 < n_nt; nt0 += gsz, ++item) {
-      if ((item & 7) != warp) continue;
-      const int ntc = min(gsz, n_nt - nt0);
-      // A rows of this thread: (pointer, q stride); rows past the y row re-read the last E column (discarded)
-      const int mA = m0 + g, mB = mA + 8;
-      const float* pA = (mA < estride) ? s.sE + mA : (mA == estride ? s.sPQ + 1 : s.sE + estride - 1);
-      const float* pB = (mB < estride) ? s.sE + mB : (mB == estride ? s.sPQ + 1 : s.sE + estride - 1);
-      const int sA = (mA == estride) ? PQS : estride, sB = (mB == estride) ? PQS : estride;
-      int ncl[SCHUR_G];
-#pragma unroll
-      for (int j = 0; j < SCHUR_G; ++j) ncl[j] = min(8 * (nt0 + j) + g, estride - 1);
-      // two accumulator sets: the cross terms (lo*hi + hi*lo) are summed on their own and added at the end; the three
-      // MMAs of a k-step are issued tile-interleaved so that dependent MMAs are SCHUR_G issues apart
-      float acc[SCHUR_G][4], acs[SCHUR_G][4];
-#pragma unroll
-      for (int j = 0; j < SCHUR_G; ++j) {
-        acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-        acs[j][0] = acs[j][1] = acs[j][2] = acs[j][3] = 0.f;
-      }
-#pragma unroll 2
-      for (int ks = 0; ks < ksteps; ++ks) {
-        const int q0 = 8 * ks + t, q1 = q0 + 4;
-        const int q0c = min(q0, nq - 1), q1c = min(q1, nq - 1);          // padding rows: Q = 0, finite E re-read
-        const float Q0 = (q0 < nq) ? s.sQ[q0c] : 0.f, Q1 = (q1 < nq) ? s.sQ[q1c] : 0.f;
-        const float* e0 = s.sE + q0c * estride;
-        const float* e1 = s.sE + q1c * estride;
-        float bv0[SCHUR_G], bv1[SCHUR_G];
-#pragma unroll
-        for (int j = 0; j < SCHUR_G; ++j) {
-          if (j < ntc) { bv0[j] = e0[ncl[j]]; bv1[j] = e1[ncl[j]]; }
-        }
-        uint32_t ah[4], al[4];
-        split_tf32(Q0 * pA[q0c * sA], ah[0], al[0]);
-        split_tf32(Q0 * pB[q0c * sB], ah[1], al[1]);
-        split_tf32(Q1 * pA[q1c * sA], ah[2], al[2]);
-        split_tf32(Q1 * pB[q1c * sB], ah[3], al[3]);
-        uint32_t bh0[SCHUR_G], bl0[SCHUR_G], bh1[SCHUR_G], bl1[SCHUR_G];
-#pragma unroll
-        for (int j = 0; j < SCHUR_G; ++j) {
-          if (j < ntc) { split_tf32(bv0[j], bh0[j], bl0[j]); split_tf32(bv1[j], bh1[j], bl1[j]); }
-        }
-#pragma unroll
-        for (int j = 0; j < SCHUR_G; ++j) if (j < ntc) mma_tf32(acs[j], al, bh0[j], bh1[j]);
-#pragma unroll
-        for (int j = 0; j < SCHUR_G; ++j) if (j < ntc) mma_tf32(acc[j], ah, bh0[j], bh1[j]);
-#pragma unroll
-        for (int j = 0; j < SCHUR_G; ++j) if (j < ntc) mma_tf32(acs[j], ah, bl0[j], bl1[j]);
-      }
-#pragma unroll
-      for (int j = 0; j < SCHUR_G; ++j) {
-#pragma unroll
-        for (int x = 0; x < 4; ++x) acc[j][x] += acs[j][x];
-      }
-      // scatter: c0,c1 = (row g, cols 2t, 2t+1), c2,c3 = (row g+8, same cols); a column pair never straddles a block
-#pragma unroll
-      for (int j = 0; j < SCHUR_G; ++j) {
-        if (j >= ntc) continue;
-        const int n = 8 * (nt0 + j) + 2 * t;
-        if (n >= estride) continue;
-        const int cb = n / 6, c = n - 6 * cb;
-        const int fb = ((cb < ch.n_free) ? s.sFrame[ch.first_free + cb] : fi) - t0;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int m = h ? mB : mA;
-          if (mt == 0 && m >= first_len) continue;                       // covered by the next row tile
-          const float v0 = acc[j][2 * h], v1 = acc[j][2 * h + 1];
-          if (m == estride) {
-            atomicAdd(&wp.y[6 * fb + c], -v0);
-            atomicAdd(&wp.y[6 * fb + c + 1], -v1);
-          } else if (m < estride) {
-            const int ca = m / 6, r = m - 6 * ca;
-            if (ca < cb) continue;
-            const int fa = ((ca < ch.n_free) ? s.sFrame[ch.first_free + ca] : fi) - t0;
-            if (fa >= fb) {
-              red_add2(wp.S + (size_t)(6 * fa + r) * n6 + 6 * fb + c, -v0, -v1);
-            } else {                                                      // transposed into block (fb, fa)
-              atomicAdd(wp.S + (size_t)(6 * fb + c) * n6 + 6 * fa + r, -v0);
-              atomicAdd(wp.S + (size_t)(6 * fb + c + 1) * n6 + 6 * fa + r, -v1);
-            }
-          }
-        }
-      }
-    }
-  }
-}
-
-
-// Sum the 27 per-lane partials (H 21, g 6) of one slot over the warp and add them to the slot's record in shared
-// memory.  Recursive halving: at each level a lane keeps one half of its values and receives the partner's partials of
-// that half (31 shuffles instead of 27 x 5); lane L ends with the total of value L.  Several warps may hold partials of
-// the same slot, hence the shared-memory atomic.
-__device__ __forceinline__ void flush_slot(const float H[21], const float g[6], float* dst, int lane) {
-  float v[32];
-#pragma unroll
-  for (int x = 0; x < 21; ++x) v[x] = H[x];
-#pragma unroll
-  for (int x = 0; x < 6; ++x) v[21 + x] = g[x];
-#pragma unroll
-  for (int x = 27; x < 32; ++x) v[x] = 0.f;
-#pragma unroll
-  for (int lvl = 0; lvl < 5; ++lvl) {
-    const int o = 16 >> lvl;
-    const bool up = (lane & o) != 0;
-#pragma unroll
-    for (int i = 0; i < o; ++i) {
-      const float send = up ? v[i] : v[i + o];
-      const float keep = up ? v[i + o] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-    }
-  }
-  if (lane < 27) atomicAdd(dst + lane, v[0]);
-}
-
-
 // grid = (gx, batch), block = 256, dynamic smem = lin_smem_bytes(pc, ebudget).  fuse_update: first apply the previous
 // iteration's back-substitution + depth retraction to the chunk's patches (saves the separate update launch).
 #ifdef PGBA_LIN_TIMING
@@ -326,11 +163,8 @@ __device__ long long g_lin_ts[32];
 #define CTA_TS(k, f) do { } while (0)
 #endif
 
-// CELLS: the first linearisation of a call in the single-window regime also builds the cell tables of its chunk
-// (build_chunk_cells, otherwise plan_cells_kernel's job): one kernel and its dependent round trips less per call.
-template <bool PLM, bool FUSE, bool CELLS>
+template <bool FUSE>
 __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb, int ebudget, int flags) {
-  __shared__ CellScratch csc;
   CTA_TS((flags & 1) ? 3 : 0, 0);
   // flags & 8 (second and later linearisations of a call, small solve in between): the previous kernel is the solve,
   // which lets this kernel start only after its own pdl_wait(), i.e. after the previous linearisation and the plan have
@@ -372,21 +206,10 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
   const int n_dups = wp.hdr->n_dups;
   const bool schur = pb.with_schur != 0;
   constexpr bool fuse_update = FUSE;
-  const bool use_mma = (flags & 2) != 0;
-  constexpr bool plm = PLM;
 
   for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
-    Chunk ch_;
-    if constexpr (CELLS) {
-      const bool built = build_chunk_cells(pb, wp, c, csc);
-      __syncthreads();                                           // cell table, kx, slots written; csc.sch final
-      ch_ = csc.sch;
-      if (!built) continue;
-    } else {
-      ch_ = wp.chunks[c];
-      if (ch_.n_patches == 0) continue;
-    }
-    const Chunk& ch = ch_;
+    const Chunk ch = wp.chunks[c];
+    if (ch.n_patches == 0) continue;
     __syncthreads();
     LIN_TS(1);
     const int ns = ch.n_slots, ncols = ch.ncols, fi = ch.frame, np = ch.n_patches;
@@ -395,7 +218,6 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
     const int* kx = wp.kx + ch.patch_base;
     const int estride = ncols * 6;
     int PB = (estride > 0) ? min(np, max(ebudget / estride, 1)) : np;
-    if (PLM) PB = min(PB, PLM_QS);                    // per-warp per-patch partials live in sHw: [8 warps][8][PLM_QS]
     // ---- early loads.  The chunk's tables are chains of dependent global loads (slot -> pose, patch id -> patch,
     //      cell -> target / weight); in the single-window regime their round trips are the kernel's critical path, so
     //      the first link of every chain is issued here, before the fused depth update, and the second links together
@@ -408,8 +230,8 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
     const int e_DW = pow2_ceil(e_w), e_PW = 32 / e_DW;
     const bool e_ok = (lane & (e_DW - 1)) < e_w;
     const int e_p = warp * e_PW + lane / e_DW, e_sl = lane & (e_DW - 1);
-    const int e_n0 = (!plm && e_ok && e_p < e_np) ? cells[e_p * ns + e_sl] : -1;
-    const int e_n1 = (!plm && e_ok && e_p + 8 * e_PW < e_np) ? cells[(e_p + 8 * e_PW) * ns + e_sl] : -1;
+    const int e_n0 = (e_ok && e_p < e_np) ? cells[e_p * ns + e_sl] : -1;
+    const int e_n1 = (e_ok && e_p + 8 * e_PW < e_np) ? cells[(e_p + 8 * e_PW) * ns + e_sl] : -1;
     UpdPre upre;
     if (fuse_update) upre = upd_prefetch(pb, wp, ch, patches, true);
     float e_px = 0.f, e_py = 0.f, e_pd = 0.f;                  // x, y never change; the depth is rewritten by the update
@@ -477,96 +299,11 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
         }
       }
       for (int x = tid; x < (b1 - b0) * estride; x += 256) s.sE[x] = 0.f;
-      if (plm) {
-        for (int x = tid; x < 8 * 8 * PLM_QS; x += 256) s.sHw[x] = 0.f;
-      }
       __syncthreads();
     LIN_TS(3);
 
-      // ---- large chunks (batched windows, global BA): lanes <-> patches, work item = (slot, batch of 32 patches), the
-      //      ns * nb items in slot-major order split evenly over the 8 warps.  All 32 lanes carry an edge (the slot-lane
-      //      mapping below runs at ns / 32 lanes for ns > 16), the per-patch sums need no shuffles (plain read-modify-write of
-      //      per-warp partials in the sHw region) and H, g are reduced once per slot (flush_slot).
-      if constexpr (PLM) {
-        const int nq = b1 - b0, nb = (nq + 31) >> 5, n_items = ns * nb;
-        const int it0 = (warp * n_items) >> 3, it1 = ((warp + 1) * n_items) >> 3;
-        // (slot, batch) of items it0, it0 + 1, it0 + 2 are carried incrementally (no divisions in the loop)
-        int s0 = it0 / nb, b0i = it0 - s0 * nb;                 // current item
-        int s2 = s0, b2 = b0i;                                  // item two ahead (cell prefetch)
-        auto advance = [&](int& s_, int& b_) { if (++b_ == nb) { b_ = 0; ++s_; } };
-        auto cell_at = [&](int it, int s_, int b_) -> int {
-          const int q_ = b_ * 32 + lane;
-          return (it < it1 && q_ < nq) ? cells[(b0 + q_) * ns + s_] : -1;
-        };
-        int n_cur = cell_at(it0, s2, b2);
-        advance(s2, b2);
-        int n_nxt = cell_at(it0 + 1, s2, b2);
-        advance(s2, b2);
-        float2 tg_cur = make_float2(0.f, 0.f), wt_cur = make_float2(0.f, 0.f);
-        if (n_cur >= 0) { tg_cur = __ldg(target + n_cur); wt_cur = __ldg(weight + n_cur); }
-        int cur_s = -1, col = -1;
-        bool col_ok = false;
-        float H[21], g[6], R[9], t[3];
-        for (int it = it0; it < it1; ++it) {
-          const int sl = s0, q = b0i * 32 + lane;
-          advance(s0, b0i);
-          const int n = n_cur;
-          const float2 tg = tg_cur, wt = wt_cur;
-          {
-            const int n_nn = cell_at(it + 2, s2, b2);
-            advance(s2, b2);
-            n_cur = n_nxt;
-            if (n_cur >= 0) { tg_cur = __ldg(target + n_cur); wt_cur = __ldg(weight + n_cur); }
-            n_nxt = n_nn;
-          }
-          if (sl != cur_s) {                                    // warp-uniform
-            if (cur_s >= 0) flush_slot(H, g, s.sH + cur_s * 28, lane);
-#pragma unroll
-            for (int x = 0; x < 21; ++x) H[x] = 0.f;
-#pragma unroll
-            for (int x = 0; x < 6; ++x) g[x] = 0.f;
-#pragma unroll
-            for (int x = 0; x < 9; ++x) R[x] = s.sRt[sl * 12 + x];
-#pragma unroll
-            for (int x = 0; x < 3; ++x) t[x] = s.sRt[sl * 12 + 9 + x];
-            col = sl - ch.first_free;
-            col_ok = col >= 0 && col < ch.n_free;
-            cur_s = sl;
-          }
-          if (n >= 0) {
-            float e[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, ck = 0.f, uk = 0.f;
-            const float4 pv = *reinterpret_cast<const float4*>(s.sPatch + q * 4);
-            edge_terms(pv.x, pv.y, pv.z, fx, fy, cx, cy, R, t, tg, wt, H, g, e, ck, uk);
-            if (col_ok && schur) {
-              float2* ed = reinterpret_cast<float2*>(s.sE + q * estride + col * 6);
-              ed[0] = make_float2(e[0], e[1]); ed[1] = make_float2(e[2], e[3]); ed[2] = make_float2(e[4], e[5]);
-            }
-            float* dst = s.sHw + warp * (8 * PLM_QS) + q;         // this warp's partials, component-major
-            dst[0] += ck;
-            dst[PLM_QS] += uk;
-            if (i_free) {
-              float ei[6];
-              adj_map(R, t, e, ei);
-#pragma unroll
-              for (int a = 0; a < 6; ++a) dst[(2 + a) * PLM_QS] -= ei[a];
-            }
-          }
-        }
-        if (cur_s >= 0) flush_slot(H, g, s.sH + cur_s * 28, lane);
-        __syncthreads();
-    LIN_TS(4);
-        for (int x = tid; x < nq * 8; x += 256) {                 // fold the 8 warps' partials into sPQ [q][PQS]
-          const int c = x / nq, q = x - c * nq;
-          float acc = 0.f;
-#pragma unroll
-          for (int ww = 0; ww < 8; ++ww) acc += s.sHw[ww * (8 * PLM_QS) + c * PLM_QS + q];
-          s.sPQ[q * PQS + c] = acc;
-        }
-        __syncthreads();
-    LIN_TS(5);
-      }
       // ---- tile loop: lanes <-> slots (DW wide), PW patches per warp step
-      for (int sb = 0, ns_here = 0; sb < (PLM ? 0 : ns); sb += ns_here) {
+      for (int sb = 0, ns_here = 0; sb < ns; sb += ns_here) {
         ns_here = slot_block_width(ns - sb, split_slots);
         const int DW = pow2_ceil(ns_here), PW = 32 / DW;
         const int sl = sb + (lane & (DW - 1));
@@ -677,10 +414,9 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
     LIN_TS(5);
       }
 
-      // ---- duplicated (patch, slot) edges: rare slow path, one thread (deterministic, no shared atomics).  With the
-      //      plan's global list, or (CELLS: the list is still being written by other CTAs) by re-scanning the chunk's own
-      //      edges: a duplicate is an edge that does not own its cell.
-      if (CELLS ? (csc.has_dup != 0) : (n_dups > 0)) {
+      // ---- duplicated (patch, slot) edges: rare slow path, one thread (deterministic, no shared atomics), from the
+      //      plan's global list
+      if (n_dups > 0) {
         if (tid == 0) {
           auto process_dup = [&](int q, int sl, int n) {
             float R[9], t[3], H[21], g[6], e[6], ei[6], ck, uk;
@@ -702,19 +438,10 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
             for (int x = 0; x < 21; ++x) s.sH[sl * 28 + x] += H[x];
             for (int x = 0; x < 6; ++x) s.sH[sl * 28 + 21 + x] += g[x];
           };
-          if constexpr (CELLS) {
-            for (int pos = ch.edge_begin; pos < ch.edge_end; ++pos) {
-              const int4 rec = wp.perm[pos];
-              const int p = cell_patch_rank(csc, rec.z - ch.kbase), sl = cell_slot_rank(csc, rec.y);
-              if (__ldcg(&cells[p * ns + sl]) == rec.x || p < b0 || p >= b1) continue;
-              process_dup(p - b0, sl, rec.x);
-            }
-          } else {
-            for (int dix = 0; dix < n_dups; ++dix) {
-              const DupEdge de = wp.dups[dix];
-              if (de.chunk != c || de.p < b0 || de.p >= b1) continue;
-              process_dup(de.p - b0, de.s, de.n);
-            }
+          for (int dix = 0; dix < n_dups; ++dix) {
+            const DupEdge de = wp.dups[dix];
+            if (de.chunk != c || de.p < b0 || de.p >= b1) continue;
+            process_dup(de.p - b0, de.s, de.n);
           }
         }
         __syncthreads();
@@ -738,10 +465,6 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
         float* eg = wp.ecells + 6 * ((int64_t)ch.ecell_base + (int64_t)b0 * ncols);
         for (int x = tid; x < (b1 - b0) * estride; x += 256) eg[x] = s.sE[x];
 
-        if (use_mma) {
-          schur_mma(s, ch, wp, b1 - b0, ncols, fi, t0, n6);
-          continue;
-        }
         if (split_slots) {
           // ---- large chunks: the phase below is bound by shared-memory wavefronts (5 loads per 12 FMAs).  Here a QUAD of
           //      lanes owns a whole 6 x 6 block (ca >= cb), each lane takes every fourth patch (7 loads per 36 FMAs, 18
@@ -1358,20 +1081,6 @@ int lin_ebudget(const Problem& pb) {
 
 cudaError_t launch_big_solve(const Problem& pb, int64_t batch, cudaStream_t stream);
 
-// Tensor-core Schur update (schur_mma): opt-in (PGBA_SCHUR_MMA=1).  Measured on the B200 (c5, 64 windows, chunks of 96
-// patches x 10 columns): 22.4 k cycles per chunk against 13.8 k for the FFMA2 path below (linearize 171 vs 134 us) -- the
-// legacy mma.sync TF32 path plus the three-way split does not beat packed fp32 FMAs at K = 96; accuracy is equivalent
-// (S to 3e-7 against the float64 oracle).  Kept, parity-tested (tests/test_ba_gpu.py), for the A/B record.
-static bool schur_on_tensor_cores(int pc) {
-  static int forced = -2;
-  if (forced == -2) {
-    const char* e = getenv("PGBA_SCHUR_MMA");
-    forced = e ? atoi(e) : -1;
-  }
-  (void)pc;
-  return forced > 0;
-}
-
 // Loads ahead of pdl_wait() in the second linearisation / the update kernel (PGBA_EARLY=0 disables, for A/B runs).
 static bool early_loads_enabled() {
   static int v = -1;
@@ -1382,49 +1091,18 @@ static bool early_loads_enabled() {
   return v != 0;
 }
 
-// Edge loop with lanes <-> patches (linearize_kernel<true>): opt-in (PGBA_PATCH_LANES=1).  Measured on the B200 (c5): every
-// lane carries an edge (the slot-lane loop runs at ~18 of 32 lanes) and the per-patch shuffles disappear, but target /
-// weight become 32-sector gathers, H / g need a 27-value warp reduction per slot and the per-warp partials one more
-// pass: 147 us against 134 us for the slot-lane loop at the same instruction count (69 M).  Kept, parity-tested, for the
-// A/B record.
-static bool patch_lanes(int pc) {
-  static int forced = -2;
-  if (forced == -2) {
-    const char* e = getenv("PGBA_PATCH_LANES");
-    forced = e ? atoi(e) : -1;
-  }
-  (void)pc;
-  return forced > 0;
-}
-
-// Opt-in (PGBA_FUSE_CELLS=1), single-window regime (<= 32 patches per chunk): the first linearisation of a call builds the
-// cell tables of its chunks itself and launch_plan skips plan_cells_kernel.  Measured on the B200 (c2, same box): 90.0 us
-// against 86.0 us with the separate kernel -- the per-chunk build is a chain of dependent round trips either way, and inside
-// the linearisation its CTA body grows from 7.4 + 9.7 us (two kernels) to 20.7 us (median, profiles/cta_trace.py).
-// Kept, parity-tested, for the A/B record.
-bool cells_in_linearize(const Problem& pb, int64_t batch) {
-  (void)batch;
-  const char* e = getenv("PGBA_FUSE_CELLS");
-  return pb.L.pc <= 32 && !patch_lanes(pb.L.pc) && (e && e[0] == '1');
-}
-
 void launch_linearize(const Problem& pb, int64_t batch, cudaStream_t stream, bool fuse_update, bool first) {
   const int gx = chunk_grid(pb, batch);
   const int ebudget = lin_ebudget(pb);
   const size_t lsm = lin_smem_bytes(pb.L.pc, ebudget);
   const bool early = fuse_update && pb.t1 > pb.t0 && !pb.L.big && early_loads_enabled();
-  const int flags = (fuse_update ? 1 : 0) | (schur_on_tensor_cores(pb.L.pc) ? 2 : 0) | (early ? 8 : 0);
+  const int flags = (fuse_update ? 1 : 0) | (early ? 8 : 0);
   auto go = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm);
     launch_k(kern, dim3((unsigned)gx, (unsigned)batch), dim3(256), lsm, stream, pb, ebudget, flags);
   };
-  if (patch_lanes(pb.L.pc)) {
-    if (fuse_update) go(linearize_kernel<true, true, false>); else go(linearize_kernel<true, false, false>);
-  } else if (first && cells_in_linearize(pb, batch)) {
-    go(linearize_kernel<false, false, true>);
-  } else {
-    if (fuse_update) go(linearize_kernel<false, true, false>); else go(linearize_kernel<false, false, false>);
-  }
+  (void)first;
+  if (fuse_update) go(linearize_kernel<true>); else go(linearize_kernel<false>);
   count_launch();
 }
 

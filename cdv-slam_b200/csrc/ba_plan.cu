@@ -458,7 +458,6 @@ static int edge_grid(int64_t E, int64_t batch) {
   return (int)(g < 1 ? 1 : g);
 }
 
-bool cells_in_linearize(const Problem& pb, int64_t batch);
 
 int chunk_grid(const Problem& pb, int64_t batch) {
   int64_t g = pb.L.ch_max;
@@ -571,7 +570,6 @@ void launch_plan(const Problem& pb, int64_t batch, cudaStream_t stream) {
     launch_k(plan_scatter_kernel, dim3(grid), dim3(256), 0, stream, pb);
     count_launch();
   }
-  if (cells_in_linearize(pb, batch)) return;          // the first linearisation builds the cell tables of its chunks
   launch_k(plan_cells_kernel, dim3((unsigned)chunk_grid(pb, batch), (unsigned)batch), dim3(256), 0, stream, pb);
   count_launch();
 }

@@ -380,6 +380,55 @@ __global__ void __launch_bounds__(256) patchify_forward_kernel(const T* __restri
   }
 }
 
+// The modes the reference applies in python on the gathered (2R+2)^2 window (cdvslam/altcorr/correlation.py:51-71), fused
+// into the gather.  'bilinear': the four (2R+1)^2 sub-windows blended with weights from coords - floor(coords), evaluated
+// the way torch evaluates the reference's expression -- float32 weights (the coordinates are float32), the half window
+// promoted to float32, separate (unfused) multiplies and adds in the same order -- so the result is float32 and equals
+// the reference's bit for bit.  'upperleft': element [0][0] of the window, in the map's dtype.
+template <typename T>
+__global__ void __launch_bounds__(256) patchify_bilinear_kernel(const T* __restrict__ net,
+                                                               const float* __restrict__ coords, int64_t M, int C,
+                                                               int H, int W, int R, float* __restrict__ out) {
+  const int d = 2 * R + 1, dd = d * d;
+  const int64_t m = blockIdx.x;
+  const int b = blockIdx.y;
+  const float x = coords[((int64_t)b * M + m) * 2], y = coords[((int64_t)b * M + m) * 2 + 1];
+  const float flx = floorf(x), fly = floorf(y);
+  const int fy = (int)fly, fx = (int)flx;
+  const float dx = __fsub_rn(x, flx), dy = __fsub_rn(y, fly);
+  const float w00 = __fmul_rn(__fsub_rn(1.f, dy), __fsub_rn(1.f, dx)), w01 = __fmul_rn(__fsub_rn(1.f, dy), dx);
+  const float w10 = __fmul_rn(dy, __fsub_rn(1.f, dx)), w11 = __fmul_rn(dy, dx);
+  const T* ng = net + (int64_t)b * C * H * W;
+  float* og = out + ((int64_t)b * M + m) * C * dd;
+  for (int o = threadIdx.x; o < C * dd; o += blockDim.x) {
+    const int c = o / dd, pos = o - c * dd;
+    const int i = fy + (pos / d - R), j = fx + (pos % d - R);
+    const T* plane = ng + (int64_t)c * H * W;
+    auto at = [&](int ii, int jj) -> float {
+      return (ii >= 0 && ii < H && jj >= 0 && jj < W) ? to_f<T>(plane[(int64_t)ii * W + jj]) : 0.f;
+    };
+    float v = __fmul_rn(w00, at(i, j));
+    v = __fadd_rn(v, __fmul_rn(w01, at(i, j + 1)));
+    v = __fadd_rn(v, __fmul_rn(w10, at(i + 1, j)));
+    v = __fadd_rn(v, __fmul_rn(w11, at(i + 1, j + 1)));
+    og[o] = v;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) patchify_upperleft_kernel(const T* __restrict__ net,
+                                                                const float* __restrict__ coords, int64_t M, int C,
+                                                                int H, int W, int R, T* __restrict__ out) {
+  const int64_t m = blockIdx.x;
+  const int b = blockIdx.y;
+  const float x = coords[((int64_t)b * M + m) * 2], y = coords[((int64_t)b * M + m) * 2 + 1];
+  const int i = (int)floorf(y) - R, j = (int)floorf(x) - R;
+  const bool ok = i >= 0 && i < H && j >= 0 && j < W;
+  const T* ng = net + (int64_t)b * C * H * W;
+  for (int c = threadIdx.x; c < C; c += blockDim.x)
+    out[((int64_t)b * M + m) * C + c] = ok ? ng[((int64_t)c * H + i) * W + j] : from_f<T>(0.f);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) patchify_backward_kernel(const T* __restrict__ pgrad,
                                                                const float* __restrict__ coords, int64_t M, int C,
@@ -396,6 +445,51 @@ __global__ void __launch_bounds__(256) patchify_backward_kernel(const T* __restr
     const int i = fy + (pos / D - R), j = fx + (pos % D - R);
     if (i >= 0 && i < H && j >= 0 && j < W) atomicAdd(&ng[((int64_t)c * H + i) * W + j], pg[o]);
   }
+}
+
+// Adjoint of patchify_bilinear_kernel / patchify_upperleft_kernel w.r.t. the map: what autograd derives for the
+// reference's python blend followed by patchify_backward_kernel (the four weighted copies of the gradient, cast to the
+// map's dtype, scattered with atomics).  grad: float32 [B, M, C, d, d] (bilinear) or T [B, M, C] (upperleft).
+template <typename T>
+__global__ void __launch_bounds__(256) patchify_bilinear_backward_kernel(const float* __restrict__ grad,
+                                                                        const float* __restrict__ coords, int64_t M,
+                                                                        int C, int H, int W, int R,
+                                                                        T* __restrict__ ngrad) {
+  const int d = 2 * R + 1, dd = d * d;
+  const int64_t m = blockIdx.x;
+  const int b = blockIdx.y;
+  const float x = coords[((int64_t)b * M + m) * 2], y = coords[((int64_t)b * M + m) * 2 + 1];
+  const float flx = floorf(x), fly = floorf(y);
+  const int fy = (int)fly, fx = (int)flx;
+  const float dx = x - flx, dy = y - fly;
+  const float w[4] = {(1.f - dy) * (1.f - dx), (1.f - dy) * dx, dy * (1.f - dx), dy * dx};
+  T* ng = ngrad + (int64_t)b * C * H * W;
+  const float* gg = grad + ((int64_t)b * M + m) * C * dd;
+  for (int o = threadIdx.x; o < C * dd; o += blockDim.x) {
+    const int c = o / dd, pos = o - c * dd;
+    const int i = fy + (pos / d - R), j = fx + (pos % d - R);
+    const float g = gg[o];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int ii = i + (t >> 1), jj = j + (t & 1);
+      if (ii >= 0 && ii < H && jj >= 0 && jj < W) atomicAdd(&ng[((int64_t)c * H + ii) * W + jj], from_f<T>(w[t] * g));
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) patchify_upperleft_backward_kernel(const T* __restrict__ grad,
+                                                                         const float* __restrict__ coords, int64_t M,
+                                                                         int C, int H, int W, int R,
+                                                                         T* __restrict__ ngrad) {
+  const int64_t m = blockIdx.x;
+  const int b = blockIdx.y;
+  const float x = coords[((int64_t)b * M + m) * 2], y = coords[((int64_t)b * M + m) * 2 + 1];
+  const int i = (int)floorf(y) - R, j = (int)floorf(x) - R;
+  if (i < 0 || i >= H || j < 0 || j >= W) return;
+  T* ng = ngrad + (int64_t)b * C * H * W;
+  for (int c = threadIdx.x; c < C; c += blockDim.x)
+    atomicAdd(&ng[((int64_t)c * H + i) * W + j], grad[((int64_t)b * M + m) * C + c]);
 }
 
 template <typename T, int NLEV>
@@ -520,6 +614,61 @@ int pcorr_patchify_backward(const void* patch_grad, const float* coords, int B, 
     patchify_backward_kernel<__half><<<grid, 256, 0, s>>>((const __half*)patch_grad, coords, M, C, H, W, radius, (__half*)net_grad);
   else
     return PCORR_ERR_DTYPE;
+  pgba::count_launch();
+  return (int)cudaGetLastError();
+}
+
+int pcorr_patchify_mode_forward(const void* net, const float* coords, int B, int64_t M, int C, int H, int W, int radius,
+                                int mode, int dtype, void* out, pcorr_stream_t stream) {
+  if (mode == PCORR_PATCH_RAW) return pcorr_patchify_forward(net, coords, B, M, C, H, W, radius, dtype, out, stream);
+  if (mode != PCORR_PATCH_BILINEAR && mode != PCORR_PATCH_UPPERLEFT) return PCORR_ERR_SHAPE;
+  if (M == 0 || B == 0) return PCORR_OK;
+  if (!net || !coords || !out) return PCORR_ERR_NULL;
+  if (B < 0 || M < 0 || C <= 0 || H <= 0 || W <= 0 || radius < 0) return PCORR_ERR_SHAPE;
+  if (M >= (int64_t)1 << 31 || B > 65535) return PCORR_ERR_UNSUPPORTED;
+  if (dtype != PCORR_F32 && dtype != PCORR_F16) return PCORR_ERR_DTYPE;
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 grid((unsigned)M, (unsigned)B);
+  if (mode == PCORR_PATCH_BILINEAR) {
+    const int d = 2 * radius + 1;
+    const int threads = (C * d * d >= 256) ? 256 : ((C * d * d + 31) / 32) * 32;
+    if (dtype == PCORR_F32)
+      patchify_bilinear_kernel<float><<<grid, threads, 0, s>>>((const float*)net, coords, M, C, H, W, radius, (float*)out);
+    else
+      patchify_bilinear_kernel<__half><<<grid, threads, 0, s>>>((const __half*)net, coords, M, C, H, W, radius, (float*)out);
+  } else {
+    const int threads = (C >= 256) ? 256 : ((C + 31) / 32) * 32;
+    if (dtype == PCORR_F32)
+      patchify_upperleft_kernel<float><<<grid, threads, 0, s>>>((const float*)net, coords, M, C, H, W, radius, (float*)out);
+    else
+      patchify_upperleft_kernel<__half><<<grid, threads, 0, s>>>((const __half*)net, coords, M, C, H, W, radius, (__half*)out);
+  }
+  pgba::count_launch();
+  return (int)cudaGetLastError();
+}
+
+int pcorr_patchify_mode_backward(const void* out_grad, const float* coords, int B, int64_t M, int C, int H, int W,
+                                 int radius, int mode, int dtype, void* net_grad, pcorr_stream_t stream) {
+  if (mode == PCORR_PATCH_RAW) return pcorr_patchify_backward(out_grad, coords, B, M, C, H, W, radius, dtype, net_grad, stream);
+  if (mode != PCORR_PATCH_BILINEAR && mode != PCORR_PATCH_UPPERLEFT) return PCORR_ERR_SHAPE;
+  if (M == 0 || B == 0) return PCORR_OK;
+  if (!out_grad || !coords || !net_grad) return PCORR_ERR_NULL;
+  if (B < 0 || M < 0 || C <= 0 || H <= 0 || W <= 0 || radius < 0) return PCORR_ERR_SHAPE;
+  if (M >= (int64_t)1 << 31 || B > 65535) return PCORR_ERR_UNSUPPORTED;
+  if (dtype != PCORR_F32 && dtype != PCORR_F16) return PCORR_ERR_DTYPE;
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 grid((unsigned)M, (unsigned)B);
+  if (mode == PCORR_PATCH_BILINEAR) {
+    if (dtype == PCORR_F32)
+      patchify_bilinear_backward_kernel<float><<<grid, 256, 0, s>>>((const float*)out_grad, coords, M, C, H, W, radius, (float*)net_grad);
+    else
+      patchify_bilinear_backward_kernel<__half><<<grid, 256, 0, s>>>((const float*)out_grad, coords, M, C, H, W, radius, (__half*)net_grad);
+  } else {
+    if (dtype == PCORR_F32)
+      patchify_upperleft_backward_kernel<float><<<grid, 128, 0, s>>>((const float*)out_grad, coords, M, C, H, W, radius, (float*)net_grad);
+    else
+      patchify_upperleft_backward_kernel<__half><<<grid, 128, 0, s>>>((const __half*)out_grad, coords, M, C, H, W, radius, (__half*)net_grad);
+  }
   pgba::count_launch();
   return (int)cudaGetLastError();
 }

@@ -51,6 +51,7 @@ def forward(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, PPF, 
                              E, F, K, P, int(PPF), int(t0), int(t1), int(iterations), int(bool(eff_impl)),
                              ws.data_ptr(), ws.numel(), native.stream_ptr(poses_.device))
     native.check(rc, "pgba_ba_solve")
+    native.note_ba_call(ws, poses_.device, E, F, K, t0, t1, 1)
     return []
 
 
@@ -94,6 +95,7 @@ def forward_host(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, 
                                   stg.data_ptr(), stg.numel(), ws.data_ptr(), ws.numel(), native.stream_ptr(dev),
                                   aux.cuda_stream)
     native.check(rc, "pgba_ba_solve_host")
+    native.note_ba_call(ws, dev, E, F, K, t0, t1, 1)
     return []
 
 
@@ -119,29 +121,43 @@ def reproject(poses, patches, intrinsics, ii, jj, kk, clamp_depth=False):
 
 def neighbors(ii, jj):
     """cuda_ba.neighbors (ba.cpp:59-97): for edges grouped by `ii` and stably ordered by `jj`, the index of the
-    previous / next edge of the same group (-1 at the ends).  Runs on the device the tensors live on, without the
-    reference's D2H -> CPU stable_sort -> H2D round trip (not part of the BA arithmetic)."""
+    previous / next edge of the same group (-1 at the ends).  One cluster kernel on the device the tensors live on
+    (pgba_neighbors), without the reference's D2H -> CPU stable_sort -> H2D round trip; returns [ix, jx] (i64, CUDA)."""
+    ii = _prep(ii, torch.int64, "ii")
+    jj = _prep(jj, torch.int64, "jj")
     n = ii.numel()
+    if jj.numel() != n:
+        raise RuntimeError("cuda_ba.neighbors: ii and jj sizes disagree")
     dev = ii.device
+    ix = torch.empty(n, dtype=torch.int64, device=dev)
+    jx = torch.empty(n, dtype=torch.int64, device=dev)
     if n == 0:
-        e = torch.empty(0, dtype=torch.int64, device=dev)
-        return [e, e.clone()]
-    o1 = torch.sort(jj, stable=True).indices
-    order = o1[torch.sort(ii[o1], stable=True).indices]
-    g = ii[order]
-    same = g[1:] == g[:-1]
-    ix = torch.full((n,), -1, dtype=torch.int64, device=dev)
-    jx = torch.full((n,), -1, dtype=torch.int64, device=dev)
-    minus1 = torch.full((n - 1,), -1, dtype=torch.int64, device=dev)
-    ix[order[1:]] = torch.where(same, order[:-1], minus1)
-    jx[order[:-1]] = torch.where(same, order[1:], minus1)
+        return [ix, jx]
+    L = native.lib()
+    nbytes = ctypes.c_size_t(0)
+    native.check(L.pgba_neighbors_workspace_bytes(n, ctypes.byref(nbytes)), "pgba_neighbors_workspace_bytes")
+    with torch.cuda.device(dev):
+        ws = native.workspace(nbytes.value, dev, pool="neighbors")
+        rc = L.pgba_neighbors(ii.data_ptr(), jj.data_ptr(), n, ix.data_ptr(), jx.data_ptr(), ws.data_ptr(), ws.numel(),
+                              native.stream_ptr(dev))
+    native.check(rc, "pgba_neighbors")
     return [ix, jx]
 
 
 def solve_system(J_Ginv_i, J_Ginv_j, ii, jj, res, ep, lm, freen):
     """cuda_ba.solve_system (ba.cpp:120-180): pose-graph normal equations A = J^T J (+ lm * diag + ep), b = -J^T res and
     the double-precision Cholesky solve of the leading 7*freen block (all when freen < 0), on the device (the reference
-    moves everything to the CPU and uses Eigen).  Returns [delta] with delta f32 [n, 7] on res.device."""
+    moves everything to the CPU and uses Eigen).  Returns [delta] with delta f32 [n, 7] on res.device.
+
+    Like the reference (ba.cpp:123-127, 171) the inputs may live on any device: its only caller passes CPU tensors from a
+    worker process (loop_closure/optim_utils.py:230, fed by long_term.py:259-266).  They are moved to the current CUDA
+    device, solved there, and delta goes back to res.device.  (A forked worker cannot initialise CUDA: start the pool
+    with the 'spawn' context, see INTEGRATION.md.)"""
+    out_device = res.device
+    if not torch.cuda.is_available():
+        raise RuntimeError("cuda_ba.solve_system: no CUDA device (there is no CPU path)")
+    dev = res.device if res.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    J_Ginv_i, J_Ginv_j, res, ii, jj = (t.to(dev) for t in (J_Ginv_i, J_Ginv_j, res, ii, jj))
     J_Ginv_i = _prep(J_Ginv_i, torch.float32, "J_Ginv_i")
     J_Ginv_j = _prep(J_Ginv_j, torch.float32, "J_Ginv_j")
     res = _prep(res, torch.float32, "res")
@@ -158,11 +174,11 @@ def solve_system(J_Ginv_i, J_Ginv_j, ii, jj, res, ep, lm, freen):
     L = native.lib()
     nbytes = ctypes.c_size_t(0)
     native.check(L.pgba_pgo_workspace_bytes(n, ctypes.byref(nbytes)), "pgba_pgo_workspace_bytes")
-    delta = torch.empty((n, 7), dtype=torch.float32, device=res.device)
-    with torch.cuda.device(res.device):
-        ws = native.workspace(nbytes.value, res.device, pool="pgo")
+    delta = torch.empty((n, 7), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        ws = native.workspace(nbytes.value, dev, pool="pgo")
         rc = L.pgba_pgo_solve(J_Ginv_i.data_ptr(), J_Ginv_j.data_ptr(), ii.data_ptr(), jj.data_ptr(), res.data_ptr(), r, n,
                               float(ep), float(lm), int(freen), delta.data_ptr(), None, ws.data_ptr(), ws.numel(),
-                              native.stream_ptr(res.device))
+                              native.stream_ptr(dev))
     native.check(rc, "pgba_pgo_solve")
-    return [delta]
+    return [delta.to(out_device)]

@@ -22,33 +22,6 @@ def _c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
-def _tiled(fmap1, maps, coords, ii, jj, radius, out):
-    """Tensor-core tiled path (fp16, C <= 24, P = 3, R = 3); returns False when the shape does not qualify.
-    Opt-in (PCORR_TILED=1): on B200 the warp-per-edge staged kernel measured faster on the c3 shape (profiles/r01)."""
-    if os.environ.get("PCORR_TILED", "0") != "1":
-        return False
-    L = native.lib()
-    B, E, _, P, _ = coords.shape
-    K, C = fmap1.shape[1], fmap1.shape[2]
-    F = maps[0].shape[1]
-    if not L.pcorr_tiled_supported(C, P, int(radius), _DT[fmap1.dtype]) or E == 0:
-        return False
-    nlev = len(maps)
-    H0, W0 = maps[0].shape[3], maps[0].shape[4]
-    H1, W1 = (maps[1].shape[3], maps[1].shape[4]) if nlev == 2 else (0, 0)
-    nbytes = ctypes.c_size_t(0)
-    native.check(L.pcorr_tiled_workspace_bytes(nlev, B, E, F, H0, W0, H1, W1, ctypes.byref(nbytes)),
-                 "pcorr_tiled_workspace_bytes")
-    with torch.cuda.device(fmap1.device):
-        ws = native.workspace(nbytes.value, fmap1.device, pool="corr")
-        rc = L.pcorr_forward_tiled(fmap1.data_ptr(), maps[0].data_ptr(), maps[1].data_ptr() if nlev == 2 else None,
-                                   coords.data_ptr(), ii.data_ptr(), jj.data_ptr(), nlev, B, E, K, F, C, H0, W0, H1, W1,
-                                   P, int(radius), _DT[fmap1.dtype], out.data_ptr(), ws.data_ptr(), ws.numel(),
-                                   native.stream_ptr(fmap1.device))
-    native.check(rc, "pcorr_forward_tiled")
-    return True
-
-
 def _tma(fmap1, maps, coords, ii, jj, radius, out):
     """Default path of the production shape (fp16, C in {24, 32}, P = 3, R = 3): channel-last maps + TMA region tiles +
     tensor cores (corr_tma.cu); returns False when the shape does not qualify.  PCORR_TMA=0 disables it (A/B runs)."""
@@ -92,7 +65,7 @@ def forward(fmap1, fmap2, coords, ii, jj, radius):
     F, H2, W2 = fmap2.shape[1], fmap2.shape[3], fmap2.shape[4]
     D = 2 * radius + 1
     out = torch.empty((B, E, D, D, P, P), dtype=fmap1.dtype, device=fmap1.device)
-    if _tiled(fmap1, [fmap2], coords, ii, jj, radius, out) or _tma(fmap1, [fmap2], coords, ii, jj, radius, out):
+    if _tma(fmap1, [fmap2], coords, ii, jj, radius, out):
         return [out]
     with torch.cuda.device(fmap1.device):
         rc = native.lib().pcorr_forward(fmap1.data_ptr(), fmap2.data_ptr(), coords.data_ptr(), ii.data_ptr(),
@@ -114,9 +87,7 @@ def forward_pyramid2(fmap1, fmap2_l0, fmap2_l1, coords, ii, jj, radius):
     F = fmap2_l0.shape[1]
     D = 2 * radius + 1
     out = torch.empty((B, E, D, D, P, P, 2), dtype=fmap1.dtype, device=fmap1.device)
-    if fmap2_l1.dtype == fmap1.dtype == fmap2_l0.dtype and (
-            _tiled(fmap1, [fmap2_l0, fmap2_l1], coords, ii, jj, radius, out) or
-            _tma(fmap1, [fmap2_l0, fmap2_l1], coords, ii, jj, radius, out)):
+    if fmap2_l1.dtype == fmap1.dtype == fmap2_l0.dtype and _tma(fmap1, [fmap2_l0, fmap2_l1], coords, ii, jj, radius, out):
         return out
     with torch.cuda.device(fmap1.device):
         rc = native.lib().pcorr_forward_pyramid2(fmap1.data_ptr(), fmap2_l0.data_ptr(), fmap2_l1.data_ptr(),
@@ -179,3 +150,48 @@ def patchify_backward(net, coords, gradient, radius):
                                                   dt, net_grad.data_ptr(), native.stream_ptr(net.device))
     native.check(rc, "pcorr_patchify_backward")
     return [net_grad]
+
+
+PATCH_MODES = {"none": 0, "raw": 0, "bilinear": 1, "upperleft": 2}
+
+
+def patchify_mode_forward(net, coords, radius, mode):
+    """Extension: altcorr.patchify(net, coords, radius, mode) in ONE kernel -- the gather of patchify_forward with the
+    'bilinear' blend / 'upperleft' crop of cdvslam/altcorr/correlation.py:56-69 fused in (pcorr_patchify_mode_forward).
+    'bilinear' returns float32 (torch's promotion of the half window against the float32 weights)."""
+    native.require_cuda(net, coords)
+    dt = _dt(net, "patchify_mode_forward")
+    net = _c(net)
+    coords = _c(coords.float())
+    B, C, H, W = net.shape
+    M = coords.shape[1]
+    if mode == 1:
+        d = 2 * radius + 1
+        out = torch.empty((B, M, C, d, d), dtype=torch.float32, device=net.device)
+    elif mode == 2:
+        out = torch.empty((B, M, C, 1, 1), dtype=net.dtype, device=net.device)
+    else:
+        return patchify_forward(net, coords, radius)[0]
+    with torch.cuda.device(net.device):
+        rc = native.lib().pcorr_patchify_mode_forward(net.data_ptr(), coords.data_ptr(), B, M, C, H, W, int(radius), mode,
+                                                      dt, out.data_ptr(), native.stream_ptr(net.device))
+    native.check(rc, "pcorr_patchify_mode_forward")
+    return out
+
+
+def patchify_mode_backward(net, coords, gradient, radius, mode):
+    """Adjoint of patchify_mode_forward w.r.t. net (pcorr_patchify_mode_backward)."""
+    if mode == 0:
+        return patchify_backward(net, coords, gradient, radius)[0]
+    native.require_cuda(net, coords, gradient)
+    dt = _dt(net, "patchify_mode_backward")
+    coords = _c(coords.float())
+    gradient = _c(gradient.float() if mode == 1 else gradient.to(net.dtype))
+    B, C, H, W = net.shape
+    M = coords.shape[1]
+    net_grad = torch.zeros_like(net, memory_format=torch.contiguous_format)
+    with torch.cuda.device(net.device):
+        rc = native.lib().pcorr_patchify_mode_backward(gradient.data_ptr(), coords.data_ptr(), B, M, C, H, W, int(radius),
+                                                       mode, dt, net_grad.data_ptr(), native.stream_ptr(net.device))
+    native.check(rc, "pcorr_patchify_mode_backward")
+    return net_grad

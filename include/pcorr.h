@@ -20,6 +20,7 @@ typedef struct CUstream_st* pcorr_stream_t; /* == cudaStream_t */
 
 enum { PCORR_OK = 0, PCORR_ERR_NULL = -1, PCORR_ERR_SHAPE = -2, PCORR_ERR_DTYPE = -3, PCORR_ERR_UNSUPPORTED = -4 };
 enum { PCORR_F32 = 0, PCORR_F16 = 1 };
+enum { PCORR_PATCH_RAW = 0, PCORR_PATCH_BILINEAR = 1, PCORR_PATCH_UPPERLEFT = 2 };
 
 /* Correlation lookup.  Replaces cuda_corr.forward == corr_cuda_forward() (reference:
  * cdvslam/altcorr/correlation_kernel.cu:83-136 kernel, :193-233 host incl. the bilinear blend and the final
@@ -41,19 +42,6 @@ int pcorr_forward_pyramid2(const void* fmap1, const void* fmap2_l0, const void* 
                            const int64_t* ii, const int64_t* jj, int B, int64_t E, int64_t K, int64_t F, int C,
                            int H0, int W0, int H1, int W1, int P, int radius, int dtype, void* out,
                            pcorr_stream_t stream);
-
-/* Tiled lookup for the production shape (fp16 features, C in {8,16,24}, P = 3, radius = 3): the (edge, level) tasks are
- * binned by fmap2 tile, each tile is staged in shared memory once and the contraction runs on the tensor cores.
- * Same results layout as pcorr_forward (nlev = 1; fmap2_l1 may be NULL) / pcorr_forward_pyramid2 (nlev = 2).
- * Needs a caller-owned, 256-byte aligned workspace of pcorr_tiled_workspace_bytes(); pcorr_tiled_supported() tells
- * whether a shape qualifies (otherwise use pcorr_forward / pcorr_forward_pyramid2). */
-int pcorr_tiled_supported(int C, int P, int radius, int dtype);
-int pcorr_tiled_workspace_bytes(int nlev, int B, int64_t E, int64_t F, int H0, int W0, int H1, int W1,
-                                size_t* bytes /* host, out */);
-int pcorr_forward_tiled(const void* fmap1, const void* fmap2_l0, const void* fmap2_l1, const float* coords,
-                        const int64_t* ii, const int64_t* jj, int nlev, int B, int64_t E, int64_t K, int64_t F, int C,
-                        int H0, int W0, int H1, int W1, int P, int radius, int dtype, void* out, void* workspace,
-                        size_t workspace_bytes, pcorr_stream_t stream);
 
 /* TMA + tensor-core lookup for the production shapes (fp16 features, C in {24, 32, 128}, P = 3, radius = 3) -- the default
  * path of cuda_corr.forward for that shape.  The frame maps are first copied to a channel-last layout in the
@@ -88,6 +76,20 @@ int pcorr_patchify_forward(const void* net, const float* coords, int B, int64_t 
  * patch gradient [B, M, C, D, D] into net_grad [B, C, H, W] (zero-filled by the caller). */
 int pcorr_patchify_backward(const void* patch_grad, const float* coords, int B, int64_t M, int C, int H, int W,
                             int radius, int dtype, void* net_grad, pcorr_stream_t stream);
+
+/* altcorr.patchify(net, coords, radius, mode) in one kernel (reference: cdvslam/altcorr/correlation.py:51-71, which runs
+ * patchify_cuda_forward and then blends / crops the (2R+2)^2 window with torch ops):
+ *   PCORR_PATCH_RAW        out [B, M, C, 2R+2, 2R+2], dtype of net  (== pcorr_patchify_forward)
+ *   PCORR_PATCH_BILINEAR   out f32 [B, M, C, 2R+1, 2R+1] (float32 also for f16 maps: torch promotes the half window against
+ *                          the float32 weights); (1-dy)(1-dx) w[:d,:d] + (1-dy)dx w[:d,1:] + dy(1-dx) w[1:,:d] + dy dx w[1:,1:]
+ *                          with unfused float32 multiplies / adds in that order, i.e. bit-identical to the reference
+ *   PCORR_PATCH_UPPERLEFT  out [B, M, C, 1, 1], dtype of net: window element [0][0]
+ * pcorr_patchify_mode_backward is the adjoint w.r.t. net (out_grad in out's layout and dtype; net_grad zero-filled by the
+ * caller, dtype of net). */
+int pcorr_patchify_mode_forward(const void* net, const float* coords, int B, int64_t M, int C, int H, int W, int radius,
+                                int mode, int dtype, void* out, pcorr_stream_t stream);
+int pcorr_patchify_mode_backward(const void* out_grad, const float* coords, int B, int64_t M, int C, int H, int W,
+                                 int radius, int mode, int dtype, void* net_grad, pcorr_stream_t stream);
 
 #ifdef __cplusplus
 }

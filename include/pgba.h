@@ -140,12 +140,25 @@ const int32_t* pgba_ba_status_ptr(const void* workspace, int64_t n_edges, int64_
 /* ---------------------------------------------------------------------------------------------------------------
  * Reprojection of all PxP pixels of each edge's patch from frame ii to frame jj.  Replaces cuda_ba.reproject ==
  * cuda_reproject() (reference: cdvslam/fastba/ba_cuda.cu:408-458, 614-645).  coords f32 [n_edges, 2, P, P].
- * clamp_depth = 0 reproduces the kernel (unguarded X/Z); clamp_depth = 1 applies Z.clamp(min=0.1) as
- * projective_ops.proj does (cdvslam/projective_ops.py:43), which is what slam.py's reproject() uses (slam.py:328).
+ * clamp_depth = 0 reproduces the kernel (intrinsics row 0, unguarded X/Z); clamp_depth = 1 is pops.transform as
+ * slam.py's reproject() calls it (slam.py:328; cdvslam/projective_ops.py:19-68): back-projection with intrinsics[ii],
+ * projection with intrinsics[jj] (intrinsics must then hold a row per referenced frame) and d = 1 / Z.clamp(min=0.1).
  * ------------------------------------------------------------------------------------------------------------- */
 int pgba_reproject(const float* poses, const float* patches, const float* intrinsics, const int64_t* ii,
                    const int64_t* jj, const int64_t* kk, int64_t n_edges, int64_t n_pose_rows, int64_t n_patch_rows,
                    int P, int clamp_depth, float* coords, pgba_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Temporal neighbours of every edge.  Replaces cuda_ba.neighbors == neighbors() (reference: cdvslam/fastba/ba.cpp:59-97;
+ * called as fastba.neighbors(kk, jj) by every network update, net_cdv.py:102-107).  Edges are grouped by ii; inside a
+ * group they are ordered by jj, ties by edge index (the reference's std::stable_sort of a group listed in input order);
+ * ix[e] / jx[e] = index of the previous / next edge of e's group in that order, -1 at the ends.  ii, jj, ix, jx i64
+ * [n_edges]; any int64 key values.  One cluster launch, no host round trip (the reference synchronises, sorts on the
+ * CPU and copies back).  Workspace: pgba_neighbors_workspace_bytes(), 256-byte aligned.
+ * ------------------------------------------------------------------------------------------------------------- */
+int pgba_neighbors_workspace_bytes(int64_t n_edges, size_t* bytes /* host, out */);
+int pgba_neighbors(const int64_t* ii, const int64_t* jj, int64_t n_edges, int64_t* ix, int64_t* jx, void* workspace,
+                   size_t workspace_bytes, pgba_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Pose-graph normal equations + solve.  Replaces cuda_ba.solve_system == solve_system() (reference:

@@ -81,13 +81,17 @@ def patchify(net, coords, radius, mode="bilinear"):
     """correlation.py:51-71."""
     patches = patchify_raw(net, coords, radius)
     if mode == "bilinear":
+        # torch evaluates the reference's expression in float32 (float32 weights; a half window is promoted), one rounding
+        # per operation, left to right -- numpy float32 arithmetic does exactly the same, so this is bit-exact
         c32 = np.asarray(coords, np.float32)
-        off = (c32 - np.floor(c32)).astype(patches.dtype)
+        off = c32 - np.floor(c32)
         dx = off[..., 0][:, :, None, None, None]
         dy = off[..., 1][:, :, None, None, None]
+        one = np.float32(1)
+        w = patches.astype(np.float32)
         d = 2 * radius + 1
-        return ((1 - dy) * (1 - dx) * patches[..., :d, :d] + (1 - dy) * dx * patches[..., :d, 1:] +
-                dy * (1 - dx) * patches[..., 1:, :d] + dy * dx * patches[..., 1:, 1:])
+        return (((one - dy) * (one - dx)) * w[..., :d, :d] + ((one - dy) * dx) * w[..., :d, 1:] +
+                (dy * (one - dx)) * w[..., 1:, :d] + (dy * dx) * w[..., 1:, 1:])
     if mode == "upperleft":
         return patches[..., :1, :1]
     return patches
@@ -106,4 +110,24 @@ def reproject(poses, patches, intrinsics, ii, jj, kk, dtype=np.float64):
     with np.errstate(divide="ignore", invalid="ignore"):
         u = fx * (Xj[..., 0] / Xj[..., 2]) + cx
         v = fy * (Xj[..., 1] / Xj[..., 2]) + cy
+    return np.stack([u, v], 1)[None]
+
+
+def transform_pops(poses, patches, intrinsics, ii, jj, kk, dtype=np.float64):
+    """pops.transform(SE3(poses), patches, intrinsics, ii, jj, kk) without jacobian / valid / depth
+    (cdvslam/projective_ops.py:53-68 with iproj :19-30 and proj :32-50), laid out as slam.py:329 hands it to corr:
+    coords [1,E,2,P,P].  Differences from reproject(): intrinsics of the source frame for the back-projection (:57), of the
+    target frame for the projection (:68), and d = 1 / Z.clamp(min=0.1) (:43) instead of the unguarded division."""
+    P = np.asarray(patches).shape[-1]
+    poses = np.asarray(poses, dtype).reshape(-1, 7)
+    patches = np.asarray(patches, dtype).reshape(-1, 3, P, P)
+    K = np.asarray(intrinsics, dtype).reshape(-1, 4)
+    Ki, Kj = K[ii][:, :, None, None], K[jj][:, :, None, None]               # [E,4,1,1]
+    tij, qij = se3.rel_se3(poses[ii, :3], poses[ii, 3:], poses[jj, :3], poses[jj, 3:])
+    pk = patches[kk]
+    Xi = np.stack([(pk[:, 0] - Ki[:, 2]) / Ki[:, 0], (pk[:, 1] - Ki[:, 3]) / Ki[:, 1], np.ones_like(pk[:, 0]), pk[:, 2]], -1)
+    Xj = se3.act_se3(tij[:, None, None], qij[:, None, None], Xi)
+    d = 1.0 / np.maximum(Xj[..., 2], 0.1)
+    u = Kj[:, 0] * (d * Xj[..., 0]) + Kj[:, 2]
+    v = Kj[:, 1] * (d * Xj[..., 1]) + Kj[:, 3]
     return np.stack([u, v], 1)[None]

@@ -77,15 +77,29 @@ def test_no_cpu_fallback():
                   iterations=2)
 
 
-def test_neighbors_host_logic_matches_oracle():
+def test_neighbors_abi_validation_and_oracle_self_check():
+    """pgba_neighbors rejects bad arguments before any CUDA call; the oracle's lexsort form equals the literal
+    group-then-stable-sort loop of the reference (ba.cpp:66-90)."""
+    L = native.lib()
+    n = ctypes.c_size_t(0)
+    assert L.pgba_neighbors_workspace_bytes(37824, ctypes.byref(n)) == 0 and n.value % 256 == 0 and n.value > 8 * 37824
+    assert L.pgba_neighbors_workspace_bytes(-1, ctypes.byref(n)) == -2
+    assert L.pgba_neighbors(None, None, 10, None, None, None, 0, None) == -1
+    assert L.pgba_neighbors(None, None, 0, None, None, None, 0, None) == 0
     import cuda_ba
+    with pytest.raises(RuntimeError, match="CUDA"):
+        cuda_ba.neighbors(torch.zeros(4, dtype=torch.int64), torch.zeros(4, dtype=torch.int64))
     rng = np.random.default_rng(0)
-    ii = rng.integers(0, 40, 500)
-    jj = rng.integers(0, 12, 500)
-    ix, jx = cuda_ba.neighbors(torch.as_tensor(ii), torch.as_tensor(jj))
+    ii = rng.integers(0, 40, 500); jj = rng.integers(0, 12, 500)
     oi, oj = neighbors_oracle.neighbors(ii, jj)
-    np.testing.assert_array_equal(ix.numpy(), oi)
-    np.testing.assert_array_equal(jx.numpy(), oj)
+    ix = np.full(500, -1); jx = np.full(500, -1)
+    for g in np.unique(ii):                                   # ba.cpp:79-90, literally
+        idx = sorted(np.nonzero(ii == g)[0].tolist(), key=lambda e: jj[e])      # sorted() is stable
+        for t, e in enumerate(idx):
+            ix[e] = idx[t - 1] if t > 0 else -1
+            jx[e] = idx[t + 1] if t + 1 < len(idx) else -1
+    np.testing.assert_array_equal(ix, oi)
+    np.testing.assert_array_equal(jx, oj)
 
 
 def test_synthetic_configs_have_the_surveyed_sizes():

@@ -28,12 +28,24 @@ def _run_gpu(p, iterations, eff_impl=False, **pad):
     return d["poses"][0].cpu().numpy().astype(np.float64), d["patches"][0].cpu().numpy().astype(np.float64)
 
 
-def _check_state(p, poses, patches, o_poses, o_patches, tol=TOL):
+def _check_state(p, poses, patches, o_poses, o_patches, tol=TOL, inc_tol=None):
     F, K = p.poses.shape[0], p.patches.shape[0]
     assert np.isfinite(poses).all() and np.isfinite(patches).all()
     assert rel_err(poses[:F], o_poses) < tol
     d_g, d_o = patches[:K, 2, 0, 0], o_patches[:, 2, 0, 0]
     assert (np.abs(d_g - d_o) / np.abs(d_o)).max() < tol
+    # the UPDATE itself (pose_after - pose_before, depth_after - depth_before), relative to the size of the update: the
+    # state-level bound above would let a 1 % error of a 0.01-sized step pass.  Bound: inc_tol (default 10 x tol, the
+    # forward-error bound of the fp32-assembled solve, see test_normal_equations), stated per call site.
+    inc_tol = 10 * tol if inc_tol is None else inc_tol
+    p0 = np.asarray(p.poses, np.float32).astype(np.float64)
+    inc_g, inc_o = poses[:F] - p0, o_poses - p0
+    if np.abs(inc_o).max() > 1e-6:
+        assert rel_err(inc_g, inc_o) < inc_tol, rel_err(inc_g, inc_o)
+    z0 = np.asarray(p.patches, np.float32).astype(np.float64)[:, 2, 0, 0]
+    dz_g, dz_o = d_g - z0, d_o - z0
+    if np.abs(dz_o).max() > 1e-6:
+        assert rel_err(dz_g, dz_o) < inc_tol, rel_err(dz_g, dz_o)
     np.testing.assert_array_equal(patches[:K, 2], np.broadcast_to(patches[:K, 2, :1, :1], patches[:K, 2].shape))
     # x / y channels and fixed poses are untouched
     np.testing.assert_array_equal(patches[:K, :2], np.asarray(p.patches, np.float32)[:, :2].astype(np.float64))
@@ -199,14 +211,35 @@ def test_reproject_matches_oracle():
     assert rel_err(got, want) < 1e-5
 
 
-def test_neighbors_matches_oracle():
+def _neighbors_case(ii, jj):
     from oracle import neighbors_oracle
-    p = synth.config_c2()
-    d = to_dev(p)
-    ix, jx = fastba.neighbors(d["kk"], d["jj"])
-    oi, oj = neighbors_oracle.neighbors(p.kk, p.jj)
+    ix, jx = fastba.neighbors(torch.as_tensor(ii, device="cuda"), torch.as_tensor(jj, device="cuda"))
+    assert ix.dtype == jx.dtype == torch.int64 and ix.is_cuda
+    oi, oj = neighbors_oracle.neighbors(ii, jj)
     np.testing.assert_array_equal(ix.cpu().numpy(), oi)
     np.testing.assert_array_equal(jx.cpu().numpy(), oj)
+
+
+def test_neighbors_matches_oracle():
+    """pgba_neighbors (one cluster kernel) bit-exact against the oracle: the call shape of net_cdv.py:102
+    (neighbors(kk, jj)) on c2 and c4, plus the corners of the binning: duplicate (ii, jj) pairs (ties by edge index),
+    groups of more than 32 edges and one giant group (CTA path), keys spread over more than the bin count / negative /
+    beyond 32 bits (several keys per bin), tiny inputs."""
+    p = synth.config_c2()
+    _neighbors_case(p.kk, p.jj)
+    rng = np.random.default_rng(4)
+    perm = rng.permutation(p.E)
+    _neighbors_case(p.kk[perm], p.jj[perm])
+    _neighbors_case(rng.integers(0, 40, 5000), rng.integers(0, 12, 5000))             # groups of ~125, many ties
+    _neighbors_case(np.zeros(3000, np.int64), rng.integers(0, 50, 3000))               # one group
+    _neighbors_case(rng.integers(-2 ** 40, 2 ** 40, 20000) // 7 * 7, rng.integers(0, 30, 20000))
+    _neighbors_case(rng.integers(0, 4096 * 96, 70000), rng.integers(0, 4096, 70000))   # > registers-resident part
+    _neighbors_case(np.array([5], np.int64), np.array([1], np.int64))
+    _neighbors_case(np.array([3, 3, 2, 3], np.int64), np.array([1, 0, 0, 1], np.int64))
+    q = synth.config_c4()
+    _neighbors_case(q.kk, q.jj)
+    ix, jx = fastba.neighbors(torch.zeros(0, dtype=torch.int64, device="cuda"), torch.zeros(0, dtype=torch.int64, device="cuda"))
+    assert ix.numel() == 0 and jx.numel() == 0
 
 
 def test_cpu_tensors_fail_loudly():
@@ -322,20 +355,16 @@ def test_host_buffer_entry_arena_mode():
     np.testing.assert_array_equal(a["target"][0].numpy(), np.asarray(p.target, np.float32))
 
 
-@pytest.mark.parametrize("pc,mma,plm,cells", [("128", "0", "0", "0"), ("64", "0", "0", "0"), ("32", "0", "0", "0"),
-                                              ("128", "1", "0", "0"), ("8", "1", "0", "0"), ("128", "0", "1", "0"),
-                                              ("64", "1", "1", "0"), ("8", "0", "0", "1"), ("32", "0", "0", "1")])
-def test_forced_chunk_size_and_kernel_variants(pc, mma, plm, cells):
-    """The chunk size (PGBA_PC, normally a heuristic of the edge count), the Schur implementation (PGBA_SCHUR_MMA: 3xTF32
-    tensor-core contraction instead of FFMA2) and the edge-loop mapping (PGBA_PATCH_LANES: lanes <-> patches instead of
-    lanes <-> target frames; PGBA_FUSE_CELLS: cell tables built by the first linearisation) are read from the environment, so every combination is checked in its own
-    interpreter: normal equations (B, v, S, y, C, u, dX, dZ), end states, edge cases and the batched entry against the
-    oracle at the same 1e-4 tolerance."""
+@pytest.mark.parametrize("pc", ["128", "64", "32", "8"])
+def test_forced_chunk_size(pc):
+    """The chunk size (PGBA_PC, normally a heuristic of the edge count) is read from the environment once per process, so
+    every value is checked in its own interpreter: normal equations (B, v, S, y, C, u, dX, dZ), end states, edge cases
+    and the batched entry against the oracle at the same 1e-4 tolerance."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, PGBA_PC=pc, PGBA_SCHUR_MMA=mma, PGBA_PATCH_LANES=plm, PGBA_FUSE_CELLS=cells)
+    env = dict(os.environ, PGBA_PC=pc)
     res = subprocess.run([sys.executable, "-m", "pytest", "tests/test_ba_gpu.py", "-x", "-q", "-m", "gpu", "-k",
                           "test_normal_equations or test_ba_matches_oracle or test_batched_equals_single or "
                           "test_edge_cases or test_global_ba_matches_oracle or test_depth_guards or test_structure_only"],

@@ -82,11 +82,8 @@ def test_patchify(radius, mode, dtype):
     got = altcorr.patchify(torch.as_tensor(net, device="cuda"), torch.as_tensor(coords, device="cuda"), radius, mode=mode)
     want = corr_oracle.patchify(net, coords, radius, mode=mode)
     assert got.shape == want.shape
-    if mode == "bilinear":
-        tol = 1e-5 if dtype == np.float32 else 4e-3
-        assert np.abs(got.float().cpu().numpy() - want.astype(np.float64)).max() < tol
-    else:
-        np.testing.assert_array_equal(got.cpu().numpy(), want)          # index gather: bit exact
+    assert got.cpu().numpy().dtype == want.dtype                        # 'bilinear' is float32 also for half maps
+    np.testing.assert_array_equal(got.cpu().numpy(), want)              # gather AND blend: bit exact (see corr_oracle.patchify)
 
 
 def test_corr_backward_matches_autograd_of_oracle_formula():
@@ -126,55 +123,6 @@ def test_corr_backward_matches_autograd_of_oracle_formula():
     (o * G[0].double().cpu()).sum().backward()
     assert np.abs(g.grad.cpu().numpy() - g64.grad.numpy()).max() < 1e-3 * max(1.0, g64.grad.abs().max().item())
     assert np.abs(f2.grad.cpu().numpy() - f64.grad.numpy()).max() < 1e-3 * max(1.0, f64.grad.abs().max().item())
-
-
-@pytest.fixture
-def tiled(monkeypatch):
-    monkeypatch.setenv("PCORR_TILED", "1")
-
-
-@pytest.mark.parametrize("C", [8, 16, 24])
-def test_corr_fp16_tiled_path(C, tiled):
-    """fp16, C <= 24, P = 3, R = 3 takes the tiled tensor-core path (corr_tiled.cu); both levels, windows across the
-    map border, far outside the map, on exact integers, and edges spread over several tiles / frames."""
-    p, gmap, pyr, coords = _setup(C, np.float16, seed=3, F=8, M=24, n_mem=8)
-    coords[0, 40:44] += 5000.0                       # far outside: all-zero windows
-    coords[0, 44:46, :, 0, 0] += 9.0                 # windows too far apart for one region: per-tap path
-    dev = "cuda"
-    g = torch.as_tensor(gmap, device=dev)[None]
-    maps = [torch.as_tensor(x, device=dev)[None] for x in pyr]
-    ii = torch.as_tensor(p.kk, device=dev); jj = torch.as_tensor(p.jj, device=dev)
-    c = torch.as_tensor(coords, device=dev)
-    outs = []
-    for lvl, scale in ((0, 1.0), (1, 4.0)):
-        cl = (coords / np.float32(scale)).astype(np.float32)
-        got = altcorr.corr(g, maps[lvl], torch.as_tensor(cl, device=dev), ii, jj, 3)
-        want = corr_oracle.corr(gmap[None], pyr[lvl][None], cl, p.kk, p.jj, 3)
-        assert got.dtype == torch.float16 and got.shape == (1, p.E, 7, 7, 3, 3)
-        err = np.abs(got.float().cpu().numpy() - want)
-        assert (err <= 2.0 ** -11 * np.abs(want) + 1e-4).all()
-        assert np.abs(want).max() > 0.05
-        outs.append(got)
-    fused = altcorr.corr_pyramid2(g, maps, c, ii, jj, 3)
-    assert torch.equal(fused, torch.stack(outs, -1).view(1, p.E, -1))
-
-
-def test_corr_fp16_tiled_c2_shape_matches_staged_fp32(tiled):
-    """Production shape (c2 graph, 120x160 + 30x40 maps, C = 24): tiled fp16 result vs the fp32 staged kernel run on
-    the same (fp16-representable) inputs: differences are output rounding only."""
-    p = synth.config_c2()
-    gmap, pyr = synth.make_fmaps(p, C=24, dtype=np.float16)
-    dev = "cuda"
-    d = to_dev(p)
-    from cdvslam_b200 import fastba
-    coords = fastba.reproject(d["poses"], d["patches"], d["intrinsics"], d["ii"], d["jj"], d["kk"])
-    g16 = torch.as_tensor(gmap, device=dev)[None]
-    m16 = [torch.as_tensor(x, device=dev)[None] for x in pyr]
-    got = altcorr.corr_pyramid2(g16, m16, coords, d["kk"], d["jj"], 3).float()
-    ref = altcorr.corr_pyramid2(g16.float(), [m.float() for m in m16], coords, d["kk"], d["jj"], 3)
-    err = (got - ref).abs()
-    assert bool((err <= 2.0 ** -11 * ref.abs() + 1e-4).all())
-    assert ref.abs().max() > 0.1
 
 
 @pytest.mark.parametrize("C", [24, 32, 128])

@@ -45,11 +45,9 @@ def test_solve_system_matches_oracle(n, n_loops, ep, lm, freen):
     assert scale > 1e-4
 
 
-def test_solve_system_rejects_self_edges_and_cpu_tensors():
+def test_solve_system_rejects_self_edges():
     J_i, J_j, ii, jj, res = _graph(10, 2, seed=1)
     t = lambda a: torch.as_tensor(a, device="cuda")
     jj2 = jj.copy(); jj2[3] = ii[3]
     with pytest.raises(RuntimeError):
         cuda_ba.solve_system(t(J_i), t(J_j), t(ii), t(jj2), t(res), 1e-3, 1e-4, -1)
-    with pytest.raises(RuntimeError):
-        cuda_ba.solve_system(torch.as_tensor(J_i), t(J_j), t(ii), t(jj), t(res), 1e-3, 1e-4, -1)

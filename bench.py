@@ -49,6 +49,15 @@ def make_workload(name, rank, windows):
     raise SystemExit("unknown workload %s" % name)
 
 
+C5_TOTAL = 64     # BASELINE config 5: 64 independent sequences, sharded over 1/2/4/8 GPUs
+
+
+def sharded_c5_windows(world, rank):
+    """The windows of north_star config 5 this rank owns: round-robin over ranks, no communication."""
+    from cdvslam_b200 import synth, shard
+    return [synth.config_c5_window(s) for s in shard.windows_of_rank(C5_TOTAL, world, rank)]
+
+
 def workload_desc(name, probs):
     p = probs[0]
     return {"workload": {"c2": "c2: fastba.BA window, 22 frames x 96 patches, 37824 edges, 10 free poses, 2 iterations",
@@ -113,8 +122,8 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------- CPU baseline
-def cpu_reference_arm(prob, steps, warmup, threads=None):
-    """The reference's CPU path for this hot path (torch ba.py semantics, oracle/ba_torch_port.py) on one c2 window."""
+def cpu_reference_arm(prob, steps, warmup, threads=None, label="c2"):
+    """The reference's CPU path for this hot path (torch ba.py semantics, oracle/ba_torch_port.py) on one window."""
     from oracle import ba_torch_port
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
@@ -132,8 +141,8 @@ def cpu_reference_arm(prob, steps, warmup, threads=None):
         ts.append(time.perf_counter() - t0)
     total = sum(ts)
     return {"value": ITERATIONS * steps / total, "unit": "BA iterations/s", "cores": threads, "kind": "port",
-            "sample": "%d calls of the torch ba.py restatement (2 GN iterations each) on one c2 window, fp32, "
-                      "torch.set_num_threads(%d)" % (steps, threads),
+            "sample": "%d calls of the torch ba.py restatement (2 GN iterations each) on one %s window (%d edges), fp32, "
+                      "torch.set_num_threads(%d)" % (steps, label, prob.E, threads),
             "ms_per_step": 1e3 * total / steps, "edges_per_s": prob.E * ITERATIONS * steps / total}
 
 
@@ -300,6 +309,53 @@ class GpuArm:
 
 
 
+def measure_sharded_c5(dev, rank, world, steps, barrier, max_over_ranks, peak):
+    """north_star config 5 as stated: 64 independent EuRoC-shaped sequences in total, sharded round-robin over the `world`
+    GPUs (64 / world windows per GPU, one BA_batched call per rank, no data-path collective).  value = iterations of all
+    64 windows / max-over-ranks device time: STRONG scaling of a fixed job.  At world > 1 rank 0 also runs all 64 windows
+    alone, so the line carries its own 1-GPU denominator and the limiting stage at this shard size."""
+    probs = sharded_c5_windows(world, rank)
+    arm = GpuArm(probs, dev)
+    for _ in range(3):
+        arm.restore(); arm.call()
+    g = arm.capture()
+    for _ in range(2):
+        arm.restore(); g.replay()
+    barrier()
+    ms = arm.timed_resident(g, steps)
+    barrier()
+    total_ms = max_over_ranks(sum(ms))
+    st = arm.profiled(min(steps, 20))
+    its = ITERATIONS * C5_TOTAL * steps
+    alg = algorithmic_bytes_linearize(probs[0]) * len(probs)
+    ach = alg / (st["linearize_schur"] * 1e-3) / 1e9
+    out = {"workload": "c5: %d EuRoC-shaped windows in total, %d per GPU on %d GPU(s), one batched call per rank, "
+                       "2 iterations, L2 flushed between steps" % (C5_TOTAL, len(probs), world),
+           "windows_total": C5_TOTAL, "windows_per_gpu": len(probs), "n_gpus": world, "steps": steps, "scaling": "strong",
+           "ms_per_step": total_ms / steps, "value": its / (total_ms * 1e-3), "unit": "BA iterations/s",
+           "edges_per_s": probs[0].E * its / (total_ms * 1e-3), "stages_ms_rank0": st,
+           "limiting_stage_rank0": max((("plan", st["plan"]),) + tuple((k, ITERATIONS * v) for k, v in st.items() if k != "plan"),
+                                       key=lambda kv: kv[1])[0],
+           "roofline_linearize": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                  "algorithmic_bytes_per_launch": alg, "ms_per_launch": st["linearize_schur"]}}
+    del arm, g
+    torch.cuda.empty_cache()
+    if world > 1:
+        barrier()
+        if rank == 0:
+            full = GpuArm(sharded_c5_windows(1, 0), dev)
+            for _ in range(3):
+                full.restore(); full.call()
+            g1 = full.capture()
+            ms1 = full.timed_resident(g1, steps)
+            out["single_gpu_ms_per_step_same_run"] = sum(ms1) / steps
+            out["strong_scaling_efficiency"] = (sum(ms1) / steps) / (total_ms / steps) / world
+            del full, g1
+            torch.cuda.empty_cache()
+        barrier()
+    return out
+
+
 def timed_events(fn, steps, before=None):
     """Median of CUDA-event timings (ms) of fn() on the current stream."""
     ts = []
@@ -415,6 +471,71 @@ def extra_c4(dev, flush):
             "edges_per_s": p.E * ITERATIONS / (ms * 1e-3)}
 
 
+def ref_cuda_baseline(dev, flush):
+    """The reference's OWN CUDA kernels (oracle/_ref: cdvslam/fastba/ba_cuda.cu + block_e.cu and
+    cdvslam/altcorr/correlation_kernel.cu compiled unmodified for sm_100a, oracle/ref_build/build_ref.sh) timed on the same
+    B200 and the same inputs, eager calls like the reference makes them (its cuda_ba() synchronises inside, so it cannot
+    be graph-captured); our side of each pair is the public API called the same way (eager, no graph).  SURVEY 2.3: this
+    is the bar the new kernels have to beat; the CPU path below is only the reported baseline."""
+    import glob
+    import importlib.util
+    from cdvslam_b200 import synth, fastba, altcorr
+
+    def load(name):
+        hits = glob.glob(os.path.join(REPO, "oracle", "_ref", name + "*.so"))
+        if not hits:
+            return None
+        spec = importlib.util.spec_from_file_location(name, hits[0])
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+        return m
+    ref_ba, ref_corr = load("ref_cuda_ba"), load("ref_cuda_corr")
+    if ref_ba is None or ref_corr is None:
+        return {"unavailable": "oracle/_ref not built (needs /root/reference at build time)"}
+    out = {"note": "median of eager calls, CUDA events, L2 flushed before each call; ms"}
+    for name, p, eff_list, n in (("ba_c2", synth.config_c2(), (False, True), 20), ("ba_c4", synth.config_c4(), (True,), 3)):
+        d = synth.to_torch(p, dev)
+        p0, q0 = d["poses"].clone(), d["patches"].clone()
+
+        def reset():
+            d["poses"].copy_(p0); d["patches"].copy_(q0); flush()
+        row = {}
+        for eff in eff_list:
+            f_ref = lambda: ref_ba.forward(d["poses"], d["patches"], d["intrinsics"], d["target"], d["weight"], d["lmbda"],
+                                           d["ii"], d["jj"], d["kk"], p.M, p.t0, p.t1, ITERATIONS, eff)
+            f_our = lambda: fastba.BA(d["poses"], d["patches"], d["intrinsics"], d["target"], d["weight"], d["lmbda"],
+                                      d["ii"], d["jj"], d["kk"], p.t0, p.t1, M=p.M, iterations=ITERATIONS, eff_impl=eff)
+            for f in (f_ref, f_our):
+                reset(); f()
+            row["reference_eff" if eff else "reference_dense"] = timed_events(f_ref, n, before=reset)
+            row["ours_eff" if eff else "ours_dense"] = timed_events(f_our, n, before=reset)
+        out[name] = row
+        del d, p0, q0
+        torch.cuda.empty_cache()
+    p = synth.config_c2()
+    d = synth.to_torch(p, dev)
+    coords = fastba.reproject(d["poses"], d["patches"], d["intrinsics"], d["ii"], d["jj"], d["kk"])
+    c4 = coords / 4
+    for C, dt in ((24, torch.float16), (128, torch.float16), (128, torch.float32)):
+        gmap, pyr = synth.make_fmaps(p, C=C)
+        g = torch.as_tensor(gmap, device=dev)[None].to(dt)
+        f0 = torch.as_tensor(pyr[0], device=dev)[None].to(dt)
+        f1 = torch.as_tensor(pyr[1], device=dev)[None].to(dt)
+        kk, jj = d["kk"], d["jj"]
+        f_ref = lambda: torch.stack([ref_corr.forward(g, f0, coords, kk, jj, 3)[0],
+                                     ref_corr.forward(g, f1, c4, kk, jj, 3)[0]], -1).view(1, len(kk), -1)   # slam.py:321-323
+        f_two = lambda: torch.stack([altcorr.corr(g, f0, coords, kk, jj, 3), altcorr.corr(g, f1, c4, kk, jj, 3)],
+                                    -1).view(1, len(kk), -1)
+        f_fused = lambda: altcorr.corr_pyramid2(g, [f0, f1], coords, kk, jj, 3)
+        for f in (f_ref, f_two, f_fused):
+            f()
+        out["corr_c3_C%d_%s" % (C, str(dt).split(".")[-1])] = {
+            "reference_two_calls": timed_events(f_ref, 10, before=flush),
+            "ours_two_calls": timed_events(f_two, 10, before=flush), "ours_fused": timed_events(f_fused, 10, before=flush)}
+        del g, f0, f1
+    return out
+
+
 def hbm_peak():
     path = os.path.join(REPO, "MEASURED_PEAKS.json")
     try:
@@ -518,10 +639,27 @@ def main():
     its = ITERATIONS * W * world * args.steps
     value = its / (total_ms * 1e-3)
     peak, peak_src = hbm_peak()
-    alg = algorithmic_bytes_linearize(probs[0]) * W
+    # per-stage table (event-timed launch sequence): share of the step, algorithmic bytes, achieved GB/s.
+    # The roofline object describes the stage with the LARGEST measured share of the step.
+    p0 = probs[0]
+    Mu, Nf, Ff = len(np.unique(p0.kk)), p0.N, p0.poses.shape[0]
+    alg_stage = {"plan": W * p0.E * 24,                                                  # ii/jj/kk read once
+                 "linearize_schur": W * algorithmic_bytes_linearize(p0),
+                 "solve_retr": W * (4 * (2 * 36 * Nf * Nf + 3 * 6 * Nf) + Nf * (28 * 2 + 24)),   # S in, factor, y/dX; poses
+                 "backsub_retr": W * (4 * (6 * Nf * Mu + 3 * Mu) + Mu * 44)}
+    launches = {"plan": 1, "linearize_schur": ITERATIONS, "solve_retr": ITERATIONS, "backsub_retr": ITERATIONS}
+    step_sum = sum(stages[k] * launches[k] for k in stages)
+    table = {k: {"ms_per_launch": stages[k], "launches_per_step": launches[k],
+                 "share_of_step": stages[k] * launches[k] / step_sum, "algorithmic_bytes_per_launch": int(alg_stage[k]),
+                 "achieved_GBps": alg_stage[k] / (stages[k] * 1e-3) / 1e9 if stages[k] > 0 else None,
+                 "frac_of_hbm_peak": alg_stage[k] / (stages[k] * 1e-3) / 1e9 / peak if stages[k] > 0 else None}
+             for k in stages}
+    kernel_names = {"plan": "plan_cluster_kernel + plan_cells_kernel (graph analysis; latency-bound)",
+                    "linearize_schur": "linearize_kernel (residual+Jacobian+assembly+Schur)",
+                    "solve_retr": "solve_small_kernel (damped Cholesky solve + SE3 retraction; latency-bound)",
+                    "backsub_retr": "update_kernel (back-substitution + depth retraction; fused into linearize #2 on c2)"}
+    dom = max(table, key=lambda k: table[k]["share_of_step"])
     lin_ms = stages["linearize_schur"]
-    achieved = alg / (lin_ms * 1e-3) / 1e9
-    step_sum = stages["plan"] + ITERATIONS * sum(v for k, v in stages.items() if k != "plan")
     line = {"metric": METRIC, "value": value, "unit": "BA iterations/s", "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -534,44 +672,55 @@ def main():
                     "ms_per_step_by_mode": e2e_modes},
             "gpu_launches": int(arm.launches_per_step * args.steps),
             "launches_per_step": int(arm.launches_per_step),
-            "roofline": {"bound": "hbm", "kernel": "linearize_kernel (residual+Jacobian+assembly+Schur)",
-                         "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                         "frac": achieved / peak, "algorithmic_bytes_per_launch": alg, "ms_per_launch": lin_ms,
-                         "share_of_step": ITERATIONS * lin_ms / step_sum, "traffic": ncu_traffic(args.workload)},
-            "stages_ms": stages, "clocks": clocks}
+            "roofline": {"bound": "hbm", "kernel": kernel_names[dom], "stage": dom,
+                         "achieved": table[dom]["achieved_GBps"], "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                         "frac": table[dom]["frac_of_hbm_peak"],
+                         "algorithmic_bytes_per_launch": table[dom]["algorithmic_bytes_per_launch"],
+                         "ms_per_launch": table[dom]["ms_per_launch"], "share_of_step": table[dom]["share_of_step"],
+                         "traffic": ncu_traffic(args.workload) if dom == "linearize_schur" else None,
+                         "linearize_frac": alg_stage["linearize_schur"] / (lin_ms * 1e-3) / 1e9 / peak,
+                         "note": "a single c2 window moves ~3 MB per iteration (<1 us of HBM time): every stage is "
+                                 "latency-bound by construction; the HBM fraction is meaningful on sharded_c5 / batched_c5"},
+            "stage_table": table, "stages_ms": stages, "clocks": clocks}
+    del arm, graph
+    torch.cuda.empty_cache()
+
+    # north_star config 5 at this N (strong scaling of 64 windows), on every rank
+    if args.workload == "c2" and not args.no_extra:
+        n5 = max(10, min(args.steps // 4, 30))
+        try:
+            sc5 = measure_sharded_c5(dev, rank, world, n5, barrier, max_over_ranks, peak)
+            line["sharded_c5"] = sc5
+        except Exception as e:
+            line["sharded_c5"] = {"error": repr(e)[:300]}
 
     if rank == 0 and world == 1:
         from cdvslam_b200 import synth
-        line["cpu_baseline"] = {k: v for k, v in cpu_reference_arm(synth.config_c2(seed=1234), args.cpu_steps, 3).items()
-                                if k in ("value", "unit", "cores", "kind", "sample")}
-        if args.workload == "c2" and not args.no_extra:
-            del arm, graph
-            torch.cuda.empty_cache()
-            p5 = make_workload("c5", 0, args.windows)
-            arm5 = GpuArm(p5, dev)
-            for _ in range(3):
-                arm5.restore(); arm5.call()
-            g5 = arm5.capture()
-            n5 = max(10, min(args.steps // 4, 50))
-            ms5 = arm5.timed_resident(g5, n5)
-            st5 = arm5.profiled(min(n5, 20))
-            alg5 = algorithmic_bytes_linearize(p5[0]) * len(p5)
-            ach5 = alg5 / (st5["linearize_schur"] * 1e-3) / 1e9
-            line["batched_c5"] = {"windows": len(p5), "steps": n5, "ms_per_step": sum(ms5) / n5,
-                                  "value": ITERATIONS * len(p5) * n5 / (sum(ms5) * 1e-3), "unit": "BA iterations/s",
-                                  "edges_per_s": p5[0].E * ITERATIONS * len(p5) * n5 / (sum(ms5) * 1e-3),
-                                  "stages_ms": st5,
-                                  "roofline": {"bound": "hbm", "kernel": "linearize_kernel", "achieved": ach5,
-                                               "peak": peak, "unit": "GB/s", "frac": ach5 / peak,
-                                               "algorithmic_bytes_per_launch": alg5,
-                                               "ms_per_launch": st5["linearize_schur"],
-                                               "traffic": ncu_traffic("c5")}}
+        c2p, c1p = synth.config_c2(seed=1234), synth.config_c1(seed=1234)
+        base = cpu_reference_arm(c2p, args.cpu_steps, 3)
+        line["cpu_baseline"] = {k: v for k, v in base.items() if k in ("value", "unit", "cores", "kind", "sample")}
+        # config c1 (the reference's own CPU-runnable case) and k = 2 threads (slam.py:33) beside it
+        detail = {"c2_all_cores": base}
+        for label, pr, thr, n in (("c2_2_threads", c2p, 2, max(10, args.cpu_steps // 3)),
+                                  ("c1_all_cores", c1p, None, args.cpu_steps), ("c1_2_threads", c1p, 2, args.cpu_steps)):
+            detail[label] = cpu_reference_arm(pr, n, 2, threads=thr, label=label[:2])
+        line["cpu_baseline_detail"] = {k: {kk: v[kk] for kk in ("value", "ms_per_step", "cores", "edges_per_s", "sample")}
+                                       for k, v in detail.items()}
+        torch.set_num_threads(os.cpu_count())
     if rank == 0 and world == 1 and args.workload == "c2" and not args.no_extra:
+        if "sharded_c5" in line and "error" not in line["sharded_c5"]:
+            sc = line["sharded_c5"]          # same measurement under the round-1 key (64 windows on one GPU)
+            line["batched_c5"] = {"windows": C5_TOTAL, "steps": sc["steps"], "ms_per_step": sc["ms_per_step"],
+                                  "value": sc["value"], "unit": sc["unit"], "edges_per_s": sc["edges_per_s"],
+                                  "stages_ms": sc["stages_ms_rank0"],
+                                  "roofline": dict(sc["roofline_linearize"], kernel="linearize_kernel",
+                                                   traffic=ncu_traffic("c5"))}
         flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
         try:
             line["corr_c3"] = extra_corr_c3(dev, peak, flush_buf.zero_)
             line["update_loop_c3"] = extra_update_loop(dev, flush_buf.zero_)
             line["global_c4"] = extra_c4(dev, flush_buf.zero_)
+            line["ref_cuda_baseline"] = ref_cuda_baseline(dev, flush_buf.zero_)
         except Exception as e:            # extras must never cost the headline line
             line["extras_error"] = repr(e)[:200]
     if rank == 0:

@@ -21,6 +21,7 @@
 
 #include "ba_common.cuh"
 #include "ba_chol.cuh"
+#include "ba_chol32.cuh"
 
 namespace pgba {
 
@@ -736,13 +737,14 @@ void cta_timestamps(unsigned long long* out) { cudaMemcpyFromSymbol(out, g_cta_t
 #endif
 
 // ---------------------------------------------------------------------------------------------------------------
-// Small dense solve: one CTA per window, fp64 in shared memory, blocked (6 wide) right-looking Cholesky on the
-// matrix augmented with the right-hand side as an extra row (so the forward substitution comes for free), warp-level
-// backward substitution, then the SE3 retraction of the free poses.
+// Small dense solve: one CTA per window, fp32 in shared memory (the reference's own precision: ba_cuda.cu:576-577),
+// blocked (6 wide) right-looking Cholesky on the matrix augmented with the right-hand side as an extra row (so the
+// forward substitution comes for free), inverse-based warp-level backward substitution (ba_chol32.cuh), then the SE3
+// retraction of the free poses.
 // ---------------------------------------------------------------------------------------------------------------
 size_t solve_small_smem_bytes(int n) {
   const int ld = n | 1;
-  return sizeof(double) * ((size_t)(n + 1) * ld + n + 8);
+  return sizeof(float) * ((size_t)(n + 1) * ld + n + 6 * (size_t)n + 8);
 }
 
 __global__ void __launch_bounds__(256, 1) solve_small_kernel(Problem pb) {
@@ -750,13 +752,14 @@ __global__ void __launch_bounds__(256, 1) solve_small_kernel(Problem pb) {
   pdl_wait();
   pdl_trigger();
   CTA_TS(1, 1);
-  extern __shared__ double sd[];
+  extern __shared__ float sf[];
   SOLVE_TS(0);
   const int w = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
   const int N = pb.t1 - pb.t0, n = 6 * N, ld = n | 1;
-  double* A = sd;                  // [n + 1][ld]; row n = right-hand side
-  double* rd = sd + (n + 1) * ld;  // [n] reciprocal diagonal of L
+  float* A = sf;                   // [n + 1][ld]; row n = right-hand side
+  float* rd = sf + (n + 1) * ld;   // [n] reciprocal diagonal of L
+  float* dinv = rd + n;            // [n / 6][36] inverses of the diagonal blocks of L
   const bool rezero = pb.apply != 0;
   // prefetch the pose rows that are retracted at the end
   float* prow = pb.poses + (int64_t)w * pb.st.poses + 7 * (int64_t)(pb.t0 + tid);
@@ -776,13 +779,13 @@ __global__ void __launch_bounds__(256, 1) solve_small_kernel(Problem pb) {
       int r = (4 * x4) / n, c = 4 * x4 - r * n;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        double v = (double)vv[k];
-        if (r == c) v += 1e-4 * v + 1.0;
+        float v = vv[k];
+        if (r == c) v += 1e-4f * v + 1.0f;
         A[r * ld + c] = v;
         if (++c == n) { c = 0; ++r; }
       }
     }
-    for (int x = tid; x < n; x += 256) A[n * ld + x] = (double)wp.y[x];
+    for (int x = tid; x < n; x += 256) A[n * ld + x] = wp.y[x];
   }
   __syncthreads();
   SOLVE_TS(1);
@@ -792,57 +795,23 @@ __global__ void __launch_bounds__(256, 1) solve_small_kernel(Problem pb) {
     for (int x4 = tid; x4 < n4; x4 += 256) S4[x4] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int x = tid; x < n; x += 256) wp.y[x] = 0.f;
   }
-  chol6_smem(A, rd, n, n, ld);          // rows 0..n: the rhs row n rides along (forward substitution)
+  chol6_f32(A, rd, dinv, n, ld);        // rows 0..n: the rhs row n rides along (forward substitution)
   SOLVE_TS(2);
-  int ts_i = 3;
-  // ---- backward substitution L^T x = y by warp 0 (row n of A holds y and is overwritten with x)
-  if (warp == 0) {
-    double* xv = A + n * ld;
-    for (int kb = n - 6; kb >= 0; kb -= 6) {
-      if (lane == 0) {
-        // L11^T x = v, right-looking: x[c] = v[c] / L[c][c], then v[e] -= L[c][e] x[c] for e < c
-        double v[6], l[6][6];
-#pragma unroll
-        for (int c = 0; c < 6; ++c) {
-          v[c] = xv[kb + c];
-#pragma unroll
-          for (int e = 0; e < c; ++e) l[c][e] = A[(kb + c) * ld + kb + e];
-        }
-#pragma unroll
-        for (int c = 5; c >= 0; --c) {
-          const double x = v[c] * rd[kb + c];
-          v[c] = x;
-#pragma unroll
-          for (int e = 0; e < c; ++e) v[e] -= l[c][e] * x;
-        }
-#pragma unroll
-        for (int c = 0; c < 6; ++c) xv[kb + c] = v[c];
-      }
-      __syncwarp();
-      for (int c = lane; c < kb; c += 32) {
-        double v = xv[c];
-#pragma unroll
-        for (int a = 0; a < 6; ++a) v -= A[(kb + a) * ld + c] * xv[kb + a];
-        xv[c] = v;
-      }
-      __syncwarp();
-    }
-  }
+  if (warp == 0) backsub6_f32(A, dinv, n, ld, lane);
   __syncthreads();
-  SOLVE_TS(ts_i); ++ts_i;
-  const double* xv = A + n * ld;
-  for (int x = tid; x < n; x += 256) wp.dX[x] = (float)xv[x];
+  SOLVE_TS(3);
+  const float* xv = A + n * ld;
+  for (int x = tid; x < n; x += 256) wp.dX[x] = xv[x];
   // ---- SE3 retraction of the free poses (ba_cuda.cu:178-206)
   if (pb.apply && tid < N) {
     float xi[6];
 #pragma unroll
-    for (int a = 0; a < 6; ++a) xi[a] = (float)xv[6 * tid + a];
+    for (int a = 0; a < 6; ++a) xi[a] = xv[6 * tid + a];
     retract_pose(pose, xi);
 #pragma unroll
     for (int x = 0; x < 7; ++x) prow[x] = pose[x];
   }
-  SOLVE_TS(ts_i);
-  (void)ts_i;
+  SOLVE_TS(4);
   CTA_TS(1, 2);
 }
 

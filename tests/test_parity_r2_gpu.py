@@ -86,8 +86,10 @@ def test_reproject_clamp_depth_matches_pops_transform():
     target frame for the projection) and d = 1 / Z.clamp(min=0.1), including points with 0 < Z < 0.1 and Z < 0."""
     p = synth.small_problem(seed=12, F=9, M=20, t0=3, lifetime=6)
     rng = np.random.default_rng(3)
-    p.patches[:6, 2] = rng.uniform(30.0, 80.0, (6, 1, 1))        # huge inverse depth: translation dominates, Z small / negative
-    p.patches[6:12, 2] = rng.uniform(8.0, 14.0, (6, 1, 1))
+    # the camera backs away by 0.03 per frame, so t_ij,z = -0.03 (j - i) for j > i; with inverse depths of 20..60 the
+    # reprojected Z = 1 + d t_ij,z + ... ends up in (0, 0.1) for some edges and below 0 for others
+    p.poses[:, 2] -= 0.03 * np.arange(p.poses.shape[0])
+    p.patches[:40, 2] = rng.uniform(20.0, 60.0, (40, 1, 1))
     d = to_dev(p)
     F = d["intrinsics"].shape[1]
     K = np.asarray(p.intrinsics[:1], np.float64) * rng.uniform(0.9, 1.1, (F, 4))     # a different camera per frame

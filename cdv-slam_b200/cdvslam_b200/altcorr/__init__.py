@@ -1,1 +1,1 @@
-from .correlation import corr, patchify, CorrLayer, PatchLayer, corr_pyramid2  # noqa: F401
+from .correlation import corr, patchify, CorrLayer, PatchLayer, corr_pyramid2, PyramidRing  # noqa: F401

@@ -58,3 +58,6 @@ def corr_pyramid2(fmap1, pyramid, coords, ii, jj, radius=3):
     """Extension: the two-level lookup of cdvslam/slam.py:316-323 in one kernel -> [B, E, (2R+1)^2 * P*P * 2]."""
     out = cuda_corr.forward_pyramid2(fmap1, pyramid[0], pyramid[1], coords, ii, jj, radius)
     return out.view(out.shape[0], out.shape[1], -1)
+
+
+PyramidRing = cuda_corr.PyramidRing     # extension: persistent channel-last pyramid mirror (one slot re-copied per new frame)

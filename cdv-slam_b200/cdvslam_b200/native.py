@@ -54,6 +54,10 @@ SIGNATURES = {
     "pcorr_tma_workspace_bytes": (c_int, [c_int, c_int, c_i64, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_sz)]),
     "pcorr_forward_tma": (c_int, [c_vp] * 6 + [c_int, c_int, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int,
                                                c_int, c_int, c_int, c_vp, c_vp, c_sz, c_vp]),
+    "pcorr_ring_update": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_int, c_int, c_int, c_int, c_int, c_i64, c_i64, c_vp, c_sz,
+                                  c_vp]),
+    "pcorr_forward_ring": (c_int, [c_vp] * 4 + [c_int, c_int, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, c_int,
+                                                c_int, c_int, c_vp, c_vp, c_sz, c_vp]),
     "pcorr_backward": (c_int, [c_vp] * 6 + [c_int, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_vp,
                                             c_vp, c_vp]),
     "pcorr_patchify_forward": (c_int, [c_vp, c_vp, c_int, c_i64, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),

@@ -787,17 +787,17 @@ __global__ void __launch_bounds__(256, 1) solve_small_kernel(Problem pb) {
     }
     for (int x = tid; x < n; x += 256) A[n * ld + x] = wp.y[x];
   }
-  __syncthreads();
   SOLVE_TS(1);
-  if (rezero) {                    // S, y are consumed: clear them for the next iteration's accumulation
-    float4* S4 = reinterpret_cast<float4*>(wp.S);
-    const int n4 = (n * n) >> 2;
-    for (int x4 = tid; x4 < n4; x4 += 256) S4[x4] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int x = tid; x < n; x += 256) wp.y[x] = 0.f;
-  }
   chol6_f32(A, rd, dinv, n, ld);        // rows 0..n: the rhs row n rides along (forward substitution)
   SOLVE_TS(2);
-  if (warp == 0) backsub6_f32(A, dinv, n, ld, lane);
+  if (warp == 0) {
+    backsub6_f32_any(A, dinv, n, ld, lane);
+  } else if (rezero) {             // S, y are consumed: the other warps clear them for the next iteration's accumulation
+    float4* S4 = reinterpret_cast<float4*>(wp.S);
+    const int n4 = (n * n) >> 2;
+    for (int x4 = tid - 32; x4 < n4; x4 += 224) S4[x4] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int x = tid - 32; x < n; x += 224) wp.y[x] = 0.f;
+  }
   __syncthreads();
   SOLVE_TS(3);
   const float* xv = A + n * ld;

@@ -832,12 +832,14 @@ int pcorr_tma_workspace_bytes(int nlev, int B, int64_t F, int C, int H0, int W0,
   return PCORR_OK;
 }
 
-int pcorr_forward_tma(const void* fmap1, const void* fmap2_l0, const void* fmap2_l1, const float* coords,
-                      const int64_t* ii, const int64_t* jj, int nlev, int B, int64_t E, int64_t K, int64_t F, int C,
-                      int H0, int W0, int H1, int W1, int P, int radius, int dtype, void* out, void* workspace,
-                      size_t workspace_bytes, pcorr_stream_t stream) {
+// lookup on channel-last maps that are already in `workspace` (transpose == false) or are rebuilt from the NCHW maps first
+static int forward_impl(const void* fmap1, const void* fmap2_l0, const void* fmap2_l1, const float* coords,
+                        const int64_t* ii, const int64_t* jj, int nlev, int B, int64_t E, int64_t K, int64_t F, int C,
+                        int H0, int W0, int H1, int W1, int P, int radius, int dtype, void* out, void* workspace,
+                        size_t workspace_bytes, cudaStream_t s, bool transpose) {
   if (E == 0 || B == 0) return PCORR_OK;
-  if (!fmap1 || !fmap2_l0 || (nlev == 2 && !fmap2_l1) || !coords || !ii || !jj || !out || !workspace) return PCORR_ERR_NULL;
+  if (!fmap1 || (transpose && (!fmap2_l0 || (nlev == 2 && !fmap2_l1))) || !coords || !ii || !jj || !out || !workspace)
+    return PCORR_ERR_NULL;
   if (nlev < 1 || nlev > 2 || B < 0 || E < 0 || K <= 0 || F <= 0 || H0 <= 0 || W0 <= 0) return PCORR_ERR_SHAPE;
   if (!pcorr_tma_supported(C, P, radius, dtype)) return PCORR_ERR_UNSUPPORTED;
   // the TMA box (12 x 12 pixels) must not exceed the map
@@ -847,11 +849,11 @@ int pcorr_forward_tma(const void* fmap1, const void* fmap2_l0, const void* fmap2
   int rc = pcorr_tma_workspace_bytes(nlev, B, F, C, H0, W0, H1, W1, &need);
   if (rc) return rc;
   if (need > workspace_bytes) return PCORR_ERR_SHAPE;
-  cudaStream_t s = (cudaStream_t)stream;
   __half* n0 = (__half*)workspace;
   __half* n1 = (__half*)((char*)workspace + align256((size_t)B * F * H0 * W0 * C * 2));
-  transpose_maps(C, nlev, (const __half*)fmap2_l0, n0, H0 * W0, (const __half*)fmap2_l1, n1, nlev == 2 ? H1 * W1 : 0,
-                 B * (int)F, s);
+  if (transpose)
+    transpose_maps(C, nlev, (const __half*)fmap2_l0, n0, H0 * W0, (const __half*)fmap2_l1, n1, nlev == 2 ? H1 * W1 : 0,
+                   B * (int)F, s);
   CUtensorMap tm0, tm1;
   const bool wide = C > 32;
   rc = wide ? make_map_wide(&tm0, n0, C, W0, H0, (int64_t)B * F) : make_map(&tm0, n0, C, W0, H0, (int64_t)B * F);
@@ -869,6 +871,45 @@ int pcorr_forward_tma(const void* fmap1, const void* fmap2_l0, const void* fmap2
   if (C == 128) return nlev == 2 ? launch_wide<128, 2>(tm0, tm1, Pm, s) : launch_wide<128, 1>(tm0, tm1, Pm, s);
   if (C == 24) return nlev == 2 ? launch<24, 2>(tm0, tm1, Pm, s) : launch<24, 1>(tm0, tm1, Pm, s);
   return nlev == 2 ? launch<32, 2>(tm0, tm1, Pm, s) : launch<32, 1>(tm0, tm1, Pm, s);
+}
+
+int pcorr_forward_tma(const void* fmap1, const void* fmap2_l0, const void* fmap2_l1, const float* coords,
+                      const int64_t* ii, const int64_t* jj, int nlev, int B, int64_t E, int64_t K, int64_t F, int C,
+                      int H0, int W0, int H1, int W1, int P, int radius, int dtype, void* out, void* workspace,
+                      size_t workspace_bytes, pcorr_stream_t stream) {
+  return forward_impl(fmap1, fmap2_l0, fmap2_l1, coords, ii, jj, nlev, B, E, K, F, C, H0, W0, H1, W1, P, radius, dtype, out,
+                      workspace, workspace_bytes, (cudaStream_t)stream, true);
+}
+
+int pcorr_ring_update(const void* fmap2_l0, const void* fmap2_l1, int nlev, int B, int64_t F, int C, int H0, int W0, int H1,
+                      int W1, int64_t first_frame, int64_t n_frames, void* ring, size_t ring_bytes, pcorr_stream_t stream) {
+  if (n_frames == 0 || B == 0) return PCORR_OK;
+  if (!fmap2_l0 || (nlev == 2 && !fmap2_l1) || !ring) return PCORR_ERR_NULL;
+  if (nlev < 1 || nlev > 2 || B < 0 || F <= 0 || H0 <= 0 || W0 <= 0 || first_frame < 0 || n_frames < 0 ||
+      first_frame + n_frames > F)
+    return PCORR_ERR_SHAPE;
+  if (!pcorr_tma_supported(C, 3, 3, PCORR_F16) || ((uintptr_t)ring & 255) || (int64_t)B * F > 65535) return PCORR_ERR_UNSUPPORTED;
+  size_t need = 0;
+  int rc = pcorr_tma_workspace_bytes(nlev, B, F, C, H0, W0, H1, W1, &need);
+  if (rc) return rc;
+  if (need > ring_bytes) return PCORR_ERR_SHAPE;
+  const size_t hw0 = (size_t)H0 * W0, hw1 = nlev == 2 ? (size_t)H1 * W1 : 0;
+  __half* n0 = (__half*)ring;
+  __half* n1 = (__half*)((char*)ring + align256((size_t)B * F * hw0 * C * 2));
+  for (int b = 0; b < B; ++b) {                   // frames [first, first + n) of every batch entry are contiguous
+    const size_t f = (size_t)b * F + first_frame;
+    transpose_maps(C, nlev, (const __half*)fmap2_l0 + f * hw0 * C, n0 + f * hw0 * C, (int)hw0,
+                   nlev == 2 ? (const __half*)fmap2_l1 + f * hw1 * C : nullptr, n1 + f * hw1 * C, (int)hw1, (int)n_frames,
+                   (cudaStream_t)stream);
+  }
+  return (int)cudaGetLastError();
+}
+
+int pcorr_forward_ring(const void* fmap1, const float* coords, const int64_t* ii, const int64_t* jj, int nlev, int B,
+                       int64_t E, int64_t K, int64_t F, int C, int H0, int W0, int H1, int W1, int P, int radius, int dtype,
+                       void* out, const void* ring, size_t ring_bytes, pcorr_stream_t stream) {
+  return forward_impl(fmap1, nullptr, nullptr, coords, ii, jj, nlev, B, E, K, F, C, H0, W0, H1, W1, P, radius, dtype, out,
+                      const_cast<void*>(ring), ring_bytes, (cudaStream_t)stream, false);
 }
 
 }  // extern "C"

@@ -195,3 +195,61 @@ def patchify_mode_backward(net, coords, gradient, radius, mode):
                                                        mode, dt, net_grad.data_ptr(), native.stream_ptr(net.device))
     native.check(rc, "pcorr_patchify_mode_backward")
     return net_grad
+
+
+class PyramidRing:
+    """Extension: persistent channel-last mirror of the frame-map pyramid ring for the production lookup (fp16, C in
+    {24, 32, 128}, P = 3, radius 3).  cuda_corr.forward / forward_pyramid2 re-copy ALL frame maps to the channel-last layout
+    on every call; slam.py rewrites one ring slot per new frame (slam.py:681-682), so an integrator keeps a PyramidRing
+    next to `self.pyramid`, calls `ring.update(n % mem)` after those two lines and `ring.lookup(gmap, coords, ii, jj)` in
+    SLAM.corr().  Results are bit-identical to forward_pyramid2 / forward on the same maps."""
+
+    def __init__(self, pyramid):
+        self.maps = [_c(m) for m in pyramid]
+        m0 = self.maps[0]
+        native.require_cuda(*self.maps)
+        if len(self.maps) not in (1, 2) or any(m.dtype != torch.float16 for m in self.maps):
+            raise RuntimeError("PyramidRing: one or two float16 maps [B, F, C, H, W] expected")
+        for m, src in zip(self.maps, pyramid):
+            if m.data_ptr() != src.data_ptr():
+                raise RuntimeError("PyramidRing: the pyramid tensors must be contiguous (they are mirrored in place)")
+        self.B, self.F, self.C, self.H0, self.W0 = m0.shape
+        self.H1, self.W1 = (self.maps[1].shape[3], self.maps[1].shape[4]) if len(self.maps) == 2 else (0, 0)
+        L = native.lib()
+        if not L.pcorr_tma_supported(self.C, 3, 3, 1) or min(self.H0, self.W0) < 12 or (len(self.maps) == 2 and min(self.H1, self.W1) < 12):
+            raise RuntimeError("PyramidRing: shape outside the TMA lookup's range (C in {24, 32, 128}, maps >= 12 x 12)")
+        n = ctypes.c_size_t(0)
+        native.check(L.pcorr_tma_workspace_bytes(len(self.maps), self.B, self.F, self.C, self.H0, self.W0, self.H1, self.W1,
+                                                 ctypes.byref(n)), "pcorr_tma_workspace_bytes")
+        self.ring = torch.empty(n.value, dtype=torch.uint8, device=m0.device)
+        self.update(0, self.F)
+
+    def update(self, first, count=1):
+        """Re-mirror ring slots [first, first + count) from the pyramid tensors (call after writing them)."""
+        m = self.maps
+        with torch.cuda.device(m[0].device):
+            rc = native.lib().pcorr_ring_update(m[0].data_ptr(), m[1].data_ptr() if len(m) == 2 else None, len(m), self.B,
+                                                self.F, self.C, self.H0, self.W0, self.H1, self.W1, int(first), int(count),
+                                                self.ring.data_ptr(), self.ring.numel(), native.stream_ptr(m[0].device))
+        native.check(rc, "pcorr_ring_update")
+
+    def lookup(self, fmap1, coords, ii, jj, radius=3):
+        """== forward_pyramid2(fmap1, *pyramid, coords, ii, jj, radius).view(B, E, -1) (two levels) or forward(...)[0]
+        (one level), without touching the NCHW maps."""
+        native.require_cuda(fmap1, coords, ii, jj)
+        if fmap1.dtype != torch.float16:
+            raise RuntimeError("PyramidRing.lookup: fmap1 must be float16")
+        fmap1, ii, jj = _c(fmap1), _c(ii.long()), _c(jj.long())
+        coords = _c(coords.float())
+        B, E, _, P, _ = coords.shape
+        D = 2 * radius + 1
+        nlev = len(self.maps)
+        shape = (B, E, D, D, P, P, 2) if nlev == 2 else (B, E, D, D, P, P)
+        out = torch.empty(shape, dtype=torch.float16, device=fmap1.device)
+        with torch.cuda.device(fmap1.device):
+            rc = native.lib().pcorr_forward_ring(fmap1.data_ptr(), coords.data_ptr(), ii.data_ptr(), jj.data_ptr(), nlev, B, E,
+                                                 fmap1.shape[1], self.F, self.C, self.H0, self.W0, self.H1, self.W1, P,
+                                                 int(radius), 1, out.data_ptr(), self.ring.data_ptr(), self.ring.numel(),
+                                                 native.stream_ptr(fmap1.device))
+        native.check(rc, "pcorr_forward_ring")
+        return out.view(B, E, -1) if nlev == 2 else out

@@ -59,6 +59,20 @@ int pcorr_forward_tma(const void* fmap1, const void* fmap2_l0, const void* fmap2
                       int H0, int W0, int H1, int W1, int P, int radius, int dtype, void* out, void* workspace,
                       size_t workspace_bytes, pcorr_stream_t stream);
 
+/* Persistent channel-last mirror ("ring") of the frame-map pyramid.  pcorr_forward_tma copies ALL frame maps to the
+ * channel-last layout on every call, although the SLAM front end rewrites exactly one ring slot per new frame
+ * (cdvslam/slam.py:681-682: pyramid[0][:, n % mem] = fmap, pyramid[1][:, n % mem] = avg_pool2d(fmap, 4, 4)).  A caller
+ * that owns a ring buffer (pcorr_tma_workspace_bytes() bytes, 256-byte aligned, contents kept between calls) instead
+ *   - calls pcorr_ring_update(...) for the slots it has just written (frames [first_frame, first_frame + n_frames) of
+ *     every batch entry; all frames once at start-up), and
+ *   - looks up with pcorr_forward_ring(...), which is pcorr_forward_tma without the per-call copy (the NCHW maps are not
+ *     read at all).  Same results bit for bit. */
+int pcorr_ring_update(const void* fmap2_l0, const void* fmap2_l1, int nlev, int B, int64_t F, int C, int H0, int W0, int H1,
+                      int W1, int64_t first_frame, int64_t n_frames, void* ring, size_t ring_bytes, pcorr_stream_t stream);
+int pcorr_forward_ring(const void* fmap1, const float* coords, const int64_t* ii, const int64_t* jj, int nlev, int B,
+                       int64_t E, int64_t K, int64_t F, int C, int H0, int W0, int H1, int W1, int P, int radius, int dtype,
+                       void* out, const void* ring, size_t ring_bytes, pcorr_stream_t stream);
+
 /* Gradient of pcorr_forward w.r.t. fmap1 and fmap2.  Replaces cuda_corr.backward == corr_cuda_backward()
  * (reference: correlation_kernel.cu:140-190, 236-286).  grad is the gradient of `out` in out's layout, f32;
  * fmap1_grad / fmap2_grad have the shapes and dtype of fmap1 / fmap2 and must be zero-filled by the caller. */

@@ -39,7 +39,8 @@ int main(int argc, char** argv) {
   printf("max |S x - y| = %.3e\n", worst);
 #ifdef PGBA_SOLVE_TIMING
   long long ts[64]; cudaMemcpyFromSymbol(ts, g_solve_ts, sizeof(ts));
-  printf("phase clocks (cycles since start):"); for (int i = 1; i < 64; ++i) if (ts[i]) printf(" [%d]%lld", i, ts[i] - ts[0]); printf("\n");
+  printf("phase clocks (cycles since start; 1 loaded, 2 factored, 3 back-substituted, 4 end; 10+/30+ worker thread and 20+/40+ look-ahead\n"
+         " warp in steps kb = 0 / 24, see ba_chol32.cuh):"); for (int i = 1; i < 64; ++i) if (ts[i]) printf(" [%d]%lld", i, ts[i] - ts[0]); printf("\n");
 #endif
   return 0;
 }

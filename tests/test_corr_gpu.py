@@ -211,3 +211,31 @@ def test_corr_fp16_tiny_maps_fall_back():
     want = corr_oracle.corr(gmap[None], fmap[None], coords, ii, jj, 3)
     err = np.abs(got.float().cpu().numpy() - want)
     assert (err <= 2.0 ** -11 * np.abs(want) + 1e-4).all()
+
+
+@pytest.mark.parametrize("C", [24, 128])
+def test_pyramid_ring_equals_per_call_transposition(C):
+    """altcorr.PyramidRing (persistent channel-last mirror, one slot re-copied per new frame) gives bit-identical lookups
+    to corr_pyramid2 / corr, which re-copy every frame map on every call; overwriting a ring slot of the pyramid without
+    update() leaves the mirror stale (old result), update(slot) brings it back in line."""
+    p, gmap, pyr, coords = _setup(C, np.float16, seed=6, F=8, M=24, n_mem=8)
+    dev = "cuda"
+    g = torch.as_tensor(gmap, device=dev)[None]
+    maps = [torch.as_tensor(x, device=dev)[None].contiguous() for x in pyr]
+    ii = torch.as_tensor(p.kk, device=dev); jj = torch.as_tensor(p.jj, device=dev)
+    c = torch.as_tensor(coords, device=dev)
+    ring = altcorr.PyramidRing(maps)
+    ref = altcorr.corr_pyramid2(g, maps, c, ii, jj, 3)
+    assert torch.equal(ring.lookup(g, c, ii, jj, 3), ref)
+    one = altcorr.PyramidRing(maps[:1])
+    assert torch.equal(one.lookup(g, c, ii, jj, 3), altcorr.corr(g, maps[0], c, ii, jj, 3))
+    # a new frame arrives in slot 3 (slam.py:681-682)
+    torch.manual_seed(1)
+    new0 = (torch.randn_like(maps[0][:, 3].float()) / 4).half()
+    maps[0][:, 3] = new0
+    maps[1][:, 3] = torch.nn.functional.avg_pool2d(new0.float(), 4, 4).half()
+    ref2 = altcorr.corr_pyramid2(g, maps, c, ii, jj, 3)
+    assert not torch.equal(ref2, ref)
+    assert torch.equal(ring.lookup(g, c, ii, jj, 3), ref)          # stale until told
+    ring.update(3)
+    assert torch.equal(ring.lookup(g, c, ii, jj, 3), ref2)

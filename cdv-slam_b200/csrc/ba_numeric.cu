@@ -22,6 +22,7 @@
 #include "ba_common.cuh"
 #include "ba_chol.cuh"
 #include "ba_chol32.cuh"
+#include "ba_umma.cuh"
 
 namespace pgba {
 
@@ -141,6 +142,154 @@ __device__ __forceinline__ UpdPre upd_prefetch(const Problem& pb, const WinPtrs&
 __device__ __forceinline__ void chunk_depth_update(const Problem& pb, const WinPtrs& wp, const Chunk& ch, float* patches,
                                                    float* sdx, bool apply, const UpdPre& pre, float* s_depth);
 
+// ---------------------------------------------------------------------------------------------------------------
+// Schur update of one patch batch on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulator in TMEM); see
+// ba_umma.cuh.  Large chunks only (batched windows, global BA): nq <= 96 patches, ncols <= 11 columns.
+//   1. (ncols == 11 only) rows 64, 65 of the product do not fit the M = 64 instruction: their 2 x 2 corner and gradient
+//      entries are five dot products on one warp; their other entries come from the symmetry D[64 + x][n] = D[n][64 + x]
+//   2. staging, in place: X = sqrt(Q) E (gradient row sqrt(Q) u) split into TF32 hi / lo, written in the canonical
+//      K-major core-matrix layout: hi over the E tile (its fp32 contents have just gone to global memory), lo over the
+//      per-warp partials region (idle in this phase).  A warp writes one 128-byte core matrix per step: conflict-free
+//   3. one thread issues 3 MMAs per 8 patches (hi hi^T, lo hi^T, hi lo^T), commits to an mbarrier
+//   4. epilogue: thread = one row of D (tcgen05.ld 32x32b, 24 columns at a time), 8-byte vector reductions into S, y
+// Ends with a __syncthreads().  mbar_parity is flipped.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __noinline__ void schur_umma(const LinSmem& s, const Chunk& ch, const WinPtrs& wp, int nq, int ncols, int fi,
+                                           int t0, int n6, uint32_t tmem, uint64_t* mbar, uint32_t& mbar_parity) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int estride = ncols * 6;
+  auto col_frame = [&](int cbk) { return ((cbk < ch.n_free) ? s.sFrame[ch.first_free + cbk] : fi) - t0; };
+  // ---- 1. corner entries of rows 64, 65 (from the fp32 tile, before it is overwritten)
+  float corner[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  if (ncols == 11 && warp == 7) {
+    for (int q = lane; q < nq; q += 32) {
+      const float Q = s.sQ[q], u = s.sPQ[q * PQS + 1];
+      const float e4 = s.sE[q * estride + 64], e5 = s.sE[q * estride + 65];
+      corner[0] = fmaf(Q * e4, e4, corner[0]);
+      corner[1] = fmaf(Q * e5, e4, corner[1]);
+      corner[2] = fmaf(Q * e5, e5, corner[2]);
+      corner[3] = fmaf(Q * u, e4, corner[3]);
+      corner[4] = fmaf(Q * u, e5, corner[4]);
+    }
+#pragma unroll
+    for (int x = 0; x < 5; ++x)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) corner[x] += __shfl_xor_sync(0xffffffffu, corner[x], o);
+  }
+  // ---- 2. staging: read everything, barrier, write in place
+  constexpr int NCM = (umma::NROWS / 8) * (umma::KMAX / 4);        // 216 core matrices per array
+  constexpr int PER_WARP = NCM / 8;                                // 27
+  float val[PER_WARP];
+#pragma unroll
+  for (int it = 0; it < PER_WARP; ++it) {
+    const int cm = warp + 8 * it;
+    const int g = cm / (umma::KMAX / 4), kq = cm - g * (umma::KMAX / 4);
+    const int n = 8 * g + (lane & 7), q = 4 * kq + (lane >> 3);
+    float v = 0.f;
+    if (q < nq && n <= estride) {
+      const float sq = sqrtf(s.sQ[q]);
+      v = sq * ((n < estride) ? s.sE[q * estride + n] : s.sPQ[q * PQS + 1]);
+    }
+    val[it] = v;
+  }
+  __syncthreads();
+  {
+    char* xhi = reinterpret_cast<char*>(s.sE);
+    char* xlo = reinterpret_cast<char*>(s.sHw);
+    const int off = (lane & 7) * 16 + (lane >> 3) * 4;
+#pragma unroll
+    for (int it = 0; it < PER_WARP; ++it) {
+      const int cm = warp + 8 * it;
+      float hi, lo;
+      umma::split_tf32(val[it], hi, lo);
+      *reinterpret_cast<float*>(xhi + cm * 128 + off) = hi;
+      *reinterpret_cast<float*>(xlo + cm * 128 + off) = lo;
+    }
+  }
+  umma::fence_smem_to_async();
+  __syncthreads();
+  // ---- 3. MMAs
+  const int nk = (nq + 7) >> 3;
+  const int N = ((estride + 1 + 7) >> 3) << 3;                      // accumulator columns actually needed
+  if (tid == 0) {
+    umma::fence_after_sync();
+    const uint32_t ahi = umma::smem_u32(s.sE), alo = umma::smem_u32(s.sHw);
+    const uint32_t idesc = umma::instr_desc_tf32_m64(N);
+    for (int ks = 0; ks < nk; ++ks) {
+      const uint64_t dhi = umma::smem_desc(ahi + ks * 2 * umma::LBO), dlo = umma::smem_desc(alo + ks * 2 * umma::LBO);
+      umma::mma_tf32(tmem, dhi, dhi, idesc, ks > 0 ? 1u : 0u);
+      umma::mma_tf32(tmem, dlo, dhi, idesc, 1u);
+      umma::mma_tf32(tmem, dhi, dlo, idesc, 1u);
+    }
+    umma::mma_commit(mbar);
+  }
+  // corner entries while the tensor core works
+  if (ncols == 11 && warp == 7 && lane == 0) {
+    const int f10 = col_frame(10);
+    float* d = wp.S + (size_t)(6 * f10) * n6 + 6 * f10;
+    atomicAdd(d + (size_t)4 * n6 + 4, -corner[0]);
+    atomicAdd(d + (size_t)5 * n6 + 4, -corner[1]);
+    atomicAdd(d + (size_t)4 * n6 + 5, -corner[1]);
+    atomicAdd(d + (size_t)5 * n6 + 5, -corner[2]);
+    atomicAdd(&wp.y[6 * f10 + 4], -corner[3]);
+    atomicAdd(&wp.y[6 * f10 + 5], -corner[4]);
+  }
+  umma::mbar_wait(mbar, mbar_parity);
+  mbar_parity ^= 1u;
+  umma::fence_after_sync();
+  // ---- 4. epilogue: M = 64 accumulator rows live in TMEM lanes 32 * (m / 16) + m % 16
+  if (warp < 4) {
+    const int m = 16 * warp + lane;                                // valid for lane < 16
+    const bool row_ok = lane < 16 && m < estride;
+    const int ca = m / 6, r = m - 6 * ca;
+    const int fa = row_ok ? col_frame(ca) : 0;
+    const uint32_t trow = tmem + ((uint32_t)(32 * warp) << 16);
+#pragma unroll
+    for (int part = 0; part < 3; ++part) {                         // 24 columns = 4 column blocks at a time
+      if (24 * part >= N) break;                                   // warp-uniform
+      float v[24];
+      umma::tmem_ld16(trow + 24 * part, v);
+      umma::tmem_ld8(trow + 24 * part + 16, v + 16);
+      umma::tmem_ld_wait();
+      if (!row_ok) continue;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int cb = 4 * part + b;
+        if (cb <= ca && cb < ncols) {                              // lower block triangle, full diagonal blocks
+          const int fb = col_frame(cb);
+          if (fa >= fb) {
+            float* dst = wp.S + (size_t)(6 * fa + r) * n6 + 6 * fb;
+            red_add2(dst, -v[6 * b], -v[6 * b + 1]);
+            red_add2(dst + 2, -v[6 * b + 2], -v[6 * b + 3]);
+            red_add2(dst + 4, -v[6 * b + 4], -v[6 * b + 5]);
+          } else {                                                 // transposed into block (fb, fa)
+            float* dst = wp.S + (size_t)(6 * fb) * n6 + 6 * fa + r;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) atomicAdd(dst + (size_t)c * n6, -v[6 * b + c]);
+          }
+        }
+        if (cb == ncols) atomicAdd(&wp.y[6 * fa + r], -v[6 * b]);  // gradient column (index estride)
+      }
+      if (part == 2 && ncols == 11) {                              // rows 64, 65 by symmetry: D[64 + x][m] = D[m][64 + x]
+        const int f10 = col_frame(10);
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {
+          const float d = -v[64 - 48 + x];
+          if (ca == 10) {                                          // inside the diagonal block: the mirrored entry
+            atomicAdd(wp.S + (size_t)(6 * f10 + 4 + x) * n6 + 6 * f10 + r, d);
+          } else if (f10 >= fa) {
+            atomicAdd(wp.S + (size_t)(6 * f10 + 4 + x) * n6 + 6 * fa + r, d);
+          } else {
+            atomicAdd(wp.S + (size_t)(6 * fa + r) * n6 + 6 * f10 + 4 + x, d);
+          }
+        }
+      }
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+}
+
 // grid = (gx, batch), block = 256, dynamic smem = lin_smem_bytes(pc, ebudget).  fuse_update: first apply the previous
 // iteration's back-substitution + depth retraction to the chunk's patches (saves the separate update launch).
 #ifdef PGBA_LIN_TIMING
@@ -179,6 +328,18 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
     LIN_TS(0);
   }
   extern __shared__ __align__(16) float smem[];
+  // tcgen05 Schur product (flags & 16): per-CTA tensor-memory allocation + one mbarrier, released at the end of the kernel
+  __shared__ uint32_t s_tmem;
+  __shared__ __align__(8) uint64_t s_mbar;
+  const bool use_umma = (flags & 16) != 0;
+  uint32_t mbar_parity = 0;
+  if (use_umma) {
+    if (threadIdx.x < 32) umma::tmem_alloc(&s_tmem);
+    if (threadIdx.x == 32) umma::mbar_init(&s_mbar, 1);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+  }
   const int pc = pb.L.pc;
   LinSmem s;
   s.sRt = smem;
@@ -466,6 +627,10 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
         float* eg = wp.ecells + 6 * ((int64_t)ch.ecell_base + (int64_t)b0 * ncols);
         for (int x = tid; x < (b1 - b0) * estride; x += 256) eg[x] = s.sE[x];
 
+        if (use_umma && split_slots && (b1 - b0) <= umma::KMAX && ncols <= 11) {
+          schur_umma(s, ch, wp, b1 - b0, ncols, fi, t0, n6, s_tmem, &s_mbar, mbar_parity);
+          continue;
+        }
         if (split_slots) {
           // ---- large chunks: the phase below is bound by shared-memory wavefronts (5 loads per 12 FMAs).  Here a QUAD of
           //      lanes owns a whole 6 x 6 block (ca >= cb), each lane takes every fourth patch (7 loads per 36 FMAs, 18
@@ -727,6 +892,11 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
     pdl_wait();
     pdl_trigger();
     CTA_TS((flags & 1) ? 3 : 0, 1);
+  }
+  if (use_umma) {
+    umma::fence_before_sync();
+    __syncthreads();
+    if (threadIdx.x < 32) umma::tmem_dealloc(s_tmem);
   }
   CTA_TS((flags & 1) ? 3 : 0, 2);
 }
@@ -1050,6 +1220,18 @@ int lin_ebudget(const Problem& pb) {
 
 cudaError_t launch_big_solve(const Problem& pb, int64_t batch, cudaStream_t stream);
 
+// Chunk Schur product on the tcgen05 tensor cores (schur_umma) for chunks of >= 64 patches (batched windows, global BA).
+// PGBA_SCHUR_UMMA=0 selects the FFMA2 quad product instead (A/B runs, parity tests run both).
+static bool schur_on_tcgen05(const Problem& pb) {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PGBA_SCHUR_UMMA");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  // the operand arrays alias the E tile (>= 27 648 bytes) and the per-warp partials region
+  return v != 0 && pb.L.pc >= 64 && pb.t1 > pb.t0 && (size_t)lin_ebudget(pb) * sizeof(float) >= (size_t)umma::X_BYTES;
+}
+
 // Loads ahead of pdl_wait() in the second linearisation / the update kernel (PGBA_EARLY=0 disables, for A/B runs).
 static bool early_loads_enabled() {
   static int v = -1;
@@ -1065,7 +1247,7 @@ void launch_linearize(const Problem& pb, int64_t batch, cudaStream_t stream, boo
   const int ebudget = lin_ebudget(pb);
   const size_t lsm = lin_smem_bytes(pb.L.pc, ebudget);
   const bool early = fuse_update && pb.t1 > pb.t0 && !pb.L.big && early_loads_enabled();
-  const int flags = (fuse_update ? 1 : 0) | (early ? 8 : 0);
+  const int flags = (fuse_update ? 1 : 0) | (early ? 8 : 0) | (schur_on_tcgen05(pb) ? 16 : 0);
   auto go = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm);
     launch_k(kern, dim3((unsigned)gx, (unsigned)batch), dim3(256), lsm, stream, pb, ebudget, flags);

@@ -1,5 +1,5 @@
-"""Accuracy of the two Schur implementations (PGBA_SCHUR_MMA=0: FFMA2, 1: 3xTF32 tensor cores) at a forced chunk size:
-relative errors of S, y, dX, dZ against the float64 oracle on c1 (ill-conditioned), c2.  Run with the env set."""
+"""Accuracy of the two Schur implementations (PGBA_SCHUR_UMMA=0: FFMA2, 1: tcgen05 3xTF32 with the accumulator in TMEM) at a forced chunk size:
+relative errors of S, y, dX, dZ against the float64 oracle on c1 (ill-conditioned), c2, one c5 window.  Run with the env set."""
 import os, sys, json
 REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [REPO, os.path.join(REPO, "cdv-slam_b200")]
@@ -8,7 +8,7 @@ from cdvslam_b200 import synth, fastba
 from oracle import ba_oracle
 from tests.helpers import to_dev, f32_problem, rel_err
 out = {"env": {k: v for k, v in os.environ.items() if k.startswith("PGBA_")}}
-for name, maker in (("c1", synth.config_c1), ("c2", synth.config_c2)):
+for name, maker in (("c1", synth.config_c1), ("c2", synth.config_c2), ("c5w0", lambda: synth.config_c5_window(0))):
     p = maker(); d = to_dev(p); q = f32_problem(p)
     _, _, dbg = ba_oracle.ba(q["poses"], q["patches"], q["intrinsics"], q["target"], q["weight"], q["lmbda"], p.ii, p.jj, p.kk, p.t0, p.t1, 1, debug=True)
     o = dbg[0]

@@ -101,10 +101,14 @@ struct LinSmem {
   float* sPQ;      // [pc][PQS]   per patch: C, u, E_i[6] (source-frame column accumulators); odd stride: lanes <-> patches is conflict-free
   float* sQ;       // [pc]
   float* sE;       // [ebudget]   E tile [patch][col][6]
+  float* sAH;      // [SMAX][36]  A_s H_s of the pose-block phase: aliases sHw, or (tcgen05 Schur: sHw holds an operand array
+                   //             while that phase runs) its own region behind the E tile
+  float* sSq;      // [pc]        sqrt(Q) (tcgen05 Schur only)
 };
 
-size_t lin_smem_bytes(int pc, int ebudget) {
-  return sizeof(float) * ((size_t)LIN_FIXED_FLOATS + (size_t)pc * (4 + PQS + 1) + (size_t)ebudget);
+size_t lin_smem_bytes(int pc, int ebudget, bool umma_regions) {
+  return sizeof(float) * ((size_t)LIN_FIXED_FLOATS + (size_t)pc * (4 + PQS + 1) + (size_t)ebudget +
+                          (umma_regions ? (size_t)SMAX * 36 + (size_t)pc : 0));
 }
 
 __device__ __forceinline__ int pow2_ceil(int x) {
@@ -142,156 +146,6 @@ __device__ __forceinline__ UpdPre upd_prefetch(const Problem& pb, const WinPtrs&
 __device__ __forceinline__ void chunk_depth_update(const Problem& pb, const WinPtrs& wp, const Chunk& ch, float* patches,
                                                    float* sdx, bool apply, const UpdPre& pre, float* s_depth);
 
-// ---------------------------------------------------------------------------------------------------------------
-// Schur update of one patch batch on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulator in TMEM); see
-// ba_umma.cuh.  Large chunks only (batched windows, global BA): nq <= 96 patches, ncols <= 11 columns.
-//   1. (ncols == 11 only) rows 64, 65 of the product do not fit the M = 64 instruction: their 2 x 2 corner and gradient
-//      entries are five dot products on one warp; their other entries come from the symmetry D[64 + x][n] = D[n][64 + x]
-//   2. staging, in place: X = sqrt(Q) E (gradient row sqrt(Q) u) split into TF32 hi / lo, written in the canonical
-//      K-major core-matrix layout: hi over the E tile (its fp32 contents have just gone to global memory), lo over the
-//      per-warp partials region (idle in this phase).  A warp writes one 128-byte core matrix per step: conflict-free
-//   3. one thread issues 3 MMAs per 8 patches (hi hi^T, lo hi^T, hi lo^T), commits to an mbarrier
-//   4. epilogue: thread = one row of D (tcgen05.ld 32x32b, 24 columns at a time), 8-byte vector reductions into S, y
-// Ends with a __syncthreads().  mbar_parity is flipped.
-// ---------------------------------------------------------------------------------------------------------------
-__device__ __noinline__ void schur_umma(const LinSmem& s, const Chunk& ch, const WinPtrs& wp, int nq, int ncols, int fi,
-                                           int t0, int n6, uint32_t tmem, uint64_t* mbar, uint32_t& mbar_parity) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int estride = ncols * 6;
-  auto col_frame = [&](int cbk) { return ((cbk < ch.n_free) ? s.sFrame[ch.first_free + cbk] : fi) - t0; };
-  // ---- 1. corner entries of rows 64, 65 (from the fp32 tile, before it is overwritten)
-  float corner[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-  if (ncols == 11 && warp == 7) {
-    for (int q = lane; q < nq; q += 32) {
-      const float Q = s.sQ[q], u = s.sPQ[q * PQS + 1];
-      const float e4 = s.sE[q * estride + 64], e5 = s.sE[q * estride + 65];
-      corner[0] = fmaf(Q * e4, e4, corner[0]);
-      corner[1] = fmaf(Q * e5, e4, corner[1]);
-      corner[2] = fmaf(Q * e5, e5, corner[2]);
-      corner[3] = fmaf(Q * u, e4, corner[3]);
-      corner[4] = fmaf(Q * u, e5, corner[4]);
-    }
-#pragma unroll
-    for (int x = 0; x < 5; ++x)
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) corner[x] += __shfl_xor_sync(0xffffffffu, corner[x], o);
-  }
-  // ---- 2. staging: read everything, barrier, write in place
-  constexpr int NCM = (umma::NROWS / 8) * (umma::KMAX / 4);        // 216 core matrices per array
-  constexpr int PER_WARP = NCM / 8;                                // 27
-  float val[PER_WARP];
-#pragma unroll
-  for (int it = 0; it < PER_WARP; ++it) {
-    const int cm = warp + 8 * it;
-    const int g = cm / (umma::KMAX / 4), kq = cm - g * (umma::KMAX / 4);
-    const int n = 8 * g + (lane & 7), q = 4 * kq + (lane >> 3);
-    float v = 0.f;
-    if (q < nq && n <= estride) {
-      const float sq = sqrtf(s.sQ[q]);
-      v = sq * ((n < estride) ? s.sE[q * estride + n] : s.sPQ[q * PQS + 1]);
-    }
-    val[it] = v;
-  }
-  __syncthreads();
-  {
-    char* xhi = reinterpret_cast<char*>(s.sE);
-    char* xlo = reinterpret_cast<char*>(s.sHw);
-    const int off = (lane & 7) * 16 + (lane >> 3) * 4;
-#pragma unroll
-    for (int it = 0; it < PER_WARP; ++it) {
-      const int cm = warp + 8 * it;
-      float hi, lo;
-      umma::split_tf32(val[it], hi, lo);
-      *reinterpret_cast<float*>(xhi + cm * 128 + off) = hi;
-      *reinterpret_cast<float*>(xlo + cm * 128 + off) = lo;
-    }
-  }
-  umma::fence_smem_to_async();
-  __syncthreads();
-  // ---- 3. MMAs
-  const int nk = (nq + 7) >> 3;
-  const int N = ((estride + 1 + 7) >> 3) << 3;                      // accumulator columns actually needed
-  if (tid == 0) {
-    umma::fence_after_sync();
-    const uint32_t ahi = umma::smem_u32(s.sE), alo = umma::smem_u32(s.sHw);
-    const uint32_t idesc = umma::instr_desc_tf32_m64(N);
-    for (int ks = 0; ks < nk; ++ks) {
-      const uint64_t dhi = umma::smem_desc(ahi + ks * 2 * umma::LBO), dlo = umma::smem_desc(alo + ks * 2 * umma::LBO);
-      umma::mma_tf32(tmem, dhi, dhi, idesc, ks > 0 ? 1u : 0u);
-      umma::mma_tf32(tmem, dlo, dhi, idesc, 1u);
-      umma::mma_tf32(tmem, dhi, dlo, idesc, 1u);
-    }
-    umma::mma_commit(mbar);
-  }
-  // corner entries while the tensor core works
-  if (ncols == 11 && warp == 7 && lane == 0) {
-    const int f10 = col_frame(10);
-    float* d = wp.S + (size_t)(6 * f10) * n6 + 6 * f10;
-    atomicAdd(d + (size_t)4 * n6 + 4, -corner[0]);
-    atomicAdd(d + (size_t)5 * n6 + 4, -corner[1]);
-    atomicAdd(d + (size_t)4 * n6 + 5, -corner[1]);
-    atomicAdd(d + (size_t)5 * n6 + 5, -corner[2]);
-    atomicAdd(&wp.y[6 * f10 + 4], -corner[3]);
-    atomicAdd(&wp.y[6 * f10 + 5], -corner[4]);
-  }
-  umma::mbar_wait(mbar, mbar_parity);
-  mbar_parity ^= 1u;
-  umma::fence_after_sync();
-  // ---- 4. epilogue: M = 64 accumulator rows live in TMEM lanes 32 * (m / 16) + m % 16
-  if (warp < 4) {
-    const int m = 16 * warp + lane;                                // valid for lane < 16
-    const bool row_ok = lane < 16 && m < estride;
-    const int ca = m / 6, r = m - 6 * ca;
-    const int fa = row_ok ? col_frame(ca) : 0;
-    const uint32_t trow = tmem + ((uint32_t)(32 * warp) << 16);
-#pragma unroll
-    for (int part = 0; part < 3; ++part) {                         // 24 columns = 4 column blocks at a time
-      if (24 * part >= N) break;                                   // warp-uniform
-      float v[24];
-      umma::tmem_ld16(trow + 24 * part, v);
-      umma::tmem_ld8(trow + 24 * part + 16, v + 16);
-      umma::tmem_ld_wait();
-      if (!row_ok) continue;
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const int cb = 4 * part + b;
-        if (cb <= ca && cb < ncols) {                              // lower block triangle, full diagonal blocks
-          const int fb = col_frame(cb);
-          if (fa >= fb) {
-            float* dst = wp.S + (size_t)(6 * fa + r) * n6 + 6 * fb;
-            red_add2(dst, -v[6 * b], -v[6 * b + 1]);
-            red_add2(dst + 2, -v[6 * b + 2], -v[6 * b + 3]);
-            red_add2(dst + 4, -v[6 * b + 4], -v[6 * b + 5]);
-          } else {                                                 // transposed into block (fb, fa)
-            float* dst = wp.S + (size_t)(6 * fb) * n6 + 6 * fa + r;
-#pragma unroll
-            for (int c = 0; c < 6; ++c) atomicAdd(dst + (size_t)c * n6, -v[6 * b + c]);
-          }
-        }
-        if (cb == ncols) atomicAdd(&wp.y[6 * fa + r], -v[6 * b]);  // gradient column (index estride)
-      }
-      if (part == 2 && ncols == 11) {                              // rows 64, 65 by symmetry: D[64 + x][m] = D[m][64 + x]
-        const int f10 = col_frame(10);
-#pragma unroll
-        for (int x = 0; x < 2; ++x) {
-          const float d = -v[64 - 48 + x];
-          if (ca == 10) {                                          // inside the diagonal block: the mirrored entry
-            atomicAdd(wp.S + (size_t)(6 * f10 + 4 + x) * n6 + 6 * f10 + r, d);
-          } else if (f10 >= fa) {
-            atomicAdd(wp.S + (size_t)(6 * f10 + 4 + x) * n6 + 6 * fa + r, d);
-          } else {
-            atomicAdd(wp.S + (size_t)(6 * fa + r) * n6 + 6 * f10 + 4 + x, d);
-          }
-        }
-      }
-    }
-  }
-  umma::fence_before_sync();
-  __syncthreads();
-}
-
-// grid = (gx, batch), block = 256, dynamic smem = lin_smem_bytes(pc, ebudget).  fuse_update: first apply the previous
-// iteration's back-substitution + depth retraction to the chunk's patches (saves the separate update launch).
 #ifdef PGBA_LIN_TIMING
 // per-CTA wall-clock trace (globaltimer, ns): [kernel slot][entry / after pdl_wait / exit][flattened CTA index < 512];
 // slots: 0 first linearize, 1 solve, 2 update, 3 linearize with the fused update (profiles/cta_trace.py)
@@ -313,7 +167,182 @@ __device__ long long g_lin_ts[32];
 #define CTA_TS(k, f) do { } while (0)
 #endif
 
-template <bool FUSE>
+// ---------------------------------------------------------------------------------------------------------------
+// Schur update of one patch batch on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulator in TMEM); see
+// ba_umma.cuh.  Large chunks only (batched windows, global BA): nq <= 96 patches, ncols <= 11 columns.  Two halves, so
+// that the pose-block phase of the chunk runs on warps 0..6 while warp 7 feeds the tensor core:
+//   schur_umma_issue
+//     1. (ncols == 11 only) rows 64, 65 of the product do not fit the M = 64 instruction: their 2 x 2 corner and gradient
+//        entries are five dot products on one warp; their other entries come from the symmetry D[64 + x][n] = D[n][64 + x]
+//     2. staging, in place: X = sqrt(Q) E (gradient row sqrt(Q) u) split into TF32 hi / lo, written in the canonical
+//        K-major core-matrix layout: hi over the E tile (its fp32 contents have just gone to global memory), lo over the
+//        per-warp partials region (idle from here on).  A warp writes one 128-byte core matrix per step: conflict-free
+//     3. ONE thread (the first of warp 7) issues 3 MMAs per 8 patches (hi hi^T, lo hi^T, hi lo^T) and commits to an
+//        mbarrier; everybody else returns at once
+//   schur_umma_finish
+//     4. wait for the accumulator; thread = one row of D (tcgen05.ld 32x32b, 24 columns at a time; warps 0..3 take the even
+//        column blocks, warps 4..7 -- same TMEM lanes -- the odd ones), 8-byte vector reductions into S, y
+// Not inlined: their register demand (27 staged values, 24 accumulator columns) stays out of the edge loop's allocation.
+// All arguments are scalars / pointers passed by value -- handing the kernel's LinSmem / Chunk / WinPtrs structs over by
+// reference forces them into local memory for the WHOLE kernel (measured: c5 linearisation 113 -> 199 us).
+// ---------------------------------------------------------------------------------------------------------------
+#ifndef SCHUR_UMMA_ATTR
+#define SCHUR_UMMA_ATTR __noinline__
+#endif
+constexpr int UMMA_ISSUE_THREAD = 224;         // first thread of warp 7
+
+__device__ SCHUR_UMMA_ATTR void schur_umma_issue(float* sE, float* sHw, const float* sQ, const float* sSq, const float* sPQ,
+                                                 float* gS, float* gy, int f10, int nq, int ncols, int n6, uint32_t tmem,
+                                                 uint64_t* mbar) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int estride = ncols * 6;
+  // ---- 1. corner entries of rows 64, 65 (from the fp32 tile, before it is overwritten)
+  if (ncols == 11 && warp == 6) {
+    float corner[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int q = lane; q < nq; q += 32) {
+      const float Q = sQ[q], u = sPQ[q * PQS + 1];
+      const float e4 = sE[q * estride + 64], e5 = sE[q * estride + 65];
+      corner[0] = fmaf(Q * e4, e4, corner[0]);
+      corner[1] = fmaf(Q * e5, e4, corner[1]);
+      corner[2] = fmaf(Q * e5, e5, corner[2]);
+      corner[3] = fmaf(Q * u, e4, corner[3]);
+      corner[4] = fmaf(Q * u, e5, corner[4]);
+    }
+#pragma unroll
+    for (int x = 0; x < 5; ++x)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) corner[x] += __shfl_xor_sync(0xffffffffu, corner[x], o);
+    if (lane == 0) {
+      float* d = gS + (size_t)(6 * f10) * n6 + 6 * f10;
+      atomicAdd(d + (size_t)4 * n6 + 4, -corner[0]);
+      atomicAdd(d + (size_t)5 * n6 + 4, -corner[1]);
+      atomicAdd(d + (size_t)4 * n6 + 5, -corner[1]);
+      atomicAdd(d + (size_t)5 * n6 + 5, -corner[2]);
+      atomicAdd(&gy[6 * f10 + 4], -corner[3]);
+      atomicAdd(&gy[6 * f10 + 5], -corner[4]);
+    }
+  }
+  LIN_TS(12);
+  // ---- 2. staging: read everything, barrier, write in place.  Core matrix cm = warp + 8 it  ->  (8-row group g, K group kq)
+  constexpr int KG = umma::KMAX / 4;                               // 24 core matrices per 8-row group
+  constexpr int PER_WARP = (umma::NROWS / 8) * KG / 8;             // 27
+  float val[PER_WARP];
+  {
+    int g = 0, kq = warp;
+#pragma unroll
+    for (int it = 0; it < PER_WARP; ++it) {
+      const int n = 8 * g + (lane & 7), q = 4 * kq + (lane >> 3);
+      // unconditional loads from clamped addresses (all 27 in flight together), selection afterwards
+      const int qc = min(q, nq - 1);
+      const float e = sE[qc * estride + min(n, estride - 1)], u = sPQ[qc * PQS + 1], sq = sSq[qc];
+      val[it] = (q < nq && n <= estride) ? sq * ((n < estride) ? e : u) : 0.f;
+      kq += 8;
+      if (kq >= KG) { kq -= KG; ++g; }
+    }
+  }
+  LIN_TS(13);
+  __syncthreads();
+  {
+    char* xhi = reinterpret_cast<char*>(sE) + (lane & 7) * 16 + (lane >> 3) * 4;
+    char* xlo = reinterpret_cast<char*>(sHw) + (lane & 7) * 16 + (lane >> 3) * 4;
+#pragma unroll
+    for (int it = 0; it < PER_WARP; ++it) {
+      const int cm = warp + 8 * it;
+      float hi, lo;
+      umma::split_tf32(val[it], hi, lo);
+      *reinterpret_cast<float*>(xhi + cm * 128) = hi;
+      *reinterpret_cast<float*>(xlo + cm * 128) = lo;
+    }
+  }
+  umma::fence_smem_to_async();
+  __syncthreads();
+  LIN_TS(14);
+  // ---- 3. MMAs
+  if (tid == UMMA_ISSUE_THREAD) {
+    const int nk = (nq + 7) >> 3;
+    const int N = ((estride + 1 + 7) >> 3) << 3;                    // accumulator columns actually needed
+    umma::fence_after_sync();
+    const uint32_t ahi = umma::smem_u32(sE), alo = umma::smem_u32(sHw);
+    const uint32_t idesc = umma::instr_desc_tf32_m64(N);
+    for (int ks = 0; ks < nk; ++ks) {
+      const uint64_t dhi = umma::smem_desc(ahi + ks * 2 * umma::LBO), dlo = umma::smem_desc(alo + ks * 2 * umma::LBO);
+      umma::mma_tf32(tmem, dhi, dhi, idesc, ks > 0 ? 1u : 0u);
+      umma::mma_tf32(tmem, dlo, dhi, idesc, 1u);
+      umma::mma_tf32(tmem, dhi, dlo, idesc, 1u);
+    }
+    umma::mma_commit(mbar);
+  }
+  __syncwarp();                 // the other lanes of the issuing warp do not run ahead into the mbarrier wait
+  LIN_TS(15);
+}
+
+// All 256 threads.  Ends with a __syncthreads(); returns the flipped mbarrier parity.
+__device__ SCHUR_UMMA_ATTR uint32_t schur_umma_finish(const int* sFrame, int first_free, int n_free, float* gS, float* gy,
+                                                     int ncols, int fi, int t0, int n6, uint32_t tmem, uint64_t* mbar,
+                                                     uint32_t mbar_parity) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int estride = ncols * 6;
+  const int N = ((estride + 1 + 7) >> 3) << 3;
+  auto col_frame = [&](int cbk) { return ((cbk < n_free) ? sFrame[first_free + cbk] : fi) - t0; };
+  umma::mbar_wait(mbar, mbar_parity);
+  umma::fence_after_sync();
+  LIN_TS(16);
+  // ---- 4. epilogue: the M = 64 accumulator rows live in TMEM lanes 32 * (m / 16) + m % 16; a warp reaches the lanes of
+  //      its quarter (warp % 4), so warps w and w + 4 share rows and split the column blocks by parity
+  {
+    const int wq = warp & 3, half = warp >> 2;
+    const int m = 16 * wq + lane;                                  // valid for lane < 16
+    const bool row_ok = lane < 16 && m < estride;
+    const int ca = m / 6, r = m - 6 * ca;
+    const int fa = row_ok ? col_frame(ca) : 0;
+    const uint32_t trow = tmem + ((uint32_t)(32 * wq) << 16);
+#pragma unroll
+    for (int part = 0; part < 3; ++part) {                         // 24 columns = 4 column blocks at a time
+      if (24 * part >= N) break;                                   // warp-uniform
+      float v[24];
+      umma::tmem_ld16(trow + 24 * part, v);
+      umma::tmem_ld8(trow + 24 * part + 16, v + 16);
+      umma::tmem_ld_wait();
+      if (!row_ok) continue;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int cb = 4 * part + b;
+        if ((cb & 1) != half) continue;
+        if (cb <= ca && cb < ncols) {                              // lower block triangle, full diagonal blocks
+          const int fb = col_frame(cb);
+          if (fa >= fb) {
+            float* dst = gS + (size_t)(6 * fa + r) * n6 + 6 * fb;
+            red_add2(dst, -v[6 * b], -v[6 * b + 1]);
+            red_add2(dst + 2, -v[6 * b + 2], -v[6 * b + 3]);
+            red_add2(dst + 4, -v[6 * b + 4], -v[6 * b + 5]);
+          } else {                                                 // transposed into block (fb, fa)
+            float* dst = gS + (size_t)(6 * fb) * n6 + 6 * fa + r;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) atomicAdd(dst + (size_t)c * n6, -v[6 * b + c]);
+          }
+        }
+        if (cb == ncols) atomicAdd(&gy[6 * fa + r], -v[6 * b]);    // gradient column (index estride)
+      }
+      if (part == 2 && ncols == 11 && half == 0) {                 // rows 64, 65 by symmetry: D[64 + x][m] = D[m][64 + x]
+        const int f10 = col_frame(10);
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {
+          const float d = -v[64 - 48 + x];
+          if (f10 >= fa) atomicAdd(gS + (size_t)(6 * f10 + 4 + x) * n6 + 6 * fa + r, d);   // incl. the diagonal block's mirror
+          else atomicAdd(gS + (size_t)(6 * fa + r) * n6 + 6 * f10 + 4 + x, d);
+        }
+      }
+    }
+  }
+  LIN_TS(17);
+  umma::fence_before_sync();
+  __syncthreads();
+  return mbar_parity ^ 1u;
+}
+
+// grid = (gx, batch), block = 256, dynamic smem = lin_smem_bytes(pc, ebudget).  fuse_update: first apply the previous
+// iteration's back-substitution + depth retraction to the chunk's patches (saves the separate update launch).
+template <bool FUSE, bool UMMA>
 __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb, int ebudget, int flags) {
   CTA_TS((flags & 1) ? 3 : 0, 0);
   // flags & 8 (second and later linearisations of a call, small solve in between): the previous kernel is the solve,
@@ -331,15 +360,8 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
   // tcgen05 Schur product (flags & 16): per-CTA tensor-memory allocation + one mbarrier, released at the end of the kernel
   __shared__ uint32_t s_tmem;
   __shared__ __align__(8) uint64_t s_mbar;
-  const bool use_umma = (flags & 16) != 0;
+  constexpr bool use_umma = UMMA;
   uint32_t mbar_parity = 0;
-  if (use_umma) {
-    if (threadIdx.x < 32) umma::tmem_alloc(&s_tmem);
-    if (threadIdx.x == 32) umma::mbar_init(&s_mbar, 1);
-    umma::fence_before_sync();
-    __syncthreads();
-    umma::fence_after_sync();
-  }
   const int pc = pb.L.pc;
   LinSmem s;
   s.sRt = smem;
@@ -351,7 +373,9 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
   s.sPQ = s.sPatch + pc * 4;
   s.sQ = s.sPQ + pc * PQS;
   s.sE = s.sQ + pc;
-  float* sAH = s.sHw;
+  s.sAH = use_umma ? s.sE + ebudget : s.sHw;
+  s.sSq = s.sAH + SMAX * 36;                           // only touched by the tcgen05 instance
+  float* sAH = s.sAH;
 
   const int w = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
@@ -367,6 +391,15 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
   const int n_chunks = wp.hdr->n_chunks;
   const int n_dups = wp.hdr->n_dups;
   const bool schur = pb.with_schur != 0;
+  // the grid is sized for the worst-case chunk count: only CTAs that own a chunk allocate tensor memory
+  const bool umma_cta = use_umma && (int)blockIdx.x < n_chunks;
+  if (umma_cta) {
+    if (threadIdx.x < 32) umma::tmem_alloc(&s_tmem);
+    if (threadIdx.x == 32) umma::mbar_init(&s_mbar, 1);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+  }
   constexpr bool fuse_update = FUSE;
 
   for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
@@ -440,6 +473,7 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
     }
     for (int x = tid; x < ns * 28; x += 256) s.sH[x] = 0.f;
 
+    bool umma_pending = false;
     for (int b0 = 0; b0 < np; b0 += PB) {
       const int b1 = min(b0 + PB, np);
       __syncthreads();
@@ -614,6 +648,7 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
         const int q = p - b0;
         const float Q = 1.0f / (s.sPQ[q * PQS] + lmbda);
         s.sQ[q] = Q;
+        if (use_umma) s.sSq[q] = sqrtf(Q);
         wp.Q[ch.patch_base + p] = Q;
         wp.u[ch.patch_base + p] = s.sPQ[q * PQS + 1];
         if (i_free && schur) {
@@ -628,7 +663,14 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
         for (int x = tid; x < (b1 - b0) * estride; x += 256) eg[x] = s.sE[x];
 
         if (use_umma && split_slots && (b1 - b0) <= umma::KMAX && ncols <= 11) {
-          schur_umma(s, ch, wp, b1 - b0, ncols, fi, t0, n6, s_tmem, &s_mbar, mbar_parity);
+          const int f10 = (ncols == 11) ? ((10 < ch.n_free) ? s.sFrame[ch.first_free + 10] : fi) - t0 : 0;
+          schur_umma_issue(s.sE, s.sHw, s.sQ, s.sSq, s.sPQ, wp.S, wp.y, f10, b1 - b0, ncols, n6, s_tmem, &s_mbar);
+          if (b1 < np) {                                  // more patch batches follow: the operand arrays are needed again
+            mbar_parity = schur_umma_finish(s.sFrame, ch.first_free, ch.n_free, wp.S, wp.y, ncols, fi, t0, n6, s_tmem,
+                                            &s_mbar, mbar_parity);
+          } else {
+            umma_pending = true;                          // finished after the pose-block phase, which overlaps the MMAs
+          }
           continue;
         }
         if (split_slots) {
@@ -775,8 +817,17 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
       }
     }
     LIN_TS(7);
-    __syncthreads();
+    // With MMAs in flight (umma_pending) the pose-block phase below runs on warps 0..6 only, synchronised by a named barrier
+    // of 224 threads, while the first thread of warp 7 is still issuing; everything the phase reads was final before the
+    // Schur phase, and schur_umma_issue ended with a CTA-wide barrier.
+    if (!umma_pending) __syncthreads();
     LIN_TS(8);
+    const bool b_active = !(umma_pending && warp == 7);
+    const int b_stride = umma_pending ? 224 : 256;
+    auto b_sync = [&]() {
+      if (!umma_pending) __syncthreads();
+      else if (warp < 7) named_bar_sync(3, 224);
+    };
 
     // ---- pose blocks of this chunk (ba_cuda.cu:364-398)
     if (N > 0) {
@@ -816,7 +867,7 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
             if (lane == 0) s.sBii[36 + a] = -v;
           }
         }
-        __syncthreads();
+        b_sync();
     LIN_TS(9);
         // B2: B_ii = sum_s AH_s A_s^T ; row a per warp: (AH A^T)[a][:] = A * (AH[a][:])^T
         if (warp < 6) {
@@ -844,11 +895,11 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
             if (lane == 0) s.sBii[warp * 6 + b] = v;
           }
         }
-        __syncthreads();
+        b_sync();
     LIN_TS(10);
       }
       // B3: scatter.  Item = (slot, row a).
-      for (int it = tid; it < ns * 6; it += 256) {
+      for (int it = b_active ? tid : ns * 6; it < ns * 6; it += b_stride) {
         const int sl = it / 6, a = it - sl * 6;
         const int fj = s.sFrame[sl];
         if (fj < t0 || fj >= pb.t1) continue;
@@ -886,6 +937,9 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
         atomicAdd(&wp.y[io + tid], s.sBii[36 + tid]);
       }
     }
+    if (use_umma && umma_pending)
+      mbar_parity = schur_umma_finish(s.sFrame, ch.first_free, ch.n_free, wp.S, wp.y, ncols, fi, t0, n6, s_tmem, &s_mbar,
+                                      mbar_parity);
     LIN_TS(11);
   }
   if (!waited) {                                                // a CTA without a chunk still has to release its dependents
@@ -893,7 +947,7 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
     pdl_trigger();
     CTA_TS((flags & 1) ? 3 : 0, 1);
   }
-  if (use_umma) {
+  if (umma_cta) {
     umma::fence_before_sync();
     __syncthreads();
     if (threadIdx.x < 32) umma::tmem_dealloc(s_tmem);
@@ -1220,13 +1274,18 @@ int lin_ebudget(const Problem& pb) {
 
 cudaError_t launch_big_solve(const Problem& pb, int64_t batch, cudaStream_t stream);
 
-// Chunk Schur product on the tcgen05 tensor cores (schur_umma) for chunks of >= 64 patches (batched windows, global BA).
-// PGBA_SCHUR_UMMA=0 selects the FFMA2 quad product instead (A/B runs, parity tests run both).
+// Chunk Schur product on the tcgen05 tensor cores (schur_umma_issue / _finish) for chunks of >= 64 patches (batched windows,
+// global BA): opt-in, PGBA_SCHUR_UMMA=1.  Measured on the B200 (c5, 64 windows, chunks of 96 patches x 10 columns, same box,
+// profiles/README.md round 2): linearisation 133 us against 112 us for the FFMA2 quad product -- the 36 small dependent
+// MMAs (M = 64, N = 64, K = 8, ~100 cycles each) and the tensor core itself are cheap, but the in-place TF32 hi / lo
+// staging of the operand arrays (4.7 k cycles) and the 64-row epilogue (2.6 k) cost as much as the 9.2 k cycles of packed
+// FMAs they replace, and busy CTAs run 22.3 instead of 20.0 us with two CTAs per SM.  Accuracy: S to 2.8e-7 .. 6.3e-7 of the
+// float64 oracle (FFMA2: 1.2e-7).  Kept, parity-tested (tests/test_ba_gpu.py::test_forced_chunk_size), for the A/B record.
 static bool schur_on_tcgen05(const Problem& pb) {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("PGBA_SCHUR_UMMA");
-    v = (e && e[0] == '0') ? 0 : 1;
+    v = (e && e[0] == '1') ? 1 : 0;
   }
   // the operand arrays alias the E tile (>= 27 648 bytes) and the per-warp partials region
   return v != 0 && pb.L.pc >= 64 && pb.t1 > pb.t0 && (size_t)lin_ebudget(pb) * sizeof(float) >= (size_t)umma::X_BYTES;
@@ -1245,15 +1304,22 @@ static bool early_loads_enabled() {
 void launch_linearize(const Problem& pb, int64_t batch, cudaStream_t stream, bool fuse_update, bool first) {
   const int gx = chunk_grid(pb, batch);
   const int ebudget = lin_ebudget(pb);
-  const size_t lsm = lin_smem_bytes(pb.L.pc, ebudget);
+  const bool umma_on = schur_on_tcgen05(pb);
+  static int extra_smem = -1;                         // PGBA_LIN_EXTRA_SMEM=1: size the FFMA2 instance like the tcgen05 one (A/B probe)
+  if (extra_smem < 0) { const char* e = getenv("PGBA_LIN_EXTRA_SMEM"); extra_smem = (e && e[0] == '1') ? 1 : 0; }
+  const size_t lsm = lin_smem_bytes(pb.L.pc, ebudget, umma_on || extra_smem);
   const bool early = fuse_update && pb.t1 > pb.t0 && !pb.L.big && early_loads_enabled();
-  const int flags = (fuse_update ? 1 : 0) | (early ? 8 : 0) | (schur_on_tcgen05(pb) ? 16 : 0);
+  const int flags = (fuse_update ? 1 : 0) | (early ? 8 : 0) | (umma_on ? 16 : 0);
   auto go = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm);
     launch_k(kern, dim3((unsigned)gx, (unsigned)batch), dim3(256), lsm, stream, pb, ebudget, flags);
   };
   (void)first;
-  if (fuse_update) go(linearize_kernel<true>); else go(linearize_kernel<false>);
+  if (flags & 16) {
+    if (fuse_update) go(linearize_kernel<true, true>); else go(linearize_kernel<false, true>);
+  } else {
+    if (fuse_update) go(linearize_kernel<true, false>); else go(linearize_kernel<false, false>);
+  }
   count_launch();
 }
 

@@ -37,3 +37,7 @@ for k in (0, 1, 2, 3, 5, 4):
     e, w, x = (t[k, 0][m] - t0) / 1e3, (t[k, 1][m] - t0) / 1e3, (t[k, 2][m] - t0) / 1e3
     print("%-30s n=%3d  entry %.1f..%.1f  wait passed %.1f..%.1f  exit %.1f..%.1f  | CTA body (exit - wait) min %.1f med %.1f max %.1f"
           % (names[k], m.sum(), e.min(), e.max(), w.min(), w.max(), x.min(), x.max(), (x - w).min(), np.median(x - w), (x - w).max()))
+    busy = (x - w) > 2.0                     # CTAs that owned a chunk (the grid is sized for the worst-case chunk count)
+    if busy.any() and busy.sum() < m.sum():
+        b = (x - w)[busy]
+        print("%-30s    busy CTAs: n=%3d  body min %.1f p25 %.1f med %.1f p75 %.1f max %.1f us" % ("", busy.sum(), b.min(), np.percentile(b, 25), np.median(b), np.percentile(b, 75), b.max()))

@@ -15,10 +15,12 @@ for it in range(8):
     arm.call(); torch.cuda.synchronize()
     buf = (ctypes.c_longlong * 32)()
     L.pgba_debug_lin_timestamps(buf)
-    t = np.array(list(buf)[:12], dtype=np.float64)
+    t = np.array(list(buf)[:18], dtype=np.float64)
     acc.append(t - t[0])
 acc = np.median(np.array(acc[2:]), axis=0)
 names = ["start (after pdl_wait)", "chunk loaded, sync", "rel poses, sync", "patches staged, sync", "edge loop + H partials, sync",
-         "H reduced, sync", "Q per patch, sync", "E copy + Schur + y", "sync", "B1 (AH), sync", "B2 (Bii), sync", "B3 scatter"]
+         "H reduced, sync", "Q per patch, sync", "E copy + Schur + y", "sync", "B1 (AH), sync", "B2 (Bii), sync", "B3 scatter",
+         "umma: corner done", "umma: staged values read", "umma: operands written, fenced", "umma: MMAs issued (thread 0)",
+         "umma: accumulator complete", "umma: epilogue done"]
 for n, a, d in zip(names, acc, np.diff(np.concatenate([[0], acc]))):
-    print("%-32s t=%8.0f cyc  (+%6.0f)" % (n, a, d))
+    print("%-36s t=%8.0f cyc  (+%6.0f)" % (n, a, d))

@@ -12,11 +12,11 @@ from tests.helpers import to_dev, f32_problem, rel_err
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
 # Accuracy of the assembled S, y in units of 2^-23 (enters the forward-error bound of dX, dZ: cond(S) * relative error of S).
-# fp32 FMA assembly: ~0.5 (measured 1.2e-7 .. 1.4e-7).  Chunks of >= 64 patches (PGBA_PC = 64 / 128 in the forced-size runs;
-# chosen automatically only for batched windows and the global BA) take the Schur product on the tcgen05 tensor cores as a
-# 3xTF32 split with fp32 accumulation in TMEM: measured 2.8e-7 .. 6.3e-7 (profiles/microbench/schur_err.py), i.e. <= 6 units.
+# fp32 FMA assembly: ~0.5 (measured 1.2e-7 .. 1.4e-7).  With PGBA_SCHUR_UMMA=1 (opt-in A/B path) chunks of >= 64 patches
+# (PGBA_PC = 64 / 128 in the forced-size runs) take the Schur product on the tcgen05 tensor cores as a 3xTF32 split with fp32
+# accumulation in TMEM: measured 2.8e-7 .. 6.3e-7 (profiles/microbench/schur_err.py), i.e. <= 6 units.
 import os as _os
-_S_ULPS = 6.0 if (_os.environ.get("PGBA_PC") in ("64", "128") and _os.environ.get("PGBA_SCHUR_UMMA", "1") != "0") else 0.5
+_S_ULPS = 6.0 if (_os.environ.get("PGBA_PC") in ("64", "128") and _os.environ.get("PGBA_SCHUR_UMMA", "0") == "1") else 0.5
 
 
 def _oracle(p, iterations, debug=False, **over):
@@ -275,7 +275,7 @@ def test_global_ba_large_solver_normal_equations(F, M, n_loops):
     assert rel_err(g["y"].cpu().numpy(), o["y"]) < TOL
     S = g["S"].cpu().numpy().astype(np.float64)
     cond = np.linalg.cond(S + np.diag(1e-4 * np.diag(S) + 1.0))
-    tol_x = max(10 * TOL, 6.0 * cond * 2.0 ** -23)             # see test_normal_equations (large chunks: tcgen05 Schur)
+    tol_x = max(10 * TOL, _S_ULPS * cond * 2.0 ** -23)         # see test_normal_equations
     assert rel_err(g["dX"].cpu().numpy(), o["dX"]) < tol_x
     assert rel_err(g["dZ"].cpu().numpy(), o["dZ"]) < tol_x
 

@@ -3,6 +3,7 @@ import cuda_ba
 from cdvslam_b200 import native
 
 last_status = native.last_ba_status     # extension: PGBA_ST_* bits of the most recent BA call (0 = every edge processed)
+last_plan_hits = native.last_ba_plan_hits   # extension: windows of the most recent call that reused their plan tables
 neighbors = cuda_ba.neighbors
 reproject = cuda_ba.reproject
 

@@ -41,6 +41,7 @@ SIGNATURES = {
                                                      c_int, c_int, c_vp, c_sz, c_vp, ctypes.POINTER(ctypes.c_float)]),
     "pgba_launch_count": (ctypes.c_longlong, []),
     "pgba_ba_status_ptr": (c_vp, [c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_i64, c_i64]),
+    "pgba_ba_plan_hit_ptr": (c_vp, [c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_i64, c_i64]),
     "pgba_pgo_workspace_bytes": (c_int, [c_i64, ctypes.POINTER(c_sz)]),
     "pgba_pgo_solve": (c_int, [c_vp] * 5 + [c_i64, c_i64, ctypes.c_float, ctypes.c_float, c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "pgba_neighbors_workspace_bytes": (c_int, [c_i64, ctypes.POINTER(c_sz)]),
@@ -174,6 +175,36 @@ def last_ba_status(device=None):
         off = ptr - ws.data_ptr()
         st |= int(ws[off:off + 4].view(torch.int32).item())
     return st
+
+
+def last_ba_plan_hits(device=None):
+    """Number of windows of the most recent BA call on `device` that reused their plan tables (fingerprint match);
+    synchronises.  See include/pgba.h, "Plan cache"."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    rec = _last_ba.get(key)
+    if rec is None:
+        return 0
+    ws, E, F, K, t0, t1, batch = rec
+    torch.cuda.current_stream(dev).synchronize()
+    L = lib()
+    hits = 0
+    for b in range(batch):
+        ptr = L.pgba_ba_plan_hit_ptr(ws.data_ptr(), E, F, K, t0, t1, batch, b)
+        if ptr:
+            off = ptr - ws.data_ptr()
+            hits += int(ws[off:off + 4].view(torch.int32).item())
+    return hits
+
+
+def invalidate_plan_cache():
+    """Forget every cached plan (zero the descriptor at the start of every BA workspace): the next call on any of them
+    rebuilds its tables.  Used by bench.py to time the cold path."""
+    for key, buf in list(_workspaces.items()):
+        if key[0] == "ba":
+            buf[:256].zero_()
+    for buf in _retired:
+        buf[:256].zero_()
 
 
 def host_arena(n_edges, n_pose_rows, n_patch_rows, P=3):

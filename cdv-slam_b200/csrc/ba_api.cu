@@ -118,6 +118,16 @@ static int check_common(const void* poses, const void* patches, const void* intr
   return PGBA_OK;
 }
 
+// PGBA_PLAN_CACHE=0: rebuild the plan tables on every call even when the edge list is unchanged (A/B runs, cold timings)
+static bool plan_cache_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PGBA_PLAN_CACHE");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
 // patches per chunk: heuristic, or the PGBA_PC environment variable (8..128, power of two) for tuning
 static int pick_pc(int64_t E, int64_t batch) {
   static int forced = -1;
@@ -138,6 +148,8 @@ static Problem make_problem(float* poses, float* patches, const float* intrinsic
   pb.lmbda = lmbda; pb.ii = ii; pb.jj = jj; pb.kk = kk; pb.n_edges_dev = n_edges_dev;
   if (st) pb.st = *st;
   pb.E = E; pb.F = (int)F; pb.K = (int)K; pb.P = P; pb.t0 = t0; pb.t1 = t1; pb.with_schur = 1; pb.apply = 1;
+  pb.plan_cache = plan_cache_enabled() ? 1 : 0;
+  pb.batch = (int)batch;
   pb.ws = ws;
   pb.L = make_layout(E, F, K, t1 - t0, batch, pick_pc(E, batch));
   return pb;
@@ -420,6 +432,7 @@ int pgba_ba_linearize_debug(const float* poses, const float* patches, const floa
                    n_edges, n_pose_rows, n_patch_rows, P, t0, t1, workspace, workspace_bytes);
   if (rc) return rc;
   pb.with_schur = with_schur ? 1 : 0;
+  pb.plan_cache = 0;
   pb.apply = 0;                                  // nothing is modified; S, y stay in the workspace for the export
   cudaStream_t s = (cudaStream_t)stream;
   cudaError_t e = clear_workspace(pb, 1, s);
@@ -441,6 +454,14 @@ const int32_t* pgba_ba_status_ptr(const void* workspace, int64_t n_edges, int64_
   const Layout L = make_layout(n_edges, n_pose_rows, n_patch_rows, t1 - t0, batch, pick_pc(n_edges, batch));
   const WinHeader* h = (const WinHeader*)((const char*)workspace + (size_t)b * L.zero_bytes + L.z_hdr);
   return &h->status;
+}
+
+const int32_t* pgba_ba_plan_hit_ptr(const void* workspace, int64_t n_edges, int64_t n_pose_rows, int64_t n_patch_rows,
+                                    int t0, int t1, int64_t batch, int64_t b) {
+  if (!workspace || b < 0 || b >= batch || n_pose_rows <= 0 || n_patch_rows <= 0 || t1 < t0) return nullptr;
+  const Layout L = make_layout(n_edges, n_pose_rows, n_patch_rows, t1 - t0, batch, pick_pc(n_edges, batch));
+  const WinHeader* h = (const WinHeader*)((const char*)workspace + (size_t)b * L.zero_bytes + L.z_hdr);
+  return &h->plan_hit;
 }
 
 int pgba_reproject(const float* poses, const float* patches, const float* intrinsics, const int64_t* ii,

@@ -28,8 +28,17 @@ struct WinHeader {      // first thing in the zero region
   int n_valid_edges;
   int ticket[4];        // "last block done" counters of the plan kernels
   int chol_info;        // 0, or 1 + index of the first non-positive pivot (big solve)
-  int pad[3];
+  int plan_hit;         // 1: this call found the window's tables valid (fingerprint match) and skipped the graph analysis
+  int pad[2];
+  // plan cache (single-launch cluster plan only; the memset of the grid-wide path clears it): 128-bit fingerprint of the
+  // window's (ii, jj, kk, edge count) the tables below were built from, and -- window 0 only, i.e. at byte offset 64 + 16 of
+  // EVERY layout -- the descriptor of the call that last ran a plan on this workspace.  A window's tables are reused only if
+  // both match, so a call with another layout in between (which rewrites the descriptor) invalidates every window.
+  unsigned long long fp[2];
+  int desc[8];          // magic, E, F, K, t0, t1, pc, batch
 };
+static_assert(sizeof(WinHeader) <= 256, "the header must fit the first 256-byte slot of the zero region");
+constexpr int PLAN_DESC_MAGIC = 0x50474241;
 
 struct Chunk {          // 64 bytes
   int frame;            // source frame i
@@ -168,6 +177,8 @@ struct Problem {
   const int64_t* ii; const int64_t* jj; const int64_t* kk; const int32_t* n_edges_dev;
   pgba_strides st;
   int64_t E; int F; int K; int P; int t0; int t1; int with_schur; int apply;
+  int plan_cache;       // 1: reuse a window's plan tables when its edge list is unchanged since the last call (see WinHeader)
+  int batch;
   void* ws; Layout L;
 };
 

@@ -137,6 +137,18 @@ int pgba_ba_linearize_debug(const float* poses, const float* patches, const floa
 const int32_t* pgba_ba_status_ptr(const void* workspace, int64_t n_edges, int64_t n_pose_rows, int64_t n_patch_rows,
                                   int t0, int t1, int64_t batch, int64_t b);
 
+/* Plan cache.  The graph analysis of a call ("plan": chunk tables, edge permutation, cell tables -- what replaces
+ * at::_unique(kk) and the EfficentE constructor of the reference) depends only on ii / jj / kk and the call's sizes.  Windows
+ * handled by the single-launch plan (everything except the global BA and batches of more than 74 windows) keep a 128-bit
+ * fingerprint of their edge list in the workspace; a call that finds the workspace untouched since a call with the same
+ * sizes and an unchanged edge list (the 12 x initialisation loop of slam.py:715-716, repeated BA calls between two
+ * frames) skips the analysis: the index arrays are still read once (for the fingerprint), everything else is reused.
+ * Requirements on the caller: none beyond the existing one that the workspace is private to these calls (any write into it
+ * by other code must also clobber its first 256 bytes).  PGBA_PLAN_CACHE=0 in the environment disables the reuse.
+ * pgba_ba_plan_hit_ptr: device pointer to an i32 that is 1 when window b of the last call reused its tables. */
+const int32_t* pgba_ba_plan_hit_ptr(const void* workspace, int64_t n_edges, int64_t n_pose_rows, int64_t n_patch_rows,
+                                    int t0, int t1, int64_t batch, int64_t b);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Reprojection of all PxP pixels of each edge's patch from frame ii to frame jj.  Replaces cuda_ba.reproject ==
  * cuda_reproject() (reference: cdvslam/fastba/ba_cuda.cu:408-458, 614-645).  coords f32 [n_edges, 2, P, P].

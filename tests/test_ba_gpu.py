@@ -477,3 +477,64 @@ def test_batched_large_chunks_graph_replay_equals_eager_and_oracle():
         torch.cuda.synchronize()
         assert rel_err(bp.cpu().numpy(), eager[0].cpu().numpy()) < 1e-5
         assert rel_err(bq[:, :, 2].cpu().numpy(), eager[1][:, :, 2].cpu().numpy()) < 1e-5
+
+
+def test_plan_cache_reuses_tables_only_for_an_unchanged_edge_list():
+    """Plan cache (include/pgba.h): a second call with the same ii / jj / kk but different poses, depths, targets and
+    weights reuses the window's tables (plan_hit) and still matches the oracle; changing one index, the edge order, t0, or
+    running a call with another layout on the same workspace in between forces a rebuild -- and every result matches the
+    oracle either way."""
+    from cdvslam_b200 import native
+
+    def run(p, **kw):
+        d = to_dev(p)
+        fastba.BA(d["poses"], d["patches"], d["intrinsics"], d["target"], d["weight"], d["lmbda"], d["ii"], d["jj"], d["kk"],
+                  p.t0, p.t1, M=p.M, iterations=2)
+        torch.cuda.synchronize()
+        hits = fastba.last_plan_hits()
+        o_poses, o_patches = _oracle(p, 2)
+        _check_state(p, d["poses"][0].cpu().numpy().astype(np.float64), d["patches"][0].cpu().numpy().astype(np.float64),
+                     o_poses, o_patches, **kw)
+        return hits
+
+    native.invalidate_plan_cache()
+    a = synth.small_problem(seed=31, F=8, M=16, t0=3, lifetime=5)
+    assert run(a) == 0                                               # cold
+    b = synth.small_problem(seed=32, F=8, M=16, t0=3, lifetime=5)      # same graph, different numbers
+    assert np.array_equal(a.kk, b.kk) and np.array_equal(a.jj, b.jj) and not np.allclose(a.target, b.target)
+    assert run(b) == 1                                               # tables reused
+    c = synth.small_problem(seed=33, F=8, M=16, t0=3, lifetime=5)
+    c.jj = c.jj.copy(); e = int(np.nonzero(c.jj == 5)[0][0]); c.jj[e] = 4   # one edge re-targeted (a duplicate edge appears)
+    q = synth.make_problem("x", 8, (c.ii, c.jj, c.kk), 3, 8, 33, 16)
+    assert run(q, tol=2e-4) == 0                                     # rebuilt
+    assert run(q, tol=2e-4) == 1
+    perm = np.random.default_rng(0).permutation(q.E)                 # same edges, another order: the tables hold edge ids
+    q.ii, q.jj, q.kk, q.target, q.weight = q.ii[perm], q.jj[perm], q.kk[perm], q.target[perm], q.weight[perm]
+    assert run(q, tol=2e-4) == 0
+    assert run(a) == 0                                               # back to the first graph: rebuilt
+    assert run(a) == 1
+    a4 = synth.small_problem(seed=31, F=8, M=16, t0=4, lifetime=5)     # other t0: other free-pose columns
+    assert run(a4) == 0
+    # a call with another layout (a batch) on the same workspace in between invalidates the single-window tables
+    assert run(a) == 0 and run(a) == 1
+    probs = [synth.small_problem(seed=40 + s, F=8, M=16, t0=3, lifetime=5) for s in range(3)]
+    ds = [to_dev(x) for x in probs]
+    cat = lambda k: torch.cat([x[k] for x in ds], 0).contiguous()
+    idx = lambda k: torch.stack([x[k] for x in ds], 0).contiguous()
+    bp, bq = cat("poses"), cat("patches")
+    args = (cat("intrinsics"), cat("target"), cat("weight"), ds[0]["lmbda"], idx("ii"), idx("jj"), idx("kk"))
+    fastba.BA_batched(bp, bq, *args, probs[0].t0, probs[0].t1, M=16, iterations=2)
+    torch.cuda.synchronize()
+    assert fastba.last_plan_hits() == 0
+    assert run(a) == 0
+    fastba.BA_batched(bp, bq, *args, probs[0].t0, probs[0].t1, M=16, iterations=2)      # batch again: its windows rebuild too
+    torch.cuda.synchronize()
+    assert fastba.last_plan_hits() == 0
+    bp2, bq2 = cat("poses"), cat("patches")
+    fastba.BA_batched(bp2, bq2, *args, probs[0].t0, probs[0].t1, M=16, iterations=2)    # unchanged lists: all three windows hit
+    torch.cuda.synchronize()
+    assert fastba.last_plan_hits() == 3
+    for s_, p_ in enumerate(probs):
+        o_poses, o_patches = _oracle(p_, 2)
+        _check_state(p_, bp2[s_].cpu().numpy().astype(np.float64), bq2[s_].cpu().numpy().astype(np.float64), o_poses, o_patches,
+                     tol=2e-4)

@@ -36,6 +36,11 @@ struct WinHeader {      // first thing in the zero region
   // both match, so a call with another layout in between (which rewrites the descriptor) invalidates every window.
   unsigned long long fp[2];
   int desc[8];          // magic, E, F, K, t0, t1, pc, batch
+  // fingerprint accumulators: the CTAs of a window's cluster add their partial sums into acc[gen & 1]; the call also clears
+  // acc[(gen + 1) & 1] for the next one and increments gen (no barrier is needed to reset an accumulator that is in use)
+  unsigned long long acc[2][2];
+  unsigned int gen;
+  int pad2[3];
 };
 static_assert(sizeof(WinHeader) <= 256, "the header must fit the first 256-byte slot of the zero region");
 constexpr int PLAN_DESC_MAGIC = 0x50474241;

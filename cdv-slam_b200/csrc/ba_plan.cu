@@ -231,8 +231,8 @@ __global__ void __launch_bounds__(256) plan_cells_kernel(Problem pb) {
     int* d = win_ptrs(pb.ws, pb.L, 0).hdr->desc;
     d[0] = PLAN_DESC_MAGIC; d[1] = (int)pb.E; d[2] = pb.F; d[3] = pb.K; d[4] = pb.t0; d[5] = pb.t1; d[6] = pb.L.pc; d[7] = pb.batch;
   }
-  if (wp.hdr->plan_hit) return;                              // tables valid (plan_cluster_kernel found the edge list unchanged)
-  const int n_chunks = wp.hdr->n_chunks;
+  const int hit = wp.hdr->plan_hit, n_chunks = wp.hdr->n_chunks;    // two independent loads, one round trip
+  if (hit) return;                                           // tables valid (plan_cluster_kernel found the edge list unchanged)
   for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) build_chunk_cells(pb, wp, c, sc);
   PCTA_TS(1, 2);
 }
@@ -287,9 +287,11 @@ __global__ void __launch_bounds__(PLAN_T, 1) plan_cluster_kernel(Problem pb) {
     const int n16 = (int)(pb.L.zero_bytes >> 4);
     for (int x = 16 + gt; x < n16; x += GT) z[x] = make_uint4(0u, 0u, 0u, 0u);
   }
-  // edges of this thread (loads are independent of P0) and their share of the window's fingerprint
+  // edges of this thread (loads are independent of P0) and, with the plan cache on, their share of the window's fingerprint
   EdgeIdx keep[PLAN_KEEP];
   int bad = 0;
+  const bool use_cache = pb.plan_cache != 0;
+  const unsigned gen = use_cache ? wp.hdr->gen : 0u;     // which accumulator this call uses (rank 0 bumps it much later)
   unsigned long long h1 = 0ull, h2 = 0ull;
   auto mix = [](unsigned long long x) {
     x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 27; x *= 0x94d049bb133111ebull; x ^= x >> 31;
@@ -298,28 +300,26 @@ __global__ void __launch_bounds__(PLAN_T, 1) plan_cluster_kernel(Problem pb) {
   auto hash_edge = [&](int e, const EdgeIdx& x) {
     const unsigned long long a = ((unsigned long long)(unsigned)x.k << 32) | (unsigned)e;
     const unsigned long long b = ((unsigned long long)(unsigned)x.i << 32) | (unsigned)x.j;
-    h1 += mix(a ^ mix(b + 0x9e3779b97f4a7c15ull));
-    h2 += mix((a + 0x632be59bd9b4e019ull) * 0xd6e8feb86659fd93ull ^ b);
+    const unsigned long long m = mix(a ^ (b * 0x9e3779b97f4a7c15ull));
+    h1 += m;
+    h2 += mix(m + b);
   };
 #pragma unroll
   for (int q = 0; q < PLAN_KEEP; ++q) {
     const int e = gt + q * GT;
     keep[q] = load_edge(pb, ii, jj, kk, e, E);        // slots with q * GT >= E: ok = false, skipped below
     if (e < E && !keep[q].ok) bad = 1;
-    if (e < E) hash_edge(e, keep[q]);
+    if (use_cache && e < E) hash_edge(e, keep[q]);
   }
   const int e_rest = PLAN_KEEP * GT + (gt - lane);     // warp-uniform start of the part that is re-read
-  const bool use_cache = pb.plan_cache != 0;
   if (use_cache) {
     for (int e0 = e_rest; e0 < E; e0 += GT) {
       const int e = e0 + lane;
       if (e < E) hash_edge(e, load_edge(pb, ii, jj, kk, e, E));
     }
     if (gt == 0) h1 += mix((unsigned long long)E + 0x51ull);
-    // CTA partial: warp shuffles, then the 32 warp sums through shared memory
+    // CTA partial (warp shuffles, then the 32 warp sums through shared memory) -> two 64-bit atomics per CTA
     __shared__ unsigned long long s_wh[2][32];
-    __shared__ unsigned long long s_fp[2];             // this CTA's partial (read by the peers)
-    __shared__ unsigned long long s_tot[2];            // the window's fingerprint
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       h1 += __shfl_xor_sync(0xffffffffu, h1, o);
@@ -330,52 +330,49 @@ __global__ void __launch_bounds__(PLAN_T, 1) plan_cluster_kernel(Problem pb) {
     if (tid < 2) {
       unsigned long long t = 0ull;
       for (int x = 0; x < PLAN_T / 32; ++x) t += s_wh[tid][x];
-      s_fp[tid] = t;
+      atomicAdd(&wp.hdr->acc[gen & 1u][tid], t);
     }
-    PLAN_TS(1);
-    cl.sync();
-    PLAN_TS(2);
-    // window total = sum of the cluster's CTA partials (distributed shared memory); same value in every CTA
+  }
+  PLAN_TS(1);
+  cl.sync();
+  PLAN_TS(2);
+  if (use_cache) {
+    // window total: same value in every CTA (all partials were added before the barrier); one L2 round trip
     __shared__ int s_hit;
+    __shared__ unsigned long long s_tot[2];
     if (tid == 0) {
-      unsigned long long t1 = 0ull, t2 = 0ull;
-      for (int r = 0; r < PLAN_CL; ++r) {
-        const unsigned long long* peer = cl.map_shared_rank(s_fp, r);
-        t1 += peer[0]; t2 += peer[1];
-      }
+      const unsigned long long t1 = __ldcg(&wp.hdr->acc[gen & 1u][0]), t2 = __ldcg(&wp.hdr->acc[gen & 1u][1]);
+      const unsigned long long f1 = __ldcg(&wp.hdr->fp[0]), f2 = __ldcg(&wp.hdr->fp[1]);
       const int* d = win_ptrs(pb.ws, pb.L, 0).hdr->desc;
       const bool same_call = d[0] == PLAN_DESC_MAGIC && d[1] == (int)pb.E && d[2] == pb.F && d[3] == pb.K && d[4] == pb.t0 &&
                              d[5] == pb.t1 && d[6] == pb.L.pc && d[7] == pb.batch;
-      const bool hit = same_call && __ldcg(&wp.hdr->fp[0]) == t1 && __ldcg(&wp.hdr->fp[1]) == t2;
-      s_hit = hit ? 1 : 0;
+      s_hit = (same_call && f1 == t1 && f2 == t2) ? 1 : 0;
       s_tot[0] = t1; s_tot[1] = t2;
     }
-    cl.sync();                                         // every CTA has read its peers' partials; s_hit / totals are final
-    if (s_hit) {                                       // uniform over the cluster: the tables of the last call are valid
+    __syncthreads();
+    h1 = s_tot[0]; h2 = s_tot[1];                       // kept for the store at the end (rank 0, thread 0)
+    if (s_hit) {                                        // uniform over the cluster: the tables of the last call are valid
       if (rank == 0 && tid == 0) {
         wp.hdr->plan_hit = 1;
         wp.hdr->ticket[0] = wp.hdr->ticket[1] = wp.hdr->ticket[2] = wp.hdr->ticket[3] = 0;
         wp.hdr->chol_info = 0;
+        wp.hdr->acc[(gen + 1u) & 1u][0] = 0ull; wp.hdr->acc[(gen + 1u) & 1u][1] = 0ull;
+        wp.hdr->gen = gen + 1u;
       }
       PCTA_TS(0, 2);
       return;
     }
-    if (rank == 0 && tid == 0) {                       // rebuild: clear the header's plan fields, invalidate the fingerprint
-      int* hz = reinterpret_cast<int*>(wp.hdr);
-      for (int x = 0; x < 16; ++x) hz[x] = 0;
-      wp.hdr->fp[0] = ~s_tot[0];
-    }
-    h1 = s_tot[0]; h2 = s_tot[1];                      // kept for the store at the end (rank 0, thread 0)
-  } else {
-    if (rank == 0 && tid == 0) {
-      int* hz = reinterpret_cast<int*>(wp.hdr);
-      for (int x = 0; x < 16; ++x) hz[x] = 0;
-      wp.hdr->fp[0] = 0ull; wp.hdr->fp[1] = 0ull;
+  }
+  if (rank == 0 && tid == 0) {                          // rebuild: clear the header's plan fields, invalidate the fingerprint
+    int* hz = reinterpret_cast<int*>(wp.hdr);
+    for (int x = 0; x < 16; ++x) hz[x] = 0;
+    wp.hdr->fp[0] = ~h1; wp.hdr->fp[1] = 0x5aull;
+    if (use_cache) {
+      wp.hdr->acc[(gen + 1u) & 1u][0] = 0ull; wp.hdr->acc[(gen + 1u) & 1u][1] = 0ull;
+      wp.hdr->gen = gen + 1u;
+    } else {
       win_ptrs(pb.ws, pb.L, 0).hdr->desc[0] = 0;
     }
-    PLAN_TS(1);
-    cl.sync();
-    PLAN_TS(2);
   }
 
   // ---- P1: per source frame min / max patch id

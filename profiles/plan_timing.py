@@ -13,7 +13,7 @@ arm = bench.GpuArm(bench.make_workload(sys.argv[1] if len(sys.argv) > 1 else "c2
 L = native.lib()
 acc = []
 for it in range(8):
-    arm.restore(); arm.flush_l2(); torch.cuda.synchronize()
+    arm.restore(); native.invalidate_plan_cache(); arm.flush_l2(); torch.cuda.synchronize()
     arm.call(); torch.cuda.synchronize()
     buf = (ctypes.c_ulonglong * 16)()
     L.pgba_debug_plan_timestamps(buf)

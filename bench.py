@@ -237,7 +237,7 @@ class GpuArm:
         d2h = sum(v.numel() * v.element_size() for v in self.out_h.values())
         return [a.elapsed_time(b) for a, b in evs], h2d, d2h
 
-    def timed_e2e_host(self, steps, use_graph, arena=False):
+    def timed_e2e_host(self, steps, use_graph, arena=False, idx32=False):
         """Host-buffer entry point (fastba.BA_host -> pgba_ba_solve_host): pinned host tensors in, results written back
         into them; H2D of every input and D2H of poses / patches are inside the call.  The state is not reset between
         steps (the in-place host tensors keep being refined; the work per call does not depend on the values)."""
@@ -245,7 +245,7 @@ class GpuArm:
         p = self.p0
         if arena:       # the nine tensors as views of one pinned allocation (native.host_arena): 2 uploads + 1 download
             hh = self.native.host_arena(self.h["ii"].shape[-1], self.h["poses"].shape[1], self.h["patches"].shape[1],
-                                        self.h["patches"].shape[-1])
+                                        self.h["patches"].shape[-1], index_dtype=torch.int32 if idx32 else torch.int64)
             for k, v in self.h.items():
                 hh[k].view(-1).copy_(v.reshape(-1)) if k not in ("ii", "jj", "kk") else hh[k].copy_(v[0])
             hh = {k: (v[None] if k in ("ii", "jj", "kk") else v) for k, v in hh.items()}
@@ -662,9 +662,11 @@ def main():
     e2e_modes["device_api_with_torch_copies"] = sum(e2e_ms) / args.steps
     e2e_mode = "device_api_with_torch_copies"
     if arm.B == 1:
-        for use_graph, arena in ((False, False), (True, False), (False, True), (True, True)):
-            ms_h, h2d_h, d2h_h = arm.timed_e2e_host(args.steps, use_graph, arena)
-            name = ("host_api_arena" if arena else "host_api") + ("_graph_replay" if use_graph else "_eager")
+        for use_graph, arena, idx32 in ((False, False, False), (True, False, False), (False, True, False), (True, True, False),
+                                        (False, True, True), (True, True, True)):
+            ms_h, h2d_h, d2h_h = arm.timed_e2e_host(args.steps, use_graph, arena, idx32)
+            name = ("host_api_arena" if arena else "host_api") + ("_i32idx" if idx32 else "") + \
+                ("_graph_replay" if use_graph else "_eager")
             e2e_modes[name] = sum(ms_h) / args.steps
             if sum(ms_h) < sum(e2e_ms):
                 e2e_ms, h2d, d2h, e2e_mode = ms_h, h2d_h, d2h_h, name

@@ -33,7 +33,10 @@ SIGNATURES = {
                                                      c_int, c_int, c_int, c_int, c_vp, c_sz, c_vp]),
     "pgba_ba_host_staging_bytes": (c_int, [c_i64, c_i64, c_i64, c_int, ctypes.POINTER(c_sz)]),
     "pgba_ba_host_arena_offsets": (c_int, [c_i64, c_i64, c_i64, c_int, ctypes.POINTER(c_sz), ctypes.POINTER(c_sz)]),
+    "pgba_ba_host_arena_offsets_i32": (c_int, [c_i64, c_i64, c_i64, c_int, ctypes.POINTER(c_sz), ctypes.POINTER(c_sz)]),
     "pgba_ba_solve_host": (c_int, [c_vp] * 9 + [c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_sz,
+                                                c_vp, c_sz, c_vp, c_vp]),
+    "pgba_ba_solve_host_i32": (c_int, [c_vp] * 9 + [c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_sz,
                                                 c_vp, c_sz, c_vp, c_vp]),
     "pgba_ba_linearize_debug": (c_int, [c_vp] * 9 + [c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int] + [c_vp] * 10 +
                                 [c_vp, c_sz, c_vp]),
@@ -207,14 +210,15 @@ def invalidate_plan_cache():
         buf[:256].zero_()
 
 
-def host_arena(n_edges, n_pose_rows, n_patch_rows, P=3):
+def host_arena(n_edges, n_pose_rows, n_patch_rows, P=3, index_dtype=torch.int64):
     """One pinned host allocation holding the nine input tensors of fastba.BA_host at the offsets of
     pgba_ba_host_arena_offsets (views with the reference's shapes, leading batch dim of 1).  BA_host then moves the
-    problem with two uploads and one download instead of nine + two."""
+    problem with two uploads and one download instead of nine + two.  index_dtype=torch.int32: ii / jj / kk views are
+    32-bit (pgba_ba_host_arena_offsets_i32): half the index upload."""
     offs = (c_sz * 9)()
     total = c_sz(0)
-    check(lib().pgba_ba_host_arena_offsets(n_edges, n_pose_rows, n_patch_rows, P, offs, ctypes.byref(total)),
-          "pgba_ba_host_arena_offsets")
+    fn = lib().pgba_ba_host_arena_offsets_i32 if index_dtype == torch.int32 else lib().pgba_ba_host_arena_offsets
+    check(fn(n_edges, n_pose_rows, n_patch_rows, P, offs, ctypes.byref(total)), "pgba_ba_host_arena_offsets")
     buf = torch.zeros(total.value, dtype=torch.uint8).pin_memory()
     E, F, K = n_edges, n_pose_rows, n_patch_rows
 
@@ -224,4 +228,4 @@ def host_arena(n_edges, n_pose_rows, n_patch_rows, P=3):
     return dict(_arena=buf, poses=view(0, torch.float32, (1, F, 7)), patches=view(1, torch.float32, (1, K, 3, P, P)),
                 intrinsics=view(2, torch.float32, (1, F, 4)), target=view(3, torch.float32, (1, E, 2)),
                 weight=view(4, torch.float32, (1, E, 2)), lmbda=view(5, torch.float32, (1,)),
-                ii=view(6, torch.int64, (E,)), jj=view(7, torch.int64, (E,)), kk=view(8, torch.int64, (E,)))
+                ii=view(6, index_dtype, (E,)), jj=view(7, index_dtype, (E,)), kk=view(8, index_dtype, (E,)))

@@ -160,6 +160,79 @@ static cudaError_t clear_workspace(const Problem& pb, int64_t batch, cudaStream_
   if (plan_clears_workspace(pb, batch)) return cudaSuccess;          // done by the first phase of plan_cluster_kernel
   return cudaMemsetAsync(pb.ws, 0, pb.L.zero_bytes * (size_t)batch, s);
 }
+
+// ---- window groups.  A batched call runs plan -> k x (linearize -> solve -> update).  The linearisation is throughput
+// bound (every SM busy); the small solve (one CTA per window) and the back-substitution are latency bound and leave most of
+// the machine idle for ~35 us per iteration on the 64-window batch.  The windows are independent, so the call splits them
+// into up to four groups after the plan: group 0 stays on the caller's stream, the others run their iterations on
+// auxiliary streams (forked and joined with events, so the whole call is still one capturable unit of work on the
+// caller's stream) and the solve / update of one group overlaps the linearisation of the next.
+// PGBA_BATCH_GROUPS=1..4 overrides the group count (A/B runs).
+constexpr int MAX_GROUPS = 4;
+struct GroupCtx { int dev; cudaStream_t main; cudaStream_t aux[MAX_GROUPS - 1]; cudaEvent_t fork, join[MAX_GROUPS - 1]; };
+
+static GroupCtx* group_ctx(cudaStream_t s) {
+  static std::mutex mu;
+  static std::vector<GroupCtx*> cache;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  for (GroupCtx* c : cache)
+    if (c->dev == dev && c->main == s) return c;
+  GroupCtx* c = new GroupCtx{};
+  c->dev = dev; c->main = s;
+  bool ok = cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming) == cudaSuccess;
+  for (int g = 0; g < MAX_GROUPS - 1 && ok; ++g)
+    ok = cudaStreamCreateWithFlags(&c->aux[g], cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&c->join[g], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) { (void)cudaGetLastError(); delete c; return nullptr; }      // (leaks the few handles created so far; never seen)
+  cache.push_back(c);
+  return c;
+}
+
+static int batch_groups(const Problem& pb, int64_t batch) {
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("PGBA_BATCH_GROUPS"); forced = e ? atoi(e) : 0; }
+  int g = 1;
+  if (!pb.L.big && pb.t1 > pb.t0) g = batch >= 32 ? 4 : (batch >= 16 ? 2 : 1);
+  if (forced >= 1 && forced <= MAX_GROUPS) g = forced;
+  if (g > batch) g = (int)batch;
+  return g < 1 ? 1 : g;
+}
+
+// plan + iterations of a batch, on window groups when that pays.  The workspace's zero regions have been dealt with
+// (clear_workspace) on `s`.  The plan of all windows runs first, on the caller's stream: its CTAs (1024 threads, the whole
+// register file of an SM) cannot share an SM with the linearisation's, so a plan per group would not overlap anything
+// (measured: 318 - 365 us against 316 us on the 64-window batch, profiles/README.md round 2).
+static cudaError_t launch_planned(const Problem& pb, int64_t batch, int iterations, cudaStream_t s) {
+  launch_plan(pb, batch, s);
+  const int G = batch_groups(pb, batch);
+  GroupCtx* gc = G > 1 ? group_ctx(s) : nullptr;
+  cudaError_t e = cudaSuccess;
+  if (!gc) {
+    for (int it = 0; it < iterations && e == cudaSuccess; ++it) e = launch_iteration(pb, batch, s, nullptr, it == 0, it + 1 < iterations);
+    return e;
+  }
+  e = cudaEventRecord(gc->fork, s);
+  if (e != cudaSuccess) return e;
+  cudaError_t first_err = cudaSuccess;
+  for (int g = 0; g < G; ++g) {
+    cudaStream_t sg = g == 0 ? s : gc->aux[g - 1];
+    cudaError_t eg = g == 0 ? cudaSuccess : cudaStreamWaitEvent(sg, gc->fork, 0);
+    Problem pg = pb;
+    pg.w0 = (int)(batch * g / G);
+    const int64_t nb = batch * (g + 1) / G - pg.w0;
+    for (int it = 0; it < iterations && eg == cudaSuccess && nb > 0; ++it)
+      eg = launch_iteration(pg, nb, sg, nullptr, it == 0, it + 1 < iterations);
+    if (g > 0) {                                    // joined whatever happened: an unjoined fork would break a stream capture
+      cudaError_t ej = cudaEventRecord(gc->join[g - 1], sg);
+      if (ej == cudaSuccess) ej = cudaStreamWaitEvent(s, gc->join[g - 1], 0);
+      if (eg == cudaSuccess) eg = ej;
+    }
+    if (first_err == cudaSuccess) first_err = eg;
+  }
+  return first_err;
+}
 }  // namespace pgba
 
 using namespace pgba;
@@ -223,11 +296,8 @@ int pgba_ba_solve_batched(float* poses, float* patches, const float* intrinsics,
   cudaStream_t s = (cudaStream_t)stream;
   cudaError_t e = clear_workspace(pb, batch, s);
   if (e != cudaSuccess) return (int)e;
-  launch_plan(pb, batch, s);
-  for (int it = 0; it < iterations; ++it) {
-    e = launch_iteration(pb, batch, s, nullptr, it == 0, it + 1 < iterations);
-    if (e != cudaSuccess) return (int)e;
-  }
+  e = launch_planned(pb, batch, iterations, s);
+  if (e != cudaSuccess) return (int)e;
   return (int)cudaGetLastError();
 }
 
@@ -285,7 +355,7 @@ int pgba_ba_solve(float* poses, float* patches, const float* intrinsics, const f
 // ---- host-buffer entry point -------------------------------------------------------------------------------------
 namespace {
 struct HostStage { size_t poses, patches, intr, target, weight, lmbda, ii, jj, kk, total; };
-HostStage host_stage(int64_t E, int64_t F, int64_t K, int P) {
+HostStage host_stage(int64_t E, int64_t F, int64_t K, int P, int index_bits = 64) {
   HostStage h{};
   size_t o = 0;
   h.poses = o;   o = align256(o + sizeof(float) * 7 * (size_t)F);
@@ -294,9 +364,10 @@ HostStage host_stage(int64_t E, int64_t F, int64_t K, int P) {
   h.target = o;  o = align256(o + sizeof(float) * 2 * (size_t)E);
   h.weight = o;  o = align256(o + sizeof(float) * 2 * (size_t)E);
   h.lmbda = o;   o = align256(o + sizeof(float));
-  h.ii = o;      o = align256(o + sizeof(int64_t) * (size_t)E);
-  h.jj = o;      o = align256(o + sizeof(int64_t) * (size_t)E);
-  h.kk = o;      o = align256(o + sizeof(int64_t) * (size_t)E);
+  const size_t ib = index_bits == 32 ? sizeof(int32_t) : sizeof(int64_t);
+  h.ii = o;      o = align256(o + ib * (size_t)E);
+  h.jj = o;      o = align256(o + ib * (size_t)E);
+  h.kk = o;      o = align256(o + ib * (size_t)E);
   h.total = o;
   return h;
 }
@@ -341,19 +412,30 @@ int pgba_ba_host_arena_offsets(int64_t n_edges, int64_t n_pose_rows, int64_t n_p
   return PGBA_OK;
 }
 
-int pgba_ba_solve_host(float* poses_h, float* patches_h, const float* intrinsics_h, const float* target_h,
-                       const float* weight_h, const float* lmbda_h, const int64_t* ii_h, const int64_t* jj_h,
-                       const int64_t* kk_h, int64_t n_edges, int64_t n_pose_rows, int64_t n_patch_rows, int P, int ppf,
-                       int t0, int t1, int iterations, int eff_impl, void* staging, size_t staging_bytes,
-                       void* workspace, size_t workspace_bytes, pgba_stream_t stream, pgba_stream_t aux_stream) {
-  (void)ppf; (void)eff_impl;
+int pgba_ba_host_arena_offsets_i32(int64_t n_edges, int64_t n_pose_rows, int64_t n_patch_rows, int P, size_t* offsets9,
+                                   size_t* bytes) {
+  if (!offsets9 || !bytes) return PGBA_ERR_NULL;
+  if (n_edges < 0 || n_pose_rows <= 0 || n_patch_rows <= 0 || P < 2) return PGBA_ERR_SHAPE;
+  const HostStage h = host_stage(n_edges, n_pose_rows, n_patch_rows, P, 32);
+  const size_t o[9] = {h.poses, h.patches, h.intr, h.target, h.weight, h.lmbda, h.ii, h.jj, h.kk};
+  for (int i = 0; i < 9; ++i) offsets9[i] = o[i];
+  *bytes = h.total;
+  return PGBA_OK;
+}
+
+static int solve_host_impl(float* poses_h, float* patches_h, const float* intrinsics_h, const float* target_h,
+                           const float* weight_h, const float* lmbda_h, const void* ii_h, const void* jj_h,
+                           const void* kk_h, int index_bits, int64_t n_edges, int64_t n_pose_rows, int64_t n_patch_rows,
+                           int P, int t0, int t1, int iterations, void* staging, size_t staging_bytes, void* workspace,
+                           size_t workspace_bytes, pgba_stream_t stream, pgba_stream_t aux_stream) {
   if (iterations < 0) return PGBA_ERR_SHAPE;
   if (!staging || ((uintptr_t)staging & 255)) return PGBA_ERR_WORKSPACE;
   int rc = check_common(poses_h, patches_h, intrinsics_h, target_h, weight_h, lmbda_h, ii_h, jj_h, kk_h, n_edges,
                         n_pose_rows, n_patch_rows, P, t0, t1);
   if (rc) return rc;
-  const HostStage h = host_stage(n_edges, n_pose_rows, n_patch_rows, P);
+  const HostStage h = host_stage(n_edges, n_pose_rows, n_patch_rows, P, index_bits);
   if (h.total > staging_bytes) return PGBA_ERR_WORKSPACE;
+  const size_t ib = index_bits == 32 ? 4 : 8;
   char* sb = (char*)staging;
   float* d_poses = (float*)(sb + h.poses);
   float* d_patches = (float*)(sb + h.patches);
@@ -364,6 +446,7 @@ int pgba_ba_solve_host(float* poses_h, float* patches_h, const float* intrinsics
                (const int64_t*)(sb + h.jj), (const int64_t*)(sb + h.kk), nullptr, &st, 1, n_edges, n_pose_rows,
                n_patch_rows, P, t0, t1, workspace, workspace_bytes);
   if (rc) return rc;
+  pb.idx32 = index_bits == 32 ? 1 : 0;
   if (iterations == 0 || n_edges == 0) return PGBA_OK;
   cudaStream_t s = (cudaStream_t)stream, a = (cudaStream_t)aux_stream;
   cudaEvent_t* ev = stage_events(s);
@@ -388,9 +471,9 @@ int pgba_ba_solve_host(float* poses_h, float* patches_h, const float* intrinsics
     PGBA_TRY(cudaMemcpyAsync(sb + h.ii, hb + h.ii, h.total - h.ii, cudaMemcpyHostToDevice, s));
     PGBA_TRY(cudaMemcpyAsync(sb, hb, h.ii, cudaMemcpyHostToDevice, a));
   } else {
-    PGBA_TRY(cudaMemcpyAsync(sb + h.ii, ii_h, 8 * E, cudaMemcpyHostToDevice, s));
-    PGBA_TRY(cudaMemcpyAsync(sb + h.jj, jj_h, 8 * E, cudaMemcpyHostToDevice, s));
-    PGBA_TRY(cudaMemcpyAsync(sb + h.kk, kk_h, 8 * E, cudaMemcpyHostToDevice, s));
+    PGBA_TRY(cudaMemcpyAsync(sb + h.ii, ii_h, ib * E, cudaMemcpyHostToDevice, s));
+    PGBA_TRY(cudaMemcpyAsync(sb + h.jj, jj_h, ib * E, cudaMemcpyHostToDevice, s));
+    PGBA_TRY(cudaMemcpyAsync(sb + h.kk, kk_h, ib * E, cudaMemcpyHostToDevice, s));
     PGBA_TRY(cudaMemcpyAsync(sb + h.target, target_h, 8 * E, cudaMemcpyHostToDevice, a));
     PGBA_TRY(cudaMemcpyAsync(sb + h.weight, weight_h, 8 * E, cudaMemcpyHostToDevice, a));
     PGBA_TRY(cudaMemcpyAsync(d_patches, patches_h, sizeof(float) * 3 * P * P * (size_t)n_patch_rows, cudaMemcpyHostToDevice, a));
@@ -418,6 +501,28 @@ int pgba_ba_solve_host(float* poses_h, float* patches_h, const float* intrinsics
 #undef PGBA_TRY
   if (e != cudaSuccess) return (int)e;
   return (int)cudaGetLastError();
+}
+
+int pgba_ba_solve_host(float* poses_h, float* patches_h, const float* intrinsics_h, const float* target_h,
+                       const float* weight_h, const float* lmbda_h, const int64_t* ii_h, const int64_t* jj_h,
+                       const int64_t* kk_h, int64_t n_edges, int64_t n_pose_rows, int64_t n_patch_rows, int P, int ppf,
+                       int t0, int t1, int iterations, int eff_impl, void* staging, size_t staging_bytes,
+                       void* workspace, size_t workspace_bytes, pgba_stream_t stream, pgba_stream_t aux_stream) {
+  (void)ppf; (void)eff_impl;
+  return solve_host_impl(poses_h, patches_h, intrinsics_h, target_h, weight_h, lmbda_h, ii_h, jj_h, kk_h, 64, n_edges,
+                         n_pose_rows, n_patch_rows, P, t0, t1, iterations, staging, staging_bytes, workspace, workspace_bytes,
+                         stream, aux_stream);
+}
+
+int pgba_ba_solve_host_i32(float* poses_h, float* patches_h, const float* intrinsics_h, const float* target_h,
+                           const float* weight_h, const float* lmbda_h, const int32_t* ii_h, const int32_t* jj_h,
+                           const int32_t* kk_h, int64_t n_edges, int64_t n_pose_rows, int64_t n_patch_rows, int P, int ppf,
+                           int t0, int t1, int iterations, int eff_impl, void* staging, size_t staging_bytes,
+                           void* workspace, size_t workspace_bytes, pgba_stream_t stream, pgba_stream_t aux_stream) {
+  (void)ppf; (void)eff_impl;
+  return solve_host_impl(poses_h, patches_h, intrinsics_h, target_h, weight_h, lmbda_h, ii_h, jj_h, kk_h, 32, n_edges,
+                         n_pose_rows, n_patch_rows, P, t0, t1, iterations, staging, staging_bytes, workspace, workspace_bytes,
+                         stream, aux_stream);
 }
 
 int pgba_ba_linearize_debug(const float* poses, const float* patches, const float* intrinsics, const float* target,

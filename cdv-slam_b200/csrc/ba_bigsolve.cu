@@ -34,7 +34,7 @@ struct BaBigSys {
 __global__ void big_damp_kernel(Problem pb) {
   pdl_wait();
   pdl_trigger();
-  const int w = blockIdx.y;
+  const int w = blockIdx.y + pb.w0;
   const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
   const int n6 = 6 * (pb.t1 - pb.t0);
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -47,7 +47,7 @@ __global__ void big_damp_kernel(Problem pb) {
 __global__ void big_finish_kernel(Problem pb) {
   pdl_wait();
   pdl_trigger();
-  const int w = blockIdx.y;
+  const int w = blockIdx.y + pb.w0;
   const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
   const int N = pb.t1 - pb.t0;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -30,17 +30,13 @@ struct WinHeader {      // first thing in the zero region
   int chol_info;        // 0, or 1 + index of the first non-positive pivot (big solve)
   int plan_hit;         // 1: this call found the window's tables valid (fingerprint match) and skipped the graph analysis
   int pad[2];
-  // plan cache (single-launch cluster plan only; the memset of the grid-wide path clears it): 128-bit fingerprint of the
-  // window's (ii, jj, kk, edge count) the tables below were built from, and -- window 0 only, i.e. at byte offset 64 + 16 of
+  // plan cache (single-launch cluster plans only; the memset of the grid-wide path clears it): 128-bit fingerprint of the
+  // window's (ii, jj, kk, edge count) the tables below were built from (per-CTA partial sums, combined over the window's
+  // cluster through distributed shared memory -- no global accumulator, so stale workspace contents cannot leak into it), and -- window 0 only, i.e. at byte offset 64 + 16 of
   // EVERY layout -- the descriptor of the call that last ran a plan on this workspace.  A window's tables are reused only if
   // both match, so a call with another layout in between (which rewrites the descriptor) invalidates every window.
   unsigned long long fp[2];
   int desc[8];          // magic, E, F, K, t0, t1, pc, batch
-  // fingerprint accumulators: the CTAs of a window's cluster add their partial sums into acc[gen & 1]; the call also clears
-  // acc[(gen + 1) & 1] for the next one and increments gen (no barrier is needed to reset an accumulator that is in use)
-  unsigned long long acc[2][2];
-  unsigned int gen;
-  int pad2[3];
 };
 static_assert(sizeof(WinHeader) <= 256, "the header must fit the first 256-byte slot of the zero region");
 constexpr int PLAN_DESC_MAGIC = 0x50474241;
@@ -184,6 +180,8 @@ struct Problem {
   int64_t E; int F; int K; int P; int t0; int t1; int with_schur; int apply;
   int plan_cache;       // 1: reuse a window's plan tables when its edge list is unchanged since the last call (see WinHeader)
   int batch;
+  int w0;               // first window handled by this launch (window groups on separate streams; 0 otherwise)
+  int idx32;            // 1: ii / jj / kk point to int32 arrays (host-buffer entry with 32-bit index uploads)
   void* ws; Layout L;
 };
 

@@ -356,6 +356,12 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
     CTA_TS((flags & 1) ? 3 : 0, 1);
     LIN_TS(0);
   }
+  if ((flags & 32) && waited && blockIdx.x == 0 && blockIdx.y == 0 && pb.w0 == 0 && threadIdx.x == 0) {
+    // first linearisation after a plan: record the descriptor of the call whose tables this workspace now holds (plan cache,
+    // see WinHeader; written here, after every window's plan has completed, because the windows' plan clusters read it)
+    int* d = win_ptrs(pb.ws, pb.L, 0).hdr->desc;
+    d[0] = PLAN_DESC_MAGIC; d[1] = (int)pb.E; d[2] = pb.F; d[3] = pb.K; d[4] = pb.t0; d[5] = pb.t1; d[6] = pb.L.pc; d[7] = pb.batch;
+  }
   extern __shared__ __align__(16) float smem[];
   // tcgen05 Schur product (flags & 16): per-CTA tensor-memory allocation + one mbarrier, released at the end of the kernel
   __shared__ uint32_t s_tmem;
@@ -377,7 +383,7 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
   s.sSq = s.sAH + SMAX * 36;                           // only touched by the tcgen05 instance
   float* sAH = s.sAH;
 
-  const int w = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int w = blockIdx.y + pb.w0, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
   const float* poses = pb.poses + (int64_t)w * pb.st.poses;
   const float* patches = pb.patches + (int64_t)w * pb.st.patches;
@@ -978,7 +984,7 @@ __global__ void __launch_bounds__(256, 1) solve_small_kernel(Problem pb) {
   CTA_TS(1, 1);
   extern __shared__ float sf[];
   SOLVE_TS(0);
-  const int w = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int w = blockIdx.x + pb.w0, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
   const int N = pb.t1 - pb.t0, n = 6 * N, ld = n | 1;
   float* A = sf;                   // [n + 1][ld]; row n = right-hand side
@@ -1163,7 +1169,7 @@ __global__ void __launch_bounds__(256) update_kernel(Problem pb, int early) {
   bool waited = early == 0;
   if (waited) { pdl_wait(); pdl_trigger(); CTA_TS(2, 1); }
   __shared__ __align__(8) float sdx[(SMAX + 1) * 6];
-  const int w = blockIdx.y;
+  const int w = blockIdx.y + pb.w0;
   const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
   float* patches = pb.patches + (int64_t)w * pb.st.patches;
   const int n_chunks = wp.hdr->n_chunks;
@@ -1192,7 +1198,7 @@ __global__ void __launch_bounds__(256) update_large_kernel(Problem pb, int early
   float* sdx = usm + tile_floats;
   bool waited = early == 0;
   if (waited) { pdl_wait(); pdl_trigger(); CTA_TS(2, 1); }
-  const int w = blockIdx.y, tid = threadIdx.x;
+  const int w = blockIdx.y + pb.w0, tid = threadIdx.x;
   const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
   float* patches = pb.patches + (int64_t)w * pb.st.patches;
   const int N = pb.t1 - pb.t0, t0 = pb.t0;
@@ -1309,12 +1315,11 @@ void launch_linearize(const Problem& pb, int64_t batch, cudaStream_t stream, boo
   if (extra_smem < 0) { const char* e = getenv("PGBA_LIN_EXTRA_SMEM"); extra_smem = (e && e[0] == '1') ? 1 : 0; }
   const size_t lsm = lin_smem_bytes(pb.L.pc, ebudget, umma_on || extra_smem);
   const bool early = fuse_update && pb.t1 > pb.t0 && !pb.L.big && early_loads_enabled();
-  const int flags = (fuse_update ? 1 : 0) | (early ? 8 : 0) | (umma_on ? 16 : 0);
+  const int flags = (fuse_update ? 1 : 0) | (early ? 8 : 0) | (umma_on ? 16 : 0) | (first ? 32 : 0);
   auto go = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm);
     launch_k(kern, dim3((unsigned)gx, (unsigned)batch), dim3(256), lsm, stream, pb, ebudget, flags);
   };
-  (void)first;
   if (flags & 16) {
     if (fuse_update) go(linearize_kernel<true, true>); else go(linearize_kernel<false, true>);
   } else {

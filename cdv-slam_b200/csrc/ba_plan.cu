@@ -44,7 +44,12 @@ __device__ __forceinline__ EdgeIdx load_edge(const Problem& pb, const int64_t* i
   EdgeIdx r;
   r.ok = false; r.i = -1; r.j = 0; r.k = 0;
   if (e < E) {
-    const int64_t i = ii[e], j = jj[e], k = kk[e];
+    int64_t i, j, k;
+    if (pb.idx32) {
+      i = reinterpret_cast<const int32_t*>(ii)[e]; j = reinterpret_cast<const int32_t*>(jj)[e]; k = reinterpret_cast<const int32_t*>(kk)[e];
+    } else {
+      i = ii[e]; j = jj[e]; k = kk[e];
+    }
     r.ok = !(i < 0 || i >= pb.F || j < 0 || j >= pb.F || k < 0 || k >= pb.K);
     if (r.ok) { r.i = (int)i; r.j = (int)j; r.k = (int)k; }
   }
@@ -73,7 +78,7 @@ __global__ void __launch_bounds__(256) plan_frames_kernel(Problem pb) {
   pdl_wait();
   pdl_trigger();
   __shared__ int scratch[40];
-  const int w = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  const int w = blockIdx.y + pb.w0, tid = threadIdx.x, lane = tid & 31;
   const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
   const int64_t* ii = pb.ii + (int64_t)w * pb.st.ii;
   const int64_t* jj = pb.jj + (int64_t)w * pb.st.jj;
@@ -142,7 +147,7 @@ __global__ void __launch_bounds__(256) plan_count_kernel(Problem pb) {
   pdl_wait();
   pdl_trigger();
   __shared__ int scratch[40];
-  const int w = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  const int w = blockIdx.y + pb.w0, tid = threadIdx.x, lane = tid & 31;
   const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
   const int64_t* ii = pb.ii + (int64_t)w * pb.st.ii;
   const int64_t* jj = pb.jj + (int64_t)w * pb.st.jj;
@@ -185,7 +190,7 @@ __global__ void __launch_bounds__(256) plan_count_kernel(Problem pb) {
 __global__ void __launch_bounds__(256) plan_scatter_kernel(Problem pb) {
   pdl_wait();
   pdl_trigger();
-  const int w = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  const int w = blockIdx.y + pb.w0, tid = threadIdx.x, lane = tid & 31;
   const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
   const int64_t* ii = pb.ii + (int64_t)w * pb.st.ii;
   const int64_t* jj = pb.jj + (int64_t)w * pb.st.jj;
@@ -225,7 +230,7 @@ __global__ void __launch_bounds__(256) plan_cells_kernel(Problem pb) {
   pdl_trigger();
   PCTA_TS(1, 1);
   __shared__ CellScratch sc;
-  const int w = blockIdx.y;
+  const int w = blockIdx.y + pb.w0;
   const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
   if (blockIdx.x == 0 && w == 0 && threadIdx.x == 0) {      // descriptor of the call whose tables this workspace now holds
     int* d = win_ptrs(pb.ws, pb.L, 0).hdr->desc;
@@ -266,8 +271,9 @@ __global__ void __launch_bounds__(PLAN_T, 1) plan_cluster_kernel(Problem pb) {
   PLAN_TS(0);
   extern __shared__ int psm[];
   __shared__ int scratch[40];
+  __shared__ unsigned long long s_part[2];           // this CTA's fingerprint sums (read by the others through DSMEM)
   cg::cluster_group cl = cg::this_cluster();
-  const int w = blockIdx.y, tid = threadIdx.x, lane = tid & 31, T = PLAN_T;
+  const int w = blockIdx.y + pb.w0, tid = threadIdx.x, lane = tid & 31, T = PLAN_T;
   const int rank = blockIdx.x;                       // the cluster spans the x dimension of the grid
   const int gt = rank * PLAN_T + tid, GT = PLAN_CL * PLAN_T;
   const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
@@ -291,7 +297,6 @@ __global__ void __launch_bounds__(PLAN_T, 1) plan_cluster_kernel(Problem pb) {
   EdgeIdx keep[PLAN_KEEP];
   int bad = 0;
   const bool use_cache = pb.plan_cache != 0;
-  const unsigned gen = use_cache ? wp.hdr->gen : 0u;     // which accumulator this call uses (rank 0 bumps it much later)
   unsigned long long h1 = 0ull, h2 = 0ull;
   auto mix = [](unsigned long long x) {
     x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 27; x *= 0x94d049bb133111ebull; x ^= x >> 31;
@@ -318,7 +323,7 @@ __global__ void __launch_bounds__(PLAN_T, 1) plan_cluster_kernel(Problem pb) {
       if (e < E) hash_edge(e, load_edge(pb, ii, jj, kk, e, E));
     }
     if (gt == 0) h1 += mix((unsigned long long)E + 0x51ull);
-    // CTA partial (warp shuffles, then the 32 warp sums through shared memory) -> two 64-bit atomics per CTA
+    // CTA partial (warp shuffles, then the 32 warp sums through shared memory), summed over the cluster through DSMEM
     __shared__ unsigned long long s_wh[2][32];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -330,7 +335,7 @@ __global__ void __launch_bounds__(PLAN_T, 1) plan_cluster_kernel(Problem pb) {
     if (tid < 2) {
       unsigned long long t = 0ull;
       for (int x = 0; x < PLAN_T / 32; ++x) t += s_wh[tid][x];
-      atomicAdd(&wp.hdr->acc[gen & 1u][tid], t);
+      s_part[tid] = t;
     }
   }
   PLAN_TS(1);
@@ -341,7 +346,12 @@ __global__ void __launch_bounds__(PLAN_T, 1) plan_cluster_kernel(Problem pb) {
     __shared__ int s_hit;
     __shared__ unsigned long long s_tot[2];
     if (tid == 0) {
-      const unsigned long long t1 = __ldcg(&wp.hdr->acc[gen & 1u][0]), t2 = __ldcg(&wp.hdr->acc[gen & 1u][1]);
+      unsigned long long t1 = 0ull, t2 = 0ull;
+#pragma unroll
+      for (int r = 0; r < PLAN_CL; ++r) {
+        const unsigned long long* rp = cl.map_shared_rank(s_part, r);
+        t1 += rp[0]; t2 += rp[1];
+      }
       const unsigned long long f1 = __ldcg(&wp.hdr->fp[0]), f2 = __ldcg(&wp.hdr->fp[1]);
       const int* d = win_ptrs(pb.ws, pb.L, 0).hdr->desc;
       const bool same_call = d[0] == PLAN_DESC_MAGIC && d[1] == (int)pb.E && d[2] == pb.F && d[3] == pb.K && d[4] == pb.t0 &&
@@ -356,9 +366,8 @@ __global__ void __launch_bounds__(PLAN_T, 1) plan_cluster_kernel(Problem pb) {
         wp.hdr->plan_hit = 1;
         wp.hdr->ticket[0] = wp.hdr->ticket[1] = wp.hdr->ticket[2] = wp.hdr->ticket[3] = 0;
         wp.hdr->chol_info = 0;
-        wp.hdr->acc[(gen + 1u) & 1u][0] = 0ull; wp.hdr->acc[(gen + 1u) & 1u][1] = 0ull;
-        wp.hdr->gen = gen + 1u;
       }
+      cl.sync();                                        // no CTA leaves while another one may still be reading its partial sums
       PCTA_TS(0, 2);
       return;
     }
@@ -367,12 +376,6 @@ __global__ void __launch_bounds__(PLAN_T, 1) plan_cluster_kernel(Problem pb) {
     int* hz = reinterpret_cast<int*>(wp.hdr);
     for (int x = 0; x < 16; ++x) hz[x] = 0;
     wp.hdr->fp[0] = ~h1; wp.hdr->fp[1] = 0x5aull;
-    if (use_cache) {
-      wp.hdr->acc[(gen + 1u) & 1u][0] = 0ull; wp.hdr->acc[(gen + 1u) & 1u][1] = 0ull;
-      wp.hdr->gen = gen + 1u;
-    } else {
-      win_ptrs(pb.ws, pb.L, 0).hdr->desc[0] = 0;
-    }
   }
 
   // ---- P1: per source frame min / max patch id
@@ -532,6 +535,491 @@ __global__ void __launch_bounds__(PLAN_T, 1) plan_cluster_kernel(Problem pb) {
   PCTA_TS(0, 2);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Direct plan: the whole graph analysis of a window -- A1 (unique patch ids) + A2 (zeroing) + the per-chunk cell tables that
+// plan_cells_kernel builds for the grid-wide path -- in ONE launch of one thread-block cluster per window, without the
+// chunk-sorted edge permutation.  Every CTA copies its share of the edge list ONCE into shared memory as packed 8-byte
+// records (source frame << 16 | target frame, patch id); all later passes run from there:
+//   D0  clear the window's zero region; load + range-check + pack the edges; fingerprint (plan cache)          | barrier
+//   D1  per source frame min / max patch id: shared-memory atomics, then one global atomic per frame and CTA     | barrier
+//   D2  chunk table (every CTA, redundantly); range of target frames seen by the window (DSMEM)
+//   D3  presence bits of (chunk, patch) and (chunk, target frame) in the CTA's own shared memory                 | barrier
+//   D4  OR of the bitmaps of all CTAs through distributed shared memory; per chunk: patch / slot counts, free-pose
+//       columns, table bases by exclusive scans (deterministic, no allocation atomics); CTA 0 writes the chunk
+//       table, the cluster writes kx / slots and fills the cell table with -1                                    | barrier
+//   D5  cells[chunk][patch rank][slot rank] = edge (atomicCAS: a second edge of the same cell goes to the duplicates list)
+// Tables that do not fit the shared-memory budget (tbl_cap: thousands of chunks, or a span of > ~1000 target frames; such
+// windows normally take the grid-wide path anyway) fall back, inside the kernel, to counting sort + build_chunk_cells.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int PD_T = 1024;
+constexpr unsigned PD_BAD = 0xffffffffu;
+
+struct DirectSmem {          // offsets (ints) into the dynamic shared memory
+  int fb, km, tbl, recs;
+};
+__host__ __device__ inline DirectSmem direct_smem(int F, int tbl_cap) {
+  DirectSmem d;
+  const int Fr = (F + 32) & ~31;
+  d.fb = 0; d.km = Fr; d.tbl = 2 * Fr; d.recs = (2 * Fr + tbl_cap + 1) & ~1;       // records are 8-byte aligned
+  return d;
+}
+size_t plan_direct_smem(int F, int tbl_cap, int e_cap) {
+  return sizeof(int) * (size_t)direct_smem(F, tbl_cap).recs + sizeof(uint2) * (size_t)e_cap;
+}
+
+template <int CL>
+__global__ void __launch_bounds__(PD_T, 1) plan_direct_kernel(Problem pb, int e_cap, int tbl_cap) {
+  PCTA_TS(0, 0);
+  pdl_wait();
+  pdl_trigger();
+  PCTA_TS(0, 1);
+  PLAN_TS(0);
+  extern __shared__ __align__(16) int psm[];
+  __shared__ int scratch[40];
+  __shared__ int s_jmm[2];                             // this CTA's min / max target frame (read by the others through DSMEM)
+  __shared__ int s_misc[8];
+  __shared__ unsigned long long s_wh[2][32];
+  __shared__ unsigned long long s_tot[2];
+  __shared__ unsigned long long s_part[2];             // this CTA's fingerprint sums
+  __shared__ CellScratch s_cells;                      // fallback path only
+  cg::cluster_group cl = cg::this_cluster();
+  const int w = blockIdx.y + pb.w0, tid = threadIdx.x, lane = tid & 31, T = PD_T;
+  const int rank = blockIdx.x;                         // the cluster spans the x dimension of the grid
+  const int gt = rank * T + tid, GT = CL * T;
+  const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
+  const int64_t* ii = pb.ii + (int64_t)w * pb.st.ii;
+  const int64_t* jj = pb.jj + (int64_t)w * pb.st.jj;
+  const int64_t* kk = pb.kk + (int64_t)w * pb.st.kk;
+  const int E = window_edges(pb, w);
+  const int pc = pb.L.pc, F = pb.F;
+  const int lpc = 31 - __clz(pc);                      // pc is a power of two
+  const DirectSmem so = direct_smem(F, tbl_cap);
+  int* s_fb = psm + so.fb;                             // [F]  first chunk of every source frame (D1: min patch id)
+  int* s_km = psm + so.km;                             // [F]  smallest patch id of every source frame (D1: max patch id + 1)
+  int* tbl = psm + so.tbl;
+  uint2* recs = reinterpret_cast<uint2*>(psm + so.recs);
+  // local records: x = q * T + tid  <->  edge e = gt + q * GT
+  const int nq = (E + GT - 1) / GT;                    // trips (uniform over the cluster); host guarantees nq * T <= e_cap
+
+  // ---- D0
+  {
+    uint4* z = reinterpret_cast<uint4*>((char*)pb.ws + (size_t)w * pb.L.zero_bytes);
+    const int n16 = (int)(pb.L.zero_bytes >> 4);
+    for (int x = 16 + gt; x < n16; x += GT) z[x] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (tid == 0) { s_jmm[0] = 0x7fffffff; s_jmm[1] = -1; }
+  for (int f = tid; f < F; f += T) { s_fb[f] = 0x7fffffff; s_km[f] = 0; }
+  __syncthreads();
+  const bool use_cache = pb.plan_cache != 0;
+  unsigned long long h1 = 0ull, h2 = 0ull;
+  auto mix = [](unsigned long long x) {
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 27; x *= 0x94d049bb133111ebull; x ^= x >> 31;
+    return x;
+  };
+  int bad = 0, jmn = 0x7fffffff, jmx = -1, n_ok = 0;
+  constexpr int LU = 4;                                // edges in flight per thread (64 registers: 4 x 3 64-bit loads)
+  for (int q0 = 0; q0 < nq; q0 += LU) {
+    EdgeIdx xs[LU];
+#pragma unroll
+    for (int u = 0; u < LU; ++u) xs[u] = load_edge(pb, ii, jj, kk, gt + (q0 + u) * GT, E);
+#pragma unroll
+    for (int u = 0; u < LU; ++u) {
+      const int q = q0 + u, e = gt + q * GT;
+      if (q >= nq) break;
+      const EdgeIdx x = xs[u];
+      uint2 r = make_uint2(PD_BAD, 0u);
+      if (e < E) {
+        if (x.ok) {
+          r = make_uint2(((unsigned)x.i << 16) | (unsigned)x.j, (unsigned)x.k);
+          jmn = min(jmn, x.j); jmx = max(jmx, x.j); ++n_ok;
+        } else {
+          bad = 1;
+        }
+        if (use_cache) {
+          const unsigned long long a = ((unsigned long long)(unsigned)x.k << 32) | (unsigned)e;
+          const unsigned long long b = ((unsigned long long)(unsigned)x.i << 32) | (unsigned)x.j;
+          const unsigned long long m = mix(a ^ (b * 0x9e3779b97f4a7c15ull));
+          h1 += m;
+          h2 += mix(m + b);
+        }
+      }
+      recs[q * T + tid] = r;
+      // D1 on the fly: per source frame min / max patch id, shared-memory atomics (edges arrive patch-major, so the lanes of
+      // a warp mostly share the frame: one vote instead of a match; look before the atomic -- the 32 warps of a CTA mostly
+      // walk the same frame and same-address shared atomics serialise)
+      {
+        const bool ok = r.x != PD_BAD;
+        const int i = ok ? x.i : -1, k = x.k;
+        const unsigned grp = __all_sync(0xffffffffu, i == __shfl_sync(0xffffffffu, i, 0)) ? 0xffffffffu : __match_any_sync(0xffffffffu, i);
+        const int kmn = __reduce_min_sync(grp, k), kmx = __reduce_max_sync(grp, k);
+        if (ok && lane == __ffs(grp) - 1) {
+          const volatile int* vf = s_fb; const volatile int* vk = s_km;
+          if (kmn < vf[i]) atomicMin(&s_fb[i], kmn);
+          if (kmx + 1 > vk[i]) atomicMax(&s_km[i], kmx + 1);
+        }
+      }
+    }
+  }
+  {
+    jmn = __reduce_min_sync(0xffffffffu, jmn);
+    jmx = __reduce_max_sync(0xffffffffu, jmx);
+    n_ok = __reduce_add_sync(0xffffffffu, n_ok);
+  }
+  if (use_cache) {
+    if (gt == 0) h1 += mix((unsigned long long)E + 0x51ull);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      h1 += __shfl_xor_sync(0xffffffffu, h1, o);
+      h2 += __shfl_xor_sync(0xffffffffu, h2, o);
+    }
+    if (lane == 0) { s_wh[0][tid >> 5] = h1; s_wh[1][tid >> 5] = h2; }
+  }
+  __syncthreads();                                     // s_jmm / s_fb / s_km initialised, records and warp sums written
+  if (lane == 0 && jmx >= 0) { atomicMin(&s_jmm[0], jmn); atomicMax(&s_jmm[1], jmx); }
+  if (use_cache && tid < 2) {                          // this CTA's share of the fingerprint, read by the others through DSMEM
+    unsigned long long t = 0ull;
+    for (int x = 0; x < PD_T / 32; ++x) t += s_wh[tid][x];
+    s_part[tid] = t;
+  }
+  PLAN_TS(1);
+  cl.sync();
+  PLAN_TS(2);
+  if (use_cache) {
+    if (tid == 0) {
+      unsigned long long t1 = 0ull, t2 = 0ull;
+#pragma unroll
+      for (int r = 0; r < CL; ++r) {
+        const unsigned long long* rp = cl.map_shared_rank(s_part, r);
+        t1 += rp[0]; t2 += rp[1];
+      }
+      const unsigned long long f1 = __ldcg(&wp.hdr->fp[0]), f2 = __ldcg(&wp.hdr->fp[1]);
+      const int* d = win_ptrs(pb.ws, pb.L, 0).hdr->desc;
+      const bool same_call = __ldcg(&d[0]) == PLAN_DESC_MAGIC && __ldcg(&d[1]) == (int)pb.E && __ldcg(&d[2]) == pb.F &&
+                             __ldcg(&d[3]) == pb.K && __ldcg(&d[4]) == pb.t0 && __ldcg(&d[5]) == pb.t1 &&
+                             __ldcg(&d[6]) == pb.L.pc && __ldcg(&d[7]) == pb.batch;
+      s_misc[0] = (same_call && f1 == t1 && f2 == t2) ? 1 : 0;
+      s_tot[0] = t1; s_tot[1] = t2;
+    }
+    __syncthreads();
+    h1 = s_tot[0]; h2 = s_tot[1];
+    if (s_misc[0]) {                                   // uniform over the cluster: the tables of the last call are valid
+      if (rank == 0 && tid == 0) {
+        wp.hdr->plan_hit = 1;
+        wp.hdr->ticket[0] = wp.hdr->ticket[1] = wp.hdr->ticket[2] = wp.hdr->ticket[3] = 0;
+        wp.hdr->chol_info = 0;
+      }
+      cl.sync();                                       // no CTA leaves while another one may still be reading its partial sums
+      PCTA_TS(0, 2);
+      return;
+    }
+  }
+  if (rank == 0 && tid == 0) {                         // rebuild: clear the header's plan fields, invalidate the fingerprint
+    int* hz = reinterpret_cast<int*>(wp.hdr);
+    for (int x = 0; x < 16; ++x) hz[x] = 0;
+    wp.hdr->fp[0] = ~h1; wp.hdr->fp[1] = 0x5aull;
+  }
+
+  // ---- D1 (the per-edge part ran inside the load loop): one global atomic per source frame and CTA
+  __syncthreads();
+  for (int f = tid; f < F; f += T) {
+    const int mx1 = s_km[f];
+    if (mx1 > 0) {
+      atomicMax(&wp.fmaxinv[f], 0x7fffffff - s_fb[f]);     // zero-initialised "min": stores max of (INT_MAX - k)
+      atomicMax(&wp.fkmax1[f], mx1);
+    }
+  }
+  PLAN_TS(3);
+  cl.sync();
+  PLAN_TS(4);
+  if (bad) atomicOr(&wp.hdr->status, PGBA_ST_INDEX_RANGE);     // after the barrier: the header was cleared by rank 0 in between
+  if (lane == 0 && n_ok) atomicAdd(&wp.hdr->n_valid_edges, n_ok);
+
+  // ---- D2 (every CTA, in its own shared memory): chunk table, target-frame range of the window
+  for (int f = tid; f < F; f += T) {
+    const int mx1 = __ldcg(&wp.fkmax1[f]);
+    const int kmin = 0x7fffffff - __ldcg(&wp.fmaxinv[f]);
+    s_km[f] = kmin;
+    s_fb[f] = mx1 > 0 ? (((mx1 - 1) - kmin) >> lpc) + 1 : 0;
+  }
+  if (tid < 32) {                                      // DSMEM: min / max target frame over the CTAs of the cluster
+    int a = 0x7fffffff, b = -1;
+    if (tid < CL) {
+      const int* r = cl.map_shared_rank(s_jmm, tid);
+      a = r[0]; b = r[1];
+    }
+    a = __reduce_min_sync(0xffffffffu, a);
+    b = __reduce_max_sync(0xffffffffu, b);
+    if (tid == 0) { s_misc[1] = a; s_misc[2] = b; }
+  }
+  __syncthreads();
+  int n_chunks = block_exclusive_scan(s_fb, F, scratch);
+  if (n_chunks > (int)pb.L.ch_max) {     // cannot happen when every patch has one source frame; stay memory-safe anyway
+    if (rank == 0 && tid == 0) atomicOr(&wp.hdr->status, PGBA_ST_CAPACITY);
+    n_chunks = 0;
+  }
+  if (rank == 0 && tid == 0) wp.hdr->n_chunks = n_chunks;
+  PLAN_TS(5);
+  const int jmin = s_misc[1], jspan = s_misc[2] - s_misc[1] + 1;
+  if (n_chunks == 0 || jspan <= 0) {                   // uniform over the cluster; nothing to build
+    cl.sync();                                         // (the DSMEM reads of s_jmm above are complete on every CTA)
+    if (use_cache && rank == 0 && tid == 0) { wp.hdr->fp[0] = h1; wp.hdr->fp[1] = h2; }
+    return;
+  }
+  const int PW = max(pc >> 5, 1), JW = (jspan + 31) >> 5, BW = PW + JW;     // bitmap words per chunk
+  const long long need = (long long)n_chunks * (3 * BW + 12);
+  const bool direct = need <= (long long)tbl_cap;
+  // table carve-up (ints): twelve per-chunk arrays, then the bitmaps
+  int* c_frame = tbl;
+  int* c_kbase = c_frame + n_chunks;
+  int* c_np = c_kbase + n_chunks;
+  int* c_ns = c_np + n_chunks;
+  int* c_ncols = c_ns + n_chunks;
+  int* c_pbase = c_ncols + n_chunks;
+  int* c_sbase = c_pbase + n_chunks;
+  int* c_cbase = c_sbase + n_chunks;
+  int* c_ebase = c_cbase + n_chunks;
+  int* c_first = c_ebase + n_chunks;
+  int* c_nfree = c_first + n_chunks;
+  int* c_icol = c_nfree + n_chunks;
+  unsigned* bm_part = reinterpret_cast<unsigned*>(c_icol + n_chunks);       // [n_chunks][BW]  this CTA's edges
+  unsigned* bm_all = bm_part + (size_t)n_chunks * BW;                       // [n_chunks][BW]  OR over the cluster
+  int* bm_pref = reinterpret_cast<int*>(bm_all + (size_t)n_chunks * BW);   // [n_chunks][BW]  set bits before each word
+
+  if (!direct) {
+    // ---- fallback: counting sort of the edges by chunk + per-chunk table build (the grid-wide kernels' algorithm, with
+    //      cluster barriers instead of kernel boundaries); correctness path for very wide windows, not tuned
+    if (rank == 0) {
+      for (int f = tid; f < F; f += T) wp.fbase[f] = s_fb[f];
+      for (int c = tid; c < n_chunks; c += T) {
+        int lo = 0, hi = F - 1;
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (s_fb[mid] <= c) lo = mid; else hi = mid - 1;
+        }
+        uint4* dst = reinterpret_cast<uint4*>(&wp.chunks[c]);
+        dst[0] = make_uint4((unsigned)lo, (unsigned)(s_km[lo] + ((c - s_fb[lo]) << lpc)), 0u, 0u);
+        dst[1] = make_uint4(0u, 0u, 0u, 0u);
+        dst[2] = make_uint4(0u, 0u, 0u, 0u);
+        dst[3] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    for (int q = 0; q < nq; ++q) {
+      const uint2 r = recs[q * T + tid];
+      const bool ok = r.x != PD_BAD;
+      const int i = ok ? (int)(r.x >> 16) : 0;
+      const int c = ok ? s_fb[i] + (((int)r.y - s_km[i]) >> lpc) : -1;
+      const unsigned grp = __match_any_sync(0xffffffffu, c);
+      if (ok && lane == __ffs(grp) - 1) atomicAdd(&wp.ccnt[c], __popc(grp));
+    }
+    cl.sync();
+    if (rank == 0) {
+      int* ccur = wp.ccur;
+      for (int c = tid; c < n_chunks; c += T) ccur[c] = __ldcg(&wp.ccnt[c]);
+      __syncthreads();
+      block_exclusive_scan(ccur, n_chunks, scratch);
+      for (int c = tid; c < n_chunks; c += T) {
+        wp.chunks[c].edge_begin = ccur[c];
+        wp.chunks[c].edge_end = ccur[c] + __ldcg(&wp.ccnt[c]);
+      }
+    }
+    cl.sync();
+    for (int q = 0; q < nq; ++q) {
+      const uint2 r = recs[q * T + tid];
+      const bool ok = r.x != PD_BAD;
+      const int i = ok ? (int)(r.x >> 16) : 0;
+      const int c = ok ? s_fb[i] + (((int)r.y - s_km[i]) >> lpc) : -1;
+      const unsigned grp = __match_any_sync(0xffffffffu, c);
+      const int leader = __ffs(grp) - 1;
+      int base = 0;
+      if (ok && lane == leader) base = atomicAdd(&wp.ccur[c], __popc(grp));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (ok) wp.perm[base + __popc(grp & ((1u << lane) - 1u))] = make_int4(gt + q * GT, (int)(r.x & 0xffffu), (int)r.y, 0);
+    }
+    cl.sync();
+    for (int c = rank; c < n_chunks; c += CL) build_chunk_cells(pb, wp, c, s_cells);
+    if (use_cache && rank == 0 && tid == 0) { wp.hdr->fp[0] = h1; wp.hdr->fp[1] = h2; }
+    PCTA_TS(0, 2);
+    return;
+  }
+
+  // ---- D3: presence bits from this CTA's edges
+  for (int c = tid; c < n_chunks; c += T) {            // source frame of chunk c: the last f with s_fb[f] <= c
+    int lo = 0, hi = F - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (s_fb[mid] <= c) lo = mid; else hi = mid - 1;
+    }
+    c_frame[c] = lo;
+    c_kbase[c] = s_km[lo] + ((c - s_fb[lo]) << lpc);
+  }
+  for (int x = tid; x < n_chunks * BW; x += T) bm_part[x] = 0u;
+  __syncthreads();
+  PLAN_TS(6);
+  const volatile unsigned* vbm = bm_part;
+  for (int q = 0; q < nq; ++q) {
+    const uint2 r = recs[q * T + tid];
+    const bool ok = r.x != PD_BAD;
+    const int i = ok ? (int)(r.x >> 16) : 0, j = (int)(r.x & 0xffffu);      // padding records: any valid address
+    const int kd = (int)r.y - s_km[i];
+    const int c = ok ? s_fb[i] + (kd >> lpc) : -1;
+    const int pl = kd & (pc - 1), js = j - jmin;
+    const int pw = ok ? c * BW + (pl >> 5) : -1;
+    const int jw = ok ? c * BW + PW + (js >> 5) : -1;
+    {
+      const unsigned grp = __all_sync(0xffffffffu, pw == __shfl_sync(0xffffffffu, pw, 0)) ? 0xffffffffu : __match_any_sync(0xffffffffu, pw);
+      const unsigned m = __reduce_or_sync(grp, 1u << (pl & 31));
+      if (ok && lane == __ffs(grp) - 1 && (vbm[pw] & m) != m) atomicOr(&bm_part[pw], m);     // look first (see D1)
+    }
+    {
+      const unsigned grp = __all_sync(0xffffffffu, jw == __shfl_sync(0xffffffffu, jw, 0)) ? 0xffffffffu : __match_any_sync(0xffffffffu, jw);
+      const unsigned m = __reduce_or_sync(grp, 1u << (js & 31));
+      if (ok && lane == __ffs(grp) - 1 && (vbm[jw] & m) != m) atomicOr(&bm_part[jw], m);
+    }
+  }
+  PLAN_TS(7);
+  cl.sync();
+  PLAN_TS(8);
+
+  // ---- D4: OR over the cluster (DSMEM), per-chunk counts and bases
+  for (int x = tid; x < n_chunks * BW; x += T) {
+    unsigned v = 0u;
+#pragma unroll
+    for (int r = 0; r < CL; ++r) v |= cl.map_shared_rank(bm_part, r)[x];
+    bm_all[x] = v;
+  }
+  __syncthreads();
+  const int t0 = pb.t0, t1 = pb.t1;
+  for (int c = tid; c < n_chunks; c += T) {
+    const unsigned* bw = bm_all + (size_t)c * BW;
+    int* pf = bm_pref + (size_t)c * BW;
+    int run = 0;
+    for (int x = 0; x < PW; ++x) { pf[x] = run; run += __popc(bw[x]); }
+    const int np = run;
+    run = 0;
+    for (int x = 0; x < JW; ++x) { pf[PW + x] = run; run += __popc(bw[PW + x]); }
+    const int ns = run;
+    auto rank_j = [&](int f) {                         // number of present target frames < f
+      const int fs = f - jmin;
+      if (fs <= 0) return 0;
+      if (fs >= jspan) return ns;
+      return pf[PW + (fs >> 5)] + __popc(bw[PW + (fs >> 5)] & ((1u << (fs & 31)) - 1u));
+    };
+    const int fi = c_frame[c];
+    const int first_free = rank_j(t0);
+    const int n_free = max(rank_j(t1) - first_free, 0);
+    const bool i_free = (fi >= t0 && fi < t1);
+    const int fis = fi - jmin;
+    const bool i_is_slot = fis >= 0 && fis < jspan && ((bw[PW + (fis >> 5)] >> (fis & 31)) & 1u);
+    int icol = -1, ncols = n_free;
+    if (i_free) {
+      if (i_is_slot) icol = rank_j(fi) - first_free;
+      else { icol = n_free; ncols = n_free + 1; }
+    }
+    const bool reject = ns > SMAX;
+    if (reject) atomicOr(&wp.hdr->status, PGBA_ST_TOO_MANY_SLOTS);
+    c_np[c] = reject ? 0 : np;
+    c_ns[c] = reject ? 0 : ns;
+    c_ncols[c] = reject ? 0 : ncols;
+    c_first[c] = first_free; c_nfree[c] = n_free; c_icol[c] = icol;
+    // table bases: exclusive scans (below) of np, ns, np * ns, np * ncols
+    c_pbase[c] = c_np[c]; c_sbase[c] = c_ns[c]; c_cbase[c] = c_np[c] * c_ns[c]; c_ebase[c] = c_np[c] * c_ncols[c];
+  }
+  __syncthreads();
+  const int tot_p = block_exclusive_scan(c_pbase, n_chunks, scratch);
+  const int tot_s = block_exclusive_scan(c_sbase, n_chunks, scratch);
+  const int tot_c = block_exclusive_scan(c_cbase, n_chunks, scratch);
+  const int tot_e = block_exclusive_scan(c_ebase, n_chunks, scratch);
+  PLAN_TS(12);
+  const bool cap_ok = tot_p <= (int)pb.L.patch_max && tot_s <= (int)pb.L.slot_max && (long long)tot_c <= (long long)pb.L.cell_cap &&
+                      (pb.t1 <= pb.t0 || (long long)tot_e <= (long long)pb.L.ecell_cap);
+  if (!cap_ok) {                                        // uniform: reject the window's tables (no edge is processed)
+    if (rank == 0 && tid == 0) { atomicOr(&wp.hdr->status, PGBA_ST_CAPACITY); wp.hdr->n_chunks = 0; }
+    cl.sync();
+    return;
+  }
+  if (rank == 0) {
+    for (int c = tid; c < n_chunks; c += T) {
+      const int np = c_np[c];
+      Chunk ch{};
+      ch.frame = c_frame[c]; ch.kbase = c_kbase[c];
+      ch.n_patches = np; ch.n_slots = c_ns[c];
+      ch.patch_base = c_pbase[c]; ch.slot_base = c_sbase[c]; ch.cell_base = c_cbase[c];
+      ch.ecell_base = (pb.t1 > pb.t0) ? c_ebase[c] : 0;
+      ch.first_free = np > 0 ? c_first[c] : 0; ch.n_free = np > 0 ? c_nfree[c] : 0;
+      ch.icol = c_icol[c]; ch.ncols = c_ncols[c];
+      const uint4* src = reinterpret_cast<const uint4*>(&ch);
+      uint4* dst = reinterpret_cast<uint4*>(&wp.chunks[c]);
+      dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+    }
+    if (tid == 0) {
+      wp.hdr->n_patches = tot_p; wp.hdr->n_slots = tot_s; wp.hdr->n_cells = tot_c; wp.hdr->n_ecells = (pb.t1 > pb.t0) ? tot_e : 0;
+    }
+  }
+  // kx / slots (item = (chunk, bit) over the cluster) and the -1 fill of the cell table
+  {
+    const int per = pc + jspan;
+    for (int it = gt; it < n_chunks * per; it += GT) {
+      const int c = it / per, b = it - c * per;
+      if (c_np[c] == 0) continue;
+      const unsigned* bw = bm_all + (size_t)c * BW;
+      const int* pf = bm_pref + (size_t)c * BW;
+      if (b < pc) {
+        if ((bw[b >> 5] >> (b & 31)) & 1u)
+          wp.kx[c_pbase[c] + pf[b >> 5] + __popc(bw[b >> 5] & ((1u << (b & 31)) - 1u))] = c_kbase[c] + b;
+      } else {
+        const int fs = b - pc;
+        if ((bw[PW + (fs >> 5)] >> (fs & 31)) & 1u)
+          wp.slots[c_sbase[c] + pf[PW + (fs >> 5)] + __popc(bw[PW + (fs >> 5)] & ((1u << (fs & 31)) - 1u))] = jmin + fs;
+      }
+    }
+    int4* c4 = reinterpret_cast<int4*>(wp.cells);       // 256-byte aligned
+    const int n4 = tot_c >> 2;
+    for (int x = gt; x < n4; x += GT) c4[x] = make_int4(-1, -1, -1, -1);
+    for (int x = (n4 << 2) + gt; x < tot_c; x += GT) wp.cells[x] = -1;
+  }
+  PLAN_TS(9);
+  cl.sync();
+  PLAN_TS(10);
+
+  // ---- D5: cells[chunk][patch rank][slot rank] = edge.  Plain stores (an atomicCAS per edge is bound by the L2 atomic
+  //      units: 18.5 us for the 2.4 M edges of the 64-window batch), then, after one more barrier, every edge reads its cell
+  //      back: an edge that finds another id there shares the cell with it (duplicated (patch, target frame) pair) and goes
+  //      to the duplicates list, which the linearisation handles on its slow path.
+  for (int q = 0; q < nq; ++q) {
+    const uint2 r = recs[q * T + tid];
+    if (r.x == PD_BAD) continue;
+    const int i = (int)(r.x >> 16), j = (int)(r.x & 0xffffu);
+    const int kd = (int)r.y - s_km[i];
+    const int c = s_fb[i] + (kd >> lpc);
+    if (c_np[c] == 0) { recs[q * T + tid] = make_uint2(PD_BAD, 0u); continue; }      // rejected chunk
+    const int pl = kd & (pc - 1), js = j - jmin;
+    const unsigned* bw = bm_all + (size_t)c * BW;
+    const int* pf = bm_pref + (size_t)c * BW;
+    const int p = pf[pl >> 5] + __popc(bw[pl >> 5] & ((1u << (pl & 31)) - 1u));
+    const int sl = pf[PW + (js >> 5)] + __popc(bw[PW + (js >> 5)] & ((1u << (js & 31)) - 1u));
+    const int idx = c_cbase[c] + p * c_ns[c] + sl;
+    wp.cells[idx] = gt + q * GT;
+    recs[q * T + tid] = make_uint2((unsigned)idx, (unsigned)c);                      // own record: no other thread reads it
+  }
+  PLAN_TS(11);
+  cl.sync();
+  for (int q = 0; q < nq; ++q) {
+    const uint2 r = recs[q * T + tid];
+    if (r.x == PD_BAD) continue;
+    const int n = gt + q * GT;
+    if (__ldcg(&wp.cells[r.x]) != n) {
+      const int c = (int)r.y, rem = (int)r.x - c_cbase[c];
+      const int d = atomicAdd(&wp.hdr->n_dups, 1);
+      DupEdge de; de.chunk = c; de.p = rem / c_ns[c]; de.s = rem - de.p * c_ns[c]; de.n = n;
+      wp.dups[d] = de;
+    }
+  }
+  if (use_cache && rank == 0 && tid == 0) { wp.hdr->fp[0] = h1; wp.hdr->fp[1] = h2; }   // the tables match this edge list
+  PLAN_TS(13);
+  PCTA_TS(0, 2);
+}
+
 static int edge_grid(int64_t E, int64_t batch) {
   int64_t g = (E + 255) / 256;
   const int64_t cap = batch > 1 ? (148 * 8 + batch - 1) / batch : 148 * 4;
@@ -576,9 +1064,6 @@ static int plan_cluster_size(int64_t batch) {
   if (2 * batch <= 148) return 2;
   return 0;
 }
-bool plan_clears_workspace(const Problem& pb, int64_t batch) {
-  return plan_cluster_enabled() && !pb.L.big && plan_cluster_size(batch) != 0;
-}
 
 // The 16-CTA cluster is a non-portable size: it needs a GPC with 16 SMs that can each hold a 1024-thread CTA.  Asked once
 // (occupancy query, no stream work); a part without such a GPC falls back to the portable 8-CTA cluster.
@@ -608,8 +1093,122 @@ static bool cluster16_available(size_t smem) {
   return cached != 0;
 }
 
+// ---- direct plan: configuration.  Cluster size: the largest of 16 (single window, needs a GPC that can host it) / 8 / 4 / 2
+// CTAs per window with which all windows of the call are co-resident (clusters are independent, so more windows than that
+// simply run in waves of 2-CTA clusters); doubled while a CTA's share of the edge list does not fit its shared memory.
+// PGBA_PLAN_DIRECT=0 selects the previous single-launch plan (plan_cluster_kernel + plan_cells_kernel) for A/B runs,
+// PGBA_PLAN_TBL_CAP=<ints> shrinks the table budget (tests: forces the in-kernel fallback).
+struct DirectCfg { int cl, e_cap, tbl_cap; size_t smem; };
+
+static bool plan_direct_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PGBA_PLAN_DIRECT"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+
+template <int CL>
+static bool direct_cluster_ok(size_t smem) {            // can a cluster of CL CTAs with this much shared memory be scheduled?
+  auto kern = plan_direct_kernel<CL>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+  if (CL > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(CL, 1);
+  cfg.blockDim = dim3(PD_T);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { (void)cudaGetLastError(); n = 0; }
+  return n > 0;
+}
+
+static bool plan_direct_config(const Problem& pb, int64_t batch, DirectCfg* out) {
+  if (!plan_direct_enabled() || pb.L.big || pb.F > 65535) return false;
+  static int tbl_forced = -1;
+  if (tbl_forced < 0) { const char* e = getenv("PGBA_PLAN_TBL_CAP"); tbl_forced = e ? atoi(e) : 0; }
+  static int cl_forced = -1;                            // PGBA_PLAN_DIRECT_CL=2/4/8/16 (A/B runs)
+  if (cl_forced < 0) { const char* e = getenv("PGBA_PLAN_DIRECT_CL"); cl_forced = e ? atoi(e) : 0; }
+  // Measured on the B200 (L2 flushed before every call, profiles/README.md round 2): on a single c2 window the direct kernel
+  // takes 23.9 us against 15.9 + ~7 us for plan_cluster_kernel + plan_cells_kernel -- every phase runs once, on cold
+  // instructions, so the larger single kernel gains nothing -- and the call is 4.8 us slower; on the 64-window batch the plan
+  // stage drops from 103 to 75 us.  Default: batches of more than 8 windows; PGBA_PLAN_DIRECT=1 forces it everywhere.
+  static int always = -1;
+  if (always < 0) { const char* e = getenv("PGBA_PLAN_DIRECT"); always = (e && e[0] == '1') ? 1 : 0; }
+  if (batch <= 8 && !always && !cl_forced && !tbl_forced) return false;
+  int cl = batch == 1 ? 16 : (8 * batch <= 148 ? 8 : (4 * batch <= 148 ? 4 : 2));
+  if (cl_forced == 2 || cl_forced == 4 || cl_forced == 8 || (cl_forced == 16 && batch == 1)) cl = cl_forced;
+  const size_t budget = 200 * 1024;                     // of the 227 KB a CTA can have: static arrays + headroom stay free
+  for (;; cl *= 2) {
+    if (cl > (batch == 1 ? 16 : 8)) return false;
+    const int64_t gtn = (int64_t)cl * PD_T;
+    const int64_t e_cap = ((pb.E + gtn - 1) / gtn) * PD_T;
+    // table budget: what the largest possible chunk table of this layout needs (see the kernel), at most 12288 ints
+    const int64_t bw_max = (pb.L.pc > 32 ? pb.L.pc / 32 : 1) + (pb.F + 31) / 32;
+    int64_t tbl_need = pb.L.ch_max * (3 * bw_max + 12);
+    if (tbl_need > 12288) tbl_need = 12288;
+    int tbl = tbl_forced > 0 ? tbl_forced : (int)tbl_need;
+    const size_t fixed = plan_direct_smem(pb.F, 0, 0);
+    if (fixed + 8 * (size_t)e_cap + 4 * 1024 > budget) continue;
+    const size_t room = (budget - fixed - 8 * (size_t)e_cap) / 4;
+    if ((size_t)tbl > room) tbl = (int)room;
+    out->cl = cl; out->e_cap = (int)e_cap; out->tbl_cap = tbl; out->smem = plan_direct_smem(pb.F, tbl, (int)e_cap);
+    break;
+  }
+  if (out->cl == 16) {                                  // non-portable size: asked once per shared-memory size class
+    static int ok16 = -1; static size_t ok16_smem = 0;
+    if (ok16 < 0 || out->smem > ok16_smem) { ok16 = direct_cluster_ok<16>(out->smem) ? 1 : 0; ok16_smem = out->smem; }
+    if (!ok16) {
+      out->cl = 8;
+      const int64_t gtn = 8 * (int64_t)PD_T;
+      out->e_cap = (int)(((pb.E + gtn - 1) / gtn) * PD_T);
+      out->smem = plan_direct_smem(pb.F, out->tbl_cap, out->e_cap);
+      if (out->smem > budget + 16 * 1024) return false;
+    }
+  }
+  return true;
+}
+
+// true: the plan kernel also clears the zero region (no memset needed)
+bool plan_clears_workspace(const Problem& pb, int64_t batch) {
+  if (!plan_cluster_enabled() || pb.L.big) return false;
+  DirectCfg dc;
+  return plan_direct_config(pb, batch, &dc) || plan_cluster_size(batch) != 0;
+}
+
+template <int CL>
+static void launch_direct(const Problem& pb, int64_t batch, const DirectCfg& c, cudaStream_t stream) {
+  auto kern = plan_direct_kernel<CL>;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)CL, (unsigned)batch);
+  cfg.blockDim = dim3(PD_T);
+  cfg.dynamicSmemBytes = c.smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+  if (CL > 8) cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  cudaLaunchKernelEx(&cfg, kern, pb, c.e_cap, c.tbl_cap);
+  count_launch();
+}
+
 void launch_plan(const Problem& pb, int64_t batch, cudaStream_t stream) {
-  if (plan_clears_workspace(pb, batch)) {
+  DirectCfg dc;
+  if (plan_cluster_enabled() && plan_direct_config(pb, batch, &dc)) {
+    if (dc.cl == 16) launch_direct<16>(pb, batch, dc, stream);
+    else if (dc.cl == 8) launch_direct<8>(pb, batch, dc, stream);
+    else if (dc.cl == 4) launch_direct<4>(pb, batch, dc, stream);
+    else launch_direct<2>(pb, batch, dc, stream);
+    return;                                             // the cell tables are built by the same kernel
+  }
+  if (plan_cluster_enabled() && !pb.L.big && plan_cluster_size(batch) != 0) {
     // single windows: a 16-CTA (non-portable) cluster -- 16 SMs pull the index arrays and every per-edge phase is half as
     // long as with 8; batches: see plan_cluster_size
     int cl_size = plan_cluster_size(batch);

@@ -70,8 +70,8 @@ def forward_host(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, 
         if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
             raise RuntimeError("cuda_ba.forward_host: %s must be a contiguous float32 CPU tensor" % name)
     for name, t in dict(ii=ii, jj=jj, kk=kk).items():
-        if t.is_cuda or t.dtype != torch.int64 or not t.is_contiguous():
-            raise RuntimeError("cuda_ba.forward_host: %s must be a contiguous int64 CPU tensor" % name)
+        if t.is_cuda or t.dtype not in (torch.int64, torch.int32) or t.dtype != ii.dtype or not t.is_contiguous():
+            raise RuntimeError("cuda_ba.forward_host: %s must be a contiguous int64 (or, all three, int32) CPU tensor" % name)
     P = patches.shape[-1]
     F = poses.numel() // 7
     K = patches.numel() // (3 * P * P)
@@ -89,7 +89,8 @@ def forward_host(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, 
         aux = _aux_streams.get(key)
         if aux is None:
             aux = _aux_streams[key] = torch.cuda.Stream(device=dev)
-        rc = L.pgba_ba_solve_host(poses.data_ptr(), patches.data_ptr(), intrinsics.data_ptr(), target.data_ptr(),
+        entry = L.pgba_ba_solve_host_i32 if ii.dtype == torch.int32 else L.pgba_ba_solve_host
+        rc = entry(poses.data_ptr(), patches.data_ptr(), intrinsics.data_ptr(), target.data_ptr(),
                                   weight.data_ptr(), lmbda.data_ptr(), ii.data_ptr(), jj.data_ptr(), kk.data_ptr(),
                                   E, F, K, P, int(PPF), int(t0), int(t1), int(iterations), int(bool(eff_impl)),
                                   stg.data_ptr(), stg.numel(), ws.data_ptr(), ws.numel(), native.stream_ptr(dev),

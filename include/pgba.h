@@ -108,6 +108,18 @@ int pgba_ba_solve_host(float* poses_h, float* patches_h, const float* intrinsics
                        int t0, int t1, int iterations, int eff_impl, void* staging, size_t staging_bytes,
                        void* workspace, size_t workspace_bytes, pgba_stream_t stream, pgba_stream_t aux_stream);
 
+/* The same with 32-bit indices (the reference API's index tensors are int64; a caller that builds its edge list on the
+ * host can write int32 into the arena and halve the index upload -- 0.45 of 1.74 MB on the default window).  The values
+ * are range-checked on the device like the 64-bit ones (PGBA_ST_INDEX_RANGE). */
+int pgba_ba_host_arena_offsets_i32(int64_t n_edges, int64_t n_pose_rows, int64_t n_patch_rows, int P,
+                                   size_t* offsets9 /* host, out */, size_t* bytes /* host, out */);
+
+int pgba_ba_solve_host_i32(float* poses_h, float* patches_h, const float* intrinsics_h, const float* target_h,
+                           const float* weight_h, const float* lmbda_h, const int32_t* ii_h, const int32_t* jj_h,
+                           const int32_t* kk_h, int64_t n_edges, int64_t n_pose_rows, int64_t n_patch_rows, int P,
+                           int ppf, int t0, int t1, int iterations, int eff_impl, void* staging, size_t staging_bytes,
+                           void* workspace, size_t workspace_bytes, pgba_stream_t stream, pgba_stream_t aux_stream);
+
 /* Measurement hooks (used by bench.py only).  pgba_ba_solve_profiled runs exactly the launch sequence of
  * pgba_ba_solve_batched with cudaEvents between the stages, SYNCHRONISES the stream and fills the host array
  * stage_ms [1 + 3*iterations]: workspace clear + plan, then per iteration {linearize+Schur, solve + pose

@@ -20,6 +20,14 @@ for it in range(8):
     t = np.array(list(buf)[:16], dtype=np.float64)
     acc.append(t - t[0])
 acc = np.median(np.array(acc[2:]), axis=0)
-names = ["start", "zero+load issued", "sync0", "P1 frames", "sync1", "P2 table", "sync2", "P3 count", "sync3", "P4 scan", "sync4", "P5 scatter", "P2a loads", "P2b scan", "P2c table", "-"]
-for n, a, d in zip(names, acc, np.diff(np.concatenate([[0], acc]))):
-    print("%-18s t=%8.0f ns  (+%6.0f)" % (n, a, d))
+direct = os.environ.get("PGBA_PLAN_DIRECT", "1") != "0"
+names_direct = ["start", "D0 zero+load+pack", "sync B1", "D1 frame min/max", "sync B2", "D2 chunk table", "D3 zero bitmaps", "D3 presence bits",
+                "sync B3", "D4 kx/slots/fill", "sync B4", "D5 stores", "D4 OR+counts+scans", "D5 verify", "-", "-"]
+names = names_direct if direct else ["start", "zero+load issued", "sync0", "P1 frames", "sync1", "P2 table", "sync2", "P3 count", "sync3", "P4 scan", "sync4", "P5 scatter", "P2a loads", "P2b scan", "P2c table", "-"]
+order = np.argsort(acc)
+prev = 0.0
+for i in order:
+    if names[i] == "-" or acc[i] < 0:
+        continue
+    print("%-22s t=%8.0f ns  (+%6.0f)" % (names[i], acc[i], acc[i] - prev))
+    prev = acc[i]

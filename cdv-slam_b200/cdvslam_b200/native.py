@@ -56,6 +56,7 @@ SIGNATURES = {
                                                     c_int, c_int, c_int, c_vp, c_vp]),
     "pcorr_tma_supported": (c_int, [c_int, c_int, c_int, c_int]),
     "pcorr_tma_workspace_bytes": (c_int, [c_int, c_int, c_i64, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_sz)]),
+    "pcorr_tma_workspace_bytes_dt": (c_int, [c_int, c_int, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_sz)]),
     "pcorr_forward_tma": (c_int, [c_vp] * 6 + [c_int, c_int, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int,
                                                c_int, c_int, c_int, c_vp, c_vp, c_sz, c_vp]),
     "pcorr_ring_update": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_int, c_int, c_int, c_int, c_int, c_i64, c_i64, c_vp, c_sz,

@@ -188,9 +188,12 @@ __global__ void __launch_bounds__(256) to_nhwc_wide_kernel(NhwcJob j0, NhwcJob j
 // (xo = j, yo = 0..6).  Results go to a small staging buffer [xo][yo * 9 + p][level] (row stride chosen so that these
 // stores are conflict-free as well) from which the unit's output is written with fully coalesced stores.
 // RS: records per volume row, SLOT: floats per record, SROW: halfs per staging row.
-template <int RS, int SLOT, int NLEV, int SROW>
+__device__ __forceinline__ void stage_store(__half* p, float v) { *p = __float2half_rn(v); }
+__device__ __forceinline__ void stage_store(float* p, float v) { *p = v; }
+
+template <int RS, int SLOT, int NLEV, int SROW, typename OT>
 __device__ __forceinline__ void blend_stage(const float* vol, const float4* wgt, const int* vbase, int lane, int lev,
-                                            __half* stage) {
+                                            OT* stage) {
   const int p_lo = lane & 3, j = lane >> 2;
 #pragma unroll
   for (int pg = 0; pg < 3; ++pg) {
@@ -204,11 +207,11 @@ __device__ __forceinline__ void blend_stage(const float* vol, const float4* wgt,
 #pragma unroll
     for (int iy = 0; iy < 8; ++iy) t1[iy] = __shfl_down_sync(0xffffffffu, t0[iy], 4);      // tap (iy, j + 1)
     if (p < PP && j < 7) {
-      __half* st = stage + j * SROW + p * NLEV + lev;
+      OT* st = stage + j * SROW + p * NLEV + lev;
 #pragma unroll
       for (int yo = 0; yo < 7; ++yo) {
         const float r = wg.x * t0[yo] + wg.y * t1[yo] + wg.z * t0[yo + 1] + wg.w * t1[yo + 1];
-        st[yo * 9 * NLEV] = __float2half_rn(r);
+        stage_store(st + yo * 9 * NLEV, r);
       }
     }
   }
@@ -705,6 +708,308 @@ __global__ void __launch_bounds__(32 * WWARPS, 1) corr_tma_wide_kernel(const __g
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// fp32 feature maps (training / parity path; C a multiple of 16, built for the 128-channel maps): the wide kernel's scheme
+// with 16-channel chunks (64-byte pixel records again, SWIZZLE_64B, the same ldmatrix addresses: an 8x8 b16 matrix is
+// 8 records x 4 floats, which is exactly the tf32 m16n8k8 A fragment) and the contraction as 3xTF32 on the tensor cores:
+// a = hi + lo with hi = tf32(a), lo = tf32(a - hi); D += A_lo B_hi + A_hi B_lo + A_hi B_hi in fp32 accumulators, i.e. the
+// dropped term is 2^-22 relative -- fp32-class results (parity bar 1e-5 absolute, tests/test_parity_r2_gpu.py).  The patch
+// fragments are re-read from shared memory per chunk (holding 128 channels x hi / lo in registers is not possible).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int FCK = 16;                      // channels per chunk (64-byte records)
+constexpr int FWARPS = 6;                    // warps per CTA (one CTA per SM)
+
+template <int C> struct __align__(512) Wide32Smem {
+  unsigned char buf[WNBUF][WCH_BYTES];     // TMA destinations (64B-swizzled pixel records of 16 floats)
+  float vol[RPX * 12];                     // region volume, 12-float records
+  float a[PP * C];                         // patch-feature record of the unit, [c][p] as in fmap1
+  float4 wgt[2][12];
+  int vbase[2][12];
+  float stage[7 * 136];
+  unsigned long long bar[WNBUF];
+};
+
+struct Params32 {
+  const float* fmap1;                  // [B, K, C, 3, 3]
+  const float* nhwc[2];                // [B*F, H, W, C] per level
+  int H[2], W[2];
+  const float* coords;
+  const int64_t* us; const int64_t* vs;
+  int B; int64_t E, K, F;
+  float* out;                          // [B, E, 7, 7, 3, 3, NLEV]
+};
+
+__device__ __forceinline__ void split_tf32(float x, unsigned& hi, unsigned& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float d[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0,
+                                         unsigned b1) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// fp32 maps [B*F, C, HW] -> [B*F, HW, C]: 64-pixel tiles through shared memory (rows padded by one float: both the
+// transposing stores and the copy-out are conflict-free), coalesced 128-byte reads per channel plane, contiguous writes.
+struct Nhwc32Job { const float* src; float* dst; int HW; int blocks_per_frame; int first_block; };
+
+template <int C>
+__global__ void __launch_bounds__(256) to_nhwc_f32_kernel(Nhwc32Job j0, Nhwc32Job j1) {
+  constexpr int PXT = 64, RS = C + 1;
+  extern __shared__ float tile32[];                     // [PXT][RS]
+  const bool second = (int)blockIdx.x >= j1.first_block;
+  const Nhwc32Job J = second ? j1 : j0;
+  const int blk = (int)blockIdx.x - J.first_block;
+  const int frame = blk / J.blocks_per_frame;
+  const int px0 = (blk - frame * J.blocks_per_frame) * PXT;
+  const int npx = min(PXT, J.HW - px0);
+  const float* sp = J.src + (int64_t)frame * C * J.HW + px0;
+  const int t = threadIdx.x;
+  constexpr int ITEMS = PXT * C / 256;
+#pragma unroll 8
+  for (int i = 0; i < ITEMS; ++i) {
+    const int x = t + 256 * i;
+    const int c = x / PXT, px = x - c * PXT;
+    if (px < npx) tile32[px * RS + c] = sp[(int64_t)c * J.HW + px];
+  }
+  __syncthreads();
+  float* d = J.dst + ((int64_t)frame * J.HW + px0) * C;
+  for (int x = t; x < npx * C; x += 256) {
+    const int px = x / C, c = x - px * C;
+    d[x] = tile32[px * RS + c];
+  }
+}
+
+template <int C, int NLEV>
+__global__ void __launch_bounds__(32 * FWARPS, 1) corr_tma_wide32_kernel(const __grid_constant__ CUtensorMap tm0,
+                                                                        const __grid_constant__ CUtensorMap tm1, Params32 P) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  static_assert(C % FCK == 0 && (C / FCK) % WNBUF == 0, "channel count must be a multiple of 32");
+  constexpr int NCH = C / FCK;                           // chunks per half-task
+  constexpr int SLOT = 12;
+  constexpr int NA4 = C * PP / 4;                        // uint4 per patch-feature record
+  constexpr int NAV = (NA4 + 31) / 32;
+  using WS = Wide32Smem<C>;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  WS& S = reinterpret_cast<WS*>(smraw + ((512u - (smem_u32(smraw) & 511u)) & 511u))[warp];
+  const uint32_t bar0 = smem_u32(&S.bar[0]);
+  const uint32_t buf0 = smem_u32(&S.buf[0][0]);
+  if (lane == 0) {
+    for (int b = 0; b < WNBUF; ++b) mbar_init(bar0 + 8 * b, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async();
+  }
+  __syncwarp();
+
+  // ldmatrix lane offsets inside a chunk buffer (identical to the fp16 wide kernel: 64-byte records, SWIZZLE_64B): the
+  // x4 load of k-step s returns a0..a3 of the tf32 m16n8k8 fragment (rows g / g + 8, floats t / t + 4 of the step)
+  const int rperm = (((lane & 7) & 3) << 1) | ((lane & 7) >> 2);
+  const int rrow = ((lane >> 3) & 1) * 8 + rperm;
+  const int sw = (rrow >> 1) & 3;
+  const uint32_t a_off_k0 = (uint32_t)(rrow * 64 + (((0 + (lane >> 4)) ^ sw) << 4));   // floats 0..7 of the chunk
+  const uint32_t a_off_k1 = (uint32_t)(rrow * 64 + (((2 + (lane >> 4)) ^ sw) << 4));   // floats 8..15
+  const int g = lane >> 2, tq = lane & 3;
+  const int gperm = ((g & 3) << 1) | (g >> 2);
+  const uint64_t tma0 = (uint64_t)&tm0, tma1 = (uint64_t)&tm1;
+
+  const int64_t total = (int64_t)P.B * P.E;
+  const int64_t ustride = (int64_t)gridDim.x * FWARPS;
+  const int64_t u_first = (int64_t)blockIdx.x * FWARPS + warp;
+  if (u_first >= total) return;
+  const int64_t n_units = (total - u_first + ustride - 1) / ustride;
+  const int64_t n_half = n_units * NLEV;
+
+  struct Raw { float x, y; int jx, ix; };
+  Raw ra{0.f, 0.f, 0, 0}, rb{0.f, 0.f, 0, 0};
+  int64_t ka = 0;
+  uint4 apre[NAV];
+  struct Geo { int x0, y0, frame, lev; bool fits; };
+  Geo gc{0, 0, 0, 0, false}, gn{0, 0, 0, 0, false};
+  uint32_t phase = 0;
+
+  auto load_raw = [&](Raw& r, int64_t k) {
+    const int64_t unit = u_first + k * ustride;
+    const int64_t m = (P.B == 1) ? unit : unit % P.E;
+    const float* cg = P.coords + unit * (2 * PP);
+    if (lane < PP) { r.x = __ldg(cg + lane); r.y = __ldg(cg + PP + lane); }
+    r.jx = (int)__ldg(P.vs + m);
+    r.ix = (int)__ldg(P.us + m);
+  };
+  auto prefetch_a = [&]() {
+    const int64_t b = (P.B == 1) ? 0 : (u_first + ka * ustride) / P.E;
+    const uint4* f1 = reinterpret_cast<const uint4*>(P.fmap1 + (b * P.K + ra.ix) * (int64_t)(C * PP));
+#pragma unroll
+    for (int k = 0; k < NAV; ++k)
+      if (lane + 32 * k < NA4) apre[k] = __ldg(f1 + lane + 32 * k);
+  };
+  auto prepare = [&](int lev, int slot) -> Geo {
+    const float x = (lev == 0) ? ra.x : ra.x * 0.25f;
+    const float y = (lev == 0) ? ra.y : ra.y * 0.25f;
+    const int fxp = safe_floor(x), fyp = safe_floor(y);
+    const int xmin = __reduce_min_sync(0xffffffffu, lane < PP ? fxp : 0x7fffffff);
+    const int xmax = __reduce_max_sync(0xffffffffu, lane < PP ? fxp : -0x7fffffff);
+    const int ymin = __reduce_min_sync(0xffffffffu, lane < PP ? fyp : 0x7fffffff);
+    const int ymax = __reduce_max_sync(0xffffffffu, lane < PP ? fyp : -0x7fffffff);
+    Geo gq;
+    gq.fits = (xmax - xmin + D <= RG) && (ymax - ymin + D <= RG);
+    gq.lev = lev;
+    const int b = (P.B == 1) ? 0 : (int)((u_first + ka * ustride) / P.E);
+    gq.frame = b * (int)P.F + ra.jx;
+    const int H = lev == 0 ? P.H[0] : P.H[1], W = lev == 0 ? P.W[0] : P.W[1];
+    gq.x0 = min(max(xmin - R, -RG), W);
+    gq.y0 = min(max(ymin - R, -RG), H);
+    if (lane < PP) {
+      const float dx = x - floorf(x), dy = y - floorf(y);
+      S.wgt[slot][lane] = make_float4((1.f - dx) * (1.f - dy), dx * (1.f - dy), (1.f - dx) * dy, dx * dy);
+      S.vbase[slot][lane] = gq.fits ? ((fyp - ymin) * RG + (fxp - xmin)) * SLOT + lane : lane;
+    }
+    __syncwarp();
+    return gq;
+  };
+  auto issue = [&](const Geo& gq, int q) {
+    if (gq.fits && lane == 0) {
+      const int b = q % WNBUF;
+      fence_proxy_async();
+      mbar_expect_tx(bar0 + 8 * b, WCH_BYTES);
+      asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                   ::"r"(buf0 + b * WCH_BYTES), "l"(gq.lev == 0 ? tma0 : tma1), "r"(bar0 + 8 * b), "r"(q * FCK), "r"(gq.x0),
+                     "r"(gq.y0), "r"(gq.frame) : "memory");
+    }
+  };
+  auto advance = [&]() {
+    ra = rb;
+    ++ka;
+    if (ka + 1 < n_units) load_raw(rb, ka + 1);
+  };
+
+  load_raw(ra, 0);
+  if (n_units > 1) load_raw(rb, 1);
+  prefetch_a();
+  gc = prepare(0, 0);
+#pragma unroll
+  for (int q = 0; q < NCH && q < WNBUF; ++q) issue(gc, q);
+  if (NLEV == 1) advance();
+
+  for (int64_t s = 0; s < n_half; ++s) {
+    const int lev = (NLEV == 1) ? 0 : (int)(s & 1);
+    const int slot = (int)(s & 1);
+    const int64_t unit = u_first + (s / NLEV) * ustride;
+    const bool have_next = s + 1 < n_half;
+    const int lev_n = (NLEV == 1) ? 0 : (int)((s + 1) & 1);
+
+    // ---- (0) new unit: patch-feature record to shared memory
+    if (lev == 0) {
+#pragma unroll
+      for (int k = 0; k < NAV; ++k)
+        if (lane + 32 * k < NA4) reinterpret_cast<uint4*>(&S.a[0])[lane + 32 * k] = apre[k];
+      __syncwarp();
+    }
+
+    // ---- (1) geometry of the next half-task, patch features of the next unit, raw values of the unit after it
+    if (have_next) {
+      gn = prepare(lev_n, slot ^ 1);
+      if (lev_n == 0) prefetch_a();
+      if (lev_n == NLEV - 1) advance();
+      if (!gc.fits) {
+#pragma unroll
+        for (int q = 0; q < NCH && q < WNBUF; ++q) issue(gn, q);
+      }
+    }
+
+    // ---- (2) contraction, chunk by chunk (3xTF32); every consumed buffer is refilled for the next half-task
+    float* vol = S.vol;
+    if (gc.fits) {
+      float d0[RPX / 16][4], d1[RPX / 16][4];
+#pragma unroll
+      for (int mt = 0; mt < RPX / 16; ++mt)
+#pragma unroll
+        for (int x = 0; x < 4; ++x) { d0[mt][x] = 0.f; d1[mt][x] = 0.f; }
+#pragma unroll 1
+      for (int q = 0; q < NCH; ++q) {
+        // B fragments of this chunk: b(k = c, n = p) = a[c * 9 + p]; n-tile 0: p = g, n-tile 1: p = 8 (g == 0 only)
+        unsigned bh0[4], bl0[4], bh1[4], bl1[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {                    // x = 2 * step + (0: k = t, 1: k = t + 4)
+          const int c = q * FCK + 4 * x + tq;
+          split_tf32(S.a[c * PP + g], bh0[x], bl0[x]);
+          split_tf32(g == 0 ? S.a[c * PP + 8] : 0.f, bh1[x], bl1[x]);
+        }
+        const int b = q % WNBUF;
+        mbar_wait(bar0 + 8 * b, (phase >> b) & 1u);
+        phase ^= 1u << b;
+        const uint32_t cb = buf0 + b * WCH_BYTES;
+#pragma unroll
+        for (int mt = 0; mt < RPX / 16; ++mt) {
+          unsigned ar[8], ah[8], al[8];
+          const uint32_t tb = cb + mt * 16 * 64;
+          ldsm_x4(ar[0], ar[1], ar[2], ar[3], tb + a_off_k0);
+          ldsm_x4(ar[4], ar[5], ar[6], ar[7], tb + a_off_k1);
+#pragma unroll
+          for (int x = 0; x < 8; ++x) split_tf32(__uint_as_float(ar[x]), ah[x], al[x]);
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const int o = 4 * ks;
+            mma_tf32(d0[mt], al[o], al[o + 1], al[o + 2], al[o + 3], bh0[2 * ks], bh0[2 * ks + 1]);
+            mma_tf32(d0[mt], ah[o], ah[o + 1], ah[o + 2], ah[o + 3], bl0[2 * ks], bl0[2 * ks + 1]);
+            mma_tf32(d0[mt], ah[o], ah[o + 1], ah[o + 2], ah[o + 3], bh0[2 * ks], bh0[2 * ks + 1]);
+            mma_tf32(d1[mt], al[o], al[o + 1], al[o + 2], al[o + 3], bh1[2 * ks], bh1[2 * ks + 1]);
+            mma_tf32(d1[mt], ah[o], ah[o + 1], ah[o + 2], ah[o + 3], bl1[2 * ks], bl1[2 * ks + 1]);
+            mma_tf32(d1[mt], ah[o], ah[o + 1], ah[o + 2], ah[o + 3], bh1[2 * ks], bh1[2 * ks + 1]);
+          }
+        }
+        __syncwarp();
+        if (q + WNBUF < NCH) issue(gc, q + WNBUF);
+        else if (have_next) issue(gn, q + WNBUF - NCH);
+      }
+#pragma unroll
+      for (int mt = 0; mt < RPX / 16; ++mt) {
+        float* v0 = vol + (mt * 16 + gperm) * SLOT;
+        *reinterpret_cast<float2*>(v0 + 2 * tq) = make_float2(d0[mt][0], d0[mt][1]);
+        *reinterpret_cast<float2*>(v0 + 8 * SLOT + 2 * tq) = make_float2(d0[mt][2], d0[mt][3]);
+        if (tq == 0) { v0[8] = d1[mt][0]; v0[8 * SLOT + 8] = d1[mt][2]; }
+      }
+    } else {
+      const int H = lev == 0 ? P.H[0] : P.H[1], W = lev == 0 ? P.W[0] : P.W[1];
+      const float* f2 = (lev == 0 ? P.nhwc[0] : P.nhwc[1]) + (int64_t)gc.frame * H * W * C;
+      const float* cg = P.coords + unit * (2 * PP);
+      for (int o = lane; o < PP * D * D; o += 32) {
+        const int p = o / (D * D), pos = o - p * (D * D);
+        const int io = pos / D, jo = pos - io * D;
+        const float xs = (lev == 0) ? cg[p] : cg[p] * 0.25f, ys = (lev == 0) ? cg[PP + p] : cg[PP + p] * 0.25f;
+        const int i1 = safe_floor(ys) + (io - R), j1 = safe_floor(xs) + (jo - R);
+        float acc = 0.f;
+        if (i1 >= 0 && i1 < H && j1 >= 0 && j1 < W) {
+          const float* src = f2 + ((int64_t)i1 * W + j1) * C;
+          for (int c = 0; c < C; ++c) acc = fmaf(S.a[c * PP + p], src[c], acc);
+        }
+        vol[pos * SLOT + p] = acc;
+      }
+    }
+    __syncwarp();
+
+    // ---- (3) blend into the staging buffer; after the unit's last level: coalesced output
+    {
+      constexpr int SROW = (NLEV == 2) ? 136 : 72;
+      if (gc.fits) blend_stage<RG, SLOT, NLEV, SROW>(vol, S.wgt[slot], S.vbase[slot], lane, lev, S.stage);
+      else blend_stage<D, SLOT, NLEV, SROW>(vol, S.wgt[slot], S.vbase[slot], lane, lev, S.stage);
+      __syncwarp();
+      if (lev == NLEV - 1) {
+        constexpr int ROWN = 63 * NLEV;                  // floats per staging row actually used
+        float* og = P.out + unit * (int64_t)(Do * Do * PP) * NLEV;
+#pragma unroll 4
+        for (int o = lane; o < Do * Do * PP * NLEV; o += 32) {
+          const int xo = o / ROWN, r = o - xo * ROWN;
+          og[o] = S.stage[xo * SROW + r];
+        }
+        __syncwarp();
+      }
+    }
+    gc = gn;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -752,7 +1057,47 @@ static int make_map_wide(CUtensorMap* tm, const void* base, int C, int W, int H,
   return r == CUDA_SUCCESS ? PCORR_OK : PCORR_ERR_UNSUPPORTED;
 }
 
+// fp32 maps: 4-D map [C, W, H, frames] with box [16, 12, 12, 1] floats (64-byte records) and SWIZZLE_64B
+static int make_map_wide32(CUtensorMap* tm, const void* base, int C, int W, int H, int64_t frames) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return PCORR_ERR_UNSUPPORTED;
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)frames};
+  const cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  const cuuint32_t box[4] = {FCK, RG, RG, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? PCORR_OK : PCORR_ERR_UNSUPPORTED;
+}
+
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+template <int C, int NLEV>
+static int launch_wide32(const CUtensorMap& tm0, const CUtensorMap& tm1, const Params32& P, cudaStream_t s) {
+  auto kern = corr_tma_wide32_kernel<C, NLEV>;
+  const size_t smem = sizeof(Wide32Smem<C>) * FWARPS + 1024;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int64_t units = (int64_t)P.B * P.E;
+  int64_t grid = (units + FWARPS - 1) / FWARPS;
+  if (grid > 148) grid = 148;
+  kern<<<(unsigned)grid, 32 * FWARPS, smem, s>>>(tm0, tm1, P);
+  pgba::count_launch();
+  return (int)cudaGetLastError();
+}
+
+static void transpose_maps32(int nlev, const float* src0, float* dst0, int HW0, const float* src1, float* dst1, int HW1,
+                             int frames, cudaStream_t s) {
+  constexpr int C = 128, PXT = 64;
+  Nhwc32Job j0{src0, dst0, HW0, (HW0 + PXT - 1) / PXT, 0};
+  Nhwc32Job j1{src1, dst1, HW1, (HW1 + PXT - 1) / PXT, j0.blocks_per_frame * frames};
+  const int blocks = j1.first_block + (nlev == 2 ? j1.blocks_per_frame * frames : 0);
+  if (nlev == 1) j1.first_block = 0x7fffffff;
+  const size_t smem = sizeof(float) * PXT * (C + 1);
+  cudaFuncSetAttribute(to_nhwc_f32_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  to_nhwc_f32_kernel<C><<<blocks, 256, smem, s>>>(j0, j1);
+  pgba::count_launch();
+}
 
 template <int C, int NLEV>
 static int launch_wide(const CUtensorMap& tm0, const CUtensorMap& tm1, const Params& P, cudaStream_t s) {
@@ -819,17 +1164,25 @@ using namespace pcorr_tma;
 extern "C" {
 
 int pcorr_tma_supported(int C, int P, int radius, int dtype) {
-  return (dtype == PCORR_F16 && P == 3 && radius == 3 && (C == 24 || C == 32 || C == 128)) ? 1 : 0;
+  if (P != 3 || radius != 3) return 0;
+  if (dtype == PCORR_F16) return (C == 24 || C == 32 || C == 128) ? 1 : 0;
+  if (dtype == PCORR_F32) return C == 128 ? 1 : 0;        // 3xTF32 tile kernel (corr_tma_wide32_kernel)
+  return 0;
 }
 
-int pcorr_tma_workspace_bytes(int nlev, int B, int64_t F, int C, int H0, int W0, int H1, int W1, size_t* bytes) {
+int pcorr_tma_workspace_bytes_dt(int nlev, int B, int64_t F, int C, int dtype, int H0, int W0, int H1, int W1, size_t* bytes) {
   if (!bytes) return PCORR_ERR_NULL;
   if (nlev < 1 || nlev > 2 || B <= 0 || F <= 0 || C <= 0 || H0 <= 0 || W0 <= 0 || (nlev == 2 && (H1 <= 0 || W1 <= 0)))
     return PCORR_ERR_SHAPE;
-  size_t n = align256((size_t)B * F * H0 * W0 * C * 2);
-  if (nlev == 2) n += align256((size_t)B * F * H1 * W1 * C * 2);
+  const size_t es = dtype == PCORR_F32 ? 4 : 2;
+  size_t n = align256((size_t)B * F * H0 * W0 * C * es);
+  if (nlev == 2) n += align256((size_t)B * F * H1 * W1 * C * es);
   *bytes = n;
   return PCORR_OK;
+}
+
+int pcorr_tma_workspace_bytes(int nlev, int B, int64_t F, int C, int H0, int W0, int H1, int W1, size_t* bytes) {
+  return pcorr_tma_workspace_bytes_dt(nlev, B, F, C, PCORR_F16, H0, W0, H1, W1, bytes);
 }
 
 // lookup on channel-last maps that are already in `workspace` (transpose == false) or are rebuilt from the NCHW maps first
@@ -846,9 +1199,29 @@ static int forward_impl(const void* fmap1, const void* fmap2_l0, const void* fma
   if (H0 < RG || W0 < RG || (nlev == 2 && (H1 < RG || W1 < RG))) return PCORR_ERR_UNSUPPORTED;
   if ((int64_t)B * F >= ((int64_t)1 << 31) || (int64_t)B * F > 65535 || ((uintptr_t)workspace & 255)) return PCORR_ERR_UNSUPPORTED;
   size_t need = 0;
-  int rc = pcorr_tma_workspace_bytes(nlev, B, F, C, H0, W0, H1, W1, &need);
+  int rc = pcorr_tma_workspace_bytes_dt(nlev, B, F, C, dtype, H0, W0, H1, W1, &need);
   if (rc) return rc;
   if (need > workspace_bytes) return PCORR_ERR_SHAPE;
+  if (dtype == PCORR_F32) {
+    float* f0 = (float*)workspace;
+    float* f1 = (float*)((char*)workspace + align256((size_t)B * F * H0 * W0 * C * 4));
+    if (transpose)
+      transpose_maps32(nlev, (const float*)fmap2_l0, f0, H0 * W0, (const float*)fmap2_l1, f1, nlev == 2 ? H1 * W1 : 0, B * (int)F, s);
+    CUtensorMap t0m, t1m;
+    rc = make_map_wide32(&t0m, f0, C, W0, H0, (int64_t)B * F);
+    if (rc) return rc;
+    if (nlev == 2) rc = make_map_wide32(&t1m, f1, C, W1, H1, (int64_t)B * F);
+    else t1m = t0m;
+    if (rc) return rc;
+    Params32 Pf{};
+    Pf.fmap1 = (const float*)fmap1;
+    Pf.nhwc[0] = f0; Pf.nhwc[1] = f1;
+    Pf.H[0] = H0; Pf.W[0] = W0; Pf.H[1] = H1; Pf.W[1] = W1;
+    Pf.coords = coords; Pf.us = ii; Pf.vs = jj;
+    Pf.B = B; Pf.E = E; Pf.K = K; Pf.F = F;
+    Pf.out = (float*)out;
+    return nlev == 2 ? launch_wide32<128, 2>(t0m, t1m, Pf, s) : launch_wide32<128, 1>(t0m, t1m, Pf, s);
+  }
   __half* n0 = (__half*)workspace;
   __half* n1 = (__half*)((char*)workspace + align256((size_t)B * F * H0 * W0 * C * 2));
   if (transpose)

@@ -23,8 +23,9 @@ def _c(t):
 
 
 def _tma(fmap1, maps, coords, ii, jj, radius, out):
-    """Default path of the production shape (fp16, C in {24, 32}, P = 3, R = 3): channel-last maps + TMA region tiles +
-    tensor cores (corr_tma.cu); returns False when the shape does not qualify.  PCORR_TMA=0 disables it (A/B runs)."""
+    """Default path of the production shapes (P = 3, R = 3; fp16 with C in {24, 32, 128}, fp32 with C = 128): channel-last
+    maps + TMA region tiles + tensor cores (corr_tma.cu; fp32: 3xTF32); returns False when the shape does not qualify.
+    PCORR_TMA=0 disables it (A/B runs)."""
     if os.environ.get("PCORR_TMA", "1") == "0":
         return False
     L = native.lib()
@@ -39,8 +40,8 @@ def _tma(fmap1, maps, coords, ii, jj, radius, out):
     if min(H0, W0) < 12 or (nlev == 2 and min(H1, W1) < 12):        # the 12 x 12 TMA box must fit the map
         return False
     nbytes = ctypes.c_size_t(0)
-    native.check(L.pcorr_tma_workspace_bytes(nlev, B, F, C, H0, W0, H1, W1, ctypes.byref(nbytes)),
-                 "pcorr_tma_workspace_bytes")
+    native.check(L.pcorr_tma_workspace_bytes_dt(nlev, B, F, C, _DT[fmap1.dtype], H0, W0, H1, W1, ctypes.byref(nbytes)),
+                 "pcorr_tma_workspace_bytes_dt")
     with torch.cuda.device(fmap1.device):
         ws = native.workspace(nbytes.value, fmap1.device, pool="corr_tma")
         rc = L.pcorr_forward_tma(fmap1.data_ptr(), maps[0].data_ptr(), maps[1].data_ptr() if nlev == 2 else None,

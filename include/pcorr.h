@@ -54,6 +54,9 @@ int pcorr_forward_pyramid2(const void* fmap1, const void* fmap2_l0, const void* 
 int pcorr_tma_supported(int C, int P, int radius, int dtype);
 int pcorr_tma_workspace_bytes(int nlev, int B, int64_t F, int C, int H0, int W0, int H1, int W1,
                               size_t* bytes /* host, out */);
+/* the same with the feature dtype stated (fp32 maps, C = 128: the 3xTF32 tile kernel needs a 4-byte channel-last copy) */
+int pcorr_tma_workspace_bytes_dt(int nlev, int B, int64_t F, int C, int dtype, int H0, int W0, int H1, int W1,
+                                 size_t* bytes /* host, out */);
 int pcorr_forward_tma(const void* fmap1, const void* fmap2_l0, const void* fmap2_l1, const float* coords,
                       const int64_t* ii, const int64_t* jj, int nlev, int B, int64_t E, int64_t K, int64_t F, int C,
                       int H0, int W0, int H1, int W1, int P, int radius, int dtype, void* out, void* workspace,

@@ -35,6 +35,21 @@ def main():
             with torch.cuda.graph(gr):
                 fn()
             res["C%d_tma%s_graph_ms" % (C, mode)] = bench.timed_events(gr.replay, 20, before=flush.zero_)
+    # fp32, C = 128: TMA tile kernel (3xTF32) vs the staged FFMA kernel
+    gmap, pyr = synth.make_fmaps(p, C=128)
+    g = torch.as_tensor(gmap, device=dev)[None].float()
+    f0 = torch.as_tensor(pyr[0], device=dev)[None].float()
+    f1 = torch.as_tensor(pyr[1], device=dev)[None].float()
+    for mode in ("1", "0"):
+        os.environ["PCORR_TMA"] = mode
+        fn = lambda: altcorr.corr_pyramid2(g, [f0, f1], coords, d["kk"], d["jj"], 3)
+        for _ in range(3):
+            fn()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            fn()
+        res["C128_f32_tma%s_graph_ms" % mode] = bench.timed_events(gr.replay, 20, before=flush.zero_)
+    os.environ["PCORR_TMA"] = "1"
     print(json.dumps(res))
 
 

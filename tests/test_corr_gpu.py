@@ -164,6 +164,42 @@ def test_corr_fp16_tma_path(C, monkeypatch):
     assert torch.equal(fused[okf], both[okf])
 
 
+def test_corr_fp32_tile_path(monkeypatch):
+    """fp32, C = 128, P = 3, R = 3 takes the TMA tile kernel with the 3xTF32 contraction (corr_tma_wide32_kernel): both
+    levels, windows across the map border, far outside the map, windows too far apart for one region (per-tap path), a
+    non-finite coordinate; against the float64 oracle at north_star's 1e-5 absolute, against the staged FFMA kernel
+    (PCORR_TMA=0), and the fused two-level call against the two single-level calls bit for bit."""
+    p, gmap, pyr, coords = _setup(128, np.float32, seed=7, F=8, M=24, n_mem=8)
+    coords[0, 40:44] += 5000.0
+    coords[0, 44:46, :, 0, 0] += 9.0
+    coords[0, 46, 0, 1, 1] = np.float32("nan")
+    dev = "cuda"
+    g = torch.as_tensor(gmap, device=dev)[None]
+    maps = [torch.as_tensor(x, device=dev)[None] for x in pyr]
+    ii = torch.as_tensor(p.kk, device=dev); jj = torch.as_tensor(p.jj, device=dev)
+    c = torch.as_tensor(coords, device=dev)
+    finite = np.isfinite(coords).all(axis=(2,))[0]
+    outs = []
+    for lvl, scale in ((0, 1.0), (1, 4.0)):
+        cl = (coords / np.float32(scale)).astype(np.float32)
+        got = altcorr.corr(g, maps[lvl], torch.as_tensor(cl, device=dev), ii, jj, 3)
+        want = corr_oracle.corr(gmap[None], pyr[lvl][None], np.nan_to_num(cl, nan=-1e7), p.kk, p.jj, 3)
+        assert got.dtype == torch.float32 and got.shape == (1, p.E, 7, 7, 3, 3)
+        err = np.abs(got.cpu().numpy() - want)
+        ok = np.broadcast_to(finite[None, :, None, None], err.shape)
+        assert err[ok].max() < 1e-5, err[ok].max()
+        assert np.abs(want).max() > 0.05
+        monkeypatch.setenv("PCORR_TMA", "0")
+        staged = altcorr.corr(g, maps[lvl], torch.as_tensor(cl, device=dev), ii, jj, 3)
+        monkeypatch.delenv("PCORR_TMA")
+        assert (got - staged).abs().cpu().numpy()[ok].max() < 1e-5
+        outs.append(got)
+    fused = altcorr.corr_pyramid2(g, maps, c, ii, jj, 3)
+    both = torch.stack(outs, -1).view(1, p.E, -1)
+    okf = torch.as_tensor(np.broadcast_to(finite[None, :, None, None, :, :, None], (1, p.E, 7, 7, 3, 3, 2)).reshape(1, p.E, -1).copy(), device=dev)
+    assert torch.equal(fused[okf], both[okf])
+
+
 def test_corr_fp16_tma_batch2():
     """B = 2: per-batch maps and coordinates, shared edge lists (the reference's [B, ...] layout)."""
     p, gmap, pyr, coords = _setup(24, np.float16, seed=4, F=6, M=16, n_mem=6)

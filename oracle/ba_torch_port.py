@@ -204,8 +204,8 @@ def ba_torch(poses, patches, intrinsics, targets, weights, lmbda, ii, jj, kk, bo
     disps = (disps + upd).clamp(min=1e-3, max=10.0)
     patches = torch.stack([x, y_, disps], dim=2)
     if dX is not None:
-        poses = poses.clone()
-        poses[:, fixedp:fixedp + n] = se3_retr(poses[:, fixedp:fixedp + n], dX)
+        # functional (no in-place write into a tensor whose slice fed the retraction: keeps the port differentiable)
+        poses = torch.cat([poses[:, :fixedp], se3_retr(poses[:, fixedp:fixedp + n], dX), poses[:, fixedp + n:]], 1)
     return poses, patches
 
 

@@ -143,6 +143,28 @@ def run_reference(problem, iterations, ep, dtype=torch.float64):
     return out
 
 
+def run_reference_grad(problem, ep, dtype=torch.float64):
+    """Gradients through ONE step of the verbatim reference BA, including its own CholeskySolver.backward (ba.py:26-37):
+    L = sum_k c_k * d_k(new inverse depths) with fixed pseudo-random c; dL/dtargets, dL/dweights.  (Gradients w.r.t. the
+    poses would need the compiled lietorch backward ops, which cannot be built here; the depth output depends on targets /
+    weights through the whole solve -- S, y, dX, dZ -- without passing through them.)"""
+    ref_ba, ref_pops, SE3 = _import_reference()
+    t = lambda a: torch.as_tensor(np.asarray(a), dtype=dtype)[None]
+    poses = SE3(t(problem.poses))
+    patches, intr = t(problem.patches), t(problem.intrinsics)
+    target = t(problem.target).requires_grad_(True)
+    weight = t(problem.weight).requires_grad_(True)
+    ii, jj, kk = (torch.as_tensor(x) for x in (problem.ii, problem.jj, problem.kk))
+    fx, fy, cx, cy = problem.intrinsics[0]
+    bounds = [-64.0, -64.0, 2 * cx + 64.0, 2 * cy + 64.0]
+    _, new_patches = ref_ba.BA(poses, patches, intr, target, weight, problem.lmbda, ii, jj, kk, bounds, ep=ep,
+                               fixedp=problem.t0)
+    c = torch.as_tensor(np.random.default_rng(7).standard_normal(new_patches.shape[1]), dtype=dtype)
+    loss = (c * new_patches[0, :, 2, 0, 0]).sum()
+    loss.backward()
+    return dict(grad_target=target.grad[0].numpy().copy(), grad_weight=weight.grad[0].numpy().copy(), loss=float(loss))
+
+
 def main():
     sys.path.insert(0, os.path.join(REPO, "cdv-slam_b200"))
     from cdvslam_b200 import synth
@@ -160,6 +182,9 @@ def main():
                             Jz=res["Jz"].astype(np.float32), coords_centre=res["coords"][:, 1, 1, :])
             meta = dict(seed_note="inputs are regenerated from cdvslam_b200.synth with the recorded constructor",
                         ep=ep, t0=prob.t0, t1=prob.t1, E=prob.E)
+            if name == "small":
+                g = run_reference_grad(prob, ep)
+                keep.update(grad_target=g["grad_target"], grad_weight=g["grad_weight"], grad_loss=np.asarray(g["loss"]))
             path = os.path.join(HERE, "ba_ref_%s_ep%g.npz" % (name, ep))
             np.savez_compressed(path, **keep, **{"meta_" + k: np.asarray(v) for k, v in meta.items()})
             print("wrote", path, {k: v.shape for k, v in keep.items()})

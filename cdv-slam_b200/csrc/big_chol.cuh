@@ -11,6 +11,8 @@
 // for the pose-graph solve) and `sys.get(w)` returns the pointers of system w (blockIdx.y).  Used by ba_bigsolve.cu
 // (global BA, reference: cdvslam/fastba/ba_cuda.cu:575-578, 589-591) and pgo.cu (cuda_ba.solve_system, ba.cpp:99-180).
 #pragma once
+#include <stdlib.h>
+
 #include "ba_common.cuh"
 #include "ba_chol.cuh"
 
@@ -252,6 +254,79 @@ __global__ void __launch_bounds__(256) big_back_kernel(Sys sys, int step) {
   big_back_finish_dev(bp, step, sz);
 }
 
+// The whole backward substitution L^T x = z in ONE launch: one CTA of 1024 threads per system walks the panels from the last
+// to the first (the 125 dependent launches of big_back_kernel cost ~9 us each on the global BA: launch + cold round trips
+// for ~50 KB of work).  The running solution lives in shared memory (n floats); per panel the 32 warps split its ACTIVE row
+// tiles (the only rows with non-zero L[r][panel]), each warp accumulating its 48 partial dot products with coalesced row
+// reads, partials are folded through shared memory, then 48 threads apply the explicit inverse of the diagonal tile.
+// The tile list and W of the next panel are independent of x, so their first touch overlaps the current panel's tail.
+// dynamic smem: (n + 32 * NB + NB) * sizeof(T)
+template <typename Sys>
+__global__ void __launch_bounds__(1024, 1) big_backsolve_kernel(Sys sys, int nsteps) {
+  pdl_wait();
+  pdl_trigger();
+  using T = typename Sys::T;
+  extern __shared__ __align__(16) unsigned char bsm[];
+  const BigSys<T> bp = sys.get(blockIdx.y);
+  const int n6 = bp.n;
+  T* sx = reinterpret_cast<T*>(bsm);                // [n]      z on entry, x as the panels complete
+  T* spart = sx + n6;                               // [32][NB] per-warp partial sums
+  T* sz = spart + 32 * NB;                          // [NB]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int x = tid; x < n6; x += 1024) sx[x] = bp.y[x];
+  __syncthreads();
+  for (int step = nsteps - 1; step >= 0; --step) {
+    const int kb = step * NB;
+    const int nh = min(NB, n6 - kb), r0 = kb + nh;
+    const int na = bp.nact[step];
+    const int* act = bp.active + (size_t)step * bp.big_tiles;
+    T acc0 = 0, acc1 = 0;                           // columns lane and lane + 32 of the panel
+    for (int ia = warp; ia < na; ia += 32) {
+      const int t = act[ia];
+      if (t == -1) continue;                        // the right-hand-side row of the factorisation
+      const int ra = r0 + t * NB, rows = min(NB, n6 - ra);
+      const T* Lp = bp.S + (size_t)ra * bp.ld + kb;
+      // 12 rows (24 loads) in flight per lane: the tile is cold in L2 / DRAM and a dependent row-by-row walk would pay a
+      // full round trip per row
+      constexpr int RB = 12;
+      for (int rb = 0; rb < rows; rb += RB) {
+        T v0[RB], v1[RB];
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          const bool in = rb + r < rows;
+          const T* row = Lp + (size_t)(rb + r) * bp.ld;
+          v0[r] = (in && lane < nh) ? row[lane] : (T)0;
+          v1[r] = (in && lane + 32 < nh) ? row[lane + 32] : (T)0;
+        }
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          const T xr = (rb + r < rows) ? sx[ra + rb + r] : (T)0;
+          acc0 += v0[r] * xr;
+          acc1 += v1[r] * xr;
+        }
+      }
+    }
+    spart[warp * NB + lane] = acc0;
+    if (lane + 32 < NB) spart[warp * NB + lane + 32] = acc1;
+    __syncthreads();
+    if (tid < nh) {
+      T s = 0;
+#pragma unroll
+      for (int w = 0; w < 32; ++w) s += spart[w * NB + tid];
+      sz[tid] = sx[kb + tid] - s;
+    }
+    __syncthreads();
+    if (tid < nh) {                                 // x[c] = sum_{e >= c} W[c][e] z[e]
+      const T* W = bp.winv + (size_t)step * NB * NB + tid * NB;
+      T a = 0;
+      for (int e = tid; e < nh; ++e) a += W[e] * sz[e];
+      sx[kb + tid] = a;
+      bp.y[kb + tid] = a;
+    }
+    __syncthreads();
+  }
+}
+
 // Host: factorisation + both substitutions of `batch` systems of order n (the damping has been applied by the caller).
 template <typename Sys>
 cudaError_t launch_big_chol(const Sys& sys, int n, int64_t batch, cudaStream_t stream) {
@@ -272,9 +347,20 @@ cudaError_t launch_big_chol(const Sys& sys, int n, int64_t batch, cudaStream_t s
       count_launch();
     }
   }
-  for (int s = nsteps - 1; s >= 0; --s) {
-    launch_k(big_back_kernel<Sys>, dim3(16, B), dim3(256), 0, stream, sys, s);
+  // backward substitution: one launch (x in shared memory) when the system fits, else one launch per panel
+  using T = typename Sys::T;
+  const size_t bsmem = sizeof(T) * ((size_t)n + 32 * NB + NB);
+  static int one_launch = -1;                       // PGBA_BIG_BACK_SPLIT=1: the per-panel kernels (A/B runs)
+  if (one_launch < 0) { const char* e = getenv("PGBA_BIG_BACK_SPLIT"); one_launch = (e && e[0] == '1') ? 0 : 1; }
+  if (one_launch && bsmem <= 200 * 1024) {
+    cudaFuncSetAttribute(big_backsolve_kernel<Sys>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem);
+    launch_k(big_backsolve_kernel<Sys>, dim3(1, B), dim3(1024), bsmem, stream, sys, nsteps);
     count_launch();
+  } else {
+    for (int s = nsteps - 1; s >= 0; --s) {
+      launch_k(big_back_kernel<Sys>, dim3(16, B), dim3(256), 0, stream, sys, s);
+      count_launch();
+    }
   }
   return cudaGetLastError();
 }

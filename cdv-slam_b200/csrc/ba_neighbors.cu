@@ -10,10 +10,9 @@
 //   P2  exclusive scan of the bin counts (every CTA scans its own copy in shared memory with warp shuffles; CTA 0 also
 //       writes the offsets to global memory for the second kernel)
 //   P3  scatter the edge ids into the bins
-// neighbors_link_kernel (grid over the bins, all SMs): per bin, order by (ii, jj, edge id) -- what the reference's
-//   stable_sort of a group in input order produces -- and link consecutive edges with equal ii.  Bins of <= 32 edges: one
-//   thread, insertion sort in local memory (the normal case: a patch has ~20 edges); larger bins: the whole CTA, rank by
-//   counting.
+// neighbors_link_kernel (all SMs): one warp per bin, bins dealt round-robin over the warps; per bin, order by (ii, jj, edge
+//   id) -- what the reference's stable_sort of a group in input order produces -- by rank counting over the lanes, and link
+//   consecutive edges with equal ii.  Bins of > 32 edges: the same in strips of 32.
 #include <cooperative_groups.h>
 
 #include "ba_common.cuh"
@@ -125,58 +124,74 @@ __global__ void __launch_bounds__(NBR_T, 1) neighbors_bin_kernel(const int64_t* 
   for (int e = gt + NBR_KEEP * GT; e < E; e += GT) slots[s_off[(unsigned)ii[e] & mask] + rank[e]] = e;
 }
 
-// grid = nb / NBR_LT CTAs of NBR_LT threads; `tmp` (E ints) receives the ordered list of the large bins
+// One WARP per bin, bins dealt round-robin over all warps of the grid (the non-empty bins are consecutive -- bin = ii mod nb
+// and patch ids are dense -- so a contiguous assignment would leave the work on a dozen SMs).  A bin of n <= 32 edges (the
+// normal case: a patch has ~20 edges) is ordered by rank counting over the lanes: lane x holds edge x of the bin, reads the
+// other lanes' (ii, jj, edge id) by shuffles and counts the smaller keys -- (ii, jj, edge id) is what the reference's
+// stable_sort of a group in input order produces; the ordered list goes through a per-warp shared-memory line and every
+// lane links its edge to the entries before / after it when they belong to the same ii.  Larger bins (a group of more
+// than 32 edges, or many keys folded into one bin): the same by the warp in strips of 32, positions by counting over the
+// whole bin, ordered list in `tmp`.
 __global__ void __launch_bounds__(NBR_LT) neighbors_link_kernel(const int64_t* __restrict__ ii, const int64_t* __restrict__ jj,
                                                                int nb, const int* __restrict__ off, const int* __restrict__ slots,
                                                                int* __restrict__ tmp, int64_t* __restrict__ ix,
                                                                int64_t* __restrict__ jx) {
   pdl_wait();
   pdl_trigger();
-  const int tid = threadIdx.x;
-  const int b = blockIdx.x * NBR_LT + tid;
-  const int o = off[b], n = off[b + 1] - o;
-  // ---- small bins, one thread each: all edge ids first, then all keys (independent loads), then the sort
-  if (n > 0 && n <= NBR_SMALL) {
-    NbrKey k[NBR_SMALL];
-    for (int x = 0; x < n; ++x) k[x].e = slots[o + x];
-    for (int x = 0; x < n; ++x) { k[x].i = ii[k[x].e]; k[x].j = jj[k[x].e]; }
-    for (int x = 1; x < n; ++x) {                     // insertion sort
-      const NbrKey v = k[x];
-      int y = x - 1;
-      while (y >= 0 && nbr_less(v, k[y])) { k[y + 1] = k[y]; --y; }
-      k[y + 1] = v;
-    }
-    for (int x = 0; x < n; ++x) {
-      ix[k[x].e] = (x > 0 && k[x - 1].i == k[x].i) ? (int64_t)k[x - 1].e : -1;
-      jx[k[x].e] = (x + 1 < n && k[x + 1].i == k[x].i) ? (int64_t)k[x + 1].e : -1;
-    }
-  }
-  // ---- large bins (a group of more than 32 edges, or many keys folded into one bin): the whole CTA, one bin after the
-  //      other: position = number of smaller keys, ordered list written to `tmp`, then linked
-  if (!__syncthreads_or(n > NBR_SMALL)) return;
-  for (int t = 0; t < NBR_LT; ++t) {
-    const int bb = blockIdx.x * NBR_LT + t;
-    const int ob = off[bb], nn = off[bb + 1] - ob;
-    if (nn <= NBR_SMALL) continue;                    // uniform over the CTA
-    for (int a = tid; a < nn; a += NBR_LT) {
-      NbrKey ka; ka.e = slots[ob + a]; ka.i = ii[ka.e]; ka.j = jj[ka.e];
-      int pos = 0;
-      for (int c = 0; c < nn; ++c) {
-        NbrKey kc; kc.e = slots[ob + c]; kc.i = ii[kc.e]; kc.j = jj[kc.e];
-        pos += nbr_less(kc, ka) ? 1 : 0;
+  __shared__ int s_e[NBR_LT / 32][32];
+  __shared__ long long s_i[NBR_LT / 32][32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int warp = blockIdx.x * (NBR_LT / 32) + wib, nwarps = gridDim.x * (NBR_LT / 32);
+  for (int b0 = warp; b0 < nb; b0 += 32 * nwarps) {
+    // the warp's next 32 bins (stride nwarps): one lane looks at one bin, the non-empty ones are then processed in turn
+    const int myb = b0 + lane * nwarps;
+    int o_l = 0, n_l = 0;
+    if (myb < nb) { o_l = off[myb]; n_l = off[myb + 1] - o_l; }
+    unsigned todo = __ballot_sync(0xffffffffu, n_l > 0);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int o = __shfl_sync(0xffffffffu, o_l, src), n = __shfl_sync(0xffffffffu, n_l, src);
+      if (n <= NBR_SMALL) {
+        int e = 0;
+        long long ki = 0, kj = 0;
+        if (lane < n) { e = slots[o + lane]; ki = ii[e]; kj = jj[e]; }
+        int pos = 0;
+        for (int y = 0; y < n; ++y) {
+          const long long yi = __shfl_sync(0xffffffffu, ki, y), yj = __shfl_sync(0xffffffffu, kj, y);
+          const int ye = __shfl_sync(0xffffffffu, e, y);
+          pos += (yi < ki || (yi == ki && (yj < kj || (yj == kj && ye < e)))) ? 1 : 0;
+        }
+        __syncwarp();
+        if (lane < n) { s_e[wib][pos] = e; s_i[wib][pos] = ki; }
+        __syncwarp();
+        if (lane < n) {
+          ix[e] = (pos > 0 && s_i[wib][pos - 1] == ki) ? (int64_t)s_e[wib][pos - 1] : -1;
+          jx[e] = (pos + 1 < n && s_i[wib][pos + 1] == ki) ? (int64_t)s_e[wib][pos + 1] : -1;
+        }
+      } else {
+        for (int a = lane; a < n; a += 32) {
+          NbrKey ka; ka.e = slots[o + a]; ka.i = ii[ka.e]; ka.j = jj[ka.e];
+          int pos = 0;
+          for (int c = 0; c < n; ++c) {
+            NbrKey kc; kc.e = slots[o + c]; kc.i = ii[kc.e]; kc.j = jj[kc.e];
+            pos += nbr_less(kc, ka) ? 1 : 0;
+          }
+          tmp[o + pos] = ka.e;
+        }
+        __threadfence_block();
+        __syncwarp();
+        for (int a = lane; a < n; a += 32) {
+          const int e = tmp[o + a];
+          const long long gi = ii[e];
+          int pe = -1, ne = -1;
+          if (a > 0) { pe = tmp[o + a - 1]; if (ii[pe] != gi) pe = -1; }
+          if (a + 1 < n) { ne = tmp[o + a + 1]; if (ii[ne] != gi) ne = -1; }
+          ix[e] = pe; jx[e] = ne;
+        }
+        __syncwarp();
       }
-      tmp[ob + pos] = ka.e;
     }
-    __syncthreads();
-    for (int a = tid; a < nn; a += NBR_LT) {
-      const int e = tmp[ob + a];
-      const long long gi = ii[e];
-      int pe = -1, ne = -1;
-      if (a > 0) { pe = tmp[ob + a - 1]; if (ii[pe] != gi) pe = -1; }
-      if (a + 1 < nn) { ne = tmp[ob + a + 1]; if (ii[ne] != gi) ne = -1; }
-      ix[e] = pe; jx[e] = ne;
-    }
-    __syncthreads();
   }
 }
 
@@ -227,7 +242,8 @@ int pgba_neighbors(const int64_t* ii, const int64_t* jj, int64_t n_edges, int64_
   cudaError_t e = cudaLaunchKernelEx(&cfg, neighbors_bin_kernel, ii, (int)n_edges, nb, cnt, rank, slots, off);
   count_launch();
   if (e != cudaSuccess) return (int)e;
-  e = launch_k(neighbors_link_kernel, dim3((unsigned)(nb / NBR_LT)), dim3(NBR_LT), 0, (cudaStream_t)stream, ii, jj, nb,
+  const int link_grid = nb / 32 < 148 * 8 ? nb / 32 : 148 * 8;      // one bin per lane and trip; >= 1 (nb >= 1024)
+  e = launch_k(neighbors_link_kernel, dim3((unsigned)link_grid), dim3(NBR_LT), 0, (cudaStream_t)stream, ii, jj, nb,
                (const int*)off, (const int*)slots, rank, ix, jx);
   count_launch();
   if (e != cudaSuccess) return (int)e;

@@ -581,10 +581,14 @@ def hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(workload):
-    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+STAGE_KERNEL = {"linearize_schur": "linearize_kernel", "solve_retr": "solve_small_kernel", "backsub_retr": "update_kernel",
+                "plan": "plan_cluster_kernel+plan_cells_kernel"}
+
+
+def ncu_traffic(workload, stage="linearize_schur"):
+    """dram bytes per launch of the stage's kernel from the committed ncu capture (profiles/traffic.json), if any."""
     try:
-        return json.load(open(os.path.join(REPO, "profiles", "traffic.json")))[workload]["linearize_kernel"]
+        return json.load(open(os.path.join(REPO, "profiles", "traffic.json")))[workload][STAGE_KERNEL[stage]]
     except Exception:
         return None
 
@@ -717,7 +721,7 @@ def main():
                          "frac": table[dom]["frac_of_hbm_peak"],
                          "algorithmic_bytes_per_launch": table[dom]["algorithmic_bytes_per_launch"],
                          "ms_per_launch": table[dom]["ms_per_launch"], "share_of_step": table[dom]["share_of_step"],
-                         "traffic": ncu_traffic(args.workload) if dom == "linearize_schur" else None,
+                         "traffic": ncu_traffic(args.workload, dom),
                          "linearize_frac": alg_stage["linearize_schur"] / (lin_ms * 1e-3) / 1e9 / peak,
                          "note": "a single c2 window moves ~3 MB per iteration (<1 us of HBM time): every stage is "
                                  "latency-bound by construction; the HBM fraction is meaningful on sharded_c5 / batched_c5"},

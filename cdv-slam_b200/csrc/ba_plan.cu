@@ -613,21 +613,36 @@ __global__ void __launch_bounds__(PD_T, 1) plan_direct_kernel(Problem pb, int e_
   __syncthreads();
   const bool use_cache = pb.plan_cache != 0;
   unsigned long long h1 = 0ull, h2 = 0ull;
-  auto mix = [](unsigned long long x) {
-    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 27; x *= 0x94d049bb133111ebull; x ^= x >> 31;
+  // fingerprint of the edge list: two 64-bit sums of per-edge values, each made of two different 32-bit mixes of (edge
+  // position, ii, jj, kk) (murmur3-style finalisers: 32-bit multiplies -- the 64-bit mixer this replaces was 16 % of the
+  // kernel's instructions).  Position-dependent, so a permuted list (other edge ids in the cell table) does not match.
+  auto mix32 = [](unsigned x) {
+    x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
     return x;
   };
   int bad = 0, jmn = 0x7fffffff, jmx = -1, n_ok = 0;
   constexpr int LU = 4;                                // edges in flight per thread (64 registers: 4 x 3 64-bit loads)
   for (int q0 = 0; q0 < nq; q0 += LU) {
-    EdgeIdx xs[LU];
+    // raw loads of LU edges first (clamped addresses, no branches in between: all 3 * LU loads are in flight together),
+    // range checks and everything else afterwards
+    long long vi[LU], vj[LU], vk[LU];
 #pragma unroll
-    for (int u = 0; u < LU; ++u) xs[u] = load_edge(pb, ii, jj, kk, gt + (q0 + u) * GT, E);
+    for (int u = 0; u < LU; ++u) {
+      const int ec = min(gt + (q0 + u) * GT, E - 1);
+      if (pb.idx32) {
+        vi[u] = reinterpret_cast<const int32_t*>(ii)[ec]; vj[u] = reinterpret_cast<const int32_t*>(jj)[ec];
+        vk[u] = reinterpret_cast<const int32_t*>(kk)[ec];
+      } else {
+        vi[u] = ii[ec]; vj[u] = jj[ec]; vk[u] = kk[ec];
+      }
+    }
 #pragma unroll
     for (int u = 0; u < LU; ++u) {
       const int q = q0 + u, e = gt + q * GT;
       if (q >= nq) break;
-      const EdgeIdx x = xs[u];
+      EdgeIdx x;
+      x.ok = e < E && !(vi[u] < 0 || vi[u] >= pb.F || vj[u] < 0 || vj[u] >= pb.F || vk[u] < 0 || vk[u] >= pb.K);
+      x.i = x.ok ? (int)vi[u] : -1; x.j = x.ok ? (int)vj[u] : 0; x.k = x.ok ? (int)vk[u] : 0;
       uint2 r = make_uint2(PD_BAD, 0u);
       if (e < E) {
         if (x.ok) {
@@ -637,11 +652,13 @@ __global__ void __launch_bounds__(PD_T, 1) plan_direct_kernel(Problem pb, int e_
           bad = 1;
         }
         if (use_cache) {
-          const unsigned long long a = ((unsigned long long)(unsigned)x.k << 32) | (unsigned)e;
-          const unsigned long long b = ((unsigned long long)(unsigned)x.i << 32) | (unsigned)x.j;
-          const unsigned long long m = mix(a ^ (b * 0x9e3779b97f4a7c15ull));
-          h1 += m;
-          h2 += mix(m + b);
+          const unsigned ij = ((unsigned)x.i << 16) ^ (unsigned)x.j;
+          const unsigned m0 = mix32((unsigned)e * 0x9e3779b1u + (unsigned)x.k);
+          const unsigned m1 = mix32(m0 ^ (ij * 0x27d4eb2fu));
+          const unsigned m2 = mix32((unsigned)x.k * 0x165667b1u + ij + m1);
+          const unsigned m3 = mix32(m2 + (unsigned)e);
+          h1 += ((unsigned long long)m0 << 32) | m1;
+          h2 += ((unsigned long long)m2 << 32) | m3;
         }
       }
       recs[q * T + tid] = r;
@@ -667,7 +684,7 @@ __global__ void __launch_bounds__(PD_T, 1) plan_direct_kernel(Problem pb, int e_
     n_ok = __reduce_add_sync(0xffffffffu, n_ok);
   }
   if (use_cache) {
-    if (gt == 0) h1 += mix((unsigned long long)E + 0x51ull);
+    if (gt == 0) h1 += ((unsigned long long)mix32((unsigned)E + 0x51u) << 32) | mix32((unsigned)E * 0x9e3779b1u);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       h1 += __shfl_xor_sync(0xffffffffu, h1, o);
@@ -856,26 +873,34 @@ __global__ void __launch_bounds__(PD_T, 1) plan_direct_kernel(Problem pb, int e_
   for (int x = tid; x < n_chunks * BW; x += T) bm_part[x] = 0u;
   __syncthreads();
   PLAN_TS(6);
-  const volatile unsigned* vbm = bm_part;
-  for (int q = 0; q < nq; ++q) {
-    const uint2 r = recs[q * T + tid];
-    const bool ok = r.x != PD_BAD;
-    const int i = ok ? (int)(r.x >> 16) : 0, j = (int)(r.x & 0xffffu);      // padding records: any valid address
-    const int kd = (int)r.y - s_km[i];
-    const int c = ok ? s_fb[i] + (kd >> lpc) : -1;
-    const int pl = kd & (pc - 1), js = j - jmin;
-    const int pw = ok ? c * BW + (pl >> 5) : -1;
-    const int jw = ok ? c * BW + PW + (js >> 5) : -1;
-    {
-      const unsigned grp = __all_sync(0xffffffffu, pw == __shfl_sync(0xffffffffu, pw, 0)) ? 0xffffffffu : __match_any_sync(0xffffffffu, pw);
-      const unsigned m = __reduce_or_sync(grp, 1u << (pl & 31));
-      if (ok && lane == __ffs(grp) - 1 && (vbm[pw] & m) != m) atomicOr(&bm_part[pw], m);     // look first (see D1)
+  // Every thread walks nq CONSECUTIVE records (consecutive edges: the API delivers them patch-major, so a thread mostly stays
+  // inside one patch): the bits of a run with the same bitmap word are collected in a register and flushed with one
+  // shared-memory atomic per run -- no warp votes.  (With lanes <-> consecutive records and one vote per record this phase
+  // was issue-bound: ~80 instructions per edge, 9.7 us on the 64-window batch.)
+  {
+    int cur_pw = -1, cur_jw = -1;
+    unsigned pbits = 0u, jbits = 0u;
+    for (int sq = 0; sq < nq; ++sq) {
+      const uint2 r = recs[tid * nq + sq];
+      if (r.x == PD_BAD) continue;
+      const int i = (int)(r.x >> 16), j = (int)(r.x & 0xffffu);
+      const int kd = (int)r.y - s_km[i];
+      const int c = s_fb[i] + (kd >> lpc);
+      const int pl = kd & (pc - 1), js = j - jmin;
+      const int pw = c * BW + (pl >> 5), jw = c * BW + PW + (js >> 5);
+      if (pw != cur_pw) {
+        if (cur_pw >= 0) atomicOr(&bm_part[cur_pw], pbits);
+        cur_pw = pw; pbits = 0u;
+      }
+      pbits |= 1u << (pl & 31);
+      if (jw != cur_jw) {
+        if (cur_jw >= 0) atomicOr(&bm_part[cur_jw], jbits);
+        cur_jw = jw; jbits = 0u;
+      }
+      jbits |= 1u << (js & 31);
     }
-    {
-      const unsigned grp = __all_sync(0xffffffffu, jw == __shfl_sync(0xffffffffu, jw, 0)) ? 0xffffffffu : __match_any_sync(0xffffffffu, jw);
-      const unsigned m = __reduce_or_sync(grp, 1u << (js & 31));
-      if (ok && lane == __ffs(grp) - 1 && (vbm[jw] & m) != m) atomicOr(&bm_part[jw], m);
-    }
+    if (cur_pw >= 0) atomicOr(&bm_part[cur_pw], pbits);
+    if (cur_jw >= 0) atomicOr(&bm_part[cur_jw], jbits);
   }
   PLAN_TS(7);
   cl.sync();
@@ -986,6 +1011,10 @@ __global__ void __launch_bounds__(PD_T, 1) plan_direct_kernel(Problem pb, int e_
   //      units: 18.5 us for the 2.4 M edges of the 64-window batch), then, after one more barrier, every edge reads its cell
   //      back: an edge that finds another id there shares the cell with it (duplicated (patch, target frame) pair) and goes
   //      to the duplicates list, which the linearisation handles on its slow path.
+  // (lanes <-> consecutive edges here, unlike D3: the lanes of a warp then write neighbouring cells of one or two table rows,
+  // i.e. a few sectors per store.  Measured alternatives, 64-window batch: consecutive records per thread with the patch part
+  // of the index cached 13.3 us; that as an index pass followed by a strided store pass 14.8 us; this loop 7.7 - 8.1 us)
+#pragma unroll 4
   for (int q = 0; q < nq; ++q) {
     const uint2 r = recs[q * T + tid];
     if (r.x == PD_BAD) continue;
@@ -1004,15 +1033,23 @@ __global__ void __launch_bounds__(PD_T, 1) plan_direct_kernel(Problem pb, int e_
   }
   PLAN_TS(11);
   cl.sync();
-  for (int q = 0; q < nq; ++q) {
-    const uint2 r = recs[q * T + tid];
-    if (r.x == PD_BAD) continue;
-    const int n = gt + q * GT;
-    if (__ldcg(&wp.cells[r.x]) != n) {
-      const int c = (int)r.y, rem = (int)r.x - c_cbase[c];
-      const int d = atomicAdd(&wp.hdr->n_dups, 1);
-      DupEdge de; de.chunk = c; de.p = rem / c_ns[c]; de.s = rem - de.p * c_ns[c]; de.n = n;
-      wp.dups[d] = de;
+  for (int q0 = 0; q0 < nq; q0 += LU) {                  // LU read-backs in flight per thread
+    uint2 rr[LU];
+    int got[LU];
+#pragma unroll
+    for (int u = 0; u < LU; ++u) {
+      rr[u] = (q0 + u < nq) ? recs[(q0 + u) * T + tid] : make_uint2(PD_BAD, 0u);
+      got[u] = (rr[u].x != PD_BAD) ? __ldcg(&wp.cells[rr[u].x]) : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < LU; ++u) {
+      const int n = gt + (q0 + u) * GT;
+      if (rr[u].x != PD_BAD && got[u] != n) {
+        const int c = (int)rr[u].y, rem = (int)rr[u].x - c_cbase[c];
+        const int d = atomicAdd(&wp.hdr->n_dups, 1);
+        DupEdge de; de.chunk = c; de.p = rem / c_ns[c]; de.s = rem - de.p * c_ns[c]; de.n = n;
+        wp.dups[d] = de;
+      }
     }
   }
   if (use_cache && rank == 0 && tid == 0) { wp.hdr->fp[0] = h1; wp.hdr->fp[1] = h2; }   // the tables match this edge list

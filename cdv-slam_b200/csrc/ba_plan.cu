@@ -621,7 +621,10 @@ __global__ void __launch_bounds__(PD_T, 1) plan_direct_kernel(Problem pb, int e_
     return x;
   };
   int bad = 0, jmn = 0x7fffffff, jmx = -1, n_ok = 0;
-  constexpr int LU = 4;                                // edges in flight per thread (64 registers: 4 x 3 64-bit loads)
+#ifndef PGBA_PD_LU
+#define PGBA_PD_LU 4
+#endif
+  constexpr int LU = PGBA_PD_LU;                       // edges in flight per thread (64 registers: 4 x 3 64-bit loads)
   for (int q0 = 0; q0 < nq; q0 += LU) {
     // raw loads of LU edges first (clamped addresses, no branches in between: all 3 * LU loads are in flight together),
     // range checks and everything else afterwards

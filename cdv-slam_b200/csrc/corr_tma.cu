@@ -711,8 +711,8 @@ __global__ void __launch_bounds__(32 * WWARPS, 1) corr_tma_wide_kernel(const __g
 // fp32 feature maps (training / parity path; C a multiple of 16, built for the 128-channel maps): the wide kernel's scheme
 // with 16-channel chunks (64-byte pixel records again, SWIZZLE_64B, the same ldmatrix addresses: an 8x8 b16 matrix is
 // 8 records x 4 floats, which is exactly the tf32 m16n8k8 A fragment) and the contraction as 3xTF32 on the tensor cores:
-// a = hi + lo with hi = tf32(a), lo = tf32(a - hi); D += A_lo B_hi + A_hi B_lo + A_hi B_hi in fp32 accumulators, i.e. the
-// dropped term is 2^-22 relative -- fp32-class results (parity bar 1e-5 absolute, tests/test_parity_r2_gpu.py).  The patch
+// a = hi + lo with hi = a rounded to tf32, lo = a - hi (see split_tf32); D += A_lo B_hi + A_hi B_lo + A_hi B_hi in fp32
+// accumulators, i.e. the dropped terms are ~2^-21 relative -- fp32-class results (parity bar 1e-5 absolute, tests/test_parity_r2_gpu.py).  The patch
 // fragments are re-read from shared memory per chunk (holding 128 channels x hi / lo in registers is not possible).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int FCK = 16;                      // channels per chunk (64-byte records)
@@ -738,10 +738,14 @@ struct Params32 {
   float* out;                          // [B, E, 7, 7, 3, 3, NLEV]
 };
 
+// a = hi + lo for the 3xTF32 contraction.  hi: a rounded to 10 mantissa bits by integer arithmetic (round half away, two
+// instructions; `cvt.rna.tf32.f32` expands to a much longer sequence and was 65 % of this kernel's instructions, ncu source
+// view profiles/r02/ncu_source_corr32_v15.txt); lo = a - hi, exact in fp32, handed to the tensor core as it is: the
+// hardware ignores the low 13 mantissa bits of a tf32 operand, i.e. truncates lo to 10 bits -- the total representation
+// error is <= 2^-11 * 2^-10 |a| = 2^-21 |a|.  (Values within 2^-11 of overflow would round up to inf: feature maps are O(1).)
 __device__ __forceinline__ void split_tf32(float x, unsigned& hi, unsigned& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-  const float r = x - __uint_as_float(hi);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
 }
 __device__ __forceinline__ void mma_tf32(float d[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0,
                                          unsigned b1) {

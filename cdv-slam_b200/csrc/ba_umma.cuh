@@ -106,14 +106,12 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// x = hi + lo: hi = x rounded to 10 mantissa bits by integer arithmetic (round half away; cvt.rna.tf32.f32 expands to a much
+// longer instruction sequence), lo = x - hi exactly; the tensor core ignores the low 13 mantissa bits of a tf32 operand, so
+// lo needs no rounding of its own (representation error <= 2^-21 |x|).
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  uint32_t h;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-  hi = __uint_as_float(h);
-  const float rem = x - hi;
-  uint32_t l;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(rem));
-  lo = __uint_as_float(l);
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+  lo = x - hi;
 }
 
 }  // namespace umma

@@ -151,7 +151,7 @@ const int32_t* pgba_ba_status_ptr(const void* workspace, int64_t n_edges, int64_
 
 /* Plan cache.  The graph analysis of a call ("plan": chunk tables, edge permutation, cell tables -- what replaces
  * at::_unique(kk) and the EfficentE constructor of the reference) depends only on ii / jj / kk and the call's sizes.  Windows
- * handled by the single-launch plan (everything except the global BA and batches of more than 74 windows) keep a 128-bit
+ * handled by the single-launch plans (everything except the global BA) keep a 128-bit
  * fingerprint of their edge list in the workspace; a call that finds the workspace untouched since a call with the same
  * sizes and an unchanged edge list (the 12 x initialisation loop of slam.py:715-716, repeated BA calls between two
  * frames) skips the analysis: the index arrays are still read once (for the fingerprint), everything else is reused.
@@ -177,7 +177,7 @@ int pgba_reproject(const float* poses, const float* patches, const float* intrin
  * called as fastba.neighbors(kk, jj) by every network update, net_cdv.py:102-107).  Edges are grouped by ii; inside a
  * group they are ordered by jj, ties by edge index (the reference's std::stable_sort of a group listed in input order);
  * ix[e] / jx[e] = index of the previous / next edge of e's group in that order, -1 at the ends.  ii, jj, ix, jx i64
- * [n_edges]; any int64 key values.  One cluster launch, no host round trip (the reference synchronises, sorts on the
+ * [n_edges]; any int64 key values.  Two launches (cluster binning kernel + warp-per-bin link kernel), no host round trip (the reference synchronises, sorts on the
  * CPU and copies back).  Workspace: pgba_neighbors_workspace_bytes(), 256-byte aligned.
  * ------------------------------------------------------------------------------------------------------------- */
 int pgba_neighbors_workspace_bytes(int64_t n_edges, size_t* bytes /* host, out */);

@@ -161,7 +161,7 @@ __device__ long long g_lin_ts[32];
 #ifndef PGBA_LIN_TS_BLOCK
 #define PGBA_LIN_TS_BLOCK 0
 #endif
-#define LIN_TS(i) do { if (threadIdx.x == 0 && blockIdx.x == PGBA_LIN_TS_BLOCK && blockIdx.y == 0) g_lin_ts[i] = clock64(); } while (0)
+#define LIN_TS(i) do { if (threadIdx.x == 0 && blockIdx.y == PGBA_LIN_TS_BLOCK && blockIdx.x == 0) g_lin_ts[i] = clock64(); } while (0)
 #else
 #define LIN_TS(i) do { } while (0)
 #define CTA_TS(k, f) do { } while (0)
@@ -340,7 +340,7 @@ __device__ SCHUR_UMMA_ATTR uint32_t schur_umma_finish(const int* sFrame, int fir
   return mbar_parity ^ 1u;
 }
 
-// grid = (gx, batch), block = 256, dynamic smem = lin_smem_bytes(pc, ebudget).  fuse_update: first apply the previous
+// grid = (batch, gx), block = 256, dynamic smem = lin_smem_bytes(pc, ebudget).  fuse_update: first apply the previous
 // iteration's back-substitution + depth retraction to the chunk's patches (saves the separate update launch).
 template <bool FUSE, bool UMMA>
 __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb, int ebudget, int flags) {
@@ -349,6 +349,9 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
   // which lets this kernel start only after its own pdl_wait(), i.e. after the previous linearisation and the plan have
   // completed.  Only dX and the poses are still being produced; the chunk tables, cells, targets / weights, patch
   // coordinates and the inputs of the fused back-substitution are final and are requested BEFORE pdl_wait().
+  // flags & 64 (not the first linearisation of the call): the plan completed kernels ago, so the chunk count is final and a
+  // CTA in a chunk slot beyond it (the grid is sized for the worst case) leaves at once, without waiting
+  if ((flags & 64) && (int)blockIdx.y >= win_ptrs(pb.ws, pb.L, blockIdx.x + pb.w0).hdr->n_chunks) return;
   bool waited = (flags & 8) == 0;
   if (waited) {
     pdl_wait();
@@ -383,7 +386,10 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
   s.sSq = s.sAH + SMAX * 36;                           // only touched by the tcgen05 instance
   float* sAH = s.sAH;
 
-  const int w = blockIdx.y + pb.w0, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // grid = (windows, chunk slots): blockIdx.x is the window, so CTAs are dispatched chunk slot by chunk slot over all
+  // windows and the slots beyond a window's chunk count (the grid is sized for the worst case) come LAST instead of taking
+  // resident-CTA slots between the real ones
+  const int w = blockIdx.x + pb.w0, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
   const float* poses = pb.poses + (int64_t)w * pb.st.poses;
   const float* patches = pb.patches + (int64_t)w * pb.st.patches;
@@ -398,7 +404,7 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
   const int n_dups = wp.hdr->n_dups;
   const bool schur = pb.with_schur != 0;
   // the grid is sized for the worst-case chunk count: only CTAs that own a chunk allocate tensor memory
-  const bool umma_cta = use_umma && (int)blockIdx.x < n_chunks;
+  const bool umma_cta = use_umma && (int)blockIdx.y < n_chunks;
   if (umma_cta) {
     if (threadIdx.x < 32) umma::tmem_alloc(&s_tmem);
     if (threadIdx.x == 32) umma::mbar_init(&s_mbar, 1);
@@ -408,7 +414,7 @@ __global__ void __launch_bounds__(256, LIN_MIN_CTAS) linearize_kernel(Problem pb
   }
   constexpr bool fuse_update = FUSE;
 
-  for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+  for (int c = blockIdx.y; c < n_chunks; c += gridDim.y) {
     const Chunk ch = wp.chunks[c];
     if (ch.n_patches == 0) continue;
     __syncthreads();
@@ -1169,11 +1175,11 @@ __global__ void __launch_bounds__(256) update_kernel(Problem pb, int early) {
   bool waited = early == 0;
   if (waited) { pdl_wait(); pdl_trigger(); CTA_TS(2, 1); }
   __shared__ __align__(8) float sdx[(SMAX + 1) * 6];
-  const int w = blockIdx.y + pb.w0;
+  const int w = blockIdx.x + pb.w0;                  // grid = (windows, chunk slots), see linearize_kernel
   const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
   float* patches = pb.patches + (int64_t)w * pb.st.patches;
   const int n_chunks = wp.hdr->n_chunks;
-  for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+  for (int c = blockIdx.y; c < n_chunks; c += gridDim.y) {
     const Chunk ch = wp.chunks[c];
     if (ch.n_patches == 0) continue;
     __syncthreads();
@@ -1198,7 +1204,7 @@ __global__ void __launch_bounds__(256) update_large_kernel(Problem pb, int early
   float* sdx = usm + tile_floats;
   bool waited = early == 0;
   if (waited) { pdl_wait(); pdl_trigger(); CTA_TS(2, 1); }
-  const int w = blockIdx.y + pb.w0, tid = threadIdx.x;
+  const int w = blockIdx.x + pb.w0, tid = threadIdx.x;   // grid = (windows, chunk slots), see linearize_kernel
   const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
   float* patches = pb.patches + (int64_t)w * pb.st.patches;
   const int N = pb.t1 - pb.t0, t0 = pb.t0;
@@ -1207,8 +1213,8 @@ __global__ void __launch_bounds__(256) update_large_kernel(Problem pb, int early
   const int n_chunks = wp.hdr->n_chunks;
   // the grid is sized for the worst-case chunk count: a CTA without a chunk leaves at once (an exiting CTA needs no wait,
   // and while it sat at pdl_wait() it would hold a slot that a CTA with a tile to prefetch could use)
-  if ((int)blockIdx.x >= n_chunks) return;
-  for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+  if ((int)blockIdx.y >= n_chunks) return;
+  for (int c = blockIdx.y; c < n_chunks; c += gridDim.y) {
     const Chunk ch = wp.chunks[c];
     if (ch.n_patches == 0) continue;
     __syncthreads();
@@ -1315,10 +1321,10 @@ void launch_linearize(const Problem& pb, int64_t batch, cudaStream_t stream, boo
   if (extra_smem < 0) { const char* e = getenv("PGBA_LIN_EXTRA_SMEM"); extra_smem = (e && e[0] == '1') ? 1 : 0; }
   const size_t lsm = lin_smem_bytes(pb.L.pc, ebudget, umma_on || extra_smem);
   const bool early = fuse_update && pb.t1 > pb.t0 && !pb.L.big && early_loads_enabled();
-  const int flags = (fuse_update ? 1 : 0) | (early ? 8 : 0) | (umma_on ? 16 : 0) | (first ? 32 : 0);
+  const int flags = (fuse_update ? 1 : 0) | (early ? 8 : 0) | (umma_on ? 16 : 0) | (first ? 32 : 64);
   auto go = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm);
-    launch_k(kern, dim3((unsigned)gx, (unsigned)batch), dim3(256), lsm, stream, pb, ebudget, flags);
+    launch_k(kern, dim3((unsigned)batch, (unsigned)gx), dim3(256), lsm, stream, pb, ebudget, flags);
   };
   if (flags & 16) {
     if (fuse_update) go(linearize_kernel<true, true>); else go(linearize_kernel<false, true>);
@@ -1357,9 +1363,9 @@ void launch_update(const Problem& pb, int64_t batch, cudaStream_t stream) {
   if (large_on && pb.L.pc > 32 && tile_floats * 4 <= 48 * 1024) {
     const size_t smem = sizeof(float) * ((size_t)tile_floats + (SMAX + 1) * 6);
     cudaFuncSetAttribute(update_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    launch_k(update_large_kernel, dim3((unsigned)gx, (unsigned)batch), dim3(256), smem, stream, pb, early, (int)tile_floats);
+    launch_k(update_large_kernel, dim3((unsigned)batch, (unsigned)gx), dim3(256), smem, stream, pb, early, (int)tile_floats);
   } else {
-    launch_k(update_kernel, dim3((unsigned)gx, (unsigned)batch), dim3(256), 0, stream, pb, early);
+    launch_k(update_kernel, dim3((unsigned)batch, (unsigned)gx), dim3(256), 0, stream, pb, early);
   }
   count_launch();
 }

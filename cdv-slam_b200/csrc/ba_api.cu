@@ -12,7 +12,7 @@ namespace pgba {
 void launch_plan(const Problem& pb, int64_t batch, cudaStream_t stream);
 cudaError_t launch_iteration(const Problem& pb, int64_t batch, cudaStream_t stream, cudaEvent_t* ev, bool first, bool more);
 void launch_linearize(const Problem& pb, int64_t batch, cudaStream_t stream, bool fuse_update, bool first);
-void launch_solve(const Problem& pb, int64_t batch, cudaStream_t stream);
+void launch_solve(const Problem& pb, int64_t batch, cudaStream_t stream, bool more = false);
 void launch_update(const Problem& pb, int64_t batch, cudaStream_t stream);
 bool solve_supported(int N);
 bool plan_clears_workspace(const Problem& pb, int64_t batch);

@@ -1,0 +1,536 @@
+// Large solve of the global (loop-closure) bundle adjustment with a nested-dissection frame ordering.
+// Replaces at::linalg_cholesky_ex + torch::cholesky_solve on the dense S of the reference
+// (cdvslam/fastba/ba_cuda.cu:575-578 for eff_impl, :589-591 dense) for >= ND_MIN_N free poses.
+//
+// The natural-order blocked Cholesky of big_chol.cuh walks 6N / 48 dependent panel steps (125 for the 1000-frame global
+// BA), three launches each, and nearly every step is latency: the pose graph is a chain (patches are seen by a few
+// neighbouring frames) plus loop closures, so a panel has a handful of non-zero tiles.  Here the free frames are reordered
+//
+//     [ chain segment 0 | chain segment 1 | ... | chain segment P-1 | border ]
+//
+// where the border holds (a) every frame that is the target of a FAR edge (|j - i| > R: the loop-closure targets) and
+// (b) for each of the P - 1 cut positions, the frames at or after the cut that share a patch with a frame before it (the
+// separator; its width follows from the data).  No patch couples frames of two different segments, so the segments are
+// eliminated IN PARALLEL, level by level (tile l of every segment in the same three launches), then the dense border:
+// max_p T_p + Bt dependent steps instead of sum_p T_p + Bt (36 instead of 125 on the 1000-frame problem).  The ordering
+// is computed on the device from the edge list (no host round trip); whatever the graph looks like the result is the
+// same Cholesky solve of the same matrix under a symmetric permutation -- a graph that is not chain-like only makes the
+// border large.  Segments and border are padded to whole tiles with identity rows.
+//
+//   nd_stats_kernel    per source frame: extent of its near edges; far edge targets -> border
+//   nd_order_kernel    separators, segment / border positions of every free frame (one CTA per window)
+//   nd_gather_kernel   S, y (natural order, written by linearize_kernel) -> permuted Sp, yp with the damping of
+//                      ba_cuda.cu:575/589 applied; S, y are re-zeroed on the way
+//   nd_potf2 / nd_trsm / nd_syrk   one panel step (stage bodies as in big_chol.cuh); during the segment levels the
+//                      border x border updates of different segments meet in the same tiles -> atomic adds there
+//   nd_backsolve_kernel  L^T x = z: border (one CTA), then the segments in parallel
+//   nd_finish_kernel   x -> dX in frame order, pose retraction (ba_cuda.cu:88-206)
+//   nd_cleanup_kernel  zeroes the tiles the factor touched (before the next iteration's gather)
+#include "big_chol.cuh"
+#include "ba_cells.cuh"
+
+namespace pgba {
+
+struct NdSys {
+  float* S; float* y; float* Sp; float* yp;
+  int ld;                 // row stride of Sp (= capacity in unknowns)
+  NdHeader* h;
+  int* lminv; int* lmax1; int* border; int* pos; int* pfb; int* pfn; int* frame_at;
+  float* winv; int* active; int* nact; int act_stride; int* chol_info;
+};
+
+__device__ __forceinline__ NdSys nd_sys(const Problem& pb, int w) {
+  const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
+  char* base = (char*)pb.ws + pb.L.body0 + (size_t)w * pb.L.body_bytes;
+  char* z = (char*)pb.ws + (size_t)w * pb.L.zero_bytes;
+  NdSys s;
+  s.S = wp.S; s.y = wp.y;
+  s.Sp = (float*)(z + pb.L.z_Sp); s.yp = (float*)(z + pb.L.z_yp);
+  s.ld = pb.L.nd_nt * NB;
+  s.h = (NdHeader*)(z + pb.L.z_nd);
+  int* f = (int*)(z + pb.L.z_ndf);
+  s.lminv = f; s.lmax1 = f + pb.F; s.border = f + 2 * pb.F; s.pos = f + 3 * pb.F; s.pfb = f + 4 * pb.F; s.pfn = f + 5 * pb.F;
+  s.frame_at = (int*)(base + pb.L.o_frame_at);
+  s.winv = (float*)(base + pb.L.o_winv);
+  s.active = (int*)(base + pb.L.o_active);
+  s.nact = (int*)(z + pb.L.z_nact);
+  s.act_stride = pb.L.big_tiles;
+  s.chol_info = &wp.hdr->chol_info;
+  return s;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// ordering
+// ---------------------------------------------------------------------------------------------------------------
+// grid = (gx, batch), block = 256
+__global__ void __launch_bounds__(256) nd_stats_kernel(Problem pb) {
+  pdl_wait();
+  pdl_trigger();
+  const int w = blockIdx.y + pb.w0, tid = threadIdx.x, lane = tid & 31;
+  const NdSys sys = nd_sys(pb, w);
+  const int64_t* ii = pb.ii + (int64_t)w * pb.st.ii;
+  const int64_t* jj = pb.jj + (int64_t)w * pb.st.jj;
+  const int64_t* kk = pb.kk + (int64_t)w * pb.st.kk;
+  const int E = pb.n_edges_dev ? min((int)pb.E, max(pb.n_edges_dev[w], 0)) : (int)pb.E;
+  const int R = pb.L.nd_R;
+  const int stride = gridDim.x * blockDim.x;
+  for (int e0 = blockIdx.x * blockDim.x; e0 < E; e0 += stride) {            // warp-uniform trip count
+    const int e = e0 + tid;
+    int i = -1, j = 0;
+    if (e < E) {
+      int64_t a, b, c;
+      if (pb.idx32) {
+        a = reinterpret_cast<const int32_t*>(ii)[e]; b = reinterpret_cast<const int32_t*>(jj)[e]; c = reinterpret_cast<const int32_t*>(kk)[e];
+      } else {
+        a = ii[e]; b = jj[e]; c = kk[e];
+      }
+      if (!(a < 0 || a >= pb.F || b < 0 || b >= pb.F || c < 0 || c >= pb.K)) { i = (int)a; j = (int)b; }   // as the plan
+    }
+    const bool ok = i >= 0;
+    const bool far = ok && (j - i > R || i - j > R);
+    if (far) sys.border[j] = 1;
+    // near edges: extent per source frame, one atomic pair per run of equal source frames in the warp
+    const int key = (ok && !far) ? i : -1;
+    const unsigned grp = __match_any_sync(0xffffffffu, key);
+    const int jmn = __reduce_min_sync(grp, j), jmx = __reduce_max_sync(grp, j);
+    if (key >= 0 && lane == __ffs(grp) - 1) {
+      atomicMax(&sys.lminv[i], 0x7fffffff - jmn);          // zero-initialised "min": stores max of (INT_MAX - j)
+      atomicMax(&sys.lmax1[i], jmx + 1);
+    }
+  }
+}
+
+// grid = (1, batch), block = 1024
+__global__ void __launch_bounds__(1024) nd_order_kernel(Problem pb) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ int s_cut[ND_MAXP + 1], s_r[ND_MAXP + 1], s_T[ND_MAXP], s_base[ND_MAXP + 1], scratch[40];
+  const int w = blockIdx.y + pb.w0, tid = threadIdx.x;
+  const NdSys sys = nd_sys(pb, w);
+  const int P = pb.L.nd_P, t0 = pb.t0, t1 = pb.t1, N = t1 - t0, F = pb.F;
+  if (tid <= P) {
+    s_cut[tid] = t0 + (int)(((int64_t)tid * N) / P);       // segment p = frames [cut[p], cut[p + 1]) minus the border
+    s_r[tid] = s_cut[tid] - 1;                             // separator of cut p = [cut[p], r[p]] (empty so far)
+  }
+  __syncthreads();
+  // a source frame whose near edges reach from before a cut to (or beyond) it: everything up to its far end is coupled
+  // with frames before the cut
+  for (int f = tid; f < F; f += 1024) {
+    int lo = f, hi = f;
+    const int a = __ldcg(&sys.lminv[f]), b = __ldcg(&sys.lmax1[f]);
+    if (a) lo = min(lo, 0x7fffffff - a);
+    if (b) hi = max(hi, b - 1);
+    if (hi > lo)
+      for (int p = 1; p < P; ++p) {
+        const int c = s_cut[p];
+        if (lo < c && c <= hi) atomicMax(&s_r[p], hi);
+      }
+  }
+  __syncthreads();
+  for (int x = tid; x < N; x += 1024) {
+    const int f = t0 + x;
+    int bd = __ldcg(&sys.border[f]) != 0;
+    for (int p = 1; p < P && !bd; ++p) bd = (f >= s_cut[p] && f <= s_r[p]);
+    sys.border[f] = bd;
+    sys.pfb[x] = bd;
+    sys.pfn[x] = !bd;
+  }
+  __syncthreads();
+  const int nb = block_exclusive_scan(sys.pfb, N, scratch);
+  __syncthreads();
+  const int nn = block_exclusive_scan(sys.pfn, N, scratch);
+  __syncthreads();
+  if (tid < P) {
+    const int hi = s_cut[tid + 1] - t0, lo = s_cut[tid] - t0;
+    const int cnt = (hi >= N ? nn : sys.pfn[hi]) - sys.pfn[lo];
+    s_T[tid] = (cnt + 7) / 8;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int p = 0; p < P; ++p) { s_base[p] = run; sys.h->T[p] = s_T[p]; sys.h->segbase[p] = run; run += s_T[p]; }
+    s_base[P] = run;
+    const int Bt = (nb + 7) / 8;
+    sys.h->bbase = run; sys.h->Bt = Bt; sys.h->nt = run + Bt; sys.h->n_border = nb;
+  }
+  for (int x = tid; x < pb.L.nd_nt * 8; x += 1024) sys.frame_at[x] = -1;
+  __syncthreads();
+  for (int x = tid; x < N; x += 1024) {
+    const int f = t0 + x;
+    int ps;
+    if (sys.border[f]) {
+      ps = s_base[P] * 8 + sys.pfb[x];
+    } else {
+      int seg = 0;
+      for (int p = 1; p < P; ++p) if (f >= s_cut[p]) seg = p;
+      ps = s_base[seg] * 8 + (sys.pfn[x] - sys.pfn[s_cut[seg] - t0]);
+    }
+    sys.pos[f] = ps;
+    sys.frame_at[ps] = f;
+  }
+}
+
+// grid = (gx, batch), block = 256.  One row of the lower block triangle of S per CTA and trip.
+__global__ void __launch_bounds__(256) nd_gather_kernel(Problem pb) {
+  pdl_wait();
+  pdl_trigger();
+  const int w = blockIdx.y + pb.w0, tid = threadIdx.x;
+  const NdSys sys = nd_sys(pb, w);
+  const int t0 = pb.t0, N = pb.t1 - t0, n6 = 6 * N;
+  const size_t ld = (size_t)sys.ld;
+  const int* __restrict__ pos = sys.pos + t0;
+  for (int r = blockIdx.x; r < n6; r += gridDim.x) {
+    const int fa = r / 6, ra = r - 6 * fa;
+    const int pa = pos[fa];
+    float2* row = reinterpret_cast<float2*>(sys.S + (size_t)r * n6);
+    const int ncol2 = 3 * (fa + 1);
+    for (int c2 = tid; c2 < ncol2; c2 += 256) {
+      float2 v = row[c2];
+      const int c = 2 * c2, fb = c / 6, cb = c - 6 * fb;
+      const bool diag = fb == fa;
+      if (!diag && v.x == 0.f && v.y == 0.f) continue;
+      row[c2] = make_float2(0.f, 0.f);
+      if (diag) {
+        if (cb == ra) v.x = v.x + (1e-4f * v.x + 1.0f);           // S += I * (1e-4 * S + 1)   (ba_cuda.cu:575/589)
+        else if (cb + 1 == ra) v.y = v.y + (1e-4f * v.y + 1.0f);
+        *reinterpret_cast<float2*>(sys.Sp + (size_t)(6 * pa + ra) * ld + 6 * pa + cb) = v;
+      } else {
+        const int pbp = pos[fb];
+        if (pa > pbp) {
+          *reinterpret_cast<float2*>(sys.Sp + (size_t)(6 * pa + ra) * ld + 6 * pbp + cb) = v;
+        } else {                                                  // the block lands above the diagonal: store its transpose
+          sys.Sp[(size_t)(6 * pbp + cb) * ld + 6 * pa + ra] = v.x;
+          sys.Sp[(size_t)(6 * pbp + cb + 1) * ld + 6 * pa + ra] = v.y;
+        }
+      }
+    }
+    if (tid == 0) { sys.yp[6 * pa + ra] = sys.y[r]; sys.y[r] = 0.f; }
+  }
+  // identity on the padding rows
+  const int npos = sys.h->nt * 8;
+  for (int x = blockIdx.x * 256 + tid; x < npos; x += gridDim.x * 256)
+    if (sys.frame_at[x] < 0) {
+#pragma unroll
+      for (int a = 0; a < 6; ++a) sys.Sp[(size_t)(6 * x + a) * ld + 6 * x + a] = 1.0f;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// factorisation.  A panel step is (mode, idx): mode 0 = tile idx of segment blockIdx.z, mode 1 = tile idx of the border.
+// Rows below panel tile k that can be non-zero: the later tiles of the same segment / of the border, then (segments
+// only) all border tiles.
+// ---------------------------------------------------------------------------------------------------------------
+struct NdPanel { int k, nsb, nbelow, bbase; };
+
+__device__ __forceinline__ bool nd_panel(const NdHeader* h, int mode, int idx, int p, NdPanel& pn) {
+  pn.bbase = h->bbase;
+  if (mode == 0) {
+    const int T = h->T[p];
+    if (idx >= T) return false;
+    pn.k = h->segbase[p] + idx; pn.nsb = T - 1 - idx; pn.nbelow = pn.nsb + h->Bt;
+  } else {
+    const int Bt = h->Bt;
+    if (idx >= Bt) return false;
+    pn.k = pn.bbase + idx; pn.nsb = Bt - 1 - idx; pn.nbelow = pn.nsb;
+  }
+  return true;
+}
+__device__ __forceinline__ int nd_tile_of(const NdPanel& pn, int c) { return c < pn.nsb ? pn.k + 1 + c : pn.bbase + (c - pn.nsb); }
+
+// grid = (1, batch, P | 1), block = 256, dynamic smem: (2 NB) x (NB | 1) doubles + NB
+__global__ void __launch_bounds__(256, 1) nd_potf2_kernel(Problem pb, int mode, int idx) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ double sd[];
+  const NdSys sys = nd_sys(pb, blockIdx.y + pb.w0);
+  NdPanel pn;
+  if (!nd_panel(sys.h, mode, idx, blockIdx.z, pn)) return;
+  const int tid = threadIdx.x, kb = pn.k * NB, ld = NB | 1;
+  double* A = sd;                       // rows 0..NB-1: diagonal tile; rows NB..2NB-1: identity (-> L^-T)
+  double* rd = sd + 2 * NB * ld;
+  float* Sd = sys.Sp + (size_t)kb * sys.ld + kb;
+  for (int x = tid; x < NB * NB; x += 256) {
+    const int r = x / NB, c = x - r * NB;
+    A[r * ld + c] = (c <= r) ? (double)Sd[(size_t)r * sys.ld + c] : 0.0;
+    A[(NB + r) * ld + c] = (r == c) ? 1.0 : 0.0;
+  }
+  chol6_smem(A, rd, NB, 2 * NB - 1, ld);
+  // rows NB + i now hold (L^-1 e_i)^T, i.e. W[i][c] = Linv[c][i]  (so X = A21 * W solves X L^T = A21)
+  float* W = sys.winv + (size_t)pn.k * NB * NB;
+  for (int x = tid; x < NB * NB; x += 256) {
+    const int r = x / NB, c = x - r * NB;
+    if (c <= r) Sd[(size_t)r * sys.ld + c] = (float)A[r * ld + c];
+    W[r * NB + c] = (float)A[(NB + r) * ld + c];
+  }
+  for (int x = tid; x < NB; x += 256)
+    if (!(rd[x] > 0.0) || !isfinite(rd[x])) atomicCAS(sys.chol_info, 0, kb + x + 1);
+  if (tid == 0) sys.nact[pn.k] = 0;
+}
+
+// grid = (nd_nt + 1, batch, P | 1), block = 256: candidate row tile blockIdx.x (== nbelow: the right-hand side)
+__global__ void __launch_bounds__(256) nd_trsm_kernel(Problem pb, int mode, int idx) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float sA[NB][NB + 1];
+  __shared__ float sW[NB][NB + 1];
+  const NdSys sys = nd_sys(pb, blockIdx.y + pb.w0);
+  NdPanel pn;
+  if (!nd_panel(sys.h, mode, idx, blockIdx.z, pn)) return;
+  const int c0 = blockIdx.x;
+  if (c0 > pn.nbelow) return;
+  const int tid = threadIdx.x, kb = pn.k * NB;
+  const bool rhs = (c0 == pn.nbelow);
+  const int t = rhs ? -1 : nd_tile_of(pn, c0);
+  const int rows = rhs ? 1 : NB;
+  float* src = rhs ? (sys.yp + kb) : (sys.Sp + (size_t)t * NB * sys.ld + kb);
+  const size_t rstride = rhs ? 0 : (size_t)sys.ld;
+  int nz = 0;
+  for (int x = tid; x < rows * NB; x += 256) {
+    const int r = x / NB, c = x - r * NB;
+    const float v = src[r * rstride + c];
+    sA[r][c] = v;
+    nz |= (v != 0.f);
+  }
+  nz = __syncthreads_or(nz);
+  if (!nz && !rhs) return;                       // an all-zero tile stays zero: inactive for this panel
+  const float* W = sys.winv + (size_t)pn.k * NB * NB;
+  for (int x = tid; x < NB * NB; x += 256) {
+    const int r = x / NB, c = x - r * NB;
+    sW[r][c] = W[x];
+  }
+  __syncthreads();
+  for (int x = tid; x < rows * NB; x += 256) {
+    const int r = x / NB, c = x - r * NB;
+    float acc = 0;
+    for (int e = 0; e <= c; ++e) acc += sA[r][e] * sW[e][c];      // W[e][c] = Linv[c][e] is zero for e > c
+    src[r * rstride + c] = acc;
+  }
+  if (tid == 0) {
+    const int slot = atomicAdd(&sys.nact[pn.k], 1);
+    sys.active[(size_t)pn.k * sys.act_stride + slot] = t;          // -1 marks the rhs row
+  }
+}
+
+// Trailing update over pairs of active row tiles of the panel: Sp[tile a][tile b] -= X_a X_b^T (a below b).
+// grid = (gx, batch, P | 1), block = 256 (16 x 16 threads, 3 x 3 outputs each)
+__global__ void __launch_bounds__(256) nd_syrk_kernel(Problem pb, int mode, int idx) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float sXa[NB][NB + 1];     // [k][row]
+  __shared__ float sXb[NB][NB + 1];
+  const NdSys sys = nd_sys(pb, blockIdx.y + pb.w0);
+  NdPanel pn;
+  if (!nd_panel(sys.h, mode, idx, blockIdx.z, pn)) return;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int kb = pn.k * NB;
+  const int na = sys.nact[pn.k];
+  const int* act = sys.active + (size_t)pn.k * sys.act_stride;
+  const int npairs = na * (na + 1) / 2;
+  const size_t ld = (size_t)sys.ld;
+  for (int pr = blockIdx.x; pr < npairs; pr += gridDim.x) {
+    int ia, ib;
+    pair_of(pr, ia, ib);
+    int ta = act[ia], tb = act[ib];
+    if (ta == -1 && tb == -1) continue;            // rhs x rhs: nothing to update
+    // "a" is the lower tile (larger row index); the rhs row is below everything
+    if (tb == -1 || (ta != -1 && tb > ta)) { const int s = ta; ta = tb; tb = s; }
+    const bool rhs = (ta == -1);
+    // segments are eliminated concurrently: their updates of border x border tiles (and of the border part of the rhs)
+    // land in the same memory
+    const bool shared_dst = (mode == 0) && tb >= pn.bbase;
+    const int ra = rhs ? 0 : ta * NB, rb = tb * NB;
+    const float* xa = rhs ? (sys.yp + kb) : (sys.Sp + (size_t)ra * ld + kb);
+    const size_t sa = rhs ? 0 : ld;
+    const int rows_a = rhs ? 1 : NB;
+    const float* xb = sys.Sp + (size_t)rb * ld + kb;
+    __syncthreads();
+    for (int x = tid; x < NB * NB; x += 256) {
+      const int r = x / NB, k = x - r * NB;
+      sXa[k][r] = (r < rows_a) ? xa[r * sa + k] : 0.f;
+      sXb[k][r] = xb[(size_t)r * ld + k];
+    }
+    __syncthreads();
+    float acc[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll 4
+    for (int k = 0; k < NB; ++k) {
+      float a[3], b[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { a[i] = sXa[k][ty + 16 * i]; b[i] = sXb[k][tx + 16 * i]; }
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc[i][j] += a[i] * b[j];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int r = ty + 16 * i, c = tx + 16 * j;
+        if (r >= rows_a) continue;
+        float* dst;
+        if (rhs) dst = sys.yp + rb + c;
+        else if (rb + c <= ra + r) dst = sys.Sp + (size_t)(ra + r) * ld + rb + c;     // lower triangle only
+        else continue;
+        if (shared_dst) atomicAdd(dst, -acc[i][j]); else *dst -= acc[i][j];
+      }
+  }
+}
+
+// Backward substitution L^T x = z, one CTA of 1024 threads per (window, segment): the running solution lives in shared
+// memory, indexed like yp; per panel the 32 warps split its active row tiles (see big_backsolve_kernel).
+// mode 1: the border panels, last to first (grid = (1, batch)); mode 0: segment blockIdx.x, after the border
+// (grid = (P, batch)).  dynamic smem: (nd_nt * NB + 32 * NB + NB) floats
+__global__ void __launch_bounds__(1024, 1) nd_backsolve_kernel(Problem pb, int mode) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ __align__(16) unsigned char bsm[];
+  const NdSys sys = nd_sys(pb, blockIdx.y + pb.w0);
+  const NdHeader* h = sys.h;
+  const int bbase = h->bbase, nt = h->nt;
+  const int p = blockIdx.x;
+  const int first = mode ? bbase : h->segbase[p], count = mode ? h->Bt : h->T[p];
+  if (count == 0) return;
+  float* sx = reinterpret_cast<float*>(bsm);           // [nd_nt * NB]
+  float* spart = sx + (size_t)pb.L.nd_nt * NB;         // [32][NB] per-warp partial sums
+  float* sz = spart + 32 * NB;                         // [NB]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t ld = (size_t)sys.ld;
+  for (int x = bbase * NB + tid; x < nt * NB; x += 1024) sx[x] = sys.yp[x];
+  if (!mode) for (int x = first * NB + tid; x < (first + count) * NB; x += 1024) sx[x] = sys.yp[x];
+  __syncthreads();
+  for (int s = count - 1; s >= 0; --s) {
+    const int k = first + s, kb = k * NB;
+    const int na = sys.nact[k];
+    const int* act = sys.active + (size_t)k * sys.act_stride;
+    float acc0 = 0, acc1 = 0;                          // columns lane and lane + 32 of the panel
+    for (int ia = warp; ia < na; ia += 32) {
+      const int t = act[ia];
+      if (t == -1) continue;                           // the right-hand-side row of the factorisation
+      const int ra = t * NB;
+      const float* Lp = sys.Sp + (size_t)ra * ld + kb;
+      constexpr int RB = 12;                           // 24 loads in flight per lane
+#pragma unroll 1
+      for (int rb = 0; rb < NB; rb += RB) {
+        float v0[RB], v1[RB];
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          const float* row = Lp + (size_t)(rb + r) * ld;
+          v0[r] = row[lane];
+          v1[r] = (lane + 32 < NB) ? row[lane + 32] : 0.f;
+        }
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          const float xr = sx[ra + rb + r];
+          acc0 += v0[r] * xr;
+          acc1 += v1[r] * xr;
+        }
+      }
+    }
+    spart[warp * NB + lane] = acc0;
+    if (lane + 32 < NB) spart[warp * NB + lane + 32] = acc1;
+    __syncthreads();
+    if (tid < NB) {
+      float sum = 0;
+#pragma unroll
+      for (int wv = 0; wv < 32; ++wv) sum += spart[wv * NB + tid];
+      sz[tid] = sx[kb + tid] - sum;
+    }
+    __syncthreads();
+    if (tid < NB) {                                    // x[c] = sum_{e >= c} W[c][e] z[e]
+      const float* W = sys.winv + (size_t)k * NB * NB + tid * NB;
+      float a = 0;
+      for (int e = tid; e < NB; ++e) a += W[e] * sz[e];
+      sx[kb + tid] = a;
+      sys.yp[kb + tid] = a;
+    }
+    __syncthreads();
+  }
+}
+
+// grid = (ceil(N / 128), batch), block = 128
+__global__ void nd_finish_kernel(Problem pb) {
+  pdl_wait();
+  pdl_trigger();
+  const int w = blockIdx.y + pb.w0;
+  const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
+  const NdSys sys = nd_sys(pb, w);
+  const int N = pb.t1 - pb.t0;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int ps = sys.pos[pb.t0 + i];
+  float xi[6];
+#pragma unroll
+  for (int a = 0; a < 6; ++a) { xi[a] = sys.yp[6 * ps + a]; wp.dX[6 * i + a] = xi[a]; }
+  if (pb.apply) retract_pose(pb.poses + (int64_t)w * pb.st.poses + 7 * (int64_t)(pb.t0 + i), xi);
+}
+
+// grid = (nd_nt, batch), block = 256: panel blockIdx.x -- its diagonal tile and its active row tiles are the only tiles of
+// that column the factorisation has written
+__global__ void __launch_bounds__(256) nd_cleanup_kernel(Problem pb) {
+  pdl_wait();
+  pdl_trigger();
+  const NdSys sys = nd_sys(pb, blockIdx.y + pb.w0);
+  const int k = blockIdx.x, tid = threadIdx.x;
+  if (k >= sys.h->nt) return;
+  const size_t ld = (size_t)sys.ld;
+  const int na = sys.nact[k];
+  const int* act = sys.active + (size_t)k * sys.act_stride;
+  for (int ia = -1; ia < na; ++ia) {
+    const int t = ia < 0 ? k : act[ia];
+    if (t < 0) continue;
+    float* tile = sys.Sp + (size_t)t * NB * ld + (size_t)k * NB;
+    for (int x = tid; x < NB * NB; x += 256) tile[(size_t)(x / NB) * ld + (x % NB)] = 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------------------------------------------
+bool nd_active(const Problem& pb) { return pb.L.nd_P > 0; }
+
+// after the plan, once per call
+void launch_nd_order(const Problem& pb, int64_t batch, cudaStream_t stream) {
+  const unsigned B = (unsigned)batch;
+  int gx = (int)((pb.E + 255) / 256);
+  if (gx > 148 * 8) gx = 148 * 8;
+  if (gx < 1) gx = 1;
+  launch_k(nd_stats_kernel, dim3(gx, B), dim3(256), 0, stream, pb);
+  count_launch();
+  launch_k(nd_order_kernel, dim3(1, B), dim3(1024), 0, stream, pb);
+  count_launch();
+}
+
+// S, y -> dX, poses of one Gauss-Newton iteration; `more`: another iteration follows
+cudaError_t launch_nd_solve(const Problem& pb, int64_t batch, cudaStream_t stream, bool more) {
+  const unsigned B = (unsigned)batch;
+  const int N = pb.t1 - pb.t0, P = pb.L.nd_P, nt = pb.L.nd_nt;
+  launch_k(nd_gather_kernel, dim3(148 * 8, B), dim3(256), 0, stream, pb);
+  count_launch();
+  const size_t psm = sizeof(double) * ((size_t)2 * NB * (NB | 1) + NB);
+  cudaFuncSetAttribute(nd_potf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm);
+  const int border_steps = (N + 7) / 8;             // worst case: every frame in the border
+  for (int mode = 0; mode < 2; ++mode) {
+    const int steps = mode == 0 ? pb.L.nd_tmax : border_steps;
+    const unsigned Z = mode == 0 ? (unsigned)P : 1u;
+    const int gx = mode == 0 ? (296 / P > 4 ? 296 / P : 4) : 296;
+    for (int s = 0; s < steps; ++s) {
+      launch_k(nd_potf2_kernel, dim3(1, B, Z), dim3(256), psm, stream, pb, mode, s);
+      launch_k(nd_trsm_kernel, dim3(nt + 1, B, Z), dim3(256), 0, stream, pb, mode, s);
+      launch_k(nd_syrk_kernel, dim3(gx, B, Z), dim3(256), 0, stream, pb, mode, s);
+      count_launch(); count_launch(); count_launch();
+    }
+  }
+  const size_t bsmem = sizeof(float) * ((size_t)nt * NB + 33 * NB);
+  cudaFuncSetAttribute(nd_backsolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem);
+  launch_k(nd_backsolve_kernel, dim3(1, B), dim3(1024), bsmem, stream, pb, 1);
+  launch_k(nd_backsolve_kernel, dim3(P, B), dim3(1024), bsmem, stream, pb, 0);
+  launch_k(nd_finish_kernel, dim3((N + 127) / 128, B), dim3(128), 0, stream, pb);
+  count_launch(); count_launch(); count_launch();
+  if (more) {
+    launch_k(nd_cleanup_kernel, dim3(nt, B), dim3(256), 0, stream, pb);
+    count_launch();
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace pgba

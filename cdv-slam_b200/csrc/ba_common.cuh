@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/pgba.h"
 
@@ -12,6 +13,7 @@ constexpr int SMAX = PGBA_MAX_SLOTS;      // distinct target frames per chunk
 constexpr int EBUDGET = 12288;            // floats of shared memory for the per-batch E tile (48 KB)
 constexpr int SOLVE_NMAX = 156;           // 6N handled by the single-CTA shared-memory solve (N <= 26)
 constexpr int BIG_NB = 48;                // panel width of the blocked global-memory Cholesky (6N > SOLVE_NMAX)
+constexpr int ND_MIN_N = 256;             // free poses from which the large solve reorders the frames (ba_bignd.cu)
 
 // ---------------------------------------------------------------------------------------------------------------
 // Workspace.  [ zero region of window 0 | ... | zero region of window B-1 | body of window 0 | ... ]
@@ -58,6 +60,22 @@ static_assert(sizeof(Chunk) == 64, "Chunk is written as four 16-byte words");
 
 struct DupEdge { int chunk, p, s, n; };
 
+// Nested-dissection ordering of the large (global BA) solve, see ba_bignd.cu.  Lives in the zero region.
+constexpr int ND_MAXP = 32;
+struct NdHeader {
+  int nt;               // tiles (48 unknowns = 8 frames each) of the permuted system actually in use
+  int bbase, Bt;        // first tile / number of tiles of the border (loop-closure targets + separators)
+  int n_border;         // border frames
+  int T[ND_MAXP];       // tiles of chain segment p
+  int segbase[ND_MAXP]; // first tile of chain segment p
+};
+static_assert(sizeof(NdHeader) <= 512, "NdHeader slot");
+
+inline bool nd_enabled() {                          // PGBA_BIG_ND=0: the natural-order blocked solver (A/B runs, tests)
+  const char* e = getenv("PGBA_BIG_ND");
+  return !(e && e[0] == '0');
+}
+
 struct Layout {         // host-computed
   int64_t E, F, K;      // edges (max per window), pose rows, patch rows
   int N;                // free poses
@@ -68,6 +86,10 @@ struct Layout {         // host-computed
   size_t z_hdr, z_fmaxinv, z_fkmax1, z_ccnt, z_nact, z_bs, z_y, z_S, zero_bytes;
   size_t o_rdiag, o_winv, o_active;   // big solve only
   int big_steps, big_tiles;
+  // nested-dissection ordering (big solve with >= ND_MIN_N free poses): P chain segments + border, permuted system of
+  // nd_nt tiles (capacity), nd_tmax = tiles of the longest possible segment, nd_R = "far edge" frame distance
+  int nd_P, nd_nt, nd_tmax, nd_R;
+  size_t z_nd, z_ndf, z_yp, z_Sp, o_frame_at;
   // body (relative to the window's body base)
   size_t o_fbase, o_ccur, o_chunks, o_perm, o_kx, o_slots, o_cells, o_dups, o_ecells, o_Q, o_u, o_dZ, o_dX, body_bytes;
   size_t body0;         // offset of the first body = batch * zero_bytes (aligned)
@@ -110,8 +132,27 @@ inline Layout make_layout(int64_t E, int64_t F, int64_t K, int N, int64_t batch,
   L.z_ccnt = o;    o = align256(o + 4 * (size_t)L.ch_max);
   L.big_steps = L.big ? (int)((n6 + BIG_NB - 1) / BIG_NB) : 0;
   L.big_tiles = L.big_steps + 1;
+  L.nd_P = 0; L.nd_nt = 0; L.nd_tmax = 0; L.nd_R = 0;
+  if (L.big && N >= ND_MIN_N && nd_enabled()) {
+    int P = N / 60;
+    if (P > ND_MAXP) P = ND_MAXP;
+    const int nt = (N + 7) / 8 + P + 1;               // every segment and the border round up to whole tiles
+    // the backward substitution keeps the whole solution in shared memory
+    if (sizeof(float) * ((size_t)nt * BIG_NB + 33 * BIG_NB) <= 200 * 1024) {
+      L.nd_P = P; L.nd_nt = nt;
+      const int lseg = (N + P - 1) / P;
+      L.nd_tmax = (lseg + 7) / 8;
+      L.nd_R = lseg / 4 > 4 ? lseg / 4 : 4;
+      L.big_steps = nt; L.big_tiles = nt + 1;         // capacity of winv / active / nact
+    }
+  }
+  const size_t np = (size_t)L.nd_nt * BIG_NB;
   L.z_nact = o;    o = align256(o + 4 * (size_t)(L.big_steps + 1));
   L.z_bs = o;      o = align256(o + 512);
+  L.z_nd = o;      o = align256(o + (L.nd_P ? 512 : 0));
+  L.z_ndf = o;     o = align256(o + (L.nd_P ? 6 * 4 * (size_t)F : 0));   // lminv, lmax1, border, pos, pfb, pfn
+  L.z_yp = o;      o = align256(o + 4 * np);
+  L.z_Sp = o;      o = align256(o + 4 * np * np);
   L.z_y = o;       o = align256(o + 4 * n6);
   L.z_S = o;       o = align256(o + 4 * n6 * n6);
   L.zero_bytes = o;
@@ -132,6 +173,7 @@ inline Layout make_layout(int64_t E, int64_t F, int64_t K, int N, int64_t batch,
   L.o_rdiag = o;  o = align256(o + (L.big ? 4 * n6 : 0));
   L.o_winv = o;   o = align256(o + (L.big ? 4 * (size_t)L.big_steps * BIG_NB * BIG_NB : 0));
   L.o_active = o; o = align256(o + (L.big ? 4 * (size_t)L.big_steps * L.big_tiles : 0));
+  L.o_frame_at = o; o = align256(o + 4 * (size_t)L.nd_nt * 8);
   L.body_bytes = o;
   L.body0 = L.zero_bytes * (size_t)batch;
   return L;

@@ -1285,6 +1285,8 @@ int lin_ebudget(const Problem& pb) {
 }
 
 cudaError_t launch_big_solve(const Problem& pb, int64_t batch, cudaStream_t stream);
+bool nd_active(const Problem& pb);
+cudaError_t launch_nd_solve(const Problem& pb, int64_t batch, cudaStream_t stream, bool more);
 
 // Chunk Schur product on the tcgen05 tensor cores (schur_umma_issue / _finish) for chunks of >= 64 patches (batched windows,
 // global BA): opt-in, PGBA_SCHUR_UMMA=1.  Measured on the B200 (c5, 64 windows, chunks of 96 patches x 10 columns, same box,
@@ -1336,11 +1338,12 @@ void launch_linearize(const Problem& pb, int64_t batch, cudaStream_t stream, boo
 
 // Solve S dX = y (damped), retract the poses (if pb.apply).  Small systems: one CTA per window, S and y are re-zeroed
 // by the kernel.  Large systems: blocked Cholesky in global memory; S holds the factor afterwards.
-void launch_solve(const Problem& pb, int64_t batch, cudaStream_t stream) {
+void launch_solve(const Problem& pb, int64_t batch, cudaStream_t stream, bool more) {
   const int N = pb.t1 - pb.t0;
   if (N <= 0) return;
   if (pb.L.big) {
-    launch_big_solve(pb, batch, stream);
+    if (nd_active(pb)) launch_nd_solve(pb, batch, stream, more);
+    else launch_big_solve(pb, batch, stream);
     return;
   }
   const size_t smem = solve_small_smem_bytes(6 * N);
@@ -1388,10 +1391,10 @@ cudaError_t launch_iteration(const Problem& pb, int64_t batch, cudaStream_t stre
   if (ev) cudaEventRecord(ev[0], stream);
   launch_linearize(pb, batch, stream, fuse && !first, first);
   if (ev) cudaEventRecord(ev[1], stream);
-  launch_solve(pb, batch, stream);
+  launch_solve(pb, batch, stream, more);
   if (ev) cudaEventRecord(ev[2], stream);
   if (!fuse || !more) launch_update(pb, batch, stream);
-  if (pb.L.big && more) {
+  if (pb.L.big && more && !nd_active(pb)) {        // (the reordered solve re-zeroes what it touched itself)
     cudaError_t e = clear_big_system(pb, batch, stream);
     if (e != cudaSuccess) return e;
   }

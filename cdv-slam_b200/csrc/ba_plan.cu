@@ -1239,6 +1239,9 @@ static void launch_direct(const Problem& pb, int64_t batch, const DirectCfg& c, 
   count_launch();
 }
 
+bool nd_active(const Problem& pb);
+void launch_nd_order(const Problem& pb, int64_t batch, cudaStream_t stream);
+
 void launch_plan(const Problem& pb, int64_t batch, cudaStream_t stream) {
   DirectCfg dc;
   if (plan_cluster_enabled() && plan_direct_config(pb, batch, &dc)) {
@@ -1292,6 +1295,7 @@ void launch_plan(const Problem& pb, int64_t batch, cudaStream_t stream) {
   }
   launch_k(plan_cells_kernel, dim3((unsigned)chunk_grid(pb, batch), (unsigned)batch), dim3(256), 0, stream, pb);
   count_launch();
+  if (nd_active(pb)) launch_nd_order(pb, batch, stream);   // frame ordering of the large solve (ba_bignd.cu)
 }
 
 #ifdef PGBA_PLAN_TIMING

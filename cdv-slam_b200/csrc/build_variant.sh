@@ -9,7 +9,7 @@ OBJ="$OUT/obj_$NAME"
 mkdir -p "$OBJ"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -Xptxas -v $*"
-SRCS="ba_plan ba_numeric ba_bigsolve ba_api ba_neighbors corr_kernels corr_tma pgo"
+SRCS="ba_plan ba_numeric ba_bigsolve ba_bignd ba_api ba_neighbors corr_kernels corr_tma pgo"
 pids=()
 for f in $SRCS; do
   "$NVCC" $FLAGS -c "$HERE/$f.cu" -o "$OBJ/$f.o" > "$OBJ/$f.log" 2>&1 &

@@ -294,6 +294,58 @@ def test_global_ba_large_solver_normal_equations(F, M, n_loops):
     _check_solve_residual(S, g["y"].cpu().numpy(), g["dX"].cpu().numpy())
 
 
+def _graph_edges(kind, F, M, rng):
+    """Global-BA graphs the frame reordering of the large solve (ba_bignd.cu) has to cope with."""
+    if kind == "chain+loops":                       # the c4 shape
+        return synth.global_edges(F, M, 25, rng)
+    if kind == "chain":                             # no loop closure: empty border apart from the separators
+        return synth.global_edges(F, M, 0, rng)
+    if kind == "many-loops":                        # most frames are loop-closure targets: the border is most of the system
+        return synth.global_edges(F, M, 4 * F, rng)
+    if kind == "wide-band":                         # patches seen up to 9 frames away: wide separators
+        kk_l, jj_l = [], []
+        for dlt in (-9, -4, -1, 1, 3, 9):
+            f = np.arange(max(0, -dlt), min(F, F - dlt))
+            kk_l.append((f[:, None] * M + np.arange(M)[None, :]).ravel())
+            jj_l.append(np.repeat(f + dlt, M))
+        kk, jj = np.concatenate(kk_l), np.concatenate(jj_l)
+        return kk // M, jj, kk
+    if kind == "shuffled":                          # the c4 shape with the edge list in random order
+        ii, jj, kk = synth.global_edges(F, M, 25, rng)
+        o = rng.permutation(len(kk))
+        return ii[o], jj[o], kk[o]
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("kind", ["chain+loops", "chain", "many-loops", "wide-band", "shuffled"])
+def test_global_ba_reordered_solver(kind, monkeypatch):
+    """>= 256 free poses: the large solve eliminates chain segments in parallel and a border last (nested-dissection frame
+    ordering computed on the device, ba_bignd.cu).  Whatever the graph looks like the result must be the solve of the same
+    damped system: dX against a float64 solve of the exported S, y, against the natural-order solver (PGBA_BIG_ND=0) and,
+    through two full iterations, against the oracle."""
+    F, M = 300, 6
+    rng = np.random.default_rng(77)
+    p = synth.make_problem("nd-" + kind, F, _graph_edges(kind, F, M, rng), 1, F, 11, M, eff_impl=True)
+    d = to_dev(p)
+    args = (d["poses"], d["patches"], d["intrinsics"], d["target"], d["weight"], d["lmbda"], d["ii"], d["jj"], d["kk"], p.t0, p.t1)
+    g = fastba.linearize_debug(*args, with_schur=True)
+    assert g["status"] == 0
+    S, y, dX = g["S"].cpu().numpy().astype(np.float64), g["y"].cpu().numpy().astype(np.float64), g["dX"].cpu().numpy()
+    _check_solve_residual(S, y, dX)
+    A = S + np.diag(1e-4 * np.diag(S) + 1.0)
+    x64 = np.linalg.solve(A, y.reshape(-1))
+    tol_x = max(10 * TOL, _S_ULPS * np.linalg.cond(A) * 2.0 ** -23)
+    assert rel_err(dX.reshape(-1), x64) < tol_x
+    monkeypatch.setenv("PGBA_BIG_ND", "0")
+    g0 = fastba.linearize_debug(*args, with_schur=True)
+    monkeypatch.delenv("PGBA_BIG_ND")
+    assert rel_err(dX, g0["dX"].cpu().numpy()) < tol_x
+    assert rel_err(g["dZ"].cpu().numpy(), g0["dZ"].cpu().numpy()) < tol_x
+    o_poses, o_patches = _oracle(p, 2)
+    poses, patches = _run_gpu(p, 2, eff_impl=True)
+    _check_state(p, poses, patches, o_poses, o_patches, tol=2e-4)
+
+
 @pytest.mark.parametrize("eff_impl", [False, True])
 def test_global_ba_matches_oracle(eff_impl):
     p = _global_problem(75, 12, 10, 5)

@@ -237,6 +237,33 @@ __device__ __forceinline__ bool nd_panel(const NdHeader* h, int mode, int idx, i
 }
 __device__ __forceinline__ int nd_tile_of(const NdPanel& pn, int c) { return c < pn.nsb ? pn.k + 1 + c : pn.bbase + (c - pn.nsb); }
 
+// Diagonal tile k: fp64 shared-memory Cholesky (ba_chol.cuh) + explicit inverse W = L^-T; resets the panel's active list.
+// All 256 threads; sd: (2 NB) x (NB | 1) doubles + NB
+__device__ __forceinline__ void nd_potf2_dev(const NdSys& sys, int k, double* sd) {
+  const int tid = threadIdx.x, kb = k * NB, ld = NB | 1;
+  double* A = sd;                       // rows 0..NB-1: diagonal tile; rows NB..2NB-1: identity (-> L^-T)
+  double* rd = sd + 2 * NB * ld;
+  float* Sd = sys.Sp + (size_t)kb * sys.ld + kb;
+  __syncthreads();
+  for (int x = tid; x < NB * NB; x += 256) {
+    const int r = x / NB, c = x - r * NB;
+    A[r * ld + c] = (c <= r) ? (double)__ldcg(&Sd[(size_t)r * sys.ld + c]) : 0.0;
+    A[(NB + r) * ld + c] = (r == c) ? 1.0 : 0.0;
+  }
+  chol6_smem(A, rd, NB, 2 * NB - 1, ld);
+  // rows NB + i now hold (L^-1 e_i)^T, i.e. W[i][c] = Linv[c][i]  (so X = A21 * W solves X L^T = A21)
+  float* W = sys.winv + (size_t)k * NB * NB;
+  for (int x = tid; x < NB * NB; x += 256) {
+    const int r = x / NB, c = x - r * NB;
+    if (c <= r) Sd[(size_t)r * sys.ld + c] = (float)A[r * ld + c];
+    W[r * NB + c] = (float)A[(NB + r) * ld + c];
+  }
+  for (int x = tid; x < NB; x += 256)
+    if (!(rd[x] > 0.0) || !isfinite(rd[x])) atomicCAS(sys.chol_info, 0, kb + x + 1);
+  if (tid == 0) sys.nact[k] = 0;
+}
+
+// The first panel of a phase (the later ones are factored by the look-ahead CTA of the previous panel's trailing update).
 // grid = (1, batch, P | 1), block = 256, dynamic smem: (2 NB) x (NB | 1) doubles + NB
 __global__ void __launch_bounds__(256, 1) nd_potf2_kernel(Problem pb, int mode, int idx) {
   pdl_wait();
@@ -245,26 +272,7 @@ __global__ void __launch_bounds__(256, 1) nd_potf2_kernel(Problem pb, int mode, 
   const NdSys sys = nd_sys(pb, blockIdx.y + pb.w0);
   NdPanel pn;
   if (!nd_panel(sys.h, mode, idx, blockIdx.z, pn)) return;
-  const int tid = threadIdx.x, kb = pn.k * NB, ld = NB | 1;
-  double* A = sd;                       // rows 0..NB-1: diagonal tile; rows NB..2NB-1: identity (-> L^-T)
-  double* rd = sd + 2 * NB * ld;
-  float* Sd = sys.Sp + (size_t)kb * sys.ld + kb;
-  for (int x = tid; x < NB * NB; x += 256) {
-    const int r = x / NB, c = x - r * NB;
-    A[r * ld + c] = (c <= r) ? (double)Sd[(size_t)r * sys.ld + c] : 0.0;
-    A[(NB + r) * ld + c] = (r == c) ? 1.0 : 0.0;
-  }
-  chol6_smem(A, rd, NB, 2 * NB - 1, ld);
-  // rows NB + i now hold (L^-1 e_i)^T, i.e. W[i][c] = Linv[c][i]  (so X = A21 * W solves X L^T = A21)
-  float* W = sys.winv + (size_t)pn.k * NB * NB;
-  for (int x = tid; x < NB * NB; x += 256) {
-    const int r = x / NB, c = x - r * NB;
-    if (c <= r) Sd[(size_t)r * sys.ld + c] = (float)A[r * ld + c];
-    W[r * NB + c] = (float)A[(NB + r) * ld + c];
-  }
-  for (int x = tid; x < NB; x += 256)
-    if (!(rd[x] > 0.0) || !isfinite(rd[x])) atomicCAS(sys.chol_info, 0, kb + x + 1);
-  if (tid == 0) sys.nact[pn.k] = 0;
+  nd_potf2_dev(sys, pn.k, sd);
 }
 
 // grid = (nd_nt + 1, batch, P | 1), block = 256: candidate row tile blockIdx.x (== nbelow: the right-hand side)
@@ -312,12 +320,18 @@ __global__ void __launch_bounds__(256) nd_trsm_kernel(Problem pb, int mode, int 
 }
 
 // Trailing update over pairs of active row tiles of the panel: Sp[tile a][tile b] -= X_a X_b^T (a below b).
-// grid = (gx, batch, P | 1), block = 256 (16 x 16 threads, 3 x 3 outputs each)
+// Look-ahead: the next panel's diagonal tile k + 1 (same segment / border) receives exactly one update from this panel --
+// the pair (k + 1, k + 1), if tile k + 1 is active at all.  CTA 0 does that pair first and then factors the tile (the
+// longest serial piece of a panel step) while the other CTAs work through the remaining pairs, so the next step starts
+// with its row-tile solve instead of a separate factorisation launch.
+// grid = (gx >= 2, batch, P | 1), block = 256 (16 x 16 threads, 3 x 3 outputs each), dynamic smem as nd_potf2_kernel
 __global__ void __launch_bounds__(256) nd_syrk_kernel(Problem pb, int mode, int idx) {
   pdl_wait();
   pdl_trigger();
+  extern __shared__ double sd[];
   __shared__ float sXa[NB][NB + 1];     // [k][row]
   __shared__ float sXb[NB][NB + 1];
+  __shared__ int s_la;
   const NdSys sys = nd_sys(pb, blockIdx.y + pb.w0);
   NdPanel pn;
   if (!nd_panel(sys.h, mode, idx, blockIdx.z, pn)) return;
@@ -327,7 +341,21 @@ __global__ void __launch_bounds__(256) nd_syrk_kernel(Problem pb, int mode, int 
   const int* act = sys.active + (size_t)pn.k * sys.act_stride;
   const int npairs = na * (na + 1) / 2;
   const size_t ld = (size_t)sys.ld;
-  for (int pr = blockIdx.x; pr < npairs; pr += gridDim.x) {
+  // look-ahead pair: index of tile k + 1 in the active list (if the phase has a next panel)
+  const bool has_next = pn.nsb > 0;
+  if (tid == 0) s_la = -1;
+  __syncthreads();
+  if (has_next)
+    for (int x = tid; x < na; x += 256) if (act[x] == pn.k + 1) s_la = x;
+  __syncthreads();
+  const int la = s_la;
+  const int la_pair = la >= 0 ? la * (la + 1) / 2 + la : -1;
+  const bool la_cta = has_next && blockIdx.x == 0;
+  // CTA 0: only the look-ahead pair (one trip); the others: every other pair
+  const int pr0 = la_cta ? (la_pair >= 0 ? la_pair : npairs) : (int)blockIdx.x - (has_next ? 1 : 0);
+  const int prs = la_cta ? npairs + 1 : (int)gridDim.x - (has_next ? 1 : 0);
+  for (int pr = pr0; pr < npairs; pr += prs) {
+    if (!la_cta && pr == la_pair) continue;
     int ia, ib;
     pair_of(pr, ia, ib);
     int ta = act[ia], tb = act[ib];
@@ -374,6 +402,7 @@ __global__ void __launch_bounds__(256) nd_syrk_kernel(Problem pb, int mode, int 
         if (shared_dst) atomicAdd(dst, -acc[i][j]); else *dst -= acc[i][j];
       }
   }
+  if (la_cta) nd_potf2_dev(sys, pn.k + 1, sd);
 }
 
 // Backward substitution L^T x = z, one CTA of 1024 threads per (window, segment): the running solution lives in shared
@@ -508,16 +537,18 @@ cudaError_t launch_nd_solve(const Problem& pb, int64_t batch, cudaStream_t strea
   count_launch();
   const size_t psm = sizeof(double) * ((size_t)2 * NB * (NB | 1) + NB);
   cudaFuncSetAttribute(nd_potf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm);
-  const int border_steps = (N + 7) / 8;             // worst case: every frame in the border
+  cudaFuncSetAttribute(nd_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm);
+  int border_steps = (N + 7) / 8;                   // worst case: every frame in the border
+  if (const char* e = getenv("PGBA_ND_BSTEPS_UNSAFE")) border_steps = atoi(e);   // timing experiments only
   for (int mode = 0; mode < 2; ++mode) {
     const int steps = mode == 0 ? pb.L.nd_tmax : border_steps;
     const unsigned Z = mode == 0 ? (unsigned)P : 1u;
     const int gx = mode == 0 ? (296 / P > 4 ? 296 / P : 4) : 296;
     for (int s = 0; s < steps; ++s) {
-      launch_k(nd_potf2_kernel, dim3(1, B, Z), dim3(256), psm, stream, pb, mode, s);
+      if (s == 0) { launch_k(nd_potf2_kernel, dim3(1, B, Z), dim3(256), psm, stream, pb, mode, s); count_launch(); }
       launch_k(nd_trsm_kernel, dim3(nt + 1, B, Z), dim3(256), 0, stream, pb, mode, s);
-      launch_k(nd_syrk_kernel, dim3(gx, B, Z), dim3(256), 0, stream, pb, mode, s);
-      count_launch(); count_launch(); count_launch();
+      launch_k(nd_syrk_kernel, dim3(gx, B, Z), dim3(256), psm, stream, pb, mode, s);
+      count_launch(); count_launch();
     }
   }
   const size_t bsmem = sizeof(float) * ((size_t)nt * NB + 33 * NB);

@@ -538,8 +538,7 @@ cudaError_t launch_nd_solve(const Problem& pb, int64_t batch, cudaStream_t strea
   const size_t psm = sizeof(double) * ((size_t)2 * NB * (NB | 1) + NB);
   cudaFuncSetAttribute(nd_potf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm);
   cudaFuncSetAttribute(nd_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm);
-  int border_steps = (N + 7) / 8;                   // worst case: every frame in the border
-  if (const char* e = getenv("PGBA_ND_BSTEPS_UNSAFE")) border_steps = atoi(e);   // timing experiments only
+  const int border_steps = (N + 7) / 8;             // worst case: every frame in the border
   for (int mode = 0; mode < 2; ++mode) {
     const int steps = mode == 0 ? pb.L.nd_tmax : border_steps;
     const unsigned Z = mode == 0 ? (unsigned)P : 1u;

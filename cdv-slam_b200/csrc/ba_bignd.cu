@@ -36,7 +36,7 @@ struct NdSys {
   int ld;                 // row stride of Sp (= capacity in unknowns)
   NdHeader* h;
   int* lminv; int* lmax1; int* border; int* pos; int* pfb; int* pfn; int* frame_at;
-  float* winv; int* active; int* nact; int act_stride; int* chol_info;
+  float* winv; float* dinv; int* active; int* nact; int act_stride; int* chol_info;
 };
 
 __device__ __forceinline__ NdSys nd_sys(const Problem& pb, int w) {
@@ -52,6 +52,7 @@ __device__ __forceinline__ NdSys nd_sys(const Problem& pb, int w) {
   s.lminv = f; s.lmax1 = f + pb.F; s.border = f + 2 * pb.F; s.pos = f + 3 * pb.F; s.pfb = f + 4 * pb.F; s.pfn = f + 5 * pb.F;
   s.frame_at = (int*)(base + pb.L.o_frame_at);
   s.winv = (float*)(base + pb.L.o_winv);
+  s.dinv = (float*)(base + pb.L.o_dinv);
   s.active = (int*)(base + pb.L.o_active);
   s.nact = (int*)(z + pb.L.z_nact);
   s.act_stride = pb.L.big_tiles;
@@ -237,34 +238,49 @@ __device__ __forceinline__ bool nd_panel(const NdHeader* h, int mode, int idx, i
 }
 __device__ __forceinline__ int nd_tile_of(const NdPanel& pn, int c) { return c < pn.nsb ? pn.k + 1 + c : pn.bbase + (c - pn.nsb); }
 
-// Diagonal tile k: fp64 shared-memory Cholesky (ba_chol.cuh) + explicit inverse W = L^-T; resets the panel's active list.
-// All 256 threads; sd: (2 NB) x (NB | 1) doubles + NB
+constexpr int ND_DINV = (NB / 6) * 36;    // floats of the 6 x 6 diagonal-block inverses of one tile
+
+// Diagonal tile k: fp64 shared-memory Cholesky (ba_chol.cuh) and the inverses of the 6 x 6 diagonal blocks of L (what the
+// row-tile solves substitute with); resets the panel's active list.  This is the serial piece of every panel step, so it
+// carries nothing else: the explicit inverse W = L^-T of the whole tile, which only the backward substitution needs, is
+// formed by one extra CTA of the row-tile solve (nd_trsm_kernel) -- with the inverse riding along as 48 extra rows the
+// factorisation took 15 us instead of ~9.
+// All 256 threads; sd: NB x (NB | 1) doubles + NB
 __device__ __forceinline__ void nd_potf2_dev(const NdSys& sys, int k, double* sd) {
   const int tid = threadIdx.x, kb = k * NB, ld = NB | 1;
-  double* A = sd;                       // rows 0..NB-1: diagonal tile; rows NB..2NB-1: identity (-> L^-T)
-  double* rd = sd + 2 * NB * ld;
+  double* A = sd;
+  double* rd = sd + NB * ld;
   float* Sd = sys.Sp + (size_t)kb * sys.ld + kb;
   __syncthreads();
   for (int x = tid; x < NB * NB; x += 256) {
     const int r = x / NB, c = x - r * NB;
     A[r * ld + c] = (c <= r) ? (double)__ldcg(&Sd[(size_t)r * sys.ld + c]) : 0.0;
-    A[(NB + r) * ld + c] = (r == c) ? 1.0 : 0.0;
   }
-  chol6_smem(A, rd, NB, 2 * NB - 1, ld);
-  // rows NB + i now hold (L^-1 e_i)^T, i.e. W[i][c] = Linv[c][i]  (so X = A21 * W solves X L^T = A21)
-  float* W = sys.winv + (size_t)k * NB * NB;
+  chol6_smem(A, rd, NB, NB - 1, ld);
   for (int x = tid; x < NB * NB; x += 256) {
     const int r = x / NB, c = x - r * NB;
     if (c <= r) Sd[(size_t)r * sys.ld + c] = (float)A[r * ld + c];
-    W[r * NB + c] = (float)A[(NB + r) * ld + c];
   }
-  for (int x = tid; x < NB; x += 256)
-    if (!(rd[x] > 0.0) || !isfinite(rd[x])) atomicCAS(sys.chol_info, 0, kb + x + 1);
+  if (tid < NB) {                         // column c of the inverse of diagonal block b: forward substitution L_bb x = e_c
+    const int b = tid / 6, c = tid - 6 * b, k6 = 6 * b;
+    double x[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      double s = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+      for (int e = 0; e < r; ++e) s -= A[(k6 + r) * ld + k6 + e] * x[e];
+      x[r] = s * rd[k6 + r];
+    }
+    float* D = sys.dinv + (size_t)k * ND_DINV + b * 36;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) D[r * 6 + c] = (float)x[r];
+    if (!(rd[tid] > 0.0) || !isfinite(rd[tid])) atomicCAS(sys.chol_info, 0, kb + tid + 1);
+  }
   if (tid == 0) sys.nact[k] = 0;
 }
 
 // The first panel of a phase (the later ones are factored by the look-ahead CTA of the previous panel's trailing update).
-// grid = (1, batch, P | 1), block = 256, dynamic smem: (2 NB) x (NB | 1) doubles + NB
+// grid = (1, batch, P | 1), block = 256, dynamic smem: NB x (NB | 1) doubles + NB
 __global__ void __launch_bounds__(256, 1) nd_potf2_kernel(Problem pb, int mode, int idx) {
   pdl_wait();
   pdl_trigger();
@@ -275,45 +291,87 @@ __global__ void __launch_bounds__(256, 1) nd_potf2_kernel(Problem pb, int mode, 
   nd_potf2_dev(sys, pn.k, sd);
 }
 
-// grid = (nd_nt + 1, batch, P | 1), block = 256: candidate row tile blockIdx.x (== nbelow: the right-hand side)
+// In place sA <- sA L^-T (X L^T = A) for `rows` rows, block column by block column: X_C = (A_C - sum_{E < C} X_E L_CE^T) D_C^T
+// with D_C the inverse of the diagonal block.  A row only ever reads its own earlier columns, so four adjacent lanes share a
+// row (the inner sums split four ways, two shuffles to combine) and nothing but a __syncwarp separates the block steps.
+// Threads 0 .. 4 * rows - 1 work (rows <= 48: warps 0..5); sL: the factor tile (lower triangle), sD: ND_DINV floats.
+__device__ __forceinline__ void nd_solve_rows(float (*sA)[NB + 1], const float (*sL)[NB + 1], const float* sD, int rows) {
+  const int tid = threadIdx.x, r = tid >> 2, part = tid & 3;
+  if (r >= rows) return;
+  const unsigned mask = rows >= 8 ? 0xffffffffu : ((1u << (4 * rows)) - 1u);      // rows is NB or 1
+  for (int C = 0; C < NB / 6; ++C) {
+    float t[6];
+#pragma unroll
+    for (int cp = 0; cp < 6; ++cp) t[cp] = 0.f;
+    for (int e = part; e < 6 * C; e += 4) {
+      const float xe = sA[r][e];
+#pragma unroll
+      for (int cp = 0; cp < 6; ++cp) t[cp] = fmaf(-xe, sL[6 * C + cp][e], t[cp]);
+    }
+#pragma unroll
+    for (int cp = 0; cp < 6; ++cp) {
+      t[cp] += __shfl_xor_sync(mask, t[cp], 1);
+      t[cp] += __shfl_xor_sync(mask, t[cp], 2);
+      t[cp] += sA[r][6 * C + cp];
+    }
+    const float* D = sD + C * 36;
+    __syncwarp(mask);                                 // every lane of the row has read the A entries of this block
+    if (part == 0) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        float x = 0.f;
+#pragma unroll
+        for (int cp = 0; cp <= c; ++cp) x = fmaf(t[cp], D[c * 6 + cp], x);
+        sA[r][6 * C + c] = x;
+      }
+    }
+    __syncwarp(mask);
+  }
+}
+
+// Row-tile solves of a panel.  grid = (nd_nt + 2, batch, P | 1), block = 256: blockIdx.x < nbelow: candidate row tile;
+// == nbelow: the right-hand side; == nbelow + 1: the explicit inverse W = L^-T of the diagonal tile (the same solve applied
+// to the identity), which the backward substitution uses later -- off the critical path of the factorisation.
 __global__ void __launch_bounds__(256) nd_trsm_kernel(Problem pb, int mode, int idx) {
   pdl_wait();
   pdl_trigger();
   __shared__ float sA[NB][NB + 1];
-  __shared__ float sW[NB][NB + 1];
+  __shared__ float sL[NB][NB + 1];
+  __shared__ float sD[ND_DINV];
   const NdSys sys = nd_sys(pb, blockIdx.y + pb.w0);
   NdPanel pn;
   if (!nd_panel(sys.h, mode, idx, blockIdx.z, pn)) return;
   const int c0 = blockIdx.x;
-  if (c0 > pn.nbelow) return;
+  if (c0 > pn.nbelow + 1) return;
   const int tid = threadIdx.x, kb = pn.k * NB;
-  const bool rhs = (c0 == pn.nbelow);
-  const int t = rhs ? -1 : nd_tile_of(pn, c0);
+  const bool rhs = (c0 == pn.nbelow), inv = (c0 == pn.nbelow + 1);
+  const int t = (rhs || inv) ? -1 : nd_tile_of(pn, c0);
   const int rows = rhs ? 1 : NB;
-  float* src = rhs ? (sys.yp + kb) : (sys.Sp + (size_t)t * NB * sys.ld + kb);
-  const size_t rstride = rhs ? 0 : (size_t)sys.ld;
+  float* src = inv ? (sys.winv + (size_t)pn.k * NB * NB) : rhs ? (sys.yp + kb) : (sys.Sp + (size_t)t * NB * sys.ld + kb);
+  const size_t rstride = inv ? (size_t)NB : rhs ? 0 : (size_t)sys.ld;
   int nz = 0;
   for (int x = tid; x < rows * NB; x += 256) {
     const int r = x / NB, c = x - r * NB;
-    const float v = src[r * rstride + c];
+    const float v = inv ? (r == c ? 1.f : 0.f) : src[r * rstride + c];
     sA[r][c] = v;
     nz |= (v != 0.f);
   }
   nz = __syncthreads_or(nz);
   if (!nz && !rhs) return;                       // an all-zero tile stays zero: inactive for this panel
-  const float* W = sys.winv + (size_t)pn.k * NB * NB;
+  const float* Ld = sys.Sp + (size_t)kb * sys.ld + kb;
   for (int x = tid; x < NB * NB; x += 256) {
     const int r = x / NB, c = x - r * NB;
-    sW[r][c] = W[x];
+    sL[r][c] = (c <= r) ? Ld[(size_t)r * sys.ld + c] : 0.f;
   }
+  for (int x = tid; x < ND_DINV; x += 256) sD[x] = sys.dinv[(size_t)pn.k * ND_DINV + x];
+  __syncthreads();
+  nd_solve_rows(sA, sL, sD, rows);
   __syncthreads();
   for (int x = tid; x < rows * NB; x += 256) {
     const int r = x / NB, c = x - r * NB;
-    float acc = 0;
-    for (int e = 0; e <= c; ++e) acc += sA[r][e] * sW[e][c];      // W[e][c] = Linv[c][e] is zero for e > c
-    src[r * rstride + c] = acc;
+    src[r * rstride + c] = sA[r][c];
   }
-  if (tid == 0) {
+  if (tid == 0 && !inv) {
     const int slot = atomicAdd(&sys.nact[pn.k], 1);
     sys.active[(size_t)pn.k * sys.act_stride + slot] = t;          // -1 marks the rhs row
   }
@@ -535,7 +593,7 @@ cudaError_t launch_nd_solve(const Problem& pb, int64_t batch, cudaStream_t strea
   const int N = pb.t1 - pb.t0, P = pb.L.nd_P, nt = pb.L.nd_nt;
   launch_k(nd_gather_kernel, dim3(148 * 8, B), dim3(256), 0, stream, pb);
   count_launch();
-  const size_t psm = sizeof(double) * ((size_t)2 * NB * (NB | 1) + NB);
+  const size_t psm = sizeof(double) * ((size_t)NB * (NB | 1) + NB);
   cudaFuncSetAttribute(nd_potf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm);
   cudaFuncSetAttribute(nd_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm);
   const int border_steps = (N + 7) / 8;             // worst case: every frame in the border
@@ -545,7 +603,7 @@ cudaError_t launch_nd_solve(const Problem& pb, int64_t batch, cudaStream_t strea
     const int gx = mode == 0 ? (296 / P > 4 ? 296 / P : 4) : 296;
     for (int s = 0; s < steps; ++s) {
       if (s == 0) { launch_k(nd_potf2_kernel, dim3(1, B, Z), dim3(256), psm, stream, pb, mode, s); count_launch(); }
-      launch_k(nd_trsm_kernel, dim3(nt + 1, B, Z), dim3(256), 0, stream, pb, mode, s);
+      launch_k(nd_trsm_kernel, dim3(nt + 2, B, Z), dim3(256), 0, stream, pb, mode, s);
       launch_k(nd_syrk_kernel, dim3(gx, B, Z), dim3(256), psm, stream, pb, mode, s);
       count_launch(); count_launch();
     }

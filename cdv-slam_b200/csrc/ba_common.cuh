@@ -89,7 +89,7 @@ struct Layout {         // host-computed
   // nested-dissection ordering (big solve with >= ND_MIN_N free poses): P chain segments + border, permuted system of
   // nd_nt tiles (capacity), nd_tmax = tiles of the longest possible segment, nd_R = "far edge" frame distance
   int nd_P, nd_nt, nd_tmax, nd_R;
-  size_t z_nd, z_ndf, z_yp, z_Sp, o_frame_at;
+  size_t z_nd, z_ndf, z_yp, z_Sp, o_frame_at, o_dinv;
   // body (relative to the window's body base)
   size_t o_fbase, o_ccur, o_chunks, o_perm, o_kx, o_slots, o_cells, o_dups, o_ecells, o_Q, o_u, o_dZ, o_dX, body_bytes;
   size_t body0;         // offset of the first body = batch * zero_bytes (aligned)
@@ -174,6 +174,7 @@ inline Layout make_layout(int64_t E, int64_t F, int64_t K, int N, int64_t batch,
   L.o_winv = o;   o = align256(o + (L.big ? 4 * (size_t)L.big_steps * BIG_NB * BIG_NB : 0));
   L.o_active = o; o = align256(o + (L.big ? 4 * (size_t)L.big_steps * L.big_tiles : 0));
   L.o_frame_at = o; o = align256(o + 4 * (size_t)L.nd_nt * 8);
+  L.o_dinv = o;   o = align256(o + 4 * (size_t)L.nd_nt * (BIG_NB / 6) * 36);   // inverses of the 6 x 6 diagonal blocks of L
   L.body_bytes = o;
   L.body0 = L.zero_bytes * (size_t)batch;
   return L;

@@ -1,0 +1,7 @@
+mkdir -p gpurun_out
+(timeout 900 python -m pytest tests/test_ba_gpu.py -m gpu -x -q -k "global") > gpurun_out/pytest_nd_v28.log 2>&1
+tail -5 gpurun_out/pytest_nd_v28.log
+timeout 300 python profiles/microbench/c4time.py 2>&1 | tail -2
+PGBA_LIB=cdv-slam_b200/lib/libpgba_ndw.so timeout 300 python profiles/microbench/c4time.py 2>&1 | tail -2
+timeout 300 python profiles/microbench/c4time.py 2>&1 | tail -1
+PGBA_LIB=cdv-slam_b200/lib/libpgba_ndw.so timeout 300 python profiles/microbench/c4time.py 2>&1 | tail -1

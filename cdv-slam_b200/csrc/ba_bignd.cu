@@ -31,6 +31,26 @@
 
 namespace pgba {
 
+#ifdef PGBA_ND_TIMING      // per-launch timeline of the factorisation (profiles/nd_timeline.py): entry, after pdl_wait, end
+__device__ unsigned long long g_nd_ts[3 * 1024][3];
+__device__ __forceinline__ unsigned long long nd_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+struct NdTs {
+  int id;
+  __device__ NdTs(int kind, int mode, int idx) : id(kind * 1024 + mode * 512 + idx) { if (threadIdx.x == 0) atomicMin(&g_nd_ts[id][0], nd_gtime()); }
+  __device__ void waited() { if (threadIdx.x == 0) atomicMin(&g_nd_ts[id][1], nd_gtime()); }
+  __device__ ~NdTs() { if (threadIdx.x == 0) atomicMax(&g_nd_ts[id][2], nd_gtime()); }
+};
+#define ND_TS(kind, mode, idx) NdTs nd_ts_(kind, mode, idx)
+#define ND_TS_WAITED() nd_ts_.waited()
+// phase clocks of CTA `cta` of the border step 5 launches: slot = kind * 64 + cta_slot * 16 + i
+__device__ unsigned long long g_nd_ph[256];
+#define ND_PH(kind, ctaslot, cta, i) do { if (threadIdx.x == 0 && mode == 1 && idx == 5 && blockIdx.x == (cta)) g_nd_ph[(kind) * 64 + (ctaslot) * 16 + (i)] = nd_gtime(); } while (0)
+#else
+#define ND_PH(kind, ctaslot, cta, i) do { } while (0)
+#define ND_TS(kind, mode, idx) do { } while (0)
+#define ND_TS_WAITED() do { } while (0)
+#endif
+
 struct NdSys {
   float* S; float* y; float* Sp; float* yp;
   int ld;                 // row stride of Sp (= capacity in unknowns)
@@ -252,9 +272,18 @@ __device__ __forceinline__ void nd_potf2_dev(const NdSys& sys, int k, double* sd
   double* rd = sd + NB * ld;
   float* Sd = sys.Sp + (size_t)kb * sys.ld + kb;
   __syncthreads();
-  for (int x = tid; x < NB * NB; x += 256) {
-    const int r = x / NB, c = x - r * NB;
-    A[r * ld + c] = (c <= r) ? (double)__ldcg(&Sd[(size_t)r * sys.ld + c]) : 0.0;
+  {
+    float v[NB * NB / 256];                     // all loads of the tile in flight before the first shared-memory store
+#pragma unroll
+    for (int i = 0; i < NB * NB / 256; ++i) {
+      const int x = tid + 256 * i, r = x / NB, c = x - r * NB;
+      v[i] = (c <= r) ? __ldcg(&Sd[(size_t)r * sys.ld + c]) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < NB * NB / 256; ++i) {
+      const int x = tid + 256 * i, r = x / NB, c = x - r * NB;
+      A[r * ld + c] = (double)v[i];
+    }
   }
   chol6_smem(A, rd, NB, NB - 1, ld);
   for (int x = tid; x < NB * NB; x += 256) {
@@ -282,12 +311,15 @@ __device__ __forceinline__ void nd_potf2_dev(const NdSys& sys, int k, double* sd
 // The first panel of a phase (the later ones are factored by the look-ahead CTA of the previous panel's trailing update).
 // grid = (1, batch, P | 1), block = 256, dynamic smem: NB x (NB | 1) doubles + NB
 __global__ void __launch_bounds__(256, 1) nd_potf2_kernel(Problem pb, int mode, int idx) {
-  pdl_wait();
-  pdl_trigger();
+  ND_TS(0, mode, idx);
   extern __shared__ double sd[];
   const NdSys sys = nd_sys(pb, blockIdx.y + pb.w0);
   NdPanel pn;
-  if (!nd_panel(sys.h, mode, idx, blockIdx.z, pn)) return;
+  const bool live = nd_panel(sys.h, mode, idx, blockIdx.z, pn);      // the ordering is final: read ahead of the wait
+  pdl_wait();
+  pdl_trigger();
+  ND_TS_WAITED();
+  if (!live) return;
   nd_potf2_dev(sys, pn.k, sd);
 }
 
@@ -300,28 +332,35 @@ __device__ __forceinline__ void nd_solve_rows(float (*sA)[NB + 1], const float (
   if (r >= rows) return;
   const unsigned mask = rows >= 8 ? 0xffffffffu : ((1u << (4 * rows)) - 1u);      // rows is NB or 1
   for (int C = 0; C < NB / 6; ++C) {
-    float t[6];
+    float t[6], t2[6], a6[6];
 #pragma unroll
-    for (int cp = 0; cp < 6; ++cp) t[cp] = 0.f;
-    for (int e = part; e < 6 * C; e += 4) {
-      const float xe = sA[r][e];
+    for (int cp = 0; cp < 6; ++cp) { t[cp] = 0.f; t2[cp] = 0.f; a6[cp] = sA[r][6 * C + cp]; }
+    // two columns per trip (e, e + 4), all 14 shared-memory loads ahead of the FMAs; a second column beyond 6 C reads
+    // entries of the diagonal block and is multiplied by zero
+    for (int e = part; e < 6 * C; e += 8) {
+      const float x0 = sA[r][e], x1 = (e + 4 < 6 * C) ? sA[r][e + 4] : 0.f;
+      float l0[6], l1[6];
 #pragma unroll
-      for (int cp = 0; cp < 6; ++cp) t[cp] = fmaf(-xe, sL[6 * C + cp][e], t[cp]);
+      for (int cp = 0; cp < 6; ++cp) { l0[cp] = sL[6 * C + cp][e]; l1[cp] = sL[6 * C + cp][e + 4]; }
+#pragma unroll
+      for (int cp = 0; cp < 6; ++cp) { t[cp] = fmaf(-x0, l0[cp], t[cp]); t2[cp] = fmaf(-x1, l1[cp], t2[cp]); }
     }
 #pragma unroll
     for (int cp = 0; cp < 6; ++cp) {
+      t[cp] += t2[cp];
       t[cp] += __shfl_xor_sync(mask, t[cp], 1);
       t[cp] += __shfl_xor_sync(mask, t[cp], 2);
-      t[cp] += sA[r][6 * C + cp];
+      t[cp] += a6[cp];
     }
     const float* D = sD + C * 36;
-    __syncwarp(mask);                                 // every lane of the row has read the A entries of this block
-    if (part == 0) {
+    // X[c] = sum_{cp <= c} t[cp] D[c][cp]: lane `part` takes c = part and c = part + 4
 #pragma unroll
-      for (int c = 0; c < 6; ++c) {
+    for (int h = 0; h < 2; ++h) {
+      const int c = part + 4 * h;
+      if (c < 6) {
         float x = 0.f;
 #pragma unroll
-        for (int cp = 0; cp <= c; ++cp) x = fmaf(t[cp], D[c * 6 + cp], x);
+        for (int cp = 0; cp < 6; ++cp) x = fmaf(t[cp], D[c * 6 + cp], x);      // D is lower triangular (zeros above)
         sA[r][6 * C + c] = x;
       }
     }
@@ -333,14 +372,18 @@ __device__ __forceinline__ void nd_solve_rows(float (*sA)[NB + 1], const float (
 // == nbelow: the right-hand side; == nbelow + 1: the explicit inverse W = L^-T of the diagonal tile (the same solve applied
 // to the identity), which the backward substitution uses later -- off the critical path of the factorisation.
 __global__ void __launch_bounds__(256) nd_trsm_kernel(Problem pb, int mode, int idx) {
-  pdl_wait();
-  pdl_trigger();
+  ND_TS(1, mode, idx);
   __shared__ float sA[NB][NB + 1];
   __shared__ float sL[NB][NB + 1];
   __shared__ float sD[ND_DINV];
   const NdSys sys = nd_sys(pb, blockIdx.y + pb.w0);
   NdPanel pn;
-  if (!nd_panel(sys.h, mode, idx, blockIdx.z, pn)) return;
+  const bool live = nd_panel(sys.h, mode, idx, blockIdx.z, pn);      // the ordering is final: read ahead of the wait
+  pdl_wait();
+  pdl_trigger();
+  ND_TS_WAITED();
+  if (!live) return;
+  ND_PH(1, 0, 3, 0);
   const int c0 = blockIdx.x;
   if (c0 > pn.nbelow + 1) return;
   const int tid = threadIdx.x, kb = pn.k * NB;
@@ -349,24 +392,37 @@ __global__ void __launch_bounds__(256) nd_trsm_kernel(Problem pb, int mode, int 
   const int rows = rhs ? 1 : NB;
   float* src = inv ? (sys.winv + (size_t)pn.k * NB * NB) : rhs ? (sys.yp + kb) : (sys.Sp + (size_t)t * NB * sys.ld + kb);
   const size_t rstride = inv ? (size_t)NB : rhs ? 0 : (size_t)sys.ld;
+  // the row tile, the factor tile and the block inverses are requested together (one round trip instead of two; the
+  // all-zero test of the row tile only decides whether the rest runs)
+  const float* Ld = sys.Sp + (size_t)kb * sys.ld + kb;
   int nz = 0;
-  for (int x = tid; x < rows * NB; x += 256) {
-    const int r = x / NB, c = x - r * NB;
-    const float v = inv ? (r == c ? 1.f : 0.f) : src[r * rstride + c];
-    sA[r][c] = v;
-    nz |= (v != 0.f);
+  {
+    constexpr int NI = NB * NB / 256;
+    float va[NI], vl[NI], vd[2];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int x = tid + 256 * i, r = x / NB, c = x - r * NB;
+      va[i] = (r >= rows) ? 0.f : inv ? (r == c ? 1.f : 0.f) : src[r * rstride + c];
+      vl[i] = (c <= r) ? Ld[(size_t)r * sys.ld + c] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) vd[i] = (tid + 256 * i < ND_DINV) ? sys.dinv[(size_t)pn.k * ND_DINV + tid + 256 * i] : 0.f;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int x = tid + 256 * i, r = x / NB, c = x - r * NB;
+      sA[r][c] = va[i];
+      sL[r][c] = vl[i];
+      nz |= (va[i] != 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) if (tid + 256 * i < ND_DINV) sD[tid + 256 * i] = vd[i];
   }
   nz = __syncthreads_or(nz);
+  ND_PH(1, 0, 3, 1);
   if (!nz && !rhs) return;                       // an all-zero tile stays zero: inactive for this panel
-  const float* Ld = sys.Sp + (size_t)kb * sys.ld + kb;
-  for (int x = tid; x < NB * NB; x += 256) {
-    const int r = x / NB, c = x - r * NB;
-    sL[r][c] = (c <= r) ? Ld[(size_t)r * sys.ld + c] : 0.f;
-  }
-  for (int x = tid; x < ND_DINV; x += 256) sD[x] = sys.dinv[(size_t)pn.k * ND_DINV + x];
-  __syncthreads();
   nd_solve_rows(sA, sL, sD, rows);
   __syncthreads();
+  ND_PH(1, 0, 3, 2);
   for (int x = tid; x < rows * NB; x += 256) {
     const int r = x / NB, c = x - r * NB;
     src[r * rstride + c] = sA[r][c];
@@ -375,6 +431,7 @@ __global__ void __launch_bounds__(256) nd_trsm_kernel(Problem pb, int mode, int 
     const int slot = atomicAdd(&sys.nact[pn.k], 1);
     sys.active[(size_t)pn.k * sys.act_stride + slot] = t;          // -1 marks the rhs row
   }
+  ND_PH(1, 0, 3, 3);
 }
 
 // Trailing update over pairs of active row tiles of the panel: Sp[tile a][tile b] -= X_a X_b^T (a below b).
@@ -384,15 +441,18 @@ __global__ void __launch_bounds__(256) nd_trsm_kernel(Problem pb, int mode, int 
 // with its row-tile solve instead of a separate factorisation launch.
 // grid = (gx >= 2, batch, P | 1), block = 256 (16 x 16 threads, 3 x 3 outputs each), dynamic smem as nd_potf2_kernel
 __global__ void __launch_bounds__(256) nd_syrk_kernel(Problem pb, int mode, int idx) {
-  pdl_wait();
-  pdl_trigger();
+  ND_TS(2, mode, idx);
   extern __shared__ double sd[];
   __shared__ float sXa[NB][NB + 1];     // [k][row]
   __shared__ float sXb[NB][NB + 1];
   __shared__ int s_la;
   const NdSys sys = nd_sys(pb, blockIdx.y + pb.w0);
   NdPanel pn;
-  if (!nd_panel(sys.h, mode, idx, blockIdx.z, pn)) return;
+  const bool live = nd_panel(sys.h, mode, idx, blockIdx.z, pn);      // the ordering is final: read ahead of the wait
+  pdl_wait();
+  pdl_trigger();
+  ND_TS_WAITED();
+  if (!live) return;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int kb = pn.k * NB;
   const int na = sys.nact[pn.k];
@@ -406,6 +466,7 @@ __global__ void __launch_bounds__(256) nd_syrk_kernel(Problem pb, int mode, int 
   if (has_next)
     for (int x = tid; x < na; x += 256) if (act[x] == pn.k + 1) s_la = x;
   __syncthreads();
+  ND_PH(2, 0, 0, 0); ND_PH(2, 1, 5, 0);
   const int la = s_la;
   const int la_pair = la >= 0 ? la * (la + 1) / 2 + la : -1;
   const bool la_cta = has_next && blockIdx.x == 0;
@@ -430,10 +491,21 @@ __global__ void __launch_bounds__(256) nd_syrk_kernel(Problem pb, int mode, int 
     const int rows_a = rhs ? 1 : NB;
     const float* xb = sys.Sp + (size_t)rb * ld + kb;
     __syncthreads();
-    for (int x = tid; x < NB * NB; x += 256) {
-      const int r = x / NB, k = x - r * NB;
-      sXa[k][r] = (r < rows_a) ? xa[r * sa + k] : 0.f;
-      sXb[k][r] = xb[(size_t)r * ld + k];
+    {
+      constexpr int NI = NB * NB / 256;
+      float va[NI], vb[NI];                       // both tiles in flight before the first shared-memory store
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const int x = tid + 256 * i, r = x / NB, k = x - r * NB;
+        va[i] = (r < rows_a) ? xa[r * sa + k] : 0.f;
+        vb[i] = xb[(size_t)r * ld + k];
+      }
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const int x = tid + 256 * i, r = x / NB, k = x - r * NB;
+        sXa[k][r] = va[i];
+        sXb[k][r] = vb[i];
+      }
     }
     __syncthreads();
     float acc[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
@@ -460,7 +532,9 @@ __global__ void __launch_bounds__(256) nd_syrk_kernel(Problem pb, int mode, int 
         if (shared_dst) atomicAdd(dst, -acc[i][j]); else *dst -= acc[i][j];
       }
   }
+  ND_PH(2, 0, 0, 1); ND_PH(2, 1, 5, 1);
   if (la_cta) nd_potf2_dev(sys, pn.k + 1, sd);
+  ND_PH(2, 0, 0, 2);
 }
 
 // Backward substitution L^T x = z, one CTA of 1024 threads per (window, segment): the running solution lives in shared
@@ -621,4 +695,21 @@ cudaError_t launch_nd_solve(const Problem& pb, int64_t batch, cudaStream_t strea
   return cudaGetLastError();
 }
 
+#ifdef PGBA_ND_TIMING
+void nd_timestamps(unsigned long long* out, int reset) {
+  if (reset) {
+    static unsigned long long init[3 * 1024][3];
+    for (auto& r : init) { r[0] = ~0ull; r[1] = ~0ull; r[2] = 0ull; }
+    cudaMemcpyToSymbol(g_nd_ts, init, sizeof(init));
+  } else {
+    cudaMemcpyFromSymbol(out, g_nd_ts, sizeof(unsigned long long) * 3 * 1024 * 3);
+    cudaMemcpyFromSymbol(out + 3 * 1024 * 3, g_nd_ph, sizeof(unsigned long long) * 256);
+  }
+}
+#endif
+
 }  // namespace pgba
+
+#ifdef PGBA_ND_TIMING
+extern "C" void pgba_nd_timestamps(unsigned long long* out, int reset) { pgba::nd_timestamps(out, reset); }
+#endif

@@ -44,7 +44,7 @@ struct NdTs {
 #define ND_TS_WAITED() nd_ts_.waited()
 // phase clocks of CTA `cta` of the border step 5 launches: slot = kind * 64 + cta_slot * 16 + i
 __device__ unsigned long long g_nd_ph[256];
-#define ND_PH(kind, ctaslot, cta, i) do { if (threadIdx.x == 0 && mode == 1 && idx == 5 && blockIdx.x == (cta)) g_nd_ph[(kind) * 64 + (ctaslot) * 16 + (i)] = nd_gtime(); } while (0)
+#define ND_PH(kind, ctaslot, cta, i) do { if (threadIdx.x == 0 && mode == 1 && idx == 5 && blockIdx.z == (cta)) g_nd_ph[(kind) * 64 + (ctaslot) * 16 + (i)] = nd_gtime(); } while (0)
 #else
 #define ND_PH(kind, ctaslot, cta, i) do { } while (0)
 #define ND_TS(kind, mode, idx) do { } while (0)
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(256) nd_gather_kernel(Problem pb) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// factorisation.  A panel step is (mode, idx): mode 0 = tile idx of segment blockIdx.z, mode 1 = tile idx of the border.
+// factorisation.  A panel step is (mode, idx): mode 0 = tile idx of segment blockIdx.x, mode 1 = tile idx of the border.
 // Rows below panel tile k that can be non-zero: the later tiles of the same segment / of the border, then (segments
 // only) all border tiles.
 // ---------------------------------------------------------------------------------------------------------------
@@ -266,11 +266,12 @@ constexpr int ND_DINV = (NB / 6) * 36;    // floats of the 6 x 6 diagonal-block 
 // formed by one extra CTA of the row-tile solve (nd_trsm_kernel) -- with the inverse riding along as 48 extra rows the
 // factorisation took 15 us instead of ~9.
 // All 256 threads; sd: NB x (NB | 1) doubles + NB
+__device__ __forceinline__ void nd_potf2_core(const NdSys& sys, int k, double* sd);
+
 __device__ __forceinline__ void nd_potf2_dev(const NdSys& sys, int k, double* sd) {
   const int tid = threadIdx.x, kb = k * NB, ld = NB | 1;
   double* A = sd;
-  double* rd = sd + NB * ld;
-  float* Sd = sys.Sp + (size_t)kb * sys.ld + kb;
+  const float* Sd = sys.Sp + (size_t)kb * sys.ld + kb;
   __syncthreads();
   {
     float v[NB * NB / 256];                     // all loads of the tile in flight before the first shared-memory store
@@ -285,6 +286,15 @@ __device__ __forceinline__ void nd_potf2_dev(const NdSys& sys, int k, double* sd
       A[r * ld + c] = (double)v[i];
     }
   }
+  nd_potf2_core(sys, k, sd);
+}
+
+// sd holds the lower triangle of diagonal tile k (zeros above) as doubles, row stride NB | 1
+__device__ __forceinline__ void nd_potf2_core(const NdSys& sys, int k, double* sd) {
+  const int tid = threadIdx.x, kb = k * NB, ld = NB | 1;
+  double* A = sd;
+  double* rd = sd + NB * ld;
+  float* Sd = sys.Sp + (size_t)kb * sys.ld + kb;
   chol6_smem(A, rd, NB, NB - 1, ld);
   for (int x = tid; x < NB * NB; x += 256) {
     const int r = x / NB, c = x - r * NB;
@@ -309,13 +319,13 @@ __device__ __forceinline__ void nd_potf2_dev(const NdSys& sys, int k, double* sd
 }
 
 // The first panel of a phase (the later ones are factored by the look-ahead CTA of the previous panel's trailing update).
-// grid = (1, batch, P | 1), block = 256, dynamic smem: NB x (NB | 1) doubles + NB
+// grid = (P | 1, batch), block = 256, dynamic smem: NB x (NB | 1) doubles + NB
 __global__ void __launch_bounds__(256, 1) nd_potf2_kernel(Problem pb, int mode, int idx) {
   ND_TS(0, mode, idx);
   extern __shared__ double sd[];
   const NdSys sys = nd_sys(pb, blockIdx.y + pb.w0);
   NdPanel pn;
-  const bool live = nd_panel(sys.h, mode, idx, blockIdx.z, pn);      // the ordering is final: read ahead of the wait
+  const bool live = nd_panel(sys.h, mode, idx, blockIdx.x, pn);      // the ordering is final: read ahead of the wait
   pdl_wait();
   pdl_trigger();
   ND_TS_WAITED();
@@ -368,7 +378,8 @@ __device__ __forceinline__ void nd_solve_rows(float (*sA)[NB + 1], const float (
   }
 }
 
-// Row-tile solves of a panel.  grid = (nd_nt + 2, batch, P | 1), block = 256: blockIdx.x < nbelow: candidate row tile;
+// Row-tile solves of a panel.  grid = (P | 1, batch, nd_nt + 2) -- segment fastest, so the candidates beyond a segment's
+// count (the grid is sized for the worst case) are dispatched last --, block = 256: blockIdx.z < nbelow: candidate row tile;
 // == nbelow: the right-hand side; == nbelow + 1: the explicit inverse W = L^-T of the diagonal tile (the same solve applied
 // to the identity), which the backward substitution uses later -- off the critical path of the factorisation.
 __global__ void __launch_bounds__(256) nd_trsm_kernel(Problem pb, int mode, int idx) {
@@ -378,13 +389,13 @@ __global__ void __launch_bounds__(256) nd_trsm_kernel(Problem pb, int mode, int 
   __shared__ float sD[ND_DINV];
   const NdSys sys = nd_sys(pb, blockIdx.y + pb.w0);
   NdPanel pn;
-  const bool live = nd_panel(sys.h, mode, idx, blockIdx.z, pn);      // the ordering is final: read ahead of the wait
+  const bool live = nd_panel(sys.h, mode, idx, blockIdx.x, pn);      // the ordering is final: read ahead of the wait
   pdl_wait();
   pdl_trigger();
   ND_TS_WAITED();
   if (!live) return;
   ND_PH(1, 0, 3, 0);
-  const int c0 = blockIdx.x;
+  const int c0 = blockIdx.z;
   if (c0 > pn.nbelow + 1) return;
   const int tid = threadIdx.x, kb = pn.k * NB;
   const bool rhs = (c0 == pn.nbelow), inv = (c0 == pn.nbelow + 1);
@@ -439,7 +450,7 @@ __global__ void __launch_bounds__(256) nd_trsm_kernel(Problem pb, int mode, int 
 // the pair (k + 1, k + 1), if tile k + 1 is active at all.  CTA 0 does that pair first and then factors the tile (the
 // longest serial piece of a panel step) while the other CTAs work through the remaining pairs, so the next step starts
 // with its row-tile solve instead of a separate factorisation launch.
-// grid = (gx >= 2, batch, P | 1), block = 256 (16 x 16 threads, 3 x 3 outputs each), dynamic smem as nd_potf2_kernel
+// grid = (P | 1, batch, gx >= 2), block = 256 (16 x 16 threads, 3 x 3 outputs each), dynamic smem as nd_potf2_kernel
 __global__ void __launch_bounds__(256) nd_syrk_kernel(Problem pb, int mode, int idx) {
   ND_TS(2, mode, idx);
   extern __shared__ double sd[];
@@ -448,33 +459,79 @@ __global__ void __launch_bounds__(256) nd_syrk_kernel(Problem pb, int mode, int 
   __shared__ int s_la;
   const NdSys sys = nd_sys(pb, blockIdx.y + pb.w0);
   NdPanel pn;
-  const bool live = nd_panel(sys.h, mode, idx, blockIdx.z, pn);      // the ordering is final: read ahead of the wait
+  const bool live = nd_panel(sys.h, mode, idx, blockIdx.x, pn);      // the ordering is final: read ahead of the wait
   pdl_wait();
   pdl_trigger();
   ND_TS_WAITED();
   if (!live) return;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int kb = pn.k * NB;
+  const size_t ld = (size_t)sys.ld;
+  const bool has_next = pn.nsb > 0;
+  const int item = blockIdx.z, nitem = gridDim.z;
+  if (has_next && item == 0) {
+    // ---- look-ahead CTA: D <- D - X X^T for the next diagonal tile D = (k + 1, k + 1), X = row tile (k + 1, k), applied in
+    // shared memory on the way into the factorisation (the updated tile never goes back to global memory: the factor
+    // overwrites it).  An inactive (all-zero) X changes nothing.  No look at the active list: this is the serial chain.
+    ND_PH(2, 0, 0, 0);
+    constexpr int NI = NB * NB / 256;
+    const int ld2 = NB | 1;
+    double* A = sd;
+    const float* X = sys.Sp + (size_t)(kb + NB) * ld + kb;
+    const float* D = sys.Sp + (size_t)(kb + NB) * ld + kb + NB;
+    float vx[NI], vd[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int x = tid + 256 * i, r = x / NB, c = x - r * NB;
+      vx[i] = X[(size_t)r * ld + c];
+      vd[i] = (c <= r) ? D[(size_t)r * ld + c] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int x = tid + 256 * i, r = x / NB, c = x - r * NB;
+      sXa[c][r] = vx[i];
+      A[r * ld2 + c] = (double)vd[i];
+    }
+    __syncthreads();
+    float acc[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll 4
+    for (int k = 0; k < NB; ++k) {
+      float a[3], b[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { a[i] = sXa[k][ty + 16 * i]; b[i] = sXa[k][tx + 16 * i]; }
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc[i][j] += a[i] * b[j];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int r = ty + 16 * i, c = tx + 16 * j;
+        if (c <= r) A[r * ld2 + c] -= (double)acc[i][j];
+      }
+    ND_PH(2, 0, 0, 1);
+    nd_potf2_core(sys, pn.k + 1, sd);
+    ND_PH(2, 0, 0, 2);
+    return;
+  }
   const int na = sys.nact[pn.k];
   const int* act = sys.active + (size_t)pn.k * sys.act_stride;
   const int npairs = na * (na + 1) / 2;
-  const size_t ld = (size_t)sys.ld;
-  // look-ahead pair: index of tile k + 1 in the active list (if the phase has a next panel)
-  const bool has_next = pn.nsb > 0;
+  // the look-ahead pair (index of tile k + 1 in the active list) belongs to CTA 0
   if (tid == 0) s_la = -1;
   __syncthreads();
   if (has_next)
     for (int x = tid; x < na; x += 256) if (act[x] == pn.k + 1) s_la = x;
   __syncthreads();
-  ND_PH(2, 0, 0, 0); ND_PH(2, 1, 5, 0);
+  ND_PH(2, 1, 5, 0);
   const int la = s_la;
   const int la_pair = la >= 0 ? la * (la + 1) / 2 + la : -1;
-  const bool la_cta = has_next && blockIdx.x == 0;
-  // CTA 0: only the look-ahead pair (one trip); the others: every other pair
-  const int pr0 = la_cta ? (la_pair >= 0 ? la_pair : npairs) : (int)blockIdx.x - (has_next ? 1 : 0);
-  const int prs = la_cta ? npairs + 1 : (int)gridDim.x - (has_next ? 1 : 0);
+  const int pr0 = item - (has_next ? 1 : 0);
+  const int prs = nitem - (has_next ? 1 : 0);
   for (int pr = pr0; pr < npairs; pr += prs) {
-    if (!la_cta && pr == la_pair) continue;
+    if (pr == la_pair) continue;
     int ia, ib;
     pair_of(pr, ia, ib);
     int ta = act[ia], tb = act[ib];
@@ -532,9 +589,7 @@ __global__ void __launch_bounds__(256) nd_syrk_kernel(Problem pb, int mode, int 
         if (shared_dst) atomicAdd(dst, -acc[i][j]); else *dst -= acc[i][j];
       }
   }
-  ND_PH(2, 0, 0, 1); ND_PH(2, 1, 5, 1);
-  if (la_cta) nd_potf2_dev(sys, pn.k + 1, sd);
-  ND_PH(2, 0, 0, 2);
+  ND_PH(2, 1, 5, 1);
 }
 
 // Backward substitution L^T x = z, one CTA of 1024 threads per (window, segment): the running solution lives in shared
@@ -674,11 +729,12 @@ cudaError_t launch_nd_solve(const Problem& pb, int64_t batch, cudaStream_t strea
   for (int mode = 0; mode < 2; ++mode) {
     const int steps = mode == 0 ? pb.L.nd_tmax : border_steps;
     const unsigned Z = mode == 0 ? (unsigned)P : 1u;
-    const int gx = mode == 0 ? (296 / P > 4 ? 296 / P : 4) : 296;
+    // CTAs per segment / for the border in the trailing update: a segment panel has ~10-15 active tiles (50-120 pairs)
+    const int gx = mode == 0 ? 64 : 296;
     for (int s = 0; s < steps; ++s) {
-      if (s == 0) { launch_k(nd_potf2_kernel, dim3(1, B, Z), dim3(256), psm, stream, pb, mode, s); count_launch(); }
-      launch_k(nd_trsm_kernel, dim3(nt + 2, B, Z), dim3(256), 0, stream, pb, mode, s);
-      launch_k(nd_syrk_kernel, dim3(gx, B, Z), dim3(256), psm, stream, pb, mode, s);
+      if (s == 0) { launch_k(nd_potf2_kernel, dim3(Z, B), dim3(256), psm, stream, pb, mode, s); count_launch(); }
+      launch_k(nd_trsm_kernel, dim3(Z, B, nt + 2), dim3(256), 0, stream, pb, mode, s);
+      launch_k(nd_syrk_kernel, dim3(Z, B, gx), dim3(256), psm, stream, pb, mode, s);
       count_launch(); count_launch();
     }
   }

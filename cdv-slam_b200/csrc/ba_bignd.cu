@@ -595,7 +595,7 @@ __global__ void __launch_bounds__(256) nd_syrk_kernel(Problem pb, int mode, int 
 // Backward substitution L^T x = z, one CTA of 1024 threads per (window, segment): the running solution lives in shared
 // memory, indexed like yp; per panel the 32 warps split its active row tiles (see big_backsolve_kernel).
 // mode 1: the border panels, last to first (grid = (1, batch)); mode 0: segment blockIdx.x, after the border
-// (grid = (P, batch)).  dynamic smem: (nd_nt * NB + 32 * NB + NB) floats
+// (grid = (P, batch)).  dynamic smem: (nd_nt * NB + 33 * NB + NB (NB + 1)) floats
 __global__ void __launch_bounds__(1024, 1) nd_backsolve_kernel(Problem pb, int mode) {
   pdl_wait();
   pdl_trigger();
@@ -614,48 +614,61 @@ __global__ void __launch_bounds__(1024, 1) nd_backsolve_kernel(Problem pb, int m
   for (int x = bbase * NB + tid; x < nt * NB; x += 1024) sx[x] = sys.yp[x];
   if (!mode) for (int x = first * NB + tid; x < (first + count) * NB; x += 1024) sx[x] = sys.yp[x];
   __syncthreads();
+  float* sW = sz + NB;                                 // [NB][NB + 1]: W = L^-T of the current diagonal tile
   for (int s = count - 1; s >= 0; --s) {
     const int k = first + s, kb = k * NB;
     const int na = sys.nact[k];
     const int* act = sys.active + (size_t)k * sys.act_stride;
+    // W of this panel: requested together with the tile rows below (nothing here depends on x), used after the reduction
+    float wv[3];
+    const float* Wg = sys.winv + (size_t)k * NB * NB;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) wv[i] = (tid + 1024 * i < NB * NB) ? Wg[tid + 1024 * i] : 0.f;
     float acc0 = 0, acc1 = 0;                          // columns lane and lane + 32 of the panel
-    for (int ia = warp; ia < na; ia += 32) {
-      const int t = act[ia];
+    // work item = (active row tile, quarter of its rows): the 32 warps share the tiles of a panel evenly (a late panel has a
+    // handful of active tiles), and an item is ONE batch of loads
+    constexpr int RB = 12;                             // 24 loads in flight per lane
+    for (int item = warp; item < 4 * na; item += 32) {
+      const int t = act[item >> 2];
       if (t == -1) continue;                           // the right-hand-side row of the factorisation
-      const int ra = t * NB;
-      const float* Lp = sys.Sp + (size_t)ra * ld + kb;
-      constexpr int RB = 12;                           // 24 loads in flight per lane
-#pragma unroll 1
-      for (int rb = 0; rb < NB; rb += RB) {
-        float v0[RB], v1[RB];
+      const int ra = t * NB, rb = (item & 3) * RB;
+      const float* Lp = sys.Sp + (size_t)(ra + rb) * ld + kb;
+      float v0[RB], v1[RB];
 #pragma unroll
-        for (int r = 0; r < RB; ++r) {
-          const float* row = Lp + (size_t)(rb + r) * ld;
-          v0[r] = row[lane];
-          v1[r] = (lane + 32 < NB) ? row[lane + 32] : 0.f;
-        }
+      for (int r = 0; r < RB; ++r) {
+        const float* row = Lp + (size_t)r * ld;
+        v0[r] = row[lane];
+        v1[r] = (lane + 32 < NB) ? row[lane + 32] : 0.f;
+      }
 #pragma unroll
-        for (int r = 0; r < RB; ++r) {
-          const float xr = sx[ra + rb + r];
-          acc0 += v0[r] * xr;
-          acc1 += v1[r] * xr;
-        }
+      for (int r = 0; r < RB; ++r) {
+        const float xr = sx[ra + rb + r];
+        acc0 += v0[r] * xr;
+        acc1 += v1[r] * xr;
       }
     }
     spart[warp * NB + lane] = acc0;
     if (lane + 32 < NB) spart[warp * NB + lane + 32] = acc1;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int x = tid + 1024 * i;
+      if (x < NB * NB) sW[(x / NB) * (NB + 1) + (x % NB)] = wv[i];
+    }
     __syncthreads();
     if (tid < NB) {
       float sum = 0;
 #pragma unroll
-      for (int wv = 0; wv < 32; ++wv) sum += spart[wv * NB + tid];
+      for (int wi = 0; wi < 32; ++wi) sum += spart[wi * NB + tid];
       sz[tid] = sx[kb + tid] - sum;
     }
     __syncthreads();
     if (tid < NB) {                                    // x[c] = sum_{e >= c} W[c][e] z[e]
-      const float* W = sys.winv + (size_t)k * NB * NB + tid * NB;
-      float a = 0;
-      for (int e = tid; e < NB; ++e) a += W[e] * sz[e];
+      const float* W = sW + tid * (NB + 1);
+      float a0 = 0, a1 = 0;
+      int e = tid;
+      for (; e + 1 < NB; e += 2) { a0 = fmaf(W[e], sz[e], a0); a1 = fmaf(W[e + 1], sz[e + 1], a1); }
+      if (e < NB) a0 = fmaf(W[e], sz[e], a0);
+      const float a = a0 + a1;
       sx[kb + tid] = a;
       sys.yp[kb + tid] = a;
     }
@@ -738,7 +751,7 @@ cudaError_t launch_nd_solve(const Problem& pb, int64_t batch, cudaStream_t strea
       count_launch(); count_launch();
     }
   }
-  const size_t bsmem = sizeof(float) * ((size_t)nt * NB + 33 * NB);
+  const size_t bsmem = sizeof(float) * ((size_t)nt * NB + 33 * NB + NB * (NB + 1));
   cudaFuncSetAttribute(nd_backsolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem);
   launch_k(nd_backsolve_kernel, dim3(1, B), dim3(1024), bsmem, stream, pb, 1);
   launch_k(nd_backsolve_kernel, dim3(P, B), dim3(1024), bsmem, stream, pb, 0);

@@ -138,7 +138,7 @@ inline Layout make_layout(int64_t E, int64_t F, int64_t K, int N, int64_t batch,
     if (P > ND_MAXP) P = ND_MAXP;
     const int nt = (N + 7) / 8 + P + 1;               // every segment and the border round up to whole tiles
     // the backward substitution keeps the whole solution in shared memory
-    if (sizeof(float) * ((size_t)nt * BIG_NB + 33 * BIG_NB) <= 200 * 1024) {
+    if (sizeof(float) * ((size_t)nt * BIG_NB + 33 * BIG_NB + BIG_NB * (BIG_NB + 1)) <= 200 * 1024) {
       L.nd_P = P; L.nd_nt = nt;
       const int lseg = (N + P - 1) / P;
       L.nd_tmax = (lseg + 7) / 8;

@@ -1,0 +1,4 @@
+mkdir -p gpurun_out
+(timeout 900 python -m pytest tests/test_ba_gpu.py -m gpu -x -q -k "global") > gpurun_out/pytest_nd_v35.log 2>&1
+tail -3 gpurun_out/pytest_nd_v35.log
+timeout 300 python profiles/microbench/c4time.py 2>&1 | tail -2

@@ -45,7 +45,10 @@ struct NdTs {
 // phase clocks of CTA `cta` of the border step 5 launches: slot = kind * 64 + cta_slot * 16 + i
 __device__ unsigned long long g_nd_ph[256];
 #define ND_PH(kind, ctaslot, cta, i) do { if (threadIdx.x == 0 && mode == 1 && idx == 5 && blockIdx.z == (cta)) g_nd_ph[(kind) * 64 + (ctaslot) * 16 + (i)] = nd_gtime(); } while (0)
+// the same clocks as the LAST CTA of segment level 2 passes them (all segments): slot = 192 + kind * 8 + i
+#define ND_PHMAX(kind, i) do { if (threadIdx.x == 0 && mode == 0 && idx == 2) atomicMax(&g_nd_ph[192 + (kind) * 8 + (i)], nd_gtime()); } while (0)
 #else
+#define ND_PHMAX(kind, i) do { } while (0)
 #define ND_PH(kind, ctaslot, cta, i) do { } while (0)
 #define ND_TS(kind, mode, idx) do { } while (0)
 #define ND_TS_WAITED() do { } while (0)
@@ -394,7 +397,7 @@ __global__ void __launch_bounds__(256) nd_trsm_kernel(Problem pb, int mode, int 
   pdl_trigger();
   ND_TS_WAITED();
   if (!live) return;
-  ND_PH(1, 0, 3, 0);
+  ND_PH(1, 0, 3, 0); ND_PHMAX(1, 0);
   const int c0 = blockIdx.z;
   if (c0 > pn.nbelow + 1) return;
   const int tid = threadIdx.x, kb = pn.k * NB;
@@ -429,11 +432,11 @@ __global__ void __launch_bounds__(256) nd_trsm_kernel(Problem pb, int mode, int 
     for (int i = 0; i < 2; ++i) if (tid + 256 * i < ND_DINV) sD[tid + 256 * i] = vd[i];
   }
   nz = __syncthreads_or(nz);
-  ND_PH(1, 0, 3, 1);
+  ND_PH(1, 0, 3, 1); ND_PHMAX(1, 1);
   if (!nz && !rhs) return;                       // an all-zero tile stays zero: inactive for this panel
   nd_solve_rows(sA, sL, sD, rows);
   __syncthreads();
-  ND_PH(1, 0, 3, 2);
+  ND_PH(1, 0, 3, 2); ND_PHMAX(1, 2);
   for (int x = tid; x < rows * NB; x += 256) {
     const int r = x / NB, c = x - r * NB;
     src[r * rstride + c] = sA[r][c];
@@ -442,7 +445,7 @@ __global__ void __launch_bounds__(256) nd_trsm_kernel(Problem pb, int mode, int 
     const int slot = atomicAdd(&sys.nact[pn.k], 1);
     sys.active[(size_t)pn.k * sys.act_stride + slot] = t;          // -1 marks the rhs row
   }
-  ND_PH(1, 0, 3, 3);
+  ND_PH(1, 0, 3, 3); ND_PHMAX(1, 3);
 }
 
 // Trailing update over pairs of active row tiles of the panel: Sp[tile a][tile b] -= X_a X_b^T (a below b).
@@ -473,7 +476,7 @@ __global__ void __launch_bounds__(256) nd_syrk_kernel(Problem pb, int mode, int 
     // ---- look-ahead CTA: D <- D - X X^T for the next diagonal tile D = (k + 1, k + 1), X = row tile (k + 1, k), applied in
     // shared memory on the way into the factorisation (the updated tile never goes back to global memory: the factor
     // overwrites it).  An inactive (all-zero) X changes nothing.  No look at the active list: this is the serial chain.
-    ND_PH(2, 0, 0, 0);
+    ND_PH(2, 0, 0, 0); ND_PHMAX(2, 0);
     constexpr int NI = NB * NB / 256;
     const int ld2 = NB | 1;
     double* A = sd;
@@ -511,9 +514,9 @@ __global__ void __launch_bounds__(256) nd_syrk_kernel(Problem pb, int mode, int 
         const int r = ty + 16 * i, c = tx + 16 * j;
         if (c <= r) A[r * ld2 + c] -= (double)acc[i][j];
       }
-    ND_PH(2, 0, 0, 1);
+    ND_PH(2, 0, 0, 1); ND_PHMAX(2, 1);
     nd_potf2_core(sys, pn.k + 1, sd);
-    ND_PH(2, 0, 0, 2);
+    ND_PH(2, 0, 0, 2); ND_PHMAX(2, 2);
     return;
   }
   const int na = sys.nact[pn.k];
@@ -525,7 +528,7 @@ __global__ void __launch_bounds__(256) nd_syrk_kernel(Problem pb, int mode, int 
   if (has_next)
     for (int x = tid; x < na; x += 256) if (act[x] == pn.k + 1) s_la = x;
   __syncthreads();
-  ND_PH(2, 1, 5, 0);
+  ND_PH(2, 1, 5, 0); ND_PHMAX(2, 3);
   const int la = s_la;
   const int la_pair = la >= 0 ? la * (la + 1) / 2 + la : -1;
   const int pr0 = item - (has_next ? 1 : 0);
@@ -589,7 +592,7 @@ __global__ void __launch_bounds__(256) nd_syrk_kernel(Problem pb, int mode, int 
         if (shared_dst) atomicAdd(dst, -acc[i][j]); else *dst -= acc[i][j];
       }
   }
-  ND_PH(2, 1, 5, 1);
+  ND_PH(2, 1, 5, 1); ND_PHMAX(2, 4);
 }
 
 // Backward substitution L^T x = z, one CTA of 1024 threads per (window, segment): the running solution lives in shared
@@ -770,6 +773,8 @@ void nd_timestamps(unsigned long long* out, int reset) {
     static unsigned long long init[3 * 1024][3];
     for (auto& r : init) { r[0] = ~0ull; r[1] = ~0ull; r[2] = 0ull; }
     cudaMemcpyToSymbol(g_nd_ts, init, sizeof(init));
+    static unsigned long long zero[256];
+    cudaMemcpyToSymbol(g_nd_ph, zero, sizeof(zero));
   } else {
     cudaMemcpyFromSymbol(out, g_nd_ts, sizeof(unsigned long long) * 3 * 1024 * 3);
     cudaMemcpyFromSymbol(out + 3 * 1024 * 3, g_nd_ph, sizeof(unsigned long long) * 256);

@@ -41,3 +41,10 @@ rel = lambda a: [round((int(v) - int(a[0])) / 1e3, 2) for v in a if v]
 print("border step 5, trsm CTA 3 (after wait, loads + zero test, solve, store + list):", rel(ph[64:68]))
 print("border step 5, syrk CTA 0 (list scan, look-ahead pair, factorisation):", rel(ph[128:131]))
 print("border step 5, syrk CTA 5 (list scan, pairs):", rel(ph[144:146]))
+
+def lvl(kind):
+    i = kind * 1024 + 2
+    return int(buf[i][1])
+for kind, nm, labels in ((1, "trsm", "after wait, loads + zero test, solve, store + list"), (2, "syrk", "look-ahead: start, pair, factorisation; others: list scan, pairs")):
+    a = ph[192 + kind * 8: 192 + kind * 8 + 5]
+    print("segment level 2, %s, LAST CTA passing (%s), us after release:" % (nm, labels), [round((int(v) - lvl(kind)) / 1e3, 2) for v in a if v])

@@ -27,6 +27,8 @@
 //   nd_finish_kernel   x -> dX in frame order, pose retraction (ba_cuda.cu:88-206)
 //   nd_cleanup_kernel  zeroes the tiles the factor touched (before the next iteration's gather)
 #include "big_chol.cuh"
+#include <cooperative_groups.h>
+
 #include "ba_cells.cuh"
 
 namespace pgba {
@@ -42,14 +44,7 @@ struct NdTs {
 };
 #define ND_TS(kind, mode, idx) NdTs nd_ts_(kind, mode, idx)
 #define ND_TS_WAITED() nd_ts_.waited()
-// phase clocks of CTA `cta` of the border step 5 launches: slot = kind * 64 + cta_slot * 16 + i
-__device__ unsigned long long g_nd_ph[256];
-#define ND_PH(kind, ctaslot, cta, i) do { if (threadIdx.x == 0 && mode == 1 && idx == 5 && blockIdx.z == (cta)) g_nd_ph[(kind) * 64 + (ctaslot) * 16 + (i)] = nd_gtime(); } while (0)
-// the same clocks as the LAST CTA of segment level 2 passes them (all segments): slot = 192 + kind * 8 + i
-#define ND_PHMAX(kind, i) do { if (threadIdx.x == 0 && mode == 0 && idx == 2) atomicMax(&g_nd_ph[192 + (kind) * 8 + (i)], nd_gtime()); } while (0)
 #else
-#define ND_PHMAX(kind, i) do { } while (0)
-#define ND_PH(kind, ctaslot, cta, i) do { } while (0)
 #define ND_TS(kind, mode, idx) do { } while (0)
 #define ND_TS_WAITED() do { } while (0)
 #endif
@@ -385,21 +380,11 @@ __device__ __forceinline__ void nd_solve_rows(float (*sA)[NB + 1], const float (
 // count (the grid is sized for the worst case) are dispatched last --, block = 256: blockIdx.z < nbelow: candidate row tile;
 // == nbelow: the right-hand side; == nbelow + 1: the explicit inverse W = L^-T of the diagonal tile (the same solve applied
 // to the identity), which the backward substitution uses later -- off the critical path of the factorisation.
-__global__ void __launch_bounds__(256) nd_trsm_kernel(Problem pb, int mode, int idx) {
-  ND_TS(1, mode, idx);
-  __shared__ float sA[NB][NB + 1];
-  __shared__ float sL[NB][NB + 1];
-  __shared__ float sD[ND_DINV];
-  const NdSys sys = nd_sys(pb, blockIdx.y + pb.w0);
-  NdPanel pn;
-  const bool live = nd_panel(sys.h, mode, idx, blockIdx.x, pn);      // the ordering is final: read ahead of the wait
-  pdl_wait();
-  pdl_trigger();
-  ND_TS_WAITED();
-  if (!live) return;
-  ND_PH(1, 0, 3, 0); ND_PHMAX(1, 0);
-  const int c0 = blockIdx.z;
-  if (c0 > pn.nbelow + 1) return;
+// One item of the row-tile launch: c0 < nbelow: candidate row tile; == nbelow: the right-hand side; == nbelow + 1: the
+// explicit inverse W = L^-T of the diagonal tile.  All 256 threads; starts with a barrier (the shared tiles may be in use).
+__device__ __forceinline__ void nd_trsm_item(const NdSys& sys, const NdPanel& pn, int c0, float (*sA)[NB + 1],
+                                             float (*sL)[NB + 1], float* sD) {
+  __syncthreads();
   const int tid = threadIdx.x, kb = pn.k * NB;
   const bool rhs = (c0 == pn.nbelow), inv = (c0 == pn.nbelow + 1);
   const int t = (rhs || inv) ? -1 : nd_tile_of(pn, c0);
@@ -432,11 +417,9 @@ __global__ void __launch_bounds__(256) nd_trsm_kernel(Problem pb, int mode, int 
     for (int i = 0; i < 2; ++i) if (tid + 256 * i < ND_DINV) sD[tid + 256 * i] = vd[i];
   }
   nz = __syncthreads_or(nz);
-  ND_PH(1, 0, 3, 1); ND_PHMAX(1, 1);
   if (!nz && !rhs) return;                       // an all-zero tile stays zero: inactive for this panel
   nd_solve_rows(sA, sL, sD, rows);
   __syncthreads();
-  ND_PH(1, 0, 3, 2); ND_PHMAX(1, 2);
   for (int x = tid; x < rows * NB; x += 256) {
     const int r = x / NB, c = x - r * NB;
     src[r * rstride + c] = sA[r][c];
@@ -445,7 +428,23 @@ __global__ void __launch_bounds__(256) nd_trsm_kernel(Problem pb, int mode, int 
     const int slot = atomicAdd(&sys.nact[pn.k], 1);
     sys.active[(size_t)pn.k * sys.act_stride + slot] = t;          // -1 marks the rhs row
   }
-  ND_PH(1, 0, 3, 3); ND_PHMAX(1, 3);
+}
+
+__global__ void __launch_bounds__(256) nd_trsm_kernel(Problem pb, int mode, int idx) {
+  ND_TS(1, mode, idx);
+  __shared__ float sA[NB][NB + 1];
+  __shared__ float sL[NB][NB + 1];
+  __shared__ float sD[ND_DINV];
+  const NdSys sys = nd_sys(pb, blockIdx.y + pb.w0);
+  NdPanel pn;
+  const bool live = nd_panel(sys.h, mode, idx, blockIdx.x, pn);      // the ordering is final: read ahead of the wait
+  pdl_wait();
+  pdl_trigger();
+  ND_TS_WAITED();
+  if (!live) return;
+  const int c0 = blockIdx.z;
+  if (c0 > pn.nbelow + 1) return;
+  nd_trsm_item(sys, pn, c0, sA, sL, sD);
 }
 
 // Trailing update over pairs of active row tiles of the panel: Sp[tile a][tile b] -= X_a X_b^T (a below b).
@@ -454,29 +453,19 @@ __global__ void __launch_bounds__(256) nd_trsm_kernel(Problem pb, int mode, int 
 // longest serial piece of a panel step) while the other CTAs work through the remaining pairs, so the next step starts
 // with its row-tile solve instead of a separate factorisation launch.
 // grid = (P | 1, batch, gx >= 2), block = 256 (16 x 16 threads, 3 x 3 outputs each), dynamic smem as nd_potf2_kernel
-__global__ void __launch_bounds__(256) nd_syrk_kernel(Problem pb, int mode, int idx) {
-  ND_TS(2, mode, idx);
-  extern __shared__ double sd[];
-  __shared__ float sXa[NB][NB + 1];     // [k][row]
-  __shared__ float sXb[NB][NB + 1];
-  __shared__ int s_la;
-  const NdSys sys = nd_sys(pb, blockIdx.y + pb.w0);
-  NdPanel pn;
-  const bool live = nd_panel(sys.h, mode, idx, blockIdx.x, pn);      // the ordering is final: read ahead of the wait
-  pdl_wait();
-  pdl_trigger();
-  ND_TS_WAITED();
-  if (!live) return;
+// The trailing update of one panel as seen by CTA `item` of `nitem` (>= 2): item 0 is the look-ahead CTA (when the phase
+// has a next panel), the others share the pairs.  All 256 threads; starts with a barrier.
+__device__ __forceinline__ void nd_syrk_items(const NdSys& sys, const NdPanel& pn, int mode, int item, int nitem,
+                                              float (*sXa)[NB + 1], float (*sXb)[NB + 1], int& s_la, double* sd) {
+  __syncthreads();
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int kb = pn.k * NB;
   const size_t ld = (size_t)sys.ld;
   const bool has_next = pn.nsb > 0;
-  const int item = blockIdx.z, nitem = gridDim.z;
   if (has_next && item == 0) {
     // ---- look-ahead CTA: D <- D - X X^T for the next diagonal tile D = (k + 1, k + 1), X = row tile (k + 1, k), applied in
     // shared memory on the way into the factorisation (the updated tile never goes back to global memory: the factor
     // overwrites it).  An inactive (all-zero) X changes nothing.  No look at the active list: this is the serial chain.
-    ND_PH(2, 0, 0, 0); ND_PHMAX(2, 0);
     constexpr int NI = NB * NB / 256;
     const int ld2 = NB | 1;
     double* A = sd;
@@ -514,9 +503,7 @@ __global__ void __launch_bounds__(256) nd_syrk_kernel(Problem pb, int mode, int 
         const int r = ty + 16 * i, c = tx + 16 * j;
         if (c <= r) A[r * ld2 + c] -= (double)acc[i][j];
       }
-    ND_PH(2, 0, 0, 1); ND_PHMAX(2, 1);
     nd_potf2_core(sys, pn.k + 1, sd);
-    ND_PH(2, 0, 0, 2); ND_PHMAX(2, 2);
     return;
   }
   const int na = sys.nact[pn.k];
@@ -528,7 +515,6 @@ __global__ void __launch_bounds__(256) nd_syrk_kernel(Problem pb, int mode, int 
   if (has_next)
     for (int x = tid; x < na; x += 256) if (act[x] == pn.k + 1) s_la = x;
   __syncthreads();
-  ND_PH(2, 1, 5, 0); ND_PHMAX(2, 3);
   const int la = s_la;
   const int la_pair = la >= 0 ? la * (la + 1) / 2 + la : -1;
   const int pr0 = item - (has_next ? 1 : 0);
@@ -592,7 +578,52 @@ __global__ void __launch_bounds__(256) nd_syrk_kernel(Problem pb, int mode, int 
         if (shared_dst) atomicAdd(dst, -acc[i][j]); else *dst -= acc[i][j];
       }
   }
-  ND_PH(2, 1, 5, 1); ND_PHMAX(2, 4);
+}
+
+__global__ void __launch_bounds__(256) nd_syrk_kernel(Problem pb, int mode, int idx) {
+  ND_TS(2, mode, idx);
+  extern __shared__ double sd[];
+  __shared__ float sXa[NB][NB + 1];     // [k][row]
+  __shared__ float sXb[NB][NB + 1];
+  __shared__ int s_la;
+  const NdSys sys = nd_sys(pb, blockIdx.y + pb.w0);
+  NdPanel pn;
+  const bool live = nd_panel(sys.h, mode, idx, blockIdx.x, pn);      // the ordering is final: read ahead of the wait
+  pdl_wait();
+  pdl_trigger();
+  ND_TS_WAITED();
+  if (!live) return;
+  nd_syrk_items(sys, pn, mode, (int)blockIdx.z, (int)gridDim.z, sXa, sXb, s_la, sd);
+}
+
+// The whole border phase in ONE cooperative launch: the number of border panels is only known on the device, and as
+// separate launches the worst case (every frame in the border: (6N / 48) steps x 2 launches) has to be enqueued although the
+// 1000-frame global BA needs 28 of 125 -- ~0.55 us per empty launch, 0.2 ms per call.  Here the panel loop runs on the
+// device with grid-wide barriers (cooperative launch: co-residency guaranteed by the driver) between the row-tile solves and
+// the trailing update.  grid = (G, batch), block = 256, dynamic smem as nd_potf2_kernel.
+__global__ void __launch_bounds__(256, 2) nd_border_kernel(Problem pb) {
+  extern __shared__ double sd[];
+  __shared__ float sA[NB][NB + 1];
+  __shared__ float sL[NB][NB + 1];
+  __shared__ float sD[ND_DINV];
+  __shared__ int s_la;
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  const NdSys sys = nd_sys(pb, blockIdx.y + pb.w0);
+  const int Bt = sys.h->Bt;
+  int Bmax = 0;                                            // every window walks the same number of barriers
+  for (int w = 0; w < (int)gridDim.y; ++w) Bmax = max(Bmax, nd_sys(pb, w + pb.w0).h->Bt);
+  const int item = blockIdx.x, nitem = gridDim.x;
+  if (item == 0 && Bt > 0) nd_potf2_dev(sys, sys.h->bbase, sd);
+  grid.sync();
+  for (int b = 0; b < Bmax; ++b) {
+    NdPanel pn;
+    const bool live = nd_panel(sys.h, 1, b, 0, pn);
+    if (live)
+      for (int c0 = item; c0 <= pn.nbelow + 1; c0 += nitem) nd_trsm_item(sys, pn, c0, sA, sL, sD);
+    grid.sync();
+    if (live) nd_syrk_items(sys, pn, 1, item, nitem, sA, sL, s_la, sd);
+    grid.sync();
+  }
 }
 
 // Backward substitution L^T x = z, one CTA of 1024 threads per (window, segment): the running solution lives in shared
@@ -742,7 +773,33 @@ cudaError_t launch_nd_solve(const Problem& pb, int64_t batch, cudaStream_t strea
   cudaFuncSetAttribute(nd_potf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm);
   cudaFuncSetAttribute(nd_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm);
   const int border_steps = (N + 7) / 8;             // worst case: every frame in the border
+  // border phase: one cooperative launch with the panel loop on the device when the grid fits (PGBA_ND_COOP=0: launches)
+  int coop_g = 0;
+  {
+    const char* e = getenv("PGBA_ND_COOP");
+    if (!(e && e[0] == '0') && batch <= 4) {
+      int dev = 0, sms = 0, per_sm = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      cudaFuncSetAttribute(nd_border_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nd_border_kernel, 256, psm);
+      int g = (per_sm > 2 ? 2 : per_sm) * sms / (int)batch;
+      if (g >= 16) coop_g = g;
+    }
+  }
   for (int mode = 0; mode < 2; ++mode) {
+    if (mode == 1 && coop_g > 0) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)coop_g, B); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = psm; cfg.stream = stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeCooperative;
+      at[0].val.cooperative = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      cudaError_t e = cudaLaunchKernelEx(&cfg, nd_border_kernel, pb);
+      if (e != cudaSuccess) return e;
+      count_launch();
+      break;
+    }
     const int steps = mode == 0 ? pb.L.nd_tmax : border_steps;
     const unsigned Z = mode == 0 ? (unsigned)P : 1u;
     // CTAs per segment / for the border in the trailing update: a segment panel has ~10-15 active tiles (50-120 pairs)
@@ -773,11 +830,8 @@ void nd_timestamps(unsigned long long* out, int reset) {
     static unsigned long long init[3 * 1024][3];
     for (auto& r : init) { r[0] = ~0ull; r[1] = ~0ull; r[2] = 0ull; }
     cudaMemcpyToSymbol(g_nd_ts, init, sizeof(init));
-    static unsigned long long zero[256];
-    cudaMemcpyToSymbol(g_nd_ph, zero, sizeof(zero));
   } else {
     cudaMemcpyFromSymbol(out, g_nd_ts, sizeof(unsigned long long) * 3 * 1024 * 3);
-    cudaMemcpyFromSymbol(out + 3 * 1024 * 3, g_nd_ph, sizeof(unsigned long long) * 256);
   }
 }
 #endif

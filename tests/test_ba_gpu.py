@@ -348,6 +348,24 @@ def test_global_ba_reordered_solver(kind, monkeypatch):
     _check_state(p, poses, patches, o_poses, o_patches, tol=max(4e-4, tol_x))
 
 
+@pytest.mark.parametrize("kind", ["chain+loops", "many-loops"])
+def test_global_ba_reordered_solver_border_as_launches(kind, monkeypatch):
+    """PGBA_ND_COOP=0: the border panels as separate launches (the form used when the cooperative grid does not fit, e.g.
+    batches of more than 4 windows) instead of one cooperative launch with the panel loop on the device."""
+    monkeypatch.setenv("PGBA_ND_COOP", "0")
+    F, M = 300, 6
+    p = synth.make_problem("nd-" + kind, F, _graph_edges(kind, F, M, np.random.default_rng(78)), 1, F, 12, M, eff_impl=True)
+    d = to_dev(p)
+    g = fastba.linearize_debug(d["poses"], d["patches"], d["intrinsics"], d["target"], d["weight"], d["lmbda"], d["ii"],
+                               d["jj"], d["kk"], p.t0, p.t1, with_schur=True)
+    assert g["status"] == 0
+    S, y = g["S"].cpu().numpy().astype(np.float64), g["y"].cpu().numpy().astype(np.float64)
+    _check_solve_residual(S, y, g["dX"].cpu().numpy())
+    A = S + np.diag(1e-4 * np.diag(S) + 1.0)
+    tol_x = max(10 * TOL, _S_ULPS * np.linalg.cond(A) * 2.0 ** -23)
+    assert rel_err(g["dX"].cpu().numpy().reshape(-1), np.linalg.solve(A, y.reshape(-1))) < tol_x
+
+
 def test_global_ba_reordered_solver_batched():
     """Two 259-pose global problems with different loop closures (hence different frame orderings) in ONE batched call:
     every kernel of the reordered large solve indexes its window's ordering, permuted system and active-tile lists."""

@@ -16,9 +16,8 @@ def call():
     torch.cuda.synchronize()
 call(); call()
 lib = ctypes.CDLL(native.LIB_PATH)
-raw = np.zeros(3 * 1024 * 3 + 256, np.uint64)
+raw = np.zeros(3 * 1024 * 3, np.uint64)
 buf = raw[:3 * 1024 * 3].reshape(3 * 1024, 3)
-ph = raw[3 * 1024 * 3:]
 lib.pgba_nd_timestamps(None, 1)
 call()
 lib.pgba_nd_timestamps(raw.ctypes.data_as(ctypes.c_void_p), 0)
@@ -37,14 +36,3 @@ for e, n, mode, idx, w, x in rows:
     print("%-6s mode %d step %3d  entered %8.2f  released %8.2f  end %8.2f  body %6.2f  gap after prev end %6.2f" % (n, mode, idx, e, w, x, x - w, w - prev_end))
     prev_end = x
 
-rel = lambda a: [round((int(v) - int(a[0])) / 1e3, 2) for v in a if v]
-print("border step 5, trsm CTA 3 (after wait, loads + zero test, solve, store + list):", rel(ph[64:68]))
-print("border step 5, syrk CTA 0 (list scan, look-ahead pair, factorisation):", rel(ph[128:131]))
-print("border step 5, syrk CTA 5 (list scan, pairs):", rel(ph[144:146]))
-
-def lvl(kind):
-    i = kind * 1024 + 2
-    return int(buf[i][1])
-for kind, nm, labels in ((1, "trsm", "after wait, loads + zero test, solve, store + list"), (2, "syrk", "look-ahead: start, pair, factorisation; others: list scan, pairs")):
-    a = ph[192 + kind * 8: 192 + kind * 8 + 5]
-    print("segment level 2, %s, LAST CTA passing (%s), us after release:" % (nm, labels), [round((int(v) - lvl(kind)) / 1e3, 2) for v in a if v])

@@ -1009,19 +1009,29 @@ __global__ void __launch_bounds__(256, 1) solve_small_kernel(Problem pb) {
   {
     const float4* S4 = reinterpret_cast<const float4*>(wp.S);
     const int n4 = (n * n) >> 2;
-    for (int x4 = tid; x4 < n4; x4 += 256) {
-      const float4 v4 = S4[x4];
-      const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
-      int r = (4 * x4) / n, c = 4 * x4 - r * n;
+    // four 16-byte loads per thread in flight before the first shared-memory store (n = 60: the whole matrix in ONE round
+    // trip; issued one per store they were four dependent trips)
+    const float yv = (tid < n) ? wp.y[tid] : 0.f;
+    for (int x0 = tid; x0 < n4; x0 += 4 * 256) {
+      float4 v4[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float v = vv[k];
-        if (r == c) v += 1e-4f * v + 1.0f;
-        A[r * ld + c] = v;
-        if (++c == n) { c = 0; ++r; }
+      for (int u = 0; u < 4; ++u) v4[u] = (x0 + 256 * u < n4) ? S4[x0 + 256 * u] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int x4 = x0 + 256 * u;
+        if (x4 >= n4) break;
+        const float vv[4] = {v4[u].x, v4[u].y, v4[u].z, v4[u].w};
+        int r = (4 * x4) / n, c = 4 * x4 - r * n;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float v = vv[k];
+          if (r == c) v += 1e-4f * v + 1.0f;
+          A[r * ld + c] = v;
+          if (++c == n) { c = 0; ++r; }
+        }
       }
     }
-    for (int x = tid; x < n; x += 256) A[n * ld + x] = wp.y[x];
+    if (tid < n) A[n * ld + tid] = yv;            // n <= 156 < 256
   }
   SOLVE_TS(1);
   chol6_f32(A, rd, dinv, n, ld);        // rows 0..n: the rhs row n rides along (forward substitution)

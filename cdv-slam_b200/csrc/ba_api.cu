@@ -129,14 +129,14 @@ static bool plan_cache_enabled() {
 }
 
 // patches per chunk: heuristic, or the PGBA_PC environment variable (8..128, power of two) for tuning
-static int pick_pc(int64_t E, int64_t batch) {
+static int pick_pc(int64_t E, int64_t batch, int64_t F, int64_t K) {
   static int forced = -1;
   if (forced < 0) {
     const char* e = getenv("PGBA_PC");
     int v = e ? atoi(e) : 0;
     forced = (v == 8 || v == 16 || v == 32 || v == 64 || v == 128) ? v : 0;
   }
-  return forced ? forced : choose_pc(E, batch);
+  return forced ? forced : choose_pc(E, batch, F, K);
 }
 
 static Problem make_problem(float* poses, float* patches, const float* intrinsics, const float* target,
@@ -151,7 +151,7 @@ static Problem make_problem(float* poses, float* patches, const float* intrinsic
   pb.plan_cache = plan_cache_enabled() ? 1 : 0;
   pb.batch = (int)batch;
   pb.ws = ws;
-  pb.L = make_layout(E, F, K, t1 - t0, batch, pick_pc(E, batch));
+  pb.L = make_layout(E, F, K, t1 - t0, batch, pick_pc(E, batch, F, K));
   return pb;
 }
 
@@ -194,7 +194,9 @@ static int batch_groups(const Problem& pb, int64_t batch) {
   static int forced = -1;
   if (forced < 0) { const char* e = getenv("PGBA_BATCH_GROUPS"); forced = e ? atoi(e) : 0; }
   int g = 1;
-  if (!pb.L.big && pb.t1 > pb.t0) g = batch >= 32 ? 4 : (batch >= 16 ? 2 : 1);
+  // measured (us per call, 1 / 2 / 4 groups): 8 windows 112.7 / 108.5 / -, 12: 112.7 / 110.8 / -, 16: 129.0 / 129.1 / 135.2,
+  // 24: - / 147.5 / 151.5, 64: 336 / 322 / 315
+  if (!pb.L.big && pb.t1 > pb.t0) g = batch >= 32 ? 4 : (batch >= 4 ? 2 : 1);
   if (forced >= 1 && forced <= MAX_GROUPS) g = forced;
   if (g > batch) g = (int)batch;
   return g < 1 ? 1 : g;
@@ -256,7 +258,7 @@ int pgba_ba_workspace_bytes(int64_t n_edges, int64_t n_pose_rows, int64_t n_patc
                             int64_t batch, size_t* bytes) {
   if (!bytes) return PGBA_ERR_NULL;
   if (n_edges < 0 || n_pose_rows <= 0 || n_patch_rows <= 0 || t1 < t0 || batch <= 0) return PGBA_ERR_SHAPE;
-  const Layout L = make_layout(n_edges, n_pose_rows, n_patch_rows, t1 - t0, batch, pick_pc(n_edges, batch));
+  const Layout L = make_layout(n_edges, n_pose_rows, n_patch_rows, t1 - t0, batch, pick_pc(n_edges, batch, n_pose_rows, n_patch_rows));
   *bytes = total_bytes(L, batch);
   return PGBA_OK;
 }
@@ -556,7 +558,7 @@ int pgba_ba_linearize_debug(const float* poses, const float* patches, const floa
 const int32_t* pgba_ba_status_ptr(const void* workspace, int64_t n_edges, int64_t n_pose_rows, int64_t n_patch_rows,
                                   int t0, int t1, int64_t batch, int64_t b) {
   if (!workspace || b < 0 || b >= batch || n_pose_rows <= 0 || n_patch_rows <= 0 || t1 < t0) return nullptr;
-  const Layout L = make_layout(n_edges, n_pose_rows, n_patch_rows, t1 - t0, batch, pick_pc(n_edges, batch));
+  const Layout L = make_layout(n_edges, n_pose_rows, n_patch_rows, t1 - t0, batch, pick_pc(n_edges, batch, n_pose_rows, n_patch_rows));
   const WinHeader* h = (const WinHeader*)((const char*)workspace + (size_t)b * L.zero_bytes + L.z_hdr);
   return &h->status;
 }
@@ -564,7 +566,7 @@ const int32_t* pgba_ba_status_ptr(const void* workspace, int64_t n_edges, int64_
 const int32_t* pgba_ba_plan_hit_ptr(const void* workspace, int64_t n_edges, int64_t n_pose_rows, int64_t n_patch_rows,
                                     int t0, int t1, int64_t batch, int64_t b) {
   if (!workspace || b < 0 || b >= batch || n_pose_rows <= 0 || n_patch_rows <= 0 || t1 < t0) return nullptr;
-  const Layout L = make_layout(n_edges, n_pose_rows, n_patch_rows, t1 - t0, batch, pick_pc(n_edges, batch));
+  const Layout L = make_layout(n_edges, n_pose_rows, n_patch_rows, t1 - t0, batch, pick_pc(n_edges, batch, n_pose_rows, n_patch_rows));
   const WinHeader* h = (const WinHeader*)((const char*)workspace + (size_t)b * L.zero_bytes + L.z_hdr);
   return &h->plan_hit;
 }

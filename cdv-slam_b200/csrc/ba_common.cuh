@@ -97,8 +97,22 @@ struct Layout {         // host-computed
 
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
-inline int choose_pc(int64_t E, int64_t batch) {
-  // throughput regime (batched windows, global BA): aim at >= ~1.5 CTAs per SM for the chunk-parallel kernels, assuming
+inline int choose_pc(int64_t E, int64_t batch, int64_t F, int64_t K) {
+  if (batch >= 2 && F > 0 && K > 0) {
+    // batches: the chunk-parallel kernels hold 2 CTAs per SM (296 slots).  Within one wave more, smaller chunks finish sooner;
+    // beyond it the largest chunks win (the large-chunk code paths do less work per edge).  Measured on c2-shaped windows
+    // (L2 flushed, us per call; chunks = windows x 22 frames x ceil(96 / pc)):
+    //    4 windows: pc 32 (264 chunks) 94.6, pc 64 (176) 100.6      8 windows: pc 32 (528) 125.0, 64 (352) 116.8, 128 (176) 114.5
+    //   12 windows: pc 64 (528) 127.0, pc 128 (264) 116.8          16 windows: pc 64 (704) 145.4, pc 128 (352) 129.0
+    // -> the largest pc that still yields >= 200 chunks, estimating the active frames as E / 24 / (patches per frame)
+    const int64_t M = K / F > 0 ? K / F : 1;
+    int64_t frames = (E / 24 + M - 1) / M;
+    if (frames < 1) frames = 1;
+    for (int pc = PMAX; pc > 8; pc >>= 1)
+      if (batch * frames * ((M + pc - 1) / pc) >= 200) return pc;
+    return 8;
+  }
+  // single window, throughput regime (global BA): aim at >= ~1.5 CTAs per SM for the chunk-parallel kernels, assuming
   // ~24 edges per patch
   int64_t want = (E * batch) / (148 * 3 / 2 * 24);
   int pc = 8;

@@ -1147,7 +1147,7 @@ static bool plan_direct_enabled() {
 }
 
 template <int CL>
-static bool direct_cluster_ok(size_t smem) {            // can a cluster of CL CTAs with this much shared memory be scheduled?
+static int direct_max_clusters(size_t smem) {           // how many clusters of CL CTAs with this much shared memory are co-resident
   auto kern = plan_direct_kernel<CL>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { (void)cudaGetLastError(); return false; }
   if (CL > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { (void)cudaGetLastError(); return false; }
@@ -1162,7 +1162,19 @@ static bool direct_cluster_ok(size_t smem) {            // can a cluster of CL C
   cfg.numAttrs = 1;
   int n = 0;
   if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { (void)cudaGetLastError(); n = 0; }
-  return n > 0;
+  return n;
+}
+template <int CL>
+static bool direct_cluster_ok(size_t smem) { return direct_max_clusters<CL>(smem) > 0; }
+
+// Co-resident clusters per cluster size (a 1024-thread CTA owns an SM, so this is a property of the chip: a cluster must fit
+// one GPC, and the GPCs do not all have a multiple of the cluster size of SMs -- 16 clusters of 8 do NOT fit the B200's 148
+// SMs although 8 * 16 <= 148: measured 59.9 us for the plan of 16 windows with 8 CTAs each, two waves, against 42.8 us with 4).
+static int direct_coresident(int cl, size_t smem) {
+  static int cache[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};
+  if (cl != 2 && cl != 4 && cl != 8) return 0;
+  if (cache[cl] < 0) cache[cl] = cl == 8 ? direct_max_clusters<8>(smem) : cl == 4 ? direct_max_clusters<4>(smem) : direct_max_clusters<2>(smem);
+  return cache[cl];
 }
 
 static bool plan_direct_config(const Problem& pb, int64_t batch, DirectCfg* out) {
@@ -1174,15 +1186,13 @@ static bool plan_direct_config(const Problem& pb, int64_t batch, DirectCfg* out)
   // Measured on the B200 (L2 flushed before every call, profiles/README.md round 2): on a single c2 window the direct kernel
   // takes 23.9 us against 15.9 + ~7 us for plan_cluster_kernel + plan_cells_kernel -- every phase runs once, on cold
   // instructions, so the larger single kernel gains nothing -- and the call is 4.8 us slower; on the 64-window batch the plan
-  // stage drops from 103 to 75 us.  Default: batches of more than 8 windows; PGBA_PLAN_DIRECT=1 forces it everywhere.
+  // stage drops from 103 to 75 us; 8 windows: call 120.8 -> 112.7 us, 4 windows: equal, 2 windows: 84.0 -> 88.2 us.
+  // Default: batches of at least 4 windows; PGBA_PLAN_DIRECT=1 forces it everywhere.
   static int always = -1;
   if (always < 0) { const char* e = getenv("PGBA_PLAN_DIRECT"); always = (e && e[0] == '1') ? 1 : 0; }
-  if (batch <= 8 && !always && !cl_forced && !tbl_forced) return false;
-  int cl = batch == 1 ? 16 : (8 * batch <= 148 ? 8 : (4 * batch <= 148 ? 4 : 2));
-  if (cl_forced == 2 || cl_forced == 4 || cl_forced == 8 || (cl_forced == 16 && batch == 1)) cl = cl_forced;
+  if (batch < 4 && !always && !cl_forced && !tbl_forced) return false;
   const size_t budget = 200 * 1024;                     // of the 227 KB a CTA can have: static arrays + headroom stay free
-  for (;; cl *= 2) {
-    if (cl > (batch == 1 ? 16 : 8)) return false;
+  auto config_for = [&](int cl, DirectCfg* c) -> bool {
     const int64_t gtn = (int64_t)cl * PD_T;
     const int64_t e_cap = ((pb.E + gtn - 1) / gtn) * PD_T;
     // table budget: what the largest possible chunk table of this layout needs (see the kernel), at most 12288 ints
@@ -1191,11 +1201,29 @@ static bool plan_direct_config(const Problem& pb, int64_t batch, DirectCfg* out)
     if (tbl_need > 12288) tbl_need = 12288;
     int tbl = tbl_forced > 0 ? tbl_forced : (int)tbl_need;
     const size_t fixed = plan_direct_smem(pb.F, 0, 0);
-    if (fixed + 8 * (size_t)e_cap + 4 * 1024 > budget) continue;
+    if (fixed + 8 * (size_t)e_cap + 4 * 1024 > budget) return false;
     const size_t room = (budget - fixed - 8 * (size_t)e_cap) / 4;
     if ((size_t)tbl > room) tbl = (int)room;
-    out->cl = cl; out->e_cap = (int)e_cap; out->tbl_cap = tbl; out->smem = plan_direct_smem(pb.F, tbl, (int)e_cap);
-    break;
+    c->cl = cl; c->e_cap = (int)e_cap; c->tbl_cap = tbl; c->smem = plan_direct_smem(pb.F, tbl, (int)e_cap);
+    return true;
+  };
+  const bool forced = cl_forced == 2 || cl_forced == 4 || cl_forced == 8 || (cl_forced == 16 && batch == 1);
+  if (forced || batch == 1) {
+    int cl = forced ? cl_forced : 16;
+    for (;; cl *= 2) {                                  // more CTAs per window = fewer edges per CTA, until the edges fit
+      if (cl > (batch == 1 ? 16 : 8)) return false;
+      if (config_for(cl, out)) break;
+    }
+  } else {
+    // batches: the largest cluster with which all windows are co-resident; if none is, the smallest that fits (fewest CTAs)
+    bool have = false;
+    for (int cl = 8; cl >= 2; cl /= 2) {
+      DirectCfg c;
+      if (!config_for(cl, &c)) break;                   // a smaller cluster needs more shared memory per CTA
+      *out = c; have = true;
+      if (batch <= direct_coresident(cl, c.smem)) break;
+    }
+    if (!have) return false;
   }
   if (out->cl == 16) {                                  // non-portable size: asked once per shared-memory size class
     static int ok16 = -1; static size_t ok16_smem = 0;

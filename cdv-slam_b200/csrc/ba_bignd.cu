@@ -11,7 +11,7 @@
 // where the border holds (a) every frame that is the target of a FAR edge (|j - i| > R: the loop-closure targets) and
 // (b) for each of the P - 1 cut positions, the frames at or after the cut that share a patch with a frame before it (the
 // separator; its width follows from the data).  No patch couples frames of two different segments, so the segments are
-// eliminated IN PARALLEL, level by level (tile l of every segment in the same three launches), then the dense border:
+// eliminated IN PARALLEL, level by level (tile l of every segment in the same two launches), then the dense border:
 // max_p T_p + Bt dependent steps instead of sum_p T_p + Bt (36 instead of 125 on the 1000-frame problem).  The ordering
 // is computed on the device from the edge list (no host round trip); whatever the graph looks like the result is the
 // same Cholesky solve of the same matrix under a symmetric permutation -- a graph that is not chain-like only makes the
@@ -21,11 +21,21 @@
 //   nd_order_kernel    separators, segment / border positions of every free frame (one CTA per window)
 //   nd_gather_kernel   S, y (natural order, written by linearize_kernel) -> permuted Sp, yp with the damping of
 //                      ba_cuda.cu:575/589 applied; S, y are re-zeroed on the way
-//   nd_potf2 / nd_trsm / nd_syrk   one panel step (stage bodies as in big_chol.cuh); during the segment levels the
-//                      border x border updates of different segments meet in the same tiles -> atomic adds there
+//   a panel step       nd_trsm_kernel: the row tiles below the diagonal tile, X L^T = A by blocked substitution with the
+//                      inverses of the 6 x 6 diagonal blocks (all-zero tiles are skipped and stay inactive for the panel), the
+//                      right-hand side as one more row, and W = L^-T of the diagonal tile for the backward substitution;
+//                      nd_syrk_kernel: trailing update over pairs of active tiles (during the segment levels the border x
+//                      border updates of different segments meet in the same tiles -> atomic adds there); its CTA 0 is the
+//                      look-ahead: it updates the NEXT diagonal tile in shared memory and factors it (fp64), so the serial
+//                      piece of a step never waits for a launch of its own.  nd_potf2_kernel only factors the first tile
+//                      of a phase.
+//   nd_border_kernel   the border phase as ONE cooperative launch: the same step bodies with the panel loop on the device and
+//                      grid-wide barriers (its step count is only known on the device; as separate launches the worst case
+//                      would have to be enqueued).  Launches remain for batches of more than 4 windows / PGBA_ND_COOP=0.
 //   nd_backsolve_kernel  L^T x = z: border (one CTA), then the segments in parallel
 //   nd_finish_kernel   x -> dX in frame order, pose retraction (ba_cuda.cu:88-206)
 //   nd_cleanup_kernel  zeroes the tiles the factor touched (before the next iteration's gather)
+// -DPGBA_ND_TIMING adds globaltimer stamps per launch (profiles/nd_timeline.py).
 #include "big_chol.cuh"
 #include <cooperative_groups.h>
 

@@ -42,10 +42,22 @@ __device__ __forceinline__ void big_potf2_dev(const BigSys<T>& bp, int step, dou
   const int nh = min(NB, n6 - kb), ld = NB | 1;
   double* A = sd;                       // rows 0..nh-1: diagonal tile; rows nh..2nh-1: identity (-> L^-T, see below)
   double* rd = sd + 2 * NB * ld;
-  for (int x = tid; x < nh * nh; x += 256) {
-    const int r = x / nh, c = x - r * nh;
-    A[r * ld + c] = (c <= r) ? (double)bp.S[(size_t)(kb + r) * bp.ld + kb + c] : 0.0;
-    A[(nh + r) * ld + c] = (r == c) ? 1.0 : 0.0;
+  {
+    constexpr int NI = NB * NB / 256;              // all loads of the tile in flight before the first shared-memory store
+    T v[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int x = tid + 256 * i, r = x / nh, c = x - r * nh;
+      v[i] = (x < nh * nh && c <= r) ? bp.S[(size_t)(kb + r) * bp.ld + kb + c] : (T)0;
+    }
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int x = tid + 256 * i, r = x / nh, c = x - r * nh;
+      if (x < nh * nh) {
+        A[r * ld + c] = (double)v[i];
+        A[(nh + r) * ld + c] = (r == c) ? 1.0 : 0.0;
+      }
+    }
   }
   chol6_smem(A, rd, nh, 2 * nh - 1, ld);
   // rows nh + i now hold (L^-1 e_i)^T, i.e. W[i][c] = Linv[c][i]  (so X = A21 * W solves X L^T = A21)
@@ -83,19 +95,26 @@ __device__ __forceinline__ void big_trsm_dev(const BigSys<T>& bp, int step, int 
   T* src = rhs ? (bp.y + kb) : (bp.S + (size_t)(r0 + t * NB) * bp.ld + kb);
   const size_t rstride = rhs ? 0 : (size_t)bp.ld;
   int nz = 0;
-  for (int x = tid; x < rows * nh; x += 256) {
-    const int r = x / nh, c = x - r * nh;
-    const T v = src[r * rstride + c];
-    sA[r][c] = v;
-    nz |= (v != (T)0);
+  {
+    // the row tile and W are requested together, all loads ahead of the first shared-memory store (one round trip instead
+    // of one per store; the all-zero test of the row tile only decides whether the product runs)
+    constexpr int NI = NB * NB / 256;
+    T va[NI], vw[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int x = tid + 256 * i, r = x / nh, c = x - r * nh;
+      va[i] = (x < rows * nh) ? src[r * rstride + c] : (T)0;
+      vw[i] = (x < nh * nh) ? bp.winv[(size_t)step * NB * NB + r * NB + c] : (T)0;
+    }
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int x = tid + 256 * i, r = x / nh, c = x - r * nh;
+      if (x < rows * nh) { sA[r][c] = va[i]; nz |= (va[i] != (T)0); }
+      if (x < nh * nh) sW[r][c] = vw[i];
+    }
   }
   nz = __syncthreads_or(nz);
   if (!nz && !rhs) return;                       // an all-zero tile stays zero: inactive for this panel
-  for (int x = tid; x < nh * nh; x += 256) {
-    const int r = x / nh, c = x - r * nh;
-    sW[r][c] = bp.winv[(size_t)step * NB * NB + r * NB + c];
-  }
-  __syncthreads();
   for (int x = tid; x < rows * nh; x += 256) {
     const int r = x / nh, c = x - r * nh;
     T acc = 0;
@@ -136,10 +155,21 @@ __device__ __forceinline__ void big_syrk_pair_dev(const BigSys<T>& bp, int step,
   const size_t sa = rhs ? 0 : (size_t)bp.ld;
   const T* xb = bp.S + (size_t)rb * bp.ld + kb;
   __syncthreads();
-  for (int x = tid; x < NB * NB; x += 256) {
-    const int r = x / NB, k = x - r * NB;
-    sXa[k][r] = (r < rows_a && k < nh) ? xa[r * sa + k] : (T)0;
-    sXb[k][r] = (r < rows_b && k < nh) ? xb[(size_t)r * bp.ld + k] : (T)0;
+  {
+    constexpr int NI = NB * NB / 256;              // both tiles in flight before the first shared-memory store
+    T va[NI], vb[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int x = tid + 256 * i, r = x / NB, k = x - r * NB;
+      va[i] = (r < rows_a && k < nh) ? xa[r * sa + k] : (T)0;
+      vb[i] = (r < rows_b && k < nh) ? xb[(size_t)r * bp.ld + k] : (T)0;
+    }
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int x = tid + 256 * i, r = x / NB, k = x - r * NB;
+      sXa[k][r] = va[i];
+      sXb[k][r] = vb[i];
+    }
   }
   __syncthreads();
   T acc[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};

@@ -29,9 +29,11 @@
 //                      look-ahead: it updates the NEXT diagonal tile in shared memory and factors it (fp64), so the serial
 //                      piece of a step never waits for a launch of its own.  nd_potf2_kernel only factors the first tile
 //                      of a phase.
-//   nd_border_kernel   the border phase as ONE cooperative launch: the same step bodies with the panel loop on the device and
-//                      grid-wide barriers (its step count is only known on the device; as separate launches the worst case
-//                      would have to be enqueued).  Launches remain for batches of more than 4 windows / PGBA_ND_COOP=0.
+//   nd_border_kernel   the border's step count is only known on the device; as separate launches the worst case would have to
+//                      be enqueued.  The first nd_nt / 4 border panels are launches (cheapest per panel), the rest ONE
+//                      cooperative launch: the same step bodies with the panel loop on the device and grid-wide barriers;
+//                      it returns at once when the launches covered the border.  All launches for batches of more than 4
+//                      windows / PGBA_ND_COOP=0.
 //   nd_backsolve_kernel  L^T x = z: border (one CTA), then the segments in parallel
 //   nd_finish_kernel   x -> dX in frame order, pose retraction (ba_cuda.cu:88-206)
 //   nd_cleanup_kernel  zeroes the tiles the factor touched (before the next iteration's gather)
@@ -611,7 +613,7 @@ __global__ void __launch_bounds__(256) nd_syrk_kernel(Problem pb, int mode, int 
 // 1000-frame global BA needs 28 of 125 -- ~0.55 us per empty launch, 0.2 ms per call.  Here the panel loop runs on the
 // device with grid-wide barriers (cooperative launch: co-residency guaranteed by the driver) between the row-tile solves and
 // the trailing update.  grid = (G, batch), block = 256, dynamic smem as nd_potf2_kernel.
-__global__ void __launch_bounds__(256, 2) nd_border_kernel(Problem pb) {
+__global__ void __launch_bounds__(256, 2) nd_border_kernel(Problem pb, int first) {
   extern __shared__ double sd[];
   __shared__ float sA[NB][NB + 1];
   __shared__ float sL[NB][NB + 1];
@@ -623,9 +625,12 @@ __global__ void __launch_bounds__(256, 2) nd_border_kernel(Problem pb) {
   int Bmax = 0;                                            // every window walks the same number of barriers
   for (int w = 0; w < (int)gridDim.y; ++w) Bmax = max(Bmax, nd_sys(pb, w + pb.w0).h->Bt);
   const int item = blockIdx.x, nitem = gridDim.x;
-  if (item == 0 && Bt > 0) nd_potf2_dev(sys, sys.h->bbase, sd);
-  grid.sync();
-  for (int b = 0; b < Bmax; ++b) {
+  if (first >= Bmax) return;                               // (every CTA of the grid sees the same counts)
+  if (first == 0) {                                        // otherwise panel `first` was factored by the look-ahead before it
+    if (item == 0 && Bt > 0) nd_potf2_dev(sys, sys.h->bbase, sd);
+    grid.sync();
+  }
+  for (int b = first; b < Bmax; ++b) {
     NdPanel pn;
     const bool live = nd_panel(sys.h, 1, b, 0, pn);
     if (live)
@@ -797,20 +802,13 @@ cudaError_t launch_nd_solve(const Problem& pb, int64_t batch, cudaStream_t strea
       if (g >= 16) coop_g = g;
     }
   }
+  // Border panels: the first `lead` as launches (a kernel boundary with programmatic dependent launch costs ~0.7 us, a
+  // grid-wide barrier ~2-3 us: 17.6 against 21.4 us per panel), the rest -- their number is only known on the device -- in the
+  // cooperative kernel, which returns at once when the launches covered them.  lead = a quarter of the tile capacity: a
+  // chain + loop-closure graph keeps 1 / 4 .. 1 / 5 of its frames in the border (c4: 28 of 142 tiles).
+  const int lead = coop_g > 0 ? (nt / 4 > 4 ? nt / 4 : 4) : border_steps;
   for (int mode = 0; mode < 2; ++mode) {
-    if (mode == 1 && coop_g > 0) {
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3((unsigned)coop_g, B); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = psm; cfg.stream = stream;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeCooperative;
-      at[0].val.cooperative = 1;
-      cfg.attrs = at; cfg.numAttrs = 1;
-      cudaError_t e = cudaLaunchKernelEx(&cfg, nd_border_kernel, pb);
-      if (e != cudaSuccess) return e;
-      count_launch();
-      break;
-    }
-    const int steps = mode == 0 ? pb.L.nd_tmax : border_steps;
+    const int steps = mode == 0 ? pb.L.nd_tmax : (lead < border_steps ? lead : border_steps);
     const unsigned Z = mode == 0 ? (unsigned)P : 1u;
     // CTAs per segment / for the border in the trailing update: a segment panel has ~10-15 active tiles (50-120 pairs)
     const int gx = mode == 0 ? 64 : 296;
@@ -819,6 +817,17 @@ cudaError_t launch_nd_solve(const Problem& pb, int64_t batch, cudaStream_t strea
       launch_k(nd_trsm_kernel, dim3(Z, B, nt + 2), dim3(256), 0, stream, pb, mode, s);
       launch_k(nd_syrk_kernel, dim3(Z, B, gx), dim3(256), psm, stream, pb, mode, s);
       count_launch(); count_launch();
+    }
+    if (mode == 1 && coop_g > 0 && steps < border_steps) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)coop_g, B); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = psm; cfg.stream = stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeCooperative;
+      at[0].val.cooperative = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      cudaError_t e = cudaLaunchKernelEx(&cfg, nd_border_kernel, pb, steps);
+      if (e != cudaSuccess) return e;
+      count_launch();
     }
   }
   const size_t bsmem = sizeof(float) * ((size_t)nt * NB + 33 * NB + NB * (NB + 1));

@@ -45,6 +45,8 @@ SIGNATURES = {
     "pgba_launch_count": (ctypes.c_longlong, []),
     "pgba_ba_status_ptr": (c_vp, [c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_i64, c_i64]),
     "pgba_ba_plan_hit_ptr": (c_vp, [c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_i64, c_i64]),
+    "pgba_ba_order_ptr": (c_vp, [c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_i64, c_i64, ctypes.POINTER(c_int),
+                                 ctypes.POINTER(c_int), ctypes.POINTER(c_vp)]),
     "pgba_pgo_workspace_bytes": (c_int, [c_i64, ctypes.POINTER(c_sz)]),
     "pgba_pgo_solve": (c_int, [c_vp] * 5 + [c_i64, c_i64, ctypes.c_float, ctypes.c_float, c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "pgba_neighbors_workspace_bytes": (c_int, [c_i64, ctypes.POINTER(c_sz)]),
@@ -199,6 +201,29 @@ def last_ba_plan_hits(device=None):
             off = ptr - ws.data_ptr()
             hits += int(ws[off:off + 4].view(torch.int32).item())
     return hits
+
+
+def last_ba_order(device=None, b=0):
+    """Frame ordering the large solve of the most recent BA call on `device` used for window b (include/pgba.h,
+    pgba_ba_order_ptr): dict(pos=i32 [F] numpy, segments, tile_capacity, tiles, border_base, border_tiles, border_frames,
+    seg_tiles, seg_base), or None when the call did not take the reordered solve.  Synchronises."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    rec = _last_ba.get(key)
+    if rec is None:
+        return None
+    ws, E, F, K, t0, t1, batch = rec
+    torch.cuda.current_stream(dev).synchronize()
+    P, cap, hdr = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_void_p(0)
+    ptr = lib().pgba_ba_order_ptr(ws.data_ptr(), E, F, K, t0, t1, batch, b, ctypes.byref(P), ctypes.byref(cap), ctypes.byref(hdr))
+    if not ptr:
+        return None
+    off, hoff = ptr - ws.data_ptr(), hdr.value - ws.data_ptr()
+    pos = ws[off:off + 4 * F].view(torch.int32).cpu().numpy()
+    h = ws[hoff:hoff + 4 * 68].view(torch.int32).cpu().numpy()
+    return dict(pos=pos, segments=P.value, tile_capacity=cap.value, tiles=int(h[0]), border_base=int(h[1]),
+                border_tiles=int(h[2]), border_frames=int(h[3]), seg_tiles=h[4:4 + P.value].copy(),
+                seg_base=h[36:36 + P.value].copy())
 
 
 def invalidate_plan_cache():

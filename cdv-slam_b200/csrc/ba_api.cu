@@ -571,6 +571,19 @@ const int32_t* pgba_ba_plan_hit_ptr(const void* workspace, int64_t n_edges, int6
   return &h->plan_hit;
 }
 
+const int32_t* pgba_ba_order_ptr(const void* workspace, int64_t n_edges, int64_t n_pose_rows, int64_t n_patch_rows,
+                                 int t0, int t1, int64_t batch, int64_t b, int32_t* segments, int32_t* tile_capacity,
+                                 const int32_t** header) {
+  if (!workspace || b < 0 || b >= batch || n_pose_rows <= 0 || n_patch_rows <= 0 || t1 < t0) return nullptr;
+  const Layout L = make_layout(n_edges, n_pose_rows, n_patch_rows, t1 - t0, batch, pick_pc(n_edges, batch, n_pose_rows, n_patch_rows));
+  if (segments) *segments = L.nd_P;
+  if (tile_capacity) *tile_capacity = L.nd_nt;
+  if (L.nd_P == 0) return nullptr;
+  const char* z = (const char*)workspace + (size_t)b * L.zero_bytes;
+  if (header) *header = (const int32_t*)(z + L.z_nd);
+  return (const int32_t*)(z + L.z_ndf) + 3 * n_pose_rows;            // lminv, lmax1, border, pos (ba_bignd.cu: nd_sys)
+}
+
 int pgba_reproject(const float* poses, const float* patches, const float* intrinsics, const int64_t* ii,
                    const int64_t* jj, const int64_t* kk, int64_t n_edges, int64_t n_pose_rows, int64_t n_patch_rows,
                    int P, int clamp_depth, float* coords, pgba_stream_t stream) {

@@ -161,6 +161,18 @@ const int32_t* pgba_ba_status_ptr(const void* workspace, int64_t n_edges, int64_
 const int32_t* pgba_ba_plan_hit_ptr(const void* workspace, int64_t n_edges, int64_t n_pose_rows, int64_t n_patch_rows,
                                     int t0, int t1, int64_t batch, int64_t b);
 
+/* Frame ordering of the large solve.  From 256 free poses the dense solve of the reference (ba_cuda.cu:575-578, 589-591)
+ * runs on a symmetric permutation of the pose system, computed on the device from the edge list by the call itself:
+ * [chain segment 0 | ... | chain segment P-1 | border], segments independent of one another (csrc/ba_bignd.cu).
+ * pgba_ba_order_ptr (diagnostics, tests): device pointer to the i32 [n_pose_rows] array `pos` of window b of the last call --
+ * pos[f] = position (in frames; 8 frames per 48 x 48 tile) of free frame f in the permuted, tile-padded system -- or NULL
+ * when the sizes do not take the reordered solve.  *segments = P, *tile_capacity = tiles the permuted system may use,
+ * *header = device pointer to 4 + 2 * 32 i32: tiles in use, first border tile, border tiles, border frames, tiles of segment
+ * p [32], first tile of segment p [32].  Read after the stream has been synchronised. */
+const int32_t* pgba_ba_order_ptr(const void* workspace, int64_t n_edges, int64_t n_pose_rows, int64_t n_patch_rows,
+                                 int t0, int t1, int64_t batch, int64_t b, int32_t* segments /* host, out */,
+                                 int32_t* tile_capacity /* host, out */, const int32_t** header /* host, out */);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Reprojection of all PxP pixels of each edge's patch from frame ii to frame jj.  Replaces cuda_ba.reproject ==
  * cuda_reproject() (reference: cdvslam/fastba/ba_cuda.cu:408-458, 614-645).  coords f32 [n_edges, 2, P, P].

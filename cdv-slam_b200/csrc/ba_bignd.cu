@@ -825,9 +825,16 @@ cudaError_t launch_nd_solve(const Problem& pb, int64_t batch, cudaStream_t strea
       at[0].id = cudaLaunchAttributeCooperative;
       at[0].val.cooperative = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
-      cudaError_t e = cudaLaunchKernelEx(&cfg, nd_border_kernel, pb, steps);
-      if (e != cudaSuccess) return e;
-      count_launch();
+      if (cudaLaunchKernelEx(&cfg, nd_border_kernel, pb, steps) == cudaSuccess) {
+        count_launch();
+      } else {                                         // e.g. the grid is not co-resident on this device: the rest as launches
+        (void)cudaGetLastError();
+        for (int s = steps; s < border_steps; ++s) {
+          launch_k(nd_trsm_kernel, dim3(Z, B, nt + 2), dim3(256), 0, stream, pb, mode, s);
+          launch_k(nd_syrk_kernel, dim3(Z, B, gx), dim3(256), psm, stream, pb, mode, s);
+          count_launch(); count_launch();
+        }
+      }
     }
   }
   const size_t bsmem = sizeof(float) * ((size_t)nt * NB + 33 * NB + NB * (NB + 1));

@@ -1,6 +1,6 @@
 // Large solve of the global (loop-closure) bundle adjustment with a nested-dissection frame ordering.
 // Replaces at::linalg_cholesky_ex + torch::cholesky_solve on the dense S of the reference
-// (cdvslam/fastba/ba_cuda.cu:575-578 for eff_impl, :589-591 dense) for >= ND_MIN_N free poses.
+// (cdvslam/fastba/ba_cuda.cu:575-578 for eff_impl, :589-591 dense) for every system beyond the single-CTA solve (>= ND_MIN_N = 27 free poses).
 //
 // The natural-order blocked Cholesky of big_chol.cuh walks 6N / 48 dependent panel steps (125 for the 1000-frame global
 // BA), three launches each, and nearly every step is latency: the pose graph is a chain (patches are seen by a few

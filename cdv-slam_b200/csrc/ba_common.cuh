@@ -13,7 +13,7 @@ constexpr int SMAX = PGBA_MAX_SLOTS;      // distinct target frames per chunk
 constexpr int EBUDGET = 12288;            // floats of shared memory for the per-batch E tile (48 KB)
 constexpr int SOLVE_NMAX = 156;           // 6N handled by the single-CTA shared-memory solve (N <= 26)
 constexpr int BIG_NB = 48;                // panel width of the blocked global-memory Cholesky (6N > SOLVE_NMAX)
-constexpr int ND_MIN_N = 256;             // free poses from which the large solve reorders the frames (ba_bignd.cu)
+constexpr int ND_MIN_N = 27;              // free poses from which the large solve reorders the frames (ba_bignd.cu): all of them
 
 // ---------------------------------------------------------------------------------------------------------------
 // Workspace.  [ zero region of window 0 | ... | zero region of window B-1 | body of window 0 | ... ]
@@ -149,6 +149,7 @@ inline Layout make_layout(int64_t E, int64_t F, int64_t K, int N, int64_t batch,
   L.nd_P = 0; L.nd_nt = 0; L.nd_tmax = 0; L.nd_R = 0;
   if (L.big && N >= ND_MIN_N && nd_enabled()) {
     int P = N / 60;
+    if (P < 1) P = 1;
     if (P > ND_MAXP) P = ND_MAXP;
     const int nt = (N + 7) / 8 + P + 1;               // every segment and the border round up to whole tiles
     // the backward substitution keeps the whole solution in shared memory

@@ -161,7 +161,7 @@ const int32_t* pgba_ba_status_ptr(const void* workspace, int64_t n_edges, int64_
 const int32_t* pgba_ba_plan_hit_ptr(const void* workspace, int64_t n_edges, int64_t n_pose_rows, int64_t n_patch_rows,
                                     int t0, int t1, int64_t batch, int64_t b);
 
-/* Frame ordering of the large solve.  From 256 free poses the dense solve of the reference (ba_cuda.cu:575-578, 589-591)
+/* Frame ordering of the large solve.  Beyond 26 free poses (6N > 156) the dense solve of the reference (ba_cuda.cu:575-578, 589-591)
  * runs on a symmetric permutation of the pose system, computed on the device from the edge list by the call itself:
  * [chain segment 0 | ... | chain segment P-1 | border], segments independent of one another (csrc/ba_bignd.cu).
  * pgba_ba_order_ptr (diagnostics, tests): device pointer to the i32 [n_pose_rows] array `pos` of window b of the last call --

@@ -9,14 +9,14 @@ against; what is checked instead is (a) the invariant the parallel elimination r
 different chain segments -- straight from the edge list, and (b) that the device computes exactly this ordering."""
 import numpy as np
 
-ND_MIN_N, ND_MAXP, NB_FRAMES = 256, 32, 8      # ba_common.cuh: ND_MIN_N, ND_MAXP; 48 unknowns = 8 frames per tile
+ND_MIN_N, ND_MAXP, NB_FRAMES = 27, 32, 8      # ba_common.cuh: ND_MIN_N, ND_MAXP; 48 unknowns = 8 frames per tile
 
 
 def parameters(N):
     """make_layout (ba_common.cuh): segments P, longest segment, far-edge distance R; None below ND_MIN_N."""
     if N < ND_MIN_N:
         return None
-    P = min(N // 60, ND_MAXP)
+    P = max(1, min(N // 60, ND_MAXP))
     lseg = (N + P - 1) // P
     return dict(P=P, tmax=(lseg + 7) // 8, R=max(lseg // 4, 4), nt=(N + 7) // 8 + P + 1)
 

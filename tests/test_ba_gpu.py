@@ -319,7 +319,7 @@ def _graph_edges(kind, F, M, rng):
 
 @pytest.mark.parametrize("kind", ["chain+loops", "chain", "many-loops", "wide-band", "shuffled"])
 def test_global_ba_reordered_solver(kind, monkeypatch):
-    """>= 256 free poses: the large solve eliminates chain segments in parallel and a border last (nested-dissection frame
+    """Several segments (N / 60 of them): the large solve eliminates chain segments in parallel and a border last (nested-dissection frame
     ordering computed on the device, ba_bignd.cu).  Whatever the graph looks like the result must be the solve of the same
     damped system: dX against a float64 solve of the exported S, y, against the natural-order solver (PGBA_BIG_ND=0) and,
     through two full iterations, against the oracle."""

@@ -61,15 +61,23 @@ def test_c4_takes_36_dependent_steps_instead_of_125():
     assert ndo.coupled_pairs_cross_segments(p.ii, p.jj, p.kk, o, p.t0, p.t1) == 0
 
 
-def test_below_the_threshold_the_natural_order_is_kept():
-    assert ndo.parameters(255) is None and ndo.parameters(256)["P"] == 4
+def test_segment_count_by_size():
+    assert ndo.parameters(26) is None and ndo.parameters(27)["P"] == 1 and ndo.parameters(256)["P"] == 4
+
+
+def test_single_segment_below_120_poses():
+    F, M, t0 = 75, 6, 1
+    ii, jj, kk = synth.global_edges(F, M, 10, np.random.default_rng(5))
+    o = ndo.order(ii, jj, kk, F, F * M, t0, F)
+    assert o["segments"] == 1 and o["border_frames"] == len(np.unique(jj[np.abs(jj - ii) > 18]))
+    assert ndo.coupled_pairs_cross_segments(ii, jj, kk, o, t0, F) == 0
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kind", KINDS)
-def test_device_ordering_equals_oracle(kind):
+@pytest.mark.parametrize("kind,F", [(k, 300) for k in KINDS] + [("chain+loops", 75), ("wide-band", 140)])
+def test_device_ordering_equals_oracle(kind, F):
     from cdvslam_b200 import fastba, native
-    F, M = 300, 6
+    M = 6
     p = synth.make_problem("nd-" + kind, F, _edges(kind, F, M, np.random.default_rng(77)), 1, F, 11, M, eff_impl=True)
     d = to_dev(p)
     fastba.BA(d["poses"], d["patches"], d["intrinsics"], d["target"], d["weight"], d["lmbda"], d["ii"], d["jj"], d["kk"],

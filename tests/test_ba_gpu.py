@@ -275,9 +275,10 @@ def _global_problem(F, M, n_loops, seed):
 
 
 @pytest.mark.parametrize("F,M,n_loops", [(40, 8, 3), (75, 12, 10)])
-def test_global_ba_large_solver_normal_equations(F, M, n_loops):
-    """6N > 156 selects the blocked global-memory Cholesky (reference: dense torch Cholesky on S, ba_cuda.cu:575-591).
-    S, y and the solution dX / dZ against the oracle; F=75 gives a ragged last panel (444 = 9*48 + 12)."""
+def test_global_ba_large_solver_normal_equations(F, M, n_loops, monkeypatch):
+    """6N > 156 selects the tile-sparse global-memory Cholesky (reference: dense torch Cholesky on S, ba_cuda.cu:575-591), here
+    with a single chain segment + the loop-closure targets as border (ba_bignd.cu); S, y and the solution dX / dZ against the
+    oracle.  The natural-order form (PGBA_BIG_ND=0; F=75 gives it a ragged last panel, 444 = 9*48 + 12) must agree."""
     p = _global_problem(F, M, n_loops, 31 + F)
     d = to_dev(p)
     o = _normal_equations_oracle(p)
@@ -292,6 +293,11 @@ def test_global_ba_large_solver_normal_equations(F, M, n_loops):
     assert rel_err(g["dX"].cpu().numpy(), o["dX"]) < tol_x
     assert rel_err(g["dZ"].cpu().numpy(), o["dZ"]) < tol_x
     _check_solve_residual(S, g["y"].cpu().numpy(), g["dX"].cpu().numpy())
+    monkeypatch.setenv("PGBA_BIG_ND", "0")
+    g0 = fastba.linearize_debug(d["poses"], d["patches"], d["intrinsics"], d["target"], d["weight"], d["lmbda"], d["ii"],
+                                d["jj"], d["kk"], p.t0, p.t1, with_schur=True)
+    assert rel_err(g0["dX"].cpu().numpy(), o["dX"]) < tol_x
+    _check_solve_residual(S, g0["y"].cpu().numpy(), g0["dX"].cpu().numpy())
 
 
 def _graph_edges(kind, F, M, rng):

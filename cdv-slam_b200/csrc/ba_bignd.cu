@@ -46,7 +46,7 @@
 namespace pgba {
 
 #ifdef PGBA_ND_TIMING      // per-launch timeline of the factorisation (profiles/nd_timeline.py): entry, after pdl_wait, end
-__device__ unsigned long long g_nd_ts[3 * 1024][3];
+__device__ unsigned long long g_nd_ts[8 * 1024][3];
 __device__ __forceinline__ unsigned long long nd_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 struct NdTs {
   int id;
@@ -203,8 +203,10 @@ __global__ void __launch_bounds__(1024) nd_order_kernel(Problem pb) {
 
 // grid = (gx, batch), block = 256.  One row of the lower block triangle of S per CTA and trip.
 __global__ void __launch_bounds__(256) nd_gather_kernel(Problem pb) {
+  ND_TS(3, 0, 0);
   pdl_wait();
   pdl_trigger();
+  ND_TS_WAITED();
   const int w = blockIdx.y + pb.w0, tid = threadIdx.x;
   const NdSys sys = nd_sys(pb, w);
   const int t0 = pb.t0, N = pb.t1 - t0, n6 = 6 * N;
@@ -614,6 +616,8 @@ __global__ void __launch_bounds__(256) nd_syrk_kernel(Problem pb, int mode, int 
 // device with grid-wide barriers (cooperative launch: co-residency guaranteed by the driver) between the row-tile solves and
 // the trailing update.  grid = (G, batch), block = 256, dynamic smem as nd_potf2_kernel.
 __global__ void __launch_bounds__(256, 2) nd_border_kernel(Problem pb, int first) {
+  ND_TS(5, 0, 0);
+  ND_TS_WAITED();
   extern __shared__ double sd[];
   __shared__ float sA[NB][NB + 1];
   __shared__ float sL[NB][NB + 1];
@@ -646,8 +650,10 @@ __global__ void __launch_bounds__(256, 2) nd_border_kernel(Problem pb, int first
 // mode 1: the border panels, last to first (grid = (1, batch)); mode 0: segment blockIdx.x, after the border
 // (grid = (P, batch)).  dynamic smem: (nd_nt * NB + 33 * NB + NB (NB + 1)) floats
 __global__ void __launch_bounds__(1024, 1) nd_backsolve_kernel(Problem pb, int mode) {
+  ND_TS(4, mode, 0);
   pdl_wait();
   pdl_trigger();
+  ND_TS_WAITED();
   extern __shared__ __align__(16) unsigned char bsm[];
   const NdSys sys = nd_sys(pb, blockIdx.y + pb.w0);
   const NdHeader* h = sys.h;
@@ -727,8 +733,10 @@ __global__ void __launch_bounds__(1024, 1) nd_backsolve_kernel(Problem pb, int m
 
 // grid = (ceil(N / 128), batch), block = 128
 __global__ void nd_finish_kernel(Problem pb) {
+  ND_TS(6, 0, 0);
   pdl_wait();
   pdl_trigger();
+  ND_TS_WAITED();
   const int w = blockIdx.y + pb.w0;
   const WinPtrs wp = win_ptrs(pb.ws, pb.L, w);
   const NdSys sys = nd_sys(pb, w);
@@ -853,11 +861,11 @@ cudaError_t launch_nd_solve(const Problem& pb, int64_t batch, cudaStream_t strea
 #ifdef PGBA_ND_TIMING
 void nd_timestamps(unsigned long long* out, int reset) {
   if (reset) {
-    static unsigned long long init[3 * 1024][3];
+    static unsigned long long init[8 * 1024][3];
     for (auto& r : init) { r[0] = ~0ull; r[1] = ~0ull; r[2] = 0ull; }
     cudaMemcpyToSymbol(g_nd_ts, init, sizeof(init));
   } else {
-    cudaMemcpyFromSymbol(out, g_nd_ts, sizeof(unsigned long long) * 3 * 1024 * 3);
+    cudaMemcpyFromSymbol(out, g_nd_ts, sizeof(unsigned long long) * 8 * 1024 * 3);
   }
 }
 #endif

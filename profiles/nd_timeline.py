@@ -16,14 +16,14 @@ def call():
     torch.cuda.synchronize()
 call(); call()
 lib = ctypes.CDLL(native.LIB_PATH)
-raw = np.zeros(3 * 1024 * 3, np.uint64)
-buf = raw[:3 * 1024 * 3].reshape(3 * 1024, 3)
+raw = np.zeros(8 * 1024 * 3, np.uint64)
+buf = raw.reshape(8 * 1024, 3)
 lib.pgba_nd_timestamps(None, 1)
 call()
 lib.pgba_nd_timestamps(raw.ctypes.data_as(ctypes.c_void_p), 0)
 ok = buf[:, 2] > 0
 t0 = buf[ok][:, 0].min()
-names = ["potf2", "trsm", "syrk"]
+names = ["potf2", "trsm", "syrk", "gather", "backsolve", "border(coop)", "finish", "?"]
 rows = []
 for i in np.nonzero(ok)[0]:
     kind, mode, idx = i // 1024, (i % 1024) // 512, i % 512
@@ -32,7 +32,7 @@ for i in np.nonzero(ok)[0]:
 rows.sort()
 prev_end = 0.0
 for e, n, mode, idx, w, x in rows:
-    if mode == 1 and idx > 34: continue
+    if mode == 1 and idx > 36: continue
     print("%-6s mode %d step %3d  entered %8.2f  released %8.2f  end %8.2f  body %6.2f  gap after prev end %6.2f" % (n, mode, idx, e, w, x, x - w, w - prev_end))
     prev_end = x
 

@@ -82,6 +82,7 @@ def linearize_debug(poses, patches, intrinsics, target, weight, lmbda, ii, jj, k
                                        dZ.data_ptr(), nu.data_ptr(), status.data_ptr(), ws.data_ptr(), ws.numel(),
                                        native.stream_ptr(dev))
     native.check(rc, "pgba_ba_linearize_debug")
+    native.note_ba_call(ws, dev, E, F, K, int(t0), int(t1), 1)
     n = int(nu.item())
     order = torch.argsort(ids[:n])
     return dict(S=S, y=y, dX=dX, kx=ids[:n][order], C=C[:n][order], u=u[:n][order], Q=Q[:n][order], dZ=dZ[:n][order],

@@ -801,13 +801,21 @@ cudaError_t launch_nd_solve(const Problem& pb, int64_t batch, cudaStream_t strea
   {
     const char* e = getenv("PGBA_ND_COOP");
     if (!(e && e[0] == '0') && batch <= 4) {
-      int dev = 0, sms = 0, per_sm = 0;
+      static int slots[64];                          // co-resident CTAs of the cooperative kernel per device (0: not asked yet)
+      int dev = 0;
       cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      cudaFuncSetAttribute(nd_border_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm);
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nd_border_kernel, 256, psm);
-      int g = (per_sm > 2 ? 2 : per_sm) * sms / (int)batch;
-      if (g >= 16) coop_g = g;
+      if (dev >= 0 && dev < 64) {
+        if (slots[dev] == 0) {
+          int sms = 0, per_sm = 0;
+          cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+          cudaFuncSetAttribute(nd_border_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm);
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nd_border_kernel, 256, psm);
+          slots[dev] = (per_sm > 2 ? 2 : per_sm) * sms;
+          if (slots[dev] <= 0) slots[dev] = -1;
+        }
+        const int g = slots[dev] / (int)batch;
+        if (g >= 16) coop_g = g;
+      }
     }
   }
   // Border panels: the first `lead` as launches (a kernel boundary with programmatic dependent launch costs ~0.7 us, a
